@@ -1,0 +1,203 @@
+/*
+ * mapdamage_b200 -- C ABI of the B200-native mapDamage hot path.
+ *
+ * The reference (ginolhac/mapDamage, pure Python on this path) has no FFI or
+ * plugin interface; its seam is two Python call sites.  Every entry point
+ * below names the reference code it replaces (paths relative to the
+ * reference's mapdamage/ package).  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success or a negative mdg_status; no function throws, exits or falls back
+ * to the CPU.  The message for the last failure on a context is returned by
+ * mdg_last_error().  A context is bound to one CUDA device and is not
+ * thread-safe; calls on different contexts may run concurrently.
+ */
+#ifndef MAPDAMAGE_B200_H
+#define MAPDAMAGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDG_ABI_VERSION 1
+
+/* Class axis of the misincorporation slab (see mdg_fetch_tables). */
+#define MDG_N_CLASSES 30
+#define MDG_CLASS_SOFTCLIP 29
+
+typedef enum {
+    MDG_OK = 0,
+    MDG_ERR_ARGUMENT = -1, /* bad pointer / size / configuration                         */
+    MDG_ERR_CUDA = -2,     /* a CUDA runtime call failed (message has the CUDA error)     */
+    MDG_ERR_NO_DEVICE = -3,/* no usable CUDA device: there is deliberately no CPU path    */
+    MDG_ERR_STATE = -4,    /* call order: e.g. counting before mdg_set_reference          */
+    MDG_ERR_CAPACITY = -5, /* batch larger than the configured staging capacity           */
+    MDG_ERR_DATA = -6,     /* record the reference would also fail on (see message)       */
+    MDG_ERR_NCCL = -7      /* NCCL missing or a collective failed                         */
+} mdg_status;
+
+typedef struct mdg_ctx mdg_ctx;
+typedef struct mdg_dev_batch mdg_dev_batch;
+
+/*
+ * Options of one pass.  length/around/min_qual are the reference's
+ * --length/-l, --around/-a, --min-basequal/-Q (config.py:143-166);
+ * n_libraries = number of (sample, library) pairs (reader.py:47-50).
+ */
+typedef struct {
+    int32_t device;       /* CUDA device ordinal                                          */
+    int32_t length;       /* L: positions tabulated from each read end                    */
+    int32_t around;       /* A: flanking reference bases tabulated                        */
+    int32_t min_qual;     /* bases with Phred < min_qual are masked (align.py:67-71)      */
+    int32_t n_libraries;
+    int32_t lg_bins;      /* dense fragment-length bins; longer ones go to an overflow list */
+    int32_t n_slots;      /* staging slots for streamed batches (>= 2 = double buffering) */
+    int32_t reserved;
+    int64_t max_reads;    /* staging capacity of one slot, in reads ...                   */
+    int64_t max_cigar_ops;/* ... CIGAR words ...                                          */
+    int64_t max_bases;    /* ... and base slots (see mdg_batch.n_bases)                   */
+} mdg_config;
+
+/*
+ * One struct-of-arrays batch of alignment records: what the reference's loops
+ * read from each pysam.AlignedSegment (main.py:165-217, rescale.py:300-344).
+ * Read i owns CIGAR words cigar[cigar_off[i] .. cigar_off[i+1]) (BAM encoding
+ * len << 4 | op), l_seq[i] bases packed 4 bits each (BAM nibble codes, high
+ * nibble first) starting at byte base_off[i] / 2 of seq4, and l_seq[i] raw
+ * Phred bytes starting at byte base_off[i] of qual.  base_off[i] is even.
+ * qual may be NULL (no read has qualities); a read whose first quality byte
+ * is 0xFF has none (BAM convention).  lib[i] indexes the library axis.
+ */
+typedef struct {
+    int64_t n_reads;
+    int64_t n_cigar;  /* = cigar_off[n_reads]                                  */
+    int64_t n_bases;  /* base slots spanned: seq4 has n_bases / 2 bytes, qual n_bases */
+    const uint16_t *flag;
+    const int32_t *tid;
+    const int32_t *pos;
+    const uint16_t *lib;
+    const uint32_t *l_seq;
+    const uint32_t *base_off;
+    const uint32_t *cigar_off; /* n_reads + 1 entries */
+    const uint32_t *cigar;
+    const uint8_t *seq4;
+    const uint8_t *qual;
+    const int32_t *tlen;
+    const int32_t *mtid;
+    const int32_t *mpos;
+} mdg_batch;
+
+/* ---- life cycle ------------------------------------------------------ */
+
+/* Creates a context on cfg->device; fails with MDG_ERR_NO_DEVICE when no GPU
+ * is present.  Replaces the accumulator construction at main.py:147-155. */
+int mdg_create(mdg_ctx **out, const mdg_config *cfg);
+void mdg_destroy(mdg_ctx *ctx);
+/* Message of the last failure (ctx may be NULL for mdg_create failures). */
+const char *mdg_last_error(const mdg_ctx *ctx);
+int mdg_abi_version(void);
+
+/* Page-locked host memory for batches/results (cudaHostAlloc). */
+void *mdg_host_alloc(size_t bytes);
+void mdg_host_free(void *ptr);
+
+/*
+ * Uploads the genome once: replaces the per-read pysam.FastaFile.fetch calls
+ * (main.py:115,180; align.py:32-33; rescale.py:213).  packed = one nibble per
+ * base, low nibble first; 0..3 = A,C,G,T (either case), 7 = anything else;
+ * contig c starts at base contig_off[c] (a multiple of 8) and has
+ * contig_len[c] bases.  n_bytes must cover the last contig rounded up to 8
+ * bases.
+ */
+int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, const uint64_t *contig_off,
+                      const uint32_t *contig_len, int32_t n_contigs);
+
+/* ---- counting pass: replaces the loop body main.py:165-217 ------------- */
+
+/*
+ * Streams one host batch: asynchronous host->device copy into the next
+ * staging slot and the counting kernels on that slot's stream.  Returns once
+ * the work is queued; the host arrays must stay valid until mdg_sync() or
+ * until n_slots further submits have been made.  Applies the read filter of
+ * reader.py:121-132 (flag & 0xF04) on the device.
+ */
+int mdg_count_submit(mdg_ctx *ctx, const mdg_batch *host);
+
+/* Keeps a batch resident in HBM (benchmarks, repeated passes). */
+int mdg_batch_upload(mdg_ctx *ctx, const mdg_batch *host, mdg_dev_batch **out);
+int mdg_batch_free(mdg_ctx *ctx, mdg_dev_batch *batch);
+/* Counting kernels over a resident batch, on the context's compute stream. */
+int mdg_count_resident(mdg_ctx *ctx, const mdg_dev_batch *batch);
+
+/* Waits for all queued work; surfaces asynchronous CUDA errors. */
+int mdg_sync(mdg_ctx *ctx);
+int mdg_reset_tables(mdg_ctx *ctx);
+
+/*
+ * Copies the accumulated tables to the host (implies mdg_sync).  Layouts
+ * (uint64, C order) -- the state of MisincorporationRates / DNAComposition /
+ * FragmentLengths (statistics.py:9-137):
+ *   misincorp [n_libraries][end 5p,3p][strand +,-][MDG_N_CLASSES][length]
+ *       class 0..3: reference base A,C,G,T; 4 + 5*g + b: reference g read as b,
+ *       g,b in A,C,G,T,gap (g != b); MDG_CLASS_SOFTCLIP: soft-clipped bases
+ *   dnacomp   [n_libraries][end][strand][A,C,G,T][length + around]
+ *       slot d < length: read base at distance d from that end;
+ *       slot length + d - 1: flanking reference base at distance d = 1..around
+ *   lghist    [n_libraries][kind pe,se][strand][lg_bins]
+ * Any pointer may be NULL to skip that table.
+ */
+int mdg_fetch_tables(mdg_ctx *ctx, uint64_t *misincorp, uint64_t *dnacomp, uint64_t *lghist);
+/* Fragment lengths >= lg_bins: rows of {lib, kind, strand, length}; returns the
+ * row count (or < 0); at most max_rows rows are written. */
+int64_t mdg_fetch_lg_overflow(mdg_ctx *ctx, int32_t *rows, int64_t max_rows);
+
+/* ---- rescale pass: replaces rescale._rescale_qual_core (rescale.py:285-365) */
+
+/*
+ * Correction model built on the host from Stats_out_MCMC_correct_prob.csv
+ * (rescale.py:23-46): lut[type C>T,G>A][1 + len5p + len3p][94] = new Phred by
+ * old Phred, inc[type][slot] = contribution of one rescaled base to MR.
+ * Slot 0 = no entry, slot p = 5' position p, slot len5p + p = 3' position -p.
+ */
+int mdg_set_rescale_model(mdg_ctx *ctx, const uint8_t *lut, const double *inc, int32_t len5p, int32_t len3p);
+
+/*
+ * Rescales one host batch (every record, no read filter: rescale.py:300).
+ * qual_out (n_bases bytes, same layout as qual), mr_out[n_reads] (the MR:f
+ * tag value) and status_out[n_reads] (0 passed through, 1 rescaled) are
+ * filled by asynchronous device->host copies; valid after mdg_sync().
+ * stats (optional, 8 uint64: pairs, improper pairs, reads without qualities,
+ * rescaled reads, alignments longer than the read, 3 reserved) accumulates.
+ */
+int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, float *mr_out,
+                       uint8_t *status_out);
+int mdg_fetch_rescale_stats(mdg_ctx *ctx, uint64_t *stats8);
+
+/* ---- multi-GPU: one context per rank, tables summed over ranks ---------- */
+
+/* 128-byte NCCL unique id, made on rank 0 and handed to the other ranks by
+ * the caller's launcher (torch.distributed / MPI / a file). */
+int mdg_nccl_unique_id(void *id128);
+int mdg_nccl_init(mdg_ctx *ctx, const void *id128, int32_t rank, int32_t n_ranks);
+/* ncclAllReduce(sum, uint64) over all count tables, in place, on the compute stream. */
+int mdg_allreduce_tables(mdg_ctx *ctx);
+
+/* ---- measurement helpers (bench.py) ------------------------------------ */
+
+/* CUDA events on the context's compute stream: which = 0 start, 1 stop. */
+int mdg_event_record(mdg_ctx *ctx, int32_t which);
+int mdg_event_elapsed_ms(mdg_ctx *ctx, float *ms);
+/* Kernels launched by this context so far. */
+int64_t mdg_launch_count(const mdg_ctx *ctx);
+/* Device duration of the counting kernels of the last pass, in ms (events
+ * recorded around every launch; valid after mdg_sync). */
+int mdg_last_kernel_ms(mdg_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPDAMAGE_B200_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of ``libmapdamage_b200.so`` (``include/mapdamage_b200.h``).
+
+There is no Python or CPU implementation behind this module: if the CUDA
+library is missing or cannot be loaded, importing the engine fails loudly.
+"""
+import ctypes as C
+from pathlib import Path
+
+LIBRARY = Path(__file__).resolve().parent / "libmapdamage_b200.so"
+
+ABI_VERSION = 1
+N_CLASSES = 30
+
+OK = 0
+ERR_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_CAPACITY, ERR_DATA, ERR_NCCL = range(-1, -8, -1)
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("mapdamage_b200 native error %d: %s" % (code, message))
+        self.code = code
+        self.message = message
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("length", C.c_int32), ("around", C.c_int32), ("min_qual", C.c_int32),
+        ("n_libraries", C.c_int32), ("lg_bins", C.c_int32), ("n_slots", C.c_int32), ("reserved", C.c_int32),
+        ("max_reads", C.c_int64), ("max_cigar_ops", C.c_int64), ("max_bases", C.c_int64),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_int64), ("n_cigar", C.c_int64), ("n_bases", C.c_int64),
+        ("flag", C.c_void_p), ("tid", C.c_void_p), ("pos", C.c_void_p), ("lib", C.c_void_p),
+        ("l_seq", C.c_void_p), ("base_off", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p),
+        ("seq4", C.c_void_p), ("qual", C.c_void_p), ("tlen", C.c_void_p), ("mtid", C.c_void_p),
+        ("mpos", C.c_void_p),
+    ]
+
+
+# every symbol include/mapdamage_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "mdg_abi_version": (C.c_int, []),
+    "mdg_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Config)]),
+    "mdg_destroy": (None, [C.c_void_p]),
+    "mdg_last_error": (C.c_char_p, [C.c_void_p]),
+    "mdg_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "mdg_host_free": (None, [C.c_void_p]),
+    "mdg_set_reference": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
+    "mdg_count_submit": (C.c_int, [C.c_void_p, C.POINTER(Batch)]),
+    "mdg_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(C.c_void_p)]),
+    "mdg_batch_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdg_count_resident": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdg_sync": (C.c_int, [C.c_void_p]),
+    "mdg_reset_tables": (C.c_int, [C.c_void_p]),
+    "mdg_fetch_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mdg_fetch_lg_overflow": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "mdg_set_rescale_model": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "mdg_rescale_submit": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mdg_fetch_rescale_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdg_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "mdg_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "mdg_allreduce_tables": (C.c_int, [C.c_void_p]),
+    "mdg_event_record": (C.c_int, [C.c_void_p, C.c_int32]),
+    "mdg_event_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mdg_launch_count": (C.c_int64, [C.c_void_p]),
+    "mdg_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not LIBRARY.is_file():
+            raise ImportError(
+                "%s is missing: build it with `python -m mapdamage_b200.build` "
+                "(mapdamage_b200 has no CPU implementation)" % LIBRARY)
+        lib = C.CDLL(str(LIBRARY))
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.mdg_abi_version() != ABI_VERSION:
+            raise ImportError("libmapdamage_b200.so has ABI %d, expected %d" % (lib.mdg_abi_version(), ABI_VERSION))
+        _lib = lib
+    return _lib
+
+
+def last_error(ctx):
+    text = load().mdg_last_error(ctx)
+    return text.decode("utf-8", "replace") if text else ""
+
+
+def check(code, ctx=None):
+    if code < 0:
+        raise NativeError(code, last_error(ctx))
+    return code

@@ -1,0 +1,713 @@
+// C ABI of mapdamage_b200 (include/mapdamage_b200.h): context, staging slots,
+// launches.  No CPU path: without a CUDA device mdg_create fails.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h>  // types only; the library is loaded with dlopen
+
+#include "../../include/mapdamage_b200.h"
+#include "mdg_count.cuh"
+#include "mdg_fast.cuh"
+#include "mdg_rescale.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi &nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *name : names) {
+            api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            api.error = std::string("cannot load libnccl: ") + dlerror();
+            return;
+        }
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy)
+            api.error = "libnccl lacks a required symbol";
+    });
+    return api;
+}
+
+// Device copy of one batch; arrays live in one allocation.
+struct DeviceArrays {
+    void *block = nullptr;
+    size_t bytes = 0;
+    int64_t cap_reads = 0, cap_cigar = 0, cap_bases = 0;
+    bool has_qual = false;
+    mdg::DevBatch view{};
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DeviceArrays arrays;
+    // rescale outputs
+    uint8_t *qual_out = nullptr;
+    float *mr_out = nullptr;
+    uint8_t *status_out = nullptr;
+};
+
+}  // namespace
+
+struct mdg_dev_batch {
+    DeviceArrays arrays;
+};
+
+struct mdg_ctx {
+    mdg_config cfg{};
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::string error;
+    cudaStream_t compute = nullptr;
+    std::vector<Slot> slots;
+    int next_slot = 0;
+    // reference genome
+    mdg::DevRef ref{};
+    void *ref_block = nullptr;
+    // tables: one allocation [misincorp | dnacomp | lghist]
+    unsigned long long *tables = nullptr;
+    size_t n_mis = 0, n_comp = 0, n_lg = 0;
+    mdg::CountTables count_tables{};
+    void *aux_block = nullptr;  // overflow rows, counters, error flag, rescale stats, fast-path worklist counter
+    unsigned long long *rescale_stats = nullptr;
+    // rescale model
+    void *model_block = nullptr;
+    mdg::RescaleModel model{};
+    // launch geometry
+    bool shared_slab = false;
+    size_t slab_bytes = 0;
+    int general_grid = 0;
+    mdg::FastPlan fast{};
+    // measurement
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> kernel_events;  // pairs
+    size_t kernel_events_used = 0;
+    int64_t launches = 0;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+};
+
+namespace {
+
+int fail(mdg_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define MDG_CUDA(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, MDG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Carves the arrays of a batch with the given capacities out of one allocation.
+int alloc_arrays(mdg_ctx *ctx, DeviceArrays &a, int64_t reads, int64_t cigar, int64_t bases, bool with_qual)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off += align_up(bytes + 16);
+        return at;
+    };
+    size_t o_flag = take(reads * 2), o_tid = take(reads * 4), o_pos = take(reads * 4), o_lib = take(reads * 2);
+    size_t o_lseq = take(reads * 4), o_boff = take(reads * 4), o_coff = take((reads + 1) * 4);
+    size_t o_cig = take(cigar * 4), o_seq = take(bases / 2 + 8), o_qual = with_qual ? take(bases + 8) : 0;
+    size_t o_tlen = take(reads * 4), o_mtid = take(reads * 4), o_mpos = take(reads * 4);
+    MDG_CUDA(ctx, cudaMalloc(&a.block, off));
+    a.bytes = off;
+    a.cap_reads = reads; a.cap_cigar = cigar; a.cap_bases = bases; a.has_qual = with_qual;
+    char *p = (char *)a.block;
+    a.view.flag = (const uint16_t *)(p + o_flag);
+    a.view.tid = (const int32_t *)(p + o_tid);
+    a.view.pos = (const int32_t *)(p + o_pos);
+    a.view.lib = (const uint16_t *)(p + o_lib);
+    a.view.l_seq = (const uint32_t *)(p + o_lseq);
+    a.view.base_off = (const uint32_t *)(p + o_boff);
+    a.view.cigar_off = (const uint32_t *)(p + o_coff);
+    a.view.cigar = (const uint32_t *)(p + o_cig);
+    a.view.seq4 = (const uint8_t *)(p + o_seq);
+    a.view.qual = with_qual ? (const uint8_t *)(p + o_qual) : nullptr;
+    a.view.tlen = (const int32_t *)(p + o_tlen);
+    a.view.mtid = (const int32_t *)(p + o_mtid);
+    a.view.mpos = (const int32_t *)(p + o_mpos);
+    return MDG_OK;
+}
+
+int check_batch(mdg_ctx *ctx, const mdg_batch *h)
+{
+    if (!h) return fail(ctx, MDG_ERR_ARGUMENT, "batch is NULL");
+    if (h->n_reads < 0 || h->n_cigar < 0 || h->n_bases < 0 || (h->n_bases & 1))
+        return fail(ctx, MDG_ERR_ARGUMENT, "batch sizes must be non-negative and n_bases even");
+    if (h->n_reads >= (1ll << 31) || h->n_cigar >= (1ll << 32) || h->n_bases >= (1ll << 32))
+        return fail(ctx, MDG_ERR_ARGUMENT, "batch too large: split it (offsets are 32-bit)");
+    if (h->n_reads &&
+        (!h->flag || !h->tid || !h->pos || !h->lib || !h->l_seq || !h->base_off || !h->cigar_off || !h->tlen ||
+         !h->mtid || !h->mpos || (h->n_cigar && !h->cigar) || (h->n_bases && !h->seq4)))
+        return fail(ctx, MDG_ERR_ARGUMENT, "batch has a NULL array");
+    return MDG_OK;
+}
+
+// Queues the host->device copies of one batch on `stream`.
+int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t stream)
+{
+    if (h->n_reads > a.cap_reads || h->n_cigar > a.cap_cigar || h->n_bases > a.cap_bases)
+        return fail(ctx, MDG_ERR_CAPACITY,
+                    "batch (%lld reads, %lld CIGAR ops, %lld bases) exceeds the slot capacity (%lld, %lld, %lld)",
+                    (long long)h->n_reads, (long long)h->n_cigar, (long long)h->n_bases, (long long)a.cap_reads,
+                    (long long)a.cap_cigar, (long long)a.cap_bases);
+    const int64_t n = h->n_reads;
+    a.view.n_reads = n;
+    if (!n) return MDG_OK;
+#define MDG_H2D(field, bytes) \
+    MDG_CUDA(ctx, cudaMemcpyAsync((void *)a.view.field, h->field, (size_t)(bytes), cudaMemcpyHostToDevice, stream))
+    MDG_H2D(flag, n * 2);
+    MDG_H2D(tid, n * 4);
+    MDG_H2D(pos, n * 4);
+    MDG_H2D(lib, n * 2);
+    MDG_H2D(l_seq, n * 4);
+    MDG_H2D(base_off, n * 4);
+    MDG_H2D(cigar_off, (n + 1) * 4);
+    MDG_H2D(cigar, h->n_cigar * 4);
+    MDG_H2D(seq4, h->n_bases / 2);
+    MDG_H2D(tlen, n * 4);
+    MDG_H2D(mtid, n * 4);
+    MDG_H2D(mpos, n * 4);
+#undef MDG_H2D
+    if (a.has_qual && h->qual)
+        MDG_CUDA(ctx, cudaMemcpyAsync((void *)a.view.qual, h->qual, (size_t)h->n_bases, cudaMemcpyHostToDevice, stream));
+    return MDG_OK;
+}
+
+int next_kernel_events(mdg_ctx *ctx, cudaEvent_t *start, cudaEvent_t *stop)
+{
+    if (ctx->kernel_events_used + 2 > ctx->kernel_events.size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            MDG_CUDA(ctx, cudaEventCreate(&e));
+            ctx->kernel_events.push_back(e);
+        }
+    }
+    *start = ctx->kernel_events[ctx->kernel_events_used++];
+    *stop = ctx->kernel_events[ctx->kernel_events_used++];
+    return MDG_OK;
+}
+
+// The counting kernels over one device batch.
+int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStream_t stream)
+{
+    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before counting");
+    if (view.n_reads == 0) return MDG_OK;
+    mdg::DevBatch b = view;
+    if (!has_qual) b.qual = nullptr;
+    mdg::CountParams p{ctx->cfg.length, ctx->cfg.around, ctx->cfg.min_qual, ctx->cfg.n_libraries, ctx->cfg.lg_bins};
+    cudaEvent_t e0, e1;
+    int rc = next_kernel_events(ctx, &e0, &e1);
+    if (rc) return rc;
+    MDG_CUDA(ctx, cudaEventRecord(e0, stream));
+    if (ctx->fast.enabled) {
+        rc = mdg::launch_fast(ctx->fast, b, ctx->ref, p, ctx->count_tables, stream, &ctx->launches);
+        if (rc) return fail(ctx, MDG_ERR_CUDA, "fast-path launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    } else {
+        int64_t warps = (b.n_reads + 0) ;
+        int grid = (int)std::min<int64_t>(ctx->general_grid, (warps + 7) / 8);
+        if (grid < 1) grid = 1;
+        if (ctx->shared_slab)
+            mdg::count_general_kernel<true><<<grid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, ctx->count_tables);
+        else
+            mdg::count_general_kernel<false><<<grid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables);
+        ctx->launches += 1;
+        MDG_CUDA(ctx, cudaGetLastError());
+    }
+    MDG_CUDA(ctx, cudaEventRecord(e1, stream));
+    return MDG_OK;
+}
+
+int check_device_errors(mdg_ctx *ctx)
+{
+    int32_t flag = 0;
+    MDG_CUDA(ctx, cudaMemcpy(&flag, ctx->count_tables.error_flag, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) {
+        int32_t zero = 0;
+        cudaMemcpy(ctx->count_tables.error_flag, &zero, sizeof zero, cudaMemcpyHostToDevice);
+        switch (flag) {
+        case mdg::DATA_ERR_LIB: return fail(ctx, MDG_ERR_DATA, "a read's library index is >= n_libraries");
+        case mdg::DATA_ERR_TID: return fail(ctx, MDG_ERR_DATA, "a mapped read has no CIGAR or a reference id outside the genome");
+        case mdg::DATA_ERR_QUAL: return fail(ctx, MDG_ERR_DATA, "a base quality above 93 cannot be rescaled");
+        case mdg::DATA_ERR_CLIP: return fail(ctx, MDG_ERR_DATA, "quality and sequence mismatch: soft clip behind a hard clip (reference rescale.py:266-273 fails the same way)");
+        default: return fail(ctx, MDG_ERR_DATA, "device reported data error %d", flag);
+        }
+    }
+    return MDG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdg_abi_version(void) { return MDG_ABI_VERSION; }
+
+const char *mdg_last_error(const mdg_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+void *mdg_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void mdg_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
+int mdg_create(mdg_ctx **out, const mdg_config *cfg)
+{
+    if (!out || !cfg) return fail(nullptr, MDG_ERR_ARGUMENT, "mdg_create: NULL argument");
+    *out = nullptr;
+    if (cfg->length < 1 || cfg->around < 0 || cfg->n_libraries < 1 || cfg->lg_bins < 1 || cfg->min_qual < 0 ||
+        cfg->n_libraries > 65535)
+        return fail(nullptr, MDG_ERR_ARGUMENT, "mdg_create: invalid length/around/min_qual/n_libraries/lg_bins");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, MDG_ERR_NO_DEVICE, "no CUDA device available (%s); mapdamage_b200 has no CPU path",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (cfg->device < 0 || cfg->device >= n_dev)
+        return fail(nullptr, MDG_ERR_ARGUMENT, "mdg_create: device %d out of range (0..%d)", cfg->device, n_dev - 1);
+    mdg_ctx *ctx = new (std::nothrow) mdg_ctx();
+    if (!ctx) return fail(nullptr, MDG_ERR_ARGUMENT, "out of host memory");
+    ctx->cfg = *cfg;
+    if (ctx->cfg.n_slots < 1) ctx->cfg.n_slots = 2;
+    auto bail = [&](int code) {
+        g_create_error = ctx->error;
+        mdg_destroy(ctx);
+        return code;
+    };
+#define MDG_CREATE_CUDA(call)                                                                       \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            fail(ctx, MDG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));               \
+            return bail(MDG_ERR_CUDA);                                                              \
+        }                                                                                           \
+    } while (0)
+    MDG_CREATE_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    MDG_CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    MDG_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    MDG_CREATE_CUDA(cudaEventCreate(&ctx->ev[0]));
+    MDG_CREATE_CUDA(cudaEventCreate(&ctx->ev[1]));
+
+    const size_t L = cfg->length, A = cfg->around, nl = cfg->n_libraries;
+    ctx->n_mis = nl * 4 * MDG_N_CLASSES * L;
+    ctx->n_comp = nl * 16 * (L + A);
+    ctx->n_lg = nl * 4 * (size_t)cfg->lg_bins;
+    const size_t n_tables = ctx->n_mis + ctx->n_comp + ctx->n_lg;
+    MDG_CREATE_CUDA(cudaMalloc(&ctx->tables, n_tables * 8));
+    MDG_CREATE_CUDA(cudaMemset(ctx->tables, 0, n_tables * 8));
+    const int64_t overflow_cap = 1 << 20;
+    const size_t aux_bytes = 256 + 64 + overflow_cap * 16;
+    MDG_CREATE_CUDA(cudaMalloc(&ctx->aux_block, aux_bytes));
+    MDG_CREATE_CUDA(cudaMemset(ctx->aux_block, 0, aux_bytes));
+    char *aux = (char *)ctx->aux_block;
+    ctx->count_tables.misincorp = ctx->tables;
+    ctx->count_tables.dnacomp = ctx->tables + ctx->n_mis;
+    ctx->count_tables.lghist = ctx->tables + ctx->n_mis + ctx->n_comp;
+    ctx->count_tables.lg_overflow_count = (unsigned long long *)(aux + 0);
+    ctx->count_tables.error_flag = (int32_t *)(aux + 8);
+    ctx->rescale_stats = (unsigned long long *)(aux + 64);
+    ctx->count_tables.lg_overflow_rows = (int32_t *)(aux + 256 + 64);
+    ctx->count_tables.lg_overflow_cap = overflow_cap;
+
+    // general kernel: shared-memory slab when there is one library and it fits
+    ctx->slab_bytes = (4 * MDG_N_CLASSES * L + 16 * (L + A) + 4 * MDG_LG_SMEM_BINS) * 4;
+    ctx->shared_slab = nl == 1 && ctx->slab_bytes + 1024 <= ctx->smem_optin;
+    int per_sm = 0;
+    if (ctx->shared_slab) {
+        MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_general_kernel<true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->slab_bytes));
+        MDG_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mdg::count_general_kernel<true>, 256,
+                                                                      ctx->slab_bytes));
+    } else {
+        MDG_CREATE_CUDA(
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mdg::count_general_kernel<false>, 256, 0));
+    }
+    if (per_sm < 1) per_sm = 1;
+    ctx->general_grid = ctx->sm_count * per_sm;
+    {
+        cudaError_t fe = mdg::plan_fast(ctx->fast, *cfg, ctx->sm_count, ctx->smem_optin);
+        if (fe != cudaSuccess) {
+            fail(ctx, MDG_ERR_CUDA, "fast-path setup failed: %s", cudaGetErrorString(fe));
+            return bail(MDG_ERR_CUDA);
+        }
+    }
+
+    // staging slots
+    ctx->slots.resize(ctx->cfg.n_slots);
+    if (cfg->max_reads > 0) {
+        for (auto &slot : ctx->slots) {
+            MDG_CREATE_CUDA(cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking));
+            int64_t bases = (cfg->max_bases + 1) & ~1ll;
+            if (alloc_arrays(ctx, slot.arrays, cfg->max_reads, cfg->max_cigar_ops, bases, true)) return bail(MDG_ERR_CUDA);
+            MDG_CREATE_CUDA(cudaMalloc(&slot.qual_out, bases + 8));
+            MDG_CREATE_CUDA(cudaMalloc(&slot.mr_out, cfg->max_reads * 4 + 8));
+            MDG_CREATE_CUDA(cudaMalloc(&slot.status_out, cfg->max_reads + 8));
+        }
+    }
+#undef MDG_CREATE_CUDA
+    *out = ctx;
+    return MDG_OK;
+}
+
+void mdg_destroy(mdg_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    if (ctx->comm && nccl_api().CommDestroy) nccl_api().CommDestroy(ctx->comm);
+    for (auto &slot : ctx->slots) {
+        if (slot.stream) cudaStreamDestroy(slot.stream);
+        cudaFree(slot.arrays.block);
+        cudaFree(slot.qual_out);
+        cudaFree(slot.mr_out);
+        cudaFree(slot.status_out);
+    }
+    mdg::free_fast(ctx->fast);
+    for (cudaEvent_t e : ctx->kernel_events) cudaEventDestroy(e);
+    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    cudaFree(ctx->ref_block);
+    cudaFree(ctx->tables);
+    cudaFree(ctx->aux_block);
+    cudaFree(ctx->model_block);
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    cudaGetLastError();
+    delete ctx;
+}
+
+int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, const uint64_t *contig_off,
+                      const uint32_t *contig_len, int32_t n_contigs)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    if (!packed || !contig_off || !contig_len || n_contigs < 1 || n_bytes < 0)
+        return fail(ctx, MDG_ERR_ARGUMENT, "mdg_set_reference: NULL or empty argument");
+    for (int c = 0; c < n_contigs; ++c) {
+        if (contig_off[c] & 7) return fail(ctx, MDG_ERR_ARGUMENT, "contig %d does not start on a multiple of 8 bases", c);
+        uint64_t end = contig_off[c] + ((uint64_t)contig_len[c] + 7) / 8 * 8;
+        if (end > (uint64_t)n_bytes * 2)
+            return fail(ctx, MDG_ERR_ARGUMENT, "contig %d extends past the packed genome (%lld bytes)", c, (long long)n_bytes);
+    }
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MDG_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(ctx->ref_block);
+    ctx->ref_block = nullptr;
+    ctx->ref = mdg::DevRef{};
+    size_t words_bytes = align_up((size_t)n_bytes + 16);
+    size_t off_bytes = align_up((size_t)n_contigs * 8);
+    size_t len_bytes = align_up((size_t)n_contigs * 4);
+    MDG_CUDA(ctx, cudaMalloc(&ctx->ref_block, words_bytes + off_bytes + len_bytes));
+    char *p = (char *)ctx->ref_block;
+    MDG_CUDA(ctx, cudaMemset(p, 0x77, words_bytes));
+    MDG_CUDA(ctx, cudaMemcpy(p, packed, (size_t)n_bytes, cudaMemcpyHostToDevice));
+    MDG_CUDA(ctx, cudaMemcpy(p + words_bytes, contig_off, (size_t)n_contigs * 8, cudaMemcpyHostToDevice));
+    MDG_CUDA(ctx, cudaMemcpy(p + words_bytes + off_bytes, contig_len, (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
+    ctx->ref.words = (const uint32_t *)p;
+    ctx->ref.contig_off = (const uint64_t *)(p + words_bytes);
+    ctx->ref.contig_len = (const uint32_t *)(p + words_bytes + off_bytes);
+    ctx->ref.n_contigs = n_contigs;
+    return MDG_OK;
+}
+
+int mdg_count_submit(mdg_ctx *ctx, const mdg_batch *host)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    int rc = check_batch(ctx, host);
+    if (rc) return rc;
+    if (ctx->slots.empty() || !ctx->slots[0].stream)
+        return fail(ctx, MDG_ERR_STATE, "context was created without staging slots (max_reads = 0)");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    Slot &slot = ctx->slots[ctx->next_slot];
+    ctx->next_slot = (ctx->next_slot + 1) % (int)ctx->slots.size();
+    MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));  // the slot's previous batch is done
+    rc = copy_batch(ctx, slot.arrays, host, slot.stream);
+    if (rc) return rc;
+    return launch_count(ctx, slot.arrays.view, host->qual != nullptr, slot.stream);
+}
+
+int mdg_batch_upload(mdg_ctx *ctx, const mdg_batch *host, mdg_dev_batch **out)
+{
+    if (!ctx || !out) return MDG_ERR_ARGUMENT;
+    *out = nullptr;
+    int rc = check_batch(ctx, host);
+    if (rc) return rc;
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    mdg_dev_batch *d = new (std::nothrow) mdg_dev_batch();
+    if (!d) return fail(ctx, MDG_ERR_ARGUMENT, "out of host memory");
+    rc = alloc_arrays(ctx, d->arrays, host->n_reads, host->n_cigar, host->n_bases, host->qual != nullptr);
+    if (!rc) rc = copy_batch(ctx, d->arrays, host, ctx->compute);
+    if (!rc && cudaStreamSynchronize(ctx->compute) != cudaSuccess)
+        rc = fail(ctx, MDG_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc) {
+        cudaFree(d->arrays.block);
+        delete d;
+        return rc;
+    }
+    *out = d;
+    return MDG_OK;
+}
+
+int mdg_batch_free(mdg_ctx *ctx, mdg_dev_batch *batch)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    if (!batch) return MDG_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(batch->arrays.block);
+    delete batch;
+    return MDG_OK;
+}
+
+int mdg_count_resident(mdg_ctx *ctx, const mdg_dev_batch *batch)
+{
+    if (!ctx || !batch) return MDG_ERR_ARGUMENT;
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    return launch_count(ctx, batch->arrays.view, batch->arrays.has_qual, ctx->compute);
+}
+
+int mdg_sync(mdg_ctx *ctx)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (auto &slot : ctx->slots)
+        if (slot.stream) MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
+    MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    return check_device_errors(ctx);
+}
+
+int mdg_reset_tables(mdg_ctx *ctx)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    int rc = mdg_sync(ctx);
+    if (rc) return rc;
+    MDG_CUDA(ctx, cudaMemset(ctx->tables, 0, (ctx->n_mis + ctx->n_comp + ctx->n_lg) * 8));
+    MDG_CUDA(ctx, cudaMemset(ctx->aux_block, 0, 256 + 64));
+    return MDG_OK;
+}
+
+int mdg_fetch_tables(mdg_ctx *ctx, uint64_t *misincorp, uint64_t *dnacomp, uint64_t *lghist)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    int rc = mdg_sync(ctx);
+    if (rc) return rc;
+    if (misincorp) MDG_CUDA(ctx, cudaMemcpy(misincorp, ctx->count_tables.misincorp, ctx->n_mis * 8, cudaMemcpyDeviceToHost));
+    if (dnacomp) MDG_CUDA(ctx, cudaMemcpy(dnacomp, ctx->count_tables.dnacomp, ctx->n_comp * 8, cudaMemcpyDeviceToHost));
+    if (lghist) MDG_CUDA(ctx, cudaMemcpy(lghist, ctx->count_tables.lghist, ctx->n_lg * 8, cudaMemcpyDeviceToHost));
+    return MDG_OK;
+}
+
+int64_t mdg_fetch_lg_overflow(mdg_ctx *ctx, int32_t *rows, int64_t max_rows)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    int rc = mdg_sync(ctx);
+    if (rc) return rc;
+    unsigned long long count = 0;
+    if (cudaMemcpy(&count, ctx->count_tables.lg_overflow_count, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(ctx, MDG_ERR_CUDA, "overflow count copy failed");
+    if ((int64_t)count > ctx->count_tables.lg_overflow_cap)
+        return fail(ctx, MDG_ERR_CAPACITY, "more than %lld fragment lengths >= lg_bins; raise lg_bins",
+                    (long long)ctx->count_tables.lg_overflow_cap);
+    int64_t n = std::min<int64_t>((int64_t)count, max_rows);
+    if (rows && n > 0 &&
+        cudaMemcpy(rows, ctx->count_tables.lg_overflow_rows, (size_t)n * 16, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(ctx, MDG_ERR_CUDA, "overflow rows copy failed");
+    return (int64_t)count;
+}
+
+int mdg_set_rescale_model(mdg_ctx *ctx, const uint8_t *lut, const double *inc, int32_t len5p, int32_t len3p)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    if (!lut || !inc || len5p < 0 || len3p < 0) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_set_rescale_model: bad argument");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MDG_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(ctx->model_block);
+    ctx->model_block = nullptr;
+    const int n_slots = 1 + len5p + len3p;
+    const size_t inc_bytes = align_up((size_t)2 * n_slots * 8), lut_bytes = (size_t)2 * n_slots * 94;
+    MDG_CUDA(ctx, cudaMalloc(&ctx->model_block, inc_bytes + lut_bytes));
+    char *p = (char *)ctx->model_block;
+    MDG_CUDA(ctx, cudaMemcpy(p, inc, (size_t)2 * n_slots * 8, cudaMemcpyHostToDevice));
+    MDG_CUDA(ctx, cudaMemcpy(p + inc_bytes, lut, lut_bytes, cudaMemcpyHostToDevice));
+    ctx->model.inc = (const double *)p;
+    ctx->model.lut = (const uint8_t *)(p + inc_bytes);
+    ctx->model.len5p = len5p;
+    ctx->model.len3p = len3p;
+    ctx->model.n_slots = n_slots;
+    return MDG_OK;
+}
+
+int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, float *mr_out, uint8_t *status_out)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    int rc = check_batch(ctx, host);
+    if (rc) return rc;
+    if (!qual_out || !mr_out || !status_out) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_rescale_submit: NULL output");
+    if (!host->qual) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_rescale_submit: batch has no quality array");
+    if (!ctx->model.lut) return fail(ctx, MDG_ERR_STATE, "mdg_set_rescale_model must be called before rescaling");
+    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before rescaling");
+    if (ctx->slots.empty() || !ctx->slots[0].stream)
+        return fail(ctx, MDG_ERR_STATE, "context was created without staging slots (max_reads = 0)");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    Slot &slot = ctx->slots[ctx->next_slot];
+    ctx->next_slot = (ctx->next_slot + 1) % (int)ctx->slots.size();
+    MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
+    rc = copy_batch(ctx, slot.arrays, host, slot.stream);
+    if (rc) return rc;
+    const int64_t n = host->n_reads;
+    if (n == 0) return MDG_OK;
+    mdg::RescaleOut out{slot.qual_out, slot.mr_out, slot.status_out, ctx->rescale_stats, ctx->count_tables.error_flag};
+    int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 7) / 8);
+    cudaEvent_t e0, e1;
+    rc = next_kernel_events(ctx, &e0, &e1);
+    if (rc) return rc;
+    MDG_CUDA(ctx, cudaEventRecord(e0, slot.stream));
+    mdg::rescale_kernel<<<grid, 256, 0, slot.stream>>>(slot.arrays.view, ctx->ref, ctx->model, out);
+    ctx->launches += 1;
+    MDG_CUDA(ctx, cudaGetLastError());
+    MDG_CUDA(ctx, cudaEventRecord(e1, slot.stream));
+    MDG_CUDA(ctx, cudaMemcpyAsync(qual_out, slot.qual_out, (size_t)host->n_bases, cudaMemcpyDeviceToHost, slot.stream));
+    MDG_CUDA(ctx, cudaMemcpyAsync(mr_out, slot.mr_out, (size_t)n * 4, cudaMemcpyDeviceToHost, slot.stream));
+    MDG_CUDA(ctx, cudaMemcpyAsync(status_out, slot.status_out, (size_t)n, cudaMemcpyDeviceToHost, slot.stream));
+    return MDG_OK;
+}
+
+int mdg_fetch_rescale_stats(mdg_ctx *ctx, uint64_t *stats8)
+{
+    if (!ctx || !stats8) return MDG_ERR_ARGUMENT;
+    int rc = mdg_sync(ctx);
+    if (rc) return rc;
+    MDG_CUDA(ctx, cudaMemcpy(stats8, ctx->rescale_stats, 64, cudaMemcpyDeviceToHost));
+    return MDG_OK;
+}
+
+int mdg_nccl_unique_id(void *id128)
+{
+    if (!id128) return MDG_ERR_ARGUMENT;
+    NcclApi &api = nccl_api();
+    if (!api.error.empty()) return fail(nullptr, MDG_ERR_NCCL, "%s", api.error.c_str());
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclResult_t r = api.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, MDG_ERR_NCCL, "ncclGetUniqueId: %s", api.GetErrorString ? api.GetErrorString(r) : "?");
+    memcpy(id128, &id, 128);
+    return MDG_OK;
+}
+
+int mdg_nccl_init(mdg_ctx *ctx, const void *id128, int32_t rank, int32_t n_ranks)
+{
+    if (!ctx || !id128) return MDG_ERR_ARGUMENT;
+    NcclApi &api = nccl_api();
+    if (!api.error.empty()) return fail(ctx, MDG_ERR_NCCL, "%s", api.error.c_str());
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = api.CommInitRank(&ctx->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) return fail(ctx, MDG_ERR_NCCL, "ncclCommInitRank: %s", api.GetErrorString ? api.GetErrorString(r) : "?");
+    return MDG_OK;
+}
+
+int mdg_allreduce_tables(mdg_ctx *ctx)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    if (!ctx->comm) return fail(ctx, MDG_ERR_STATE, "mdg_nccl_init must be called before mdg_allreduce_tables");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    for (auto &slot : ctx->slots)
+        if (slot.stream) MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
+    NcclApi &api = nccl_api();
+    const size_t n = ctx->n_mis + ctx->n_comp + ctx->n_lg;
+    ncclResult_t r = api.AllReduce(ctx->tables, ctx->tables, n, ncclUint64, ncclSum, ctx->comm, ctx->compute);
+    if (r != ncclSuccess) return fail(ctx, MDG_ERR_NCCL, "ncclAllReduce: %s", api.GetErrorString ? api.GetErrorString(r) : "?");
+    ctx->launches += 1;
+    return MDG_OK;
+}
+
+int mdg_event_record(mdg_ctx *ctx, int32_t which)
+{
+    if (!ctx || which < 0 || which > 1) return MDG_ERR_ARGUMENT;
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MDG_CUDA(ctx, cudaEventRecord(ctx->ev[which], ctx->compute));
+    return MDG_OK;
+}
+
+int mdg_event_elapsed_ms(mdg_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return MDG_ERR_ARGUMENT;
+    MDG_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    MDG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev[0], ctx->ev[1]));
+    return MDG_OK;
+}
+
+int64_t mdg_launch_count(const mdg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int mdg_last_kernel_ms(mdg_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return MDG_ERR_ARGUMENT;
+    int rc = mdg_sync(ctx);
+    if (rc) return rc;
+    float total = 0.f;
+    for (size_t i = 0; i + 1 < ctx->kernel_events_used; i += 2) {
+        float t = 0.f;
+        MDG_CUDA(ctx, cudaEventElapsedTime(&t, ctx->kernel_events[i], ctx->kernel_events[i + 1]));
+        total += t;
+    }
+    ctx->kernel_events_used = 0;
+    *ms = total;
+    return MDG_OK;
+}
+
+}  // extern "C"

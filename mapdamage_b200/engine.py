@@ -1,0 +1,251 @@
+"""Python face of the CUDA engine: one :class:`DamageEngine` per GPU.
+
+This is the object the host-side mirrors of the reference's loops drive
+(:mod:`mapdamage_b200.counting` for ``main.py:165-231`` and
+:mod:`mapdamage_b200.rescale` for ``rescale.py:285-365``).  It only marshals
+numpy arrays across the C ABI of ``include/mapdamage_b200.h``; all per-read
+work happens in the sm_100a kernels.  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .batch import ReadBatch
+
+_FIELDS = ("flag", "tid", "pos", "lib", "l_seq", "base_off", "cigar_off", "cigar", "seq4",
+           "tlen", "mtid", "mpos")
+
+
+def batch_struct(batch):
+    """``mdg_batch`` view of a :class:`ReadBatch` (no copies)."""
+    n_bases = batch.total_bases
+    if batch.seq4.shape[0] * 2 < n_bases:
+        raise ValueError("seq4 shorter than the batch's base span")
+    qual = batch.qual
+    if qual is not None and qual.shape[0] < n_bases:
+        # the library copies n_bases quality bytes; pad the odd tail slot
+        qual = np.concatenate([qual, np.full(n_bases - qual.shape[0], 0xFF, np.uint8)])
+        batch.qual = qual
+    s = _native.Batch()
+    s.n_reads = batch.n
+    s.n_cigar = int(batch.cigar.shape[0])
+    s.n_bases = n_bases
+    for name in _FIELDS:
+        setattr(s, name, getattr(batch, name).ctypes.data)
+    s.qual = None if qual is None else qual.ctypes.data
+    return s
+
+
+class PinnedArena:
+    """numpy arrays carved out of page-locked host memory (``mdg_host_alloc``)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._blocks = []
+
+    def empty(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        nbytes = max(1, count * dtype.itemsize)
+        ptr = self._lib.mdg_host_alloc(nbytes)
+        if not ptr:
+            raise MemoryError("cudaHostAlloc(%d bytes) failed" % nbytes)
+        self._blocks.append(ptr)
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def copy(self, array):
+        out = self.empty(array.shape, array.dtype)
+        out[...] = array
+        return out
+
+    def batch(self, batch):
+        """Copy of ``batch`` whose arrays live in pinned memory."""
+        arrays = {name: self.copy(getattr(batch, name)) for name in _FIELDS}
+        arrays["qual"] = None if batch.qual is None else self.copy(batch.qual)
+        return ReadBatch(**arrays)
+
+    def close(self):
+        for ptr in self._blocks:
+            self._lib.mdg_host_free(ptr)
+        self._blocks = []
+
+
+class DeviceBatch:
+    """A batch resident in HBM (``mdg_batch_upload``)."""
+
+    def __init__(self, engine, handle, n_reads):
+        self.engine, self.handle, self.n = engine, handle, n_reads
+
+    def free(self):
+        if self.handle:
+            self.engine._lib.mdg_batch_free(self.engine._ctx, self.handle)
+            self.handle = None
+
+
+class DamageEngine:
+    def __init__(self, length=70, around=10, min_qual=0, n_libraries=1, lg_bins=8192, device=0,
+                 n_slots=2, max_reads=1 << 20, max_cigar_ops=None, max_bases=None):
+        self._lib = _native.load()
+        self._ctx = C.c_void_p()
+        self.length, self.around, self.min_qual = length, around, min_qual
+        self.n_libraries, self.lg_bins, self.device = n_libraries, lg_bins, device
+        self.max_reads = max_reads
+        self.max_cigar_ops = max_cigar_ops if max_cigar_ops is not None else 4 * max_reads
+        self.max_bases = max_bases if max_bases is not None else 160 * max_reads
+        cfg = _native.Config(device, length, around, min_qual, n_libraries, lg_bins, n_slots, 0,
+                             max_reads, self.max_cigar_ops, self.max_bases)
+        code = self._lib.mdg_create(C.byref(self._ctx), C.byref(cfg))
+        if code < 0:
+            raise _native.NativeError(code, _native.last_error(None))
+        self._keepalive = []
+        self._arena = None
+
+    # -- life cycle ------------------------------------------------------
+    def close(self):
+        if self._ctx:
+            self._lib.mdg_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+        if self._arena is not None:
+            self._arena.close()
+            self._arena = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, code):
+        return _native.check(code, self._ctx)
+
+    @property
+    def arena(self):
+        if self._arena is None:
+            self._arena = PinnedArena(self._lib)
+        return self._arena
+
+    # -- inputs ----------------------------------------------------------
+    def set_reference(self, reference):
+        packed, offsets, lengths = reference.packed()
+        self._check(self._lib.mdg_set_reference(
+            self._ctx, packed.ctypes.data, packed.shape[0], offsets.ctypes.data,
+            lengths.ctypes.data, len(reference.names)))
+
+    def upload(self, batch):
+        handle = C.c_void_p()
+        s = batch_struct(batch)
+        self._check(self._lib.mdg_batch_upload(self._ctx, C.byref(s), C.byref(handle)))
+        return DeviceBatch(self, handle, batch.n)
+
+    def fits(self, batch):
+        return (batch.n <= self.max_reads and batch.cigar.shape[0] <= self.max_cigar_ops
+                and batch.total_bases <= self.max_bases)
+
+    # -- counting pass ---------------------------------------------------
+    def count(self, batch):
+        """Queues one host batch (async copy + kernels); see :meth:`sync`."""
+        s = batch_struct(batch)
+        self._keepalive.append((batch, s))
+        self._check(self._lib.mdg_count_submit(self._ctx, C.byref(s)))
+
+    def count_resident(self, device_batch):
+        self._check(self._lib.mdg_count_resident(self._ctx, device_batch.handle))
+
+    def sync(self):
+        try:
+            self._check(self._lib.mdg_sync(self._ctx))
+        finally:
+            self._keepalive = []
+
+    def reset(self):
+        self._check(self._lib.mdg_reset_tables(self._ctx))
+        self._keepalive = []
+
+    def tables(self):
+        """``(misincorp, dnacomp, lghist)`` uint64 slabs (layouts: mapdamage_b200.h)."""
+        L, A, nl = self.length, self.around, self.n_libraries
+        mis = np.zeros((nl, 2, 2, _native.N_CLASSES, L), dtype=np.uint64)
+        comp = np.zeros((nl, 2, 2, 4, L + A), dtype=np.uint64)
+        lg = np.zeros((nl, 2, 2, self.lg_bins), dtype=np.uint64)
+        self._check(self._lib.mdg_fetch_tables(self._ctx, mis.ctypes.data, comp.ctypes.data, lg.ctypes.data))
+        self._keepalive = []
+        return mis, comp, lg
+
+    def lg_overflow(self):
+        """Fragment lengths beyond ``lg_bins`` as ``(lib, kind, strand, length, count)`` rows."""
+        n = self._check(self._lib.mdg_fetch_lg_overflow(self._ctx, None, 0))
+        if not n:
+            return []
+        rows = np.zeros((n, 4), dtype=np.int32)
+        self._check(self._lib.mdg_fetch_lg_overflow(self._ctx, rows.ctypes.data, n))
+        uniq, counts = np.unique(rows, axis=0, return_counts=True)
+        return [tuple(int(x) for x in row) + (int(c),) for row, c in zip(uniq, counts)]
+
+    # -- rescale pass ----------------------------------------------------
+    def set_rescale_model(self, model):
+        lut = np.ascontiguousarray(model.lut, dtype=np.uint8)
+        inc = np.ascontiguousarray(model.inc, dtype=np.float64)
+        self._check(self._lib.mdg_set_rescale_model(
+            self._ctx, lut.ctypes.data, inc.ctypes.data, model.len5p, model.len3p))
+
+    def rescale(self, batch, out=None):
+        """Queues the rescale of one batch; returns ``(qual_out, mr, status)`` arrays
+        that are valid after :meth:`sync`."""
+        s = batch_struct(batch)
+        if out is None:
+            out = (np.empty(max(1, s.n_bases), dtype=np.uint8), np.empty(max(1, batch.n), dtype=np.float32),
+                   np.empty(max(1, batch.n), dtype=np.uint8))
+        qual_out, mr, status = out
+        self._keepalive.append((batch, s, out))
+        self._check(self._lib.mdg_rescale_submit(
+            self._ctx, C.byref(s), qual_out.ctypes.data, mr.ctypes.data, status.ctypes.data))
+        return qual_out[:s.n_bases], mr[:batch.n], status[:batch.n]
+
+    def rescale_stats(self):
+        stats = np.zeros(8, dtype=np.uint64)
+        self._check(self._lib.mdg_fetch_rescale_stats(self._ctx, stats.ctypes.data))
+        keys = ("pairs", "improper_pairs", "without_quals", "rescaled", "alignment_longer_than_read")
+        return {k: int(v) for k, v in zip(keys, stats)}
+
+    # -- multi-GPU -------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_uint8 * 128)()
+        code = _native.load().mdg_nccl_unique_id(buf)
+        if code < 0:
+            raise _native.NativeError(code, _native.last_error(None))
+        return bytes(buf)
+
+    def nccl_init(self, unique_id, rank, n_ranks):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.mdg_nccl_init(self._ctx, buf, rank, n_ranks))
+
+    def allreduce_tables(self):
+        self._check(self._lib.mdg_allreduce_tables(self._ctx))
+
+    # -- measurement -----------------------------------------------------
+    def event_record(self, which):
+        self._check(self._lib.mdg_event_record(self._ctx, which))
+
+    def event_elapsed_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.mdg_event_elapsed_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self._lib.mdg_launch_count(self._ctx))
+
+    def kernel_ms(self):
+        """Summed device time of the kernels launched since the last call."""
+        ms = C.c_float()
+        self._check(self._lib.mdg_last_kernel_ms(self._ctx, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA path, through the C ABI, against the golden vectors of the
+unmodified reference and against the CPU oracle on seeded synthetic batches."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_cases
+from helpers import (assert_tables_equal, expected_rescale, load_counting_case,
+                     load_rescale_case, render_tables)
+from mapdamage_b200 import _native, synth
+from mapdamage_b200.engine import DamageEngine
+from mapdamage_b200.rescale_model import RescaleModel, get_corr_prob
+
+pytestmark = pytest.mark.gpu
+
+
+def run_engine(batch, reference, n_lib=1, length=70, around=10, min_qual=0, lg_bins=8192, chunks=1,
+               resident=False):
+    with DamageEngine(length=length, around=around, min_qual=min_qual, n_libraries=n_lib,
+                      lg_bins=lg_bins, max_reads=max(1024, batch.n)) as engine:
+        engine.set_reference(reference)
+        if resident:
+            dev = engine.upload(batch)
+            engine.count_resident(dev)
+            engine.sync()
+            dev.free()
+        else:
+            for part in batch.split(chunks):
+                engine.count(part)
+        mis, comp, lg = engine.tables()
+        overflow = engine.lg_overflow()
+        assert engine.launch_count() > 0
+    return mis, comp, lg, overflow
+
+
+@pytest.mark.parametrize("case_dir,params", [c for c in golden_cases("counting")
+                                              if not c.values[1]["exception"]])
+def test_counting_golden(case_dir, params, tmp_path):
+    batch, reference, libraries, _ = load_counting_case(case_dir, params, tmp_path)
+    L, A = params["length"], params["around"]
+    mis, comp, lg, overflow = run_engine(batch, reference, n_lib=len(libraries), length=L, around=A,
+                                         min_qual=params["minqual"], chunks=3)
+    assert not overflow
+    render_tables(tmp_path / "out", libraries, L, A, mis, comp, lg)
+    assert_tables_equal(tmp_path / "out", case_dir)
+
+
+SYNTH = {
+    "se100": dict(length=(100, 100), mix=(1, 0, 0, 0), paired=False),
+    "se100_noqual": dict(length=(100, 100), mix=(1, 0, 0, 0), paired=False, with_qual=False),
+    "pe_mixed": dict(length=(50, 150), mix=(7, 1, 1, 1), paired=True),
+    "short": dict(length=(20, 45), mix=(6, 1, 1, 2), paired=False, read_n_rate=0.01, filtered_rate=0.05),
+    "long": dict(length=(180, 400), mix=(5, 2, 2, 1), paired=True, read_n_rate=0.002),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SYNTH))
+@pytest.mark.parametrize("min_qual,n_lib,resident", [(0, 1, False), (20, 1, True), (0, 3, False), (13, 2, True)])
+def test_counting_vs_oracle(name, min_qual, n_lib, resident):
+    reference = synth.make_reference([300_000, 150_000, 4_000], seed=5, other_rate=0.002)
+    batch = synth.simulate_reads(reference, 60_000, seed=6, n_libs=n_lib, **SYNTH[name])
+    want = oracle.count(batch, reference, minqual=min_qual, n_lib=n_lib, lg_bins=8192, threads=4)
+    got = run_engine(batch, reference, n_lib=n_lib, min_qual=min_qual, chunks=2, resident=resident)
+    for key, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
+        assert np.array_equal(a, b), key
+    assert want[0].sum() > 0 and want[1].sum() > 0
+
+
+@pytest.mark.parametrize("length,around", [(1, 0), (5, 40), (200, 3), (900, 10)])
+def test_counting_table_shapes(length, around):
+    """Extreme --length / --around, including a slab too large for shared memory."""
+    reference = synth.make_reference([50_000], seed=8)
+    batch = synth.simulate_reads(reference, 20_000, seed=9, length=(30, 120), mix=(4, 1, 1, 1))
+    want = oracle.count(batch, reference, length=length, around=around, lg_bins=8192, threads=4)
+    got = run_engine(batch, reference, length=length, around=around)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
+def test_fragment_length_overflow():
+    reference = synth.make_reference([50_000], seed=8)
+    batch = synth.simulate_reads(reference, 5_000, seed=9, length=(30, 120), paired=True)
+    want = oracle.count(batch, reference, lg_bins=8192)[2]
+    mis, comp, lg, overflow = run_engine(batch, reference, lg_bins=64)
+    assert np.array_equal(lg, want[..., :64])
+    dense = np.zeros_like(want)
+    for lib, kind, strand, length, count in overflow:
+        dense[lib, kind, strand, length] += count
+    assert np.array_equal(dense[..., 64:], want[..., 64:]) and dense[..., :64].sum() == 0
+
+
+def test_empty_and_reset():
+    reference = synth.make_reference([10_000], seed=8)
+    batch = synth.simulate_reads(reference, 1_000, seed=9)
+    with DamageEngine(max_reads=2048) as engine:
+        engine.set_reference(reference)
+        engine.count(batch.slice(0, 0))
+        assert all(t.sum() == 0 for t in engine.tables())
+        engine.count(batch)
+        first = engine.tables()
+        engine.count(batch)
+        twice = engine.tables()
+        assert all(np.array_equal(2 * a, b) for a, b in zip(first, twice))
+        engine.reset()
+        assert all(t.sum() == 0 for t in engine.tables())
+
+
+def test_errors_are_loud():
+    reference = synth.make_reference([10_000], seed=8)
+    batch = synth.simulate_reads(reference, 1_000, seed=9)
+    with DamageEngine(max_reads=100) as engine:
+        with pytest.raises(_native.NativeError) as info:
+            engine.count(batch)
+        assert info.value.code == _native.ERR_STATE  # no reference yet
+        engine.set_reference(reference)
+        with pytest.raises(_native.NativeError) as info:
+            engine.count(batch)
+        assert info.value.code == _native.ERR_CAPACITY
+    with DamageEngine(max_reads=2048) as engine:
+        engine.set_reference(reference)
+        batch.lib[5] = 3
+        engine.count(batch)
+        with pytest.raises(_native.NativeError) as info:
+            engine.sync()
+        assert info.value.code == _native.ERR_DATA
+
+
+@pytest.mark.parametrize("case_dir,params", [c for c in golden_cases("rescale")
+                                              if not c.values[1]["exception"]])
+def test_rescale_golden(case_dir, params):
+    batch, reference, _, records = load_rescale_case(case_dir)
+    model = RescaleModel.from_csv(case_dir / "Stats_out_MCMC_correct_prob.csv",
+                                  params["length_5p"], params["length_3p"])
+    with DamageEngine(max_reads=max(1024, batch.n)) as engine:
+        engine.set_reference(reference)
+        engine.set_rescale_model(model)
+        qual, mr, status = engine.rescale(batch)
+        if params["rc"] != 0:
+            with pytest.raises(_native.NativeError) as info:
+                engine.sync()
+            assert info.value.code == _native.ERR_DATA
+            assert "quality and sequence mismatch" in info.value.message
+            return
+        engine.sync()
+        stats = engine.rescale_stats()
+    want = expected_rescale(case_dir)
+    for i, (want_qual, want_mr) in enumerate(want):
+        off, n = int(batch.base_off[i]), int(batch.l_seq[i])
+        if want_qual is not None:
+            got = (qual[off:off + n] + 33).astype(np.uint8).tobytes().decode("latin-1")
+            assert got == want_qual, "record %d (%s)" % (i, records[i].qname)
+        if want_mr is None:
+            assert status[i] == 0
+        else:
+            assert status[i] == 1 and mr[i] == want_mr, "record %d MR %r != %r" % (i, mr[i], want_mr)
+    n_warn = sum("longer than the actual read" in m for m in params["log"])
+    assert stats["alignment_longer_than_read"] == n_warn
+
+
+@pytest.mark.parametrize("name", ["se100", "pe_mixed", "short", "long"])
+@pytest.mark.parametrize("l5,l3", [(12, 12), (30, 7)])
+def test_rescale_vs_oracle(name, l5, l3):
+    reference = synth.make_reference([300_000, 150_000, 4_000], seed=5, other_rate=0.002)
+    batch = synth.simulate_reads(reference, 50_000, seed=7, **SYNTH[name])
+    corr = {("C", "T", p): 0.9 * 0.67 ** (p - 1) for p in range(1, l5 + 1)}
+    corr.update({("G", "A", -p): 0.85 * 0.6 ** (p - 1) for p in range(1, l3 + 1)})
+    corr.update({("G", "A", p): 0.013 for p in range(1, l5 + 1)})
+    corr.update({("C", "T", -p): 0.021 for p in range(1, l3 + 1)})
+    model = RescaleModel(corr, l5, l3)
+    want_qual, want_mr, want_status, subs, rc = oracle.rescale(batch, reference, corr)
+    assert rc == 0
+    with DamageEngine(max_reads=batch.n) as engine:
+        engine.set_reference(reference)
+        engine.set_rescale_model(model)
+        qual, mr, status = engine.rescale(batch)
+        engine.sync()
+        stats = engine.rescale_stats()
+    assert np.array_equal(status, want_status)
+    assert np.array_equal(mr[status == 1], want_mr[want_status == 1])
+    # compare the quality bytes of real bases only (pad slots are unspecified)
+    mask = np.zeros(qual.shape[0], dtype=bool)
+    starts = batch.base_off.astype(np.int64)
+    idx = np.repeat(starts, batch.l_seq) + (np.arange(int(batch.l_seq.sum())) -
+                                             np.repeat(np.cumsum(batch.l_seq) - batch.l_seq, batch.l_seq))
+    mask[idx] = True
+    assert np.array_equal(qual[mask], want_qual[:qual.shape[0]][mask])
+    assert (qual[mask] != batch.qual[:qual.shape[0]][mask]).sum() > 100
+    assert stats["rescaled"] == int(want_status.sum()) == subs.n_rescaled
+    assert stats["pairs"] == subs.n_pairs and stats["improper_pairs"] == subs.n_improper
