@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Headline benchmark: aligned reads/s of the misincorporation + composition counting pass.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" is one pass of the counting path over the whole workload (BASELINE.json
+configs[1]: 50 M synthetic 100 bp single-end reads with C->T / G->A damage on a 1 Mb random
+reference, ``-l 70 -a 10 -Q 0``), cut into batches that fit the 32-bit offsets of one
+``mdg_batch``.  With N > 1 every rank counts its own 50 M-read shard (weak scaling) and each
+step ends with the NCCL all-reduce of the count tables.
+
+* ``value``  -- whole-job reads/s with the batches resident in HBM, timed with CUDA events on
+  the stream the kernels run on, max over ranks.
+* ``e2e``    -- the same pass through the public API (``DamageEngine.count`` ->
+  ``mdg_count_submit``) from pinned HOST batches: host->device copies, kernels and the
+  device->host read of the tables are all inside the timed region.
+* ``roofline`` -- algorithmic bytes per launch / mean device time of a counting launch, against
+  the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+* ``cpu_baseline`` -- the CPU oracle (a C port of the reference's algorithm, oracle/) timed on
+  this box's host cores over a bounded sample of the same workload.
+
+``--impl reference`` times the CPU implementation alone (the reference itself is pure Python
+on pysam and cannot travel to the GPU box; the arm runs the oracle port on every host thread).
+The oracle is only ever the checker / the CPU baseline here, never the thing measured as ours.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for _p in (ROOT, ROOT / "oracle"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
+
+METRIC = "aligned reads/sec (misincorporation+composition pass)"
+UNIT = "reads/s"
+LENGTH, AROUND = 70, 10
+READ_LEN = 100
+REF_BASES = 1_000_000
+# 15 B of record fields + 4 B per CIGAR op + packed read + packed reference span with flanks
+ALGO_BYTES_PER_READ = 15 + 4 * 1 + (READ_LEN + 1) // 2 + (READ_LEN + 2 * AROUND + 1) // 2  # = 129
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU per step")
+    ap.add_argument("--batch-reads", type=int, default=1 << 22)
+    ap.add_argument("--seed", type=int, default=20260101)
+    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="reads timed on the CPU oracle")
+    ap.add_argument("--check-sample", type=int, default=200_000, help="reads checked against the oracle")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """``nvidia-smi`` clocks and throttle reasons sampled while a region is timed."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+    REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        self.device = device
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thread.join(timeout=5)
+        return False
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            if len(row) < 7:
+                continue
+            try:
+                sm.append(float(row[0]))
+                mx.append(float(row[1]))
+            except ValueError:
+                continue
+            for name, state in zip(self.REASONS, row[3:7]):
+                if state.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.is_file():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """DRAM bytes per counting launch from the committed ncu capture of this workload, if any."""
+    path = ROOT / "profiles" / "traffic.json"
+    if path.is_file():
+        try:
+            return json.loads(path.read_text())
+        except ValueError:
+            pass
+    return None
+
+
+# ---------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """The CPU implementation alone, on every host thread (rank 0 only)."""
+    if rank != 0:
+        return
+    import oracle
+    from mapdamage_b200 import synth
+
+    cores = os.cpu_count() or 1
+    sample = min(args.reads, 2_000_000)
+    reference = synth.make_reference([REF_BASES], seed=args.seed)
+    batch = synth.simulate_reads(reference, sample, seed=args.seed + 1, length=(READ_LEN, READ_LEN),
+                                 with_qual=False, threads=min(cores, 16))
+    for _ in range(args.warmup):
+        oracle.count(batch, reference, length=LENGTH, around=AROUND, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.count(batch, reference, length=LENGTH, around=AROUND, threads=cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    what = "%d reads per step of the same synthetic workload (host-generated, seed %d)" % (sample, args.seed + 1)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64",
+        "data": "synthetic",
+        "config": {"workload": "50M x 100bp SE aDNA reads, 1 Mb reference, -l 70 -a 10 -Q 0 (bounded sample)",
+                   "reads_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": what,
+                         "note": "C port of the reference's Python loop (oracle/mdg_oracle.c), pinned to the "
+                                 "unmodified reference by tests/golden; the Python original runs ~18 k reads/s "
+                                 "on one core (SURVEY.md section 6)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------
+def gpu_arm(args, rank, local_rank, world):
+    import torch
+
+    from mapdamage_b200 import synth
+    from mapdamage_b200.engine import DamageEngine
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_batches = max(1, -(-args.reads // args.batch_reads))
+    sizes = [args.reads // n_batches + (1 if i < args.reads % n_batches else 0) for i in range(n_batches)]
+    cap = max(sizes)
+    engine = DamageEngine(length=LENGTH, around=AROUND, min_qual=0, n_libraries=1, lg_bins=8192,
+                          device=local_rank, n_slots=2, max_reads=cap, max_cigar_ops=cap,
+                          max_bases=cap * (READ_LEN + (READ_LEN & 1)))
+    reference = synth.make_reference([REF_BASES], seed=args.seed)
+    engine.set_reference(reference)
+    if world > 1:
+        box = [DamageEngine.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        engine.nccl_init(box[0], rank, world)
+
+    resident = [engine.synth_batch(n, seed=args.seed + 1000 * rank + i, length=(READ_LEN, READ_LEN),
+                                   with_qual=False) for i, n in enumerate(sizes)]
+
+    def one_pass():
+        for dev in resident:
+            engine.count_resident(dev)
+        if world > 1:
+            engine.allreduce_tables()
+
+    # ---- correctness before speed: oracle parity on a sample, invariants at full size ----
+    host0 = engine.download(resident[0])
+    check = {}
+    if rank == 0:
+        import oracle
+
+        sample = host0.slice(0, min(args.check_sample, host0.n))
+        want = oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192,
+                            threads=min(8, os.cpu_count() or 1))
+        engine.reset()
+        engine.count(sample)
+        got = engine.tables()
+        for name, a, b in zip(("misincorporation", "dnacomp", "lgdistribution"), got, want):
+            if not np.array_equal(a, b):
+                raise SystemExit("bench: %s table differs from the oracle on the %d-read sample" % (name, sample.n))
+        check["oracle_sample_reads"] = sample.n
+    engine.reset()
+    for dev in resident:
+        engine.count_resident(dev)
+    mis, comp, lg = engine.tables()
+    total = sum(sizes)
+    # every read is 100M on an N-free genome: each end/position sees every read exactly once
+    per_pos = mis[0, :, :, 0:4, :].sum(axis=(1, 2))
+    if not (np.all(per_pos == total) and int(lg.sum()) == total and int(lg[0, 1, :, READ_LEN].sum()) == total):
+        raise SystemExit("bench: full-size invariants failed (reference-base totals / length histogram)")
+    if not np.all(comp[0, :, :, :, :LENGTH].sum(axis=(1, 2)) == total):
+        raise SystemExit("bench: full-size invariants failed (read composition totals)")
+    check["full_size_invariants"] = "ok"
+
+    # ---- value: resident batches, CUDA events on the compute stream ----
+    for _ in range(args.warmup):
+        one_pass()
+    engine.sync()
+    engine.kernel_ms()
+    launches0 = engine.launch_count()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        engine.event_record(0)
+        for _ in range(args.steps):
+            one_pass()
+        engine.event_record(1)
+        ms = engine.event_elapsed_ms()
+        barrier()
+    ms = max_over_ranks(ms)
+    launches = engine.launch_count() - launches0
+    kernel_ms = engine.kernel_ms()
+    n_count_launch_groups = args.steps * n_batches
+    value = world * total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: pinned host batches through the public API ----
+    e2e = None
+    if not args.no_e2e:
+        host = [engine.download(dev, pinned=True) for dev in resident]
+        h2d = sum(engine.h2d_bytes(b) for b in host)
+        d2h = int(mis.nbytes + comp.nbytes + lg.nbytes)
+        engine.reset()
+
+        def e2e_pass():
+            for b in host:
+                engine.count(b)
+            if world > 1:
+                engine.allreduce_tables()
+            return engine.tables()
+
+        for _ in range(min(args.warmup, 3)):
+            e2e_pass()
+        barrier()
+        engine.event_record(0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            tables = e2e_pass()
+        engine.event_record(1)
+        e2e_ms = engine.event_elapsed_ms()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        e2e_ms = max_over_ranks(max(e2e_ms, wall_ms))
+        e2e = {"value": world * total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_ms / args.steps,
+               "timing": "max(CUDA events on the compute stream, host wall clock) around submit..fetch, max over ranks"}
+        del tables
+
+    # ---- CPU baseline on a bounded sample (rank 0, single GPU runs only) ----
+    cpu = None
+    if rank == 0 and world == 1:
+        import oracle
+
+        sample = host0.slice(0, min(args.cpu_sample, host0.n))
+        t0 = time.perf_counter()
+        oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, threads=1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample.n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "first %d reads of batch 0 of this workload, one thread, %.1f s" % (sample.n, dt)}
+
+    if rank == 0:
+        peak, peak_source = measured_peak()
+        launch_ms = kernel_ms / n_count_launch_groups
+        bytes_per_launch = ALGO_BYTES_PER_READ * total / n_batches
+        achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        traffic = recorded_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
+            "config": {
+                "workload": "configs[1]: 50M x 100bp SE aDNA reads (C->T/G->A damage), 1 Mb reference, -l 70 -a 10 -Q 0",
+                "reads_per_gpu_per_step": total, "batches_per_step": n_batches, "seed": args.seed,
+                "l2": "inputs larger than L2 (%.1f GB of resident batches per pass vs 126 MB)" % (
+                    total * 90 / 1e9),
+                "parallelism": "reads sharded per GPU; NCCL all-reduce of the count tables per step" if world > 1
+                else "single GPU",
+            },
+            "clocks": clocks.summary(),
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                "peak_source": peak_source, "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
+                "reads_per_launch": total / n_batches, "kernel_ms_per_launch": launch_ms,
+                "kernel_share_of_step": kernel_ms / ms,
+                "frac_of_nominal_8TBps": achieved / 8000.0,
+            },
+            "cpu_baseline": cpu,
+            "check": check,
+        }
+        print(json.dumps(line))
+    engine.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -186,6 +186,38 @@ int mdg_nccl_init(mdg_ctx *ctx, const void *id128, int32_t rank, int32_t n_ranks
 /* ncclAllReduce(sum, uint64) over all count tables, in place, on the compute stream. */
 int mdg_allreduce_tables(mdg_ctx *ctx);
 
+/* ---- synthetic input in HBM (bench.py, tests) ------------------------- */
+
+/*
+ * Parameters of the seeded synthetic aDNA generator (mirrors
+ * mapdamage_b200/synth.py): reads drawn from the uploaded genome, C->T damage
+ * with p = damage0 * damage_decay^i at distance i from the left end of the
+ * alignment and G->A mirrored from the right end (BAM orientation), uniform
+ * substitution errors, CIGARs mixed by the weights mix[] = {plain match, one
+ * 1-3 bp insertion, one 1-3 bp deletion, 0-10 bp soft clips}.
+ */
+typedef struct {
+    uint64_t seed;
+    int64_t n_reads;
+    int32_t len_lo, len_hi;  /* stored read length, uniform in [len_lo, len_hi]       */
+    int32_t mix[4];
+    int32_t paired;          /* 1: inward-facing proper pairs, records 2q and 2q+1    */
+    int32_t with_qual;       /* 1: base qualities uniform in 2..40                     */
+    int32_t n_libraries;     /* lib[] uniform in [0, n_libraries)                      */
+    int32_t reserved;
+    float error_rate, read_n_rate, filtered_rate;
+    float damage0, damage_decay;
+    float reserved2;
+} mdg_synth_params;
+
+/* Generates a batch directly in device memory (no host copy); needs mdg_set_reference. */
+int mdg_synth_batch(mdg_ctx *ctx, const mdg_synth_params *params, mdg_dev_batch **out);
+int mdg_batch_sizes(mdg_ctx *ctx, const mdg_dev_batch *batch, int64_t *n_reads, int64_t *n_cigar, int64_t *n_bases);
+/* Copies a resident batch into caller-allocated host arrays (sized by
+ * mdg_batch_sizes; host->qual may be NULL).  The arrays are written through
+ * the const pointers of mdg_batch. */
+int mdg_batch_download(mdg_ctx *ctx, const mdg_dev_batch *batch, const mdg_batch *host);
+
 /* ---- measurement helpers (bench.py) ------------------------------------ */
 
 /* CUDA events on the context's compute stream: which = 0 start, 1 stop. */

@@ -40,6 +40,16 @@ class Batch(C.Structure):
     ]
 
 
+class SynthParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("n_reads", C.c_int64), ("len_lo", C.c_int32), ("len_hi", C.c_int32),
+        ("mix", C.c_int32 * 4), ("paired", C.c_int32), ("with_qual", C.c_int32),
+        ("n_libraries", C.c_int32), ("reserved", C.c_int32),
+        ("error_rate", C.c_float), ("read_n_rate", C.c_float), ("filtered_rate", C.c_float),
+        ("damage0", C.c_float), ("damage_decay", C.c_float), ("reserved2", C.c_float),
+    ]
+
+
 # every symbol include/mapdamage_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mdg_abi_version": (C.c_int, []),
@@ -60,6 +70,10 @@ SYMBOLS = {
     "mdg_set_rescale_model": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "mdg_rescale_submit": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdg_fetch_rescale_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdg_synth_batch": (C.c_int, [C.c_void_p, C.POINTER(SynthParams), C.POINTER(C.c_void_p)]),
+    "mdg_batch_sizes": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64)]),
+    "mdg_batch_download": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Batch)]),
     "mdg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mdg_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "mdg_allreduce_tables": (C.c_int, [C.c_void_p]),

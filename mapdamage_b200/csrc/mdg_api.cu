@@ -1,5 +1,6 @@
 // C ABI of mapdamage_b200 (include/mapdamage_b200.h): context, staging slots,
 // launches.  No CPU path: without a CUDA device mdg_create fails.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -16,6 +17,7 @@
 #include "mdg_count.cuh"
 #include "mdg_fast.cuh"
 #include "mdg_rescale.cuh"
+#include "mdg_synth.cuh"
 
 namespace {
 
@@ -62,6 +64,7 @@ struct DeviceArrays {
     void *block = nullptr;
     size_t bytes = 0;
     int64_t cap_reads = 0, cap_cigar = 0, cap_bases = 0;
+    int64_t n_cigar = 0, n_bases = 0;
     bool has_qual = false;
     mdg::DevBatch view{};
 };
@@ -92,6 +95,8 @@ struct mdg_ctx {
     // reference genome
     mdg::DevRef ref{};
     void *ref_block = nullptr;
+    uint64_t ref_total_bases = 0;
+    uint32_t ref_min_contig = 0;
     // tables: one allocation [misincorp | dnacomp | lghist]
     unsigned long long *tables = nullptr;
     size_t n_mis = 0, n_comp = 0, n_lg = 0;
@@ -187,7 +192,8 @@ int check_batch(mdg_ctx *ctx, const mdg_batch *h)
 }
 
 // Queues the host->device copies of one batch on `stream`.
-int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t stream)
+// The counting pass reads neither the mate fields nor (with min_qual = 0) the qualities: they stay on the host.
+int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t stream, bool mates, bool quals)
 {
     if (h->n_reads > a.cap_reads || h->n_cigar > a.cap_cigar || h->n_bases > a.cap_bases)
         return fail(ctx, MDG_ERR_CAPACITY,
@@ -196,6 +202,8 @@ int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t s
                     (long long)a.cap_cigar, (long long)a.cap_bases);
     const int64_t n = h->n_reads;
     a.view.n_reads = n;
+    a.n_cigar = h->n_cigar;
+    a.n_bases = h->n_bases;
     if (!n) return MDG_OK;
 #define MDG_H2D(field, bytes) \
     MDG_CUDA(ctx, cudaMemcpyAsync((void *)a.view.field, h->field, (size_t)(bytes), cudaMemcpyHostToDevice, stream))
@@ -209,10 +217,12 @@ int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t s
     MDG_H2D(cigar, h->n_cigar * 4);
     MDG_H2D(seq4, h->n_bases / 2);
     MDG_H2D(tlen, n * 4);
-    MDG_H2D(mtid, n * 4);
-    MDG_H2D(mpos, n * 4);
+    if (mates) {
+        MDG_H2D(mtid, n * 4);
+        MDG_H2D(mpos, n * 4);
+    }
 #undef MDG_H2D
-    if (a.has_qual && h->qual)
+    if (quals && a.has_qual && h->qual)
         MDG_CUDA(ctx, cudaMemcpyAsync((void *)a.view.qual, h->qual, (size_t)h->n_bases, cudaMemcpyHostToDevice, stream));
     return MDG_OK;
 }
@@ -461,6 +471,12 @@ int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, cons
     ctx->ref.contig_off = (const uint64_t *)(p + words_bytes);
     ctx->ref.contig_len = (const uint32_t *)(p + words_bytes + off_bytes);
     ctx->ref.n_contigs = n_contigs;
+    ctx->ref_total_bases = 0;
+    ctx->ref_min_contig = 0xffffffffu;
+    for (int c = 0; c < n_contigs; ++c) {
+        ctx->ref_total_bases += contig_len[c];
+        ctx->ref_min_contig = std::min(ctx->ref_min_contig, contig_len[c]);
+    }
     return MDG_OK;
 }
 
@@ -475,9 +491,10 @@ int mdg_count_submit(mdg_ctx *ctx, const mdg_batch *host)
     Slot &slot = ctx->slots[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % (int)ctx->slots.size();
     MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));  // the slot's previous batch is done
-    rc = copy_batch(ctx, slot.arrays, host, slot.stream);
+    const bool quals = host->qual != nullptr && ctx->cfg.min_qual > 0;
+    rc = copy_batch(ctx, slot.arrays, host, slot.stream, false, quals);
     if (rc) return rc;
-    return launch_count(ctx, slot.arrays.view, host->qual != nullptr, slot.stream);
+    return launch_count(ctx, slot.arrays.view, quals, slot.stream);
 }
 
 int mdg_batch_upload(mdg_ctx *ctx, const mdg_batch *host, mdg_dev_batch **out)
@@ -490,7 +507,7 @@ int mdg_batch_upload(mdg_ctx *ctx, const mdg_batch *host, mdg_dev_batch **out)
     mdg_dev_batch *d = new (std::nothrow) mdg_dev_batch();
     if (!d) return fail(ctx, MDG_ERR_ARGUMENT, "out of host memory");
     rc = alloc_arrays(ctx, d->arrays, host->n_reads, host->n_cigar, host->n_bases, host->qual != nullptr);
-    if (!rc) rc = copy_batch(ctx, d->arrays, host, ctx->compute);
+    if (!rc) rc = copy_batch(ctx, d->arrays, host, ctx->compute, true, true);
     if (!rc && cudaStreamSynchronize(ctx->compute) != cudaSuccess)
         rc = fail(ctx, MDG_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc) {
@@ -606,7 +623,7 @@ int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, f
     Slot &slot = ctx->slots[ctx->next_slot];
     ctx->next_slot = (ctx->next_slot + 1) % (int)ctx->slots.size();
     MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
-    rc = copy_batch(ctx, slot.arrays, host, slot.stream);
+    rc = copy_batch(ctx, slot.arrays, host, slot.stream, true, true);
     if (rc) return rc;
     const int64_t n = host->n_reads;
     if (n == 0) return MDG_OK;
@@ -632,6 +649,128 @@ int mdg_fetch_rescale_stats(mdg_ctx *ctx, uint64_t *stats8)
     int rc = mdg_sync(ctx);
     if (rc) return rc;
     MDG_CUDA(ctx, cudaMemcpy(stats8, ctx->rescale_stats, 64, cudaMemcpyDeviceToHost));
+    return MDG_OK;
+}
+
+int mdg_synth_batch(mdg_ctx *ctx, const mdg_synth_params *sp, mdg_dev_batch **out)
+{
+    if (!ctx || !sp || !out) return MDG_ERR_ARGUMENT;
+    *out = nullptr;
+    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before mdg_synth_batch");
+    const int64_t mix_total = (int64_t)sp->mix[0] + sp->mix[1] + sp->mix[2] + sp->mix[3];
+    if (sp->n_reads < 1 || sp->n_reads >= (1ll << 31) || sp->len_lo < 1 || sp->len_hi < sp->len_lo ||
+        sp->len_hi > 60000 || mix_total < 1 || mix_total > 65535 || sp->mix[0] < 0 || sp->mix[1] < 0 ||
+        sp->mix[2] < 0 || sp->mix[3] < 0 || sp->n_libraries < 1 || (sp->paired && (sp->n_reads & 1)))
+        return fail(ctx, MDG_ERR_ARGUMENT, "mdg_synth_batch: invalid parameters");
+    if ((int64_t)ctx->ref_min_contig < (int64_t)sp->len_hi + 16)
+        return fail(ctx, MDG_ERR_ARGUMENT, "mdg_synth_batch: a contig is shorter than a read (%u < %d + 16)",
+                    ctx->ref_min_contig, sp->len_hi);
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    mdg::SynthDev p{};
+    p.seed = sp->seed;
+    p.n_reads = sp->n_reads;
+    p.len_lo = sp->len_lo;
+    p.len_hi = sp->len_hi;
+    uint32_t cum = 0;
+    for (int k = 0; k < 4; ++k) p.mix_cum[k] = cum += (uint32_t)sp->mix[k];
+    p.paired = sp->paired;
+    p.with_qual = sp->with_qual;
+    p.n_lib = sp->n_libraries;
+    auto u24 = [](float x) { return (uint32_t)(std::min(std::max(x, 0.f), 1.f) * 16777216.f); };
+    p.error_u24 = u24(sp->error_rate);
+    p.read_n_u24 = u24(sp->read_n_rate);
+    p.filtered_u24 = u24(sp->filtered_rate);
+    p.damage0 = sp->damage0;
+    p.decay = sp->damage_decay;
+    p.genome_bases = ctx->ref_total_bases;
+
+    const int64_t n_blocks = (sp->n_reads + 255) / 256;
+    unsigned long long *totals = nullptr;
+    MDG_CUDA(ctx, cudaMalloc(&totals, (size_t)(n_blocks + 1) * 16));
+    mdg::synth_block_totals<<<(unsigned)n_blocks, 256, 0, ctx->compute>>>(p, totals);
+    mdg::synth_scan_totals<<<1, 1024, 0, ctx->compute>>>(totals, n_blocks);
+    unsigned long long grand[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(grand, totals + 2 * n_blocks, 16, cudaMemcpyDeviceToHost, ctx->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->compute);
+    if (e != cudaSuccess) {
+        cudaFree(totals);
+        return fail(ctx, MDG_ERR_CUDA, "mdg_synth_batch: sizing pass failed: %s", cudaGetErrorString(e));
+    }
+    if (grand[0] >= (1ull << 32) || grand[1] >= (1ull << 32)) {
+        cudaFree(totals);
+        return fail(ctx, MDG_ERR_ARGUMENT, "mdg_synth_batch: %llu bases exceed the 32-bit offsets of one batch; "
+                    "generate fewer reads per batch", grand[0]);
+    }
+    mdg_dev_batch *d = new (std::nothrow) mdg_dev_batch();
+    if (!d) {
+        cudaFree(totals);
+        return fail(ctx, MDG_ERR_ARGUMENT, "out of host memory");
+    }
+    int rc = alloc_arrays(ctx, d->arrays, sp->n_reads, (int64_t)grand[1], (int64_t)grand[0], sp->with_qual != 0);
+    if (rc) {
+        cudaFree(totals);
+        delete d;
+        return rc;
+    }
+    d->arrays.view.n_reads = sp->n_reads;
+    d->arrays.n_cigar = (int64_t)grand[1];
+    d->arrays.n_bases = (int64_t)grand[0];
+    const mdg::DevBatch &v = d->arrays.view;
+    mdg::SynthOut o{(uint16_t *)v.flag, (int32_t *)v.tid, (int32_t *)v.pos, (uint16_t *)v.lib, (uint32_t *)v.l_seq,
+                    (uint32_t *)v.base_off, (uint32_t *)v.cigar_off, (uint32_t *)v.cigar, (uint8_t *)v.seq4,
+                    (uint8_t *)v.qual, (int32_t *)v.tlen, (int32_t *)v.mtid, (int32_t *)v.mpos};
+    mdg::synth_fill<<<(unsigned)n_blocks, 256, 0, ctx->compute>>>(p, ctx->ref, totals, o);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->compute);
+    cudaFree(totals);
+    if (e != cudaSuccess) {
+        cudaFree(d->arrays.block);
+        delete d;
+        return fail(ctx, MDG_ERR_CUDA, "mdg_synth_batch: fill failed: %s", cudaGetErrorString(e));
+    }
+    *out = d;
+    return MDG_OK;
+}
+
+int mdg_batch_sizes(mdg_ctx *ctx, const mdg_dev_batch *batch, int64_t *n_reads, int64_t *n_cigar, int64_t *n_bases)
+{
+    if (!ctx || !batch) return MDG_ERR_ARGUMENT;
+    if (n_reads) *n_reads = batch->arrays.view.n_reads;
+    if (n_cigar) *n_cigar = batch->arrays.n_cigar;
+    if (n_bases) *n_bases = batch->arrays.n_bases;
+    return MDG_OK;
+}
+
+int mdg_batch_download(mdg_ctx *ctx, const mdg_dev_batch *batch, const mdg_batch *h)
+{
+    if (!ctx || !batch) return MDG_ERR_ARGUMENT;
+    int rc = check_batch(ctx, h);
+    if (rc) return rc;
+    const DeviceArrays &a = batch->arrays;
+    const int64_t n = a.view.n_reads;
+    if (h->n_reads != n || h->n_cigar != a.n_cigar || h->n_bases != a.n_bases)
+        return fail(ctx, MDG_ERR_ARGUMENT, "mdg_batch_download: host arrays must be sized by mdg_batch_sizes");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+#define MDG_D2H(field, bytes) \
+    MDG_CUDA(ctx, cudaMemcpy((void *)h->field, a.view.field, (size_t)(bytes), cudaMemcpyDeviceToHost))
+    MDG_D2H(flag, n * 2);
+    MDG_D2H(tid, n * 4);
+    MDG_D2H(pos, n * 4);
+    MDG_D2H(lib, n * 2);
+    MDG_D2H(l_seq, n * 4);
+    MDG_D2H(base_off, n * 4);
+    MDG_D2H(cigar_off, (n + 1) * 4);
+    MDG_D2H(cigar, a.n_cigar * 4);
+    MDG_D2H(seq4, a.n_bases / 2);
+    MDG_D2H(tlen, n * 4);
+    MDG_D2H(mtid, n * 4);
+    MDG_D2H(mpos, n * 4);
+    if (h->qual) {
+        if (!a.has_qual) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_batch_download: the resident batch has no qualities");
+        MDG_D2H(qual, a.n_bases);
+    }
+#undef MDG_D2H
     return MDG_OK;
 }
 

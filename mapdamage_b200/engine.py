@@ -75,8 +75,8 @@ class PinnedArena:
 class DeviceBatch:
     """A batch resident in HBM (``mdg_batch_upload``)."""
 
-    def __init__(self, engine, handle, n_reads):
-        self.engine, self.handle, self.n = engine, handle, n_reads
+    def __init__(self, engine, handle, n_reads, has_qual=True):
+        self.engine, self.handle, self.n, self.has_qual = engine, handle, n_reads, has_qual
 
     def free(self):
         if self.handle:
@@ -144,7 +144,50 @@ class DamageEngine:
         handle = C.c_void_p()
         s = batch_struct(batch)
         self._check(self._lib.mdg_batch_upload(self._ctx, C.byref(s), C.byref(handle)))
-        return DeviceBatch(self, handle, batch.n)
+        return DeviceBatch(self, handle, batch.n, has_qual=batch.qual is not None)
+
+    def synth_batch(self, n_reads, seed=1, length=(100, 100), mix=(1, 0, 0, 0), paired=False,
+                    with_qual=True, n_libs=1, error_rate=0.002, read_n_rate=0.0, filtered_rate=0.0,
+                    damage0=0.3, damage_decay=0.7):
+        """Seeded synthetic aDNA batch generated directly in HBM (``mdg_synth_batch``)."""
+        if isinstance(length, int):
+            length = (length, length)
+        params = _native.SynthParams(
+            seed, n_reads, length[0], length[1], (C.c_int32 * 4)(*mix), int(paired), int(with_qual),
+            n_libs, 0, error_rate, read_n_rate, filtered_rate, damage0, damage_decay, 0.0)
+        handle = C.c_void_p()
+        self._check(self._lib.mdg_synth_batch(self._ctx, C.byref(params), C.byref(handle)))
+        return DeviceBatch(self, handle, n_reads, has_qual=bool(with_qual))
+
+    def download(self, device_batch, pinned=False):
+        """Host :class:`ReadBatch` copy of a resident batch (pinned memory on request)."""
+        n, n_cigar, n_bases = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._lib.mdg_batch_sizes(self._ctx, device_batch.handle, C.byref(n), C.byref(n_cigar),
+                                              C.byref(n_bases)))
+        n, n_cigar, n_bases = n.value, n_cigar.value, n_bases.value
+        empty = self.arena.empty if pinned else (lambda shape, dtype: np.empty(shape, dtype))
+        arrays = {name: empty(n, dtype) for name, dtype in ReadBatch.FIELDS if name != "cigar_off"}
+        arrays["cigar_off"] = empty(n + 1, np.uint32)
+        arrays["cigar"] = empty(n_cigar, np.uint32)
+        arrays["seq4"] = empty(n_bases // 2, np.uint8)
+        arrays["qual"] = empty(n_bases, np.uint8) if device_batch.has_qual else None
+        s = _native.Batch()
+        s.n_reads, s.n_cigar, s.n_bases = n, n_cigar, n_bases
+        for name in _FIELDS:
+            setattr(s, name, arrays[name].ctypes.data)
+        s.qual = None if arrays["qual"] is None else arrays["qual"].ctypes.data
+        self._check(self._lib.mdg_batch_download(self._ctx, device_batch.handle, C.byref(s)))
+        return ReadBatch(**arrays)
+
+    def h2d_bytes(self, batch, rescale=False):
+        """Bytes ``count`` (or ``rescale``) copies to the device for ``batch`` (see ``copy_batch``)."""
+        n = batch.n
+        total = n * (2 + 4 + 4 + 2 + 4 + 4 + 4) + (n + 1) * 4 + batch.cigar.nbytes + batch.total_bases // 2
+        if rescale:
+            total += 8 * n
+        if batch.qual is not None and (rescale or self.min_qual > 0):
+            total += batch.total_bases
+        return total
 
     def fits(self, batch):
         return (batch.n <= self.max_reads and batch.cigar.shape[0] <= self.max_cigar_ops

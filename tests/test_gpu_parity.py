@@ -187,3 +187,41 @@ def test_rescale_vs_oracle(name, l5, l3):
     assert (qual[mask] != batch.qual[:qual.shape[0]][mask]).sum() > 100
     assert stats["rescaled"] == int(want_status.sum()) == subs.n_rescaled
     assert stats["pairs"] == subs.n_pairs and stats["improper_pairs"] == subs.n_improper
+
+
+DEVICE_SYNTH = {
+    "se100": dict(length=(100, 100)),
+    "pe_mixed": dict(length=(50, 150), mix=(7, 1, 1, 1), paired=True),
+    "short_libs": dict(length=(20, 45), mix=(6, 1, 1, 2), read_n_rate=0.01, filtered_rate=0.05, n_libs=3),
+    "noqual": dict(length=(100, 100), with_qual=False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(DEVICE_SYNTH))
+@pytest.mark.parametrize("min_qual", [0, 17])
+def test_device_generated_batches(name, min_qual):
+    """Batches generated in HBM (mdg_synth_batch): well-formed, damaged, and counted like the oracle counts them."""
+    kw = dict(DEVICE_SYNTH[name])
+    n_lib = kw.get("n_libs", 1)
+    reference = synth.make_reference([300_000, 150_000, 4_000], seed=5, other_rate=0.002)
+    with DamageEngine(min_qual=min_qual, n_libraries=n_lib, max_reads=1024) as engine:
+        engine.set_reference(reference)
+        dev = engine.synth_batch(80_000, seed=11, **kw)
+        engine.count_resident(dev)
+        got = engine.tables()
+        host = engine.download(dev)
+        again = engine.synth_batch(80_000, seed=11, **kw)
+        host2 = engine.download(again)
+        dev.free()
+        again.free()
+    host.validate()
+    assert np.array_equal(host.seq4, host2.seq4) and np.array_equal(host.pos, host2.pos)  # deterministic in the seed
+    want = oracle.count(host, reference, minqual=min_qual, n_lib=n_lib, lg_bins=8192, threads=4)
+    for key, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
+        assert np.array_equal(a, b), key
+    mis = want[0].sum(axis=(0, 2))  # [end][class][pos]
+    c_to_t = mis[0, 4 + 5 * 1 + 3, 0] / max(1, mis[0, 1, 0])
+    g_to_a = mis[1, 4 + 5 * 2 + 0, 0] / max(1, mis[1, 2, 0])
+    assert 0.2 < c_to_t < 0.4 and 0.2 < g_to_a < 0.4  # the injected 5' C>T / 3' G>A damage is there
+    if kw.get("paired"):
+        assert want[2][:, 0].sum() > 0 and np.all(host.flag & 1)
