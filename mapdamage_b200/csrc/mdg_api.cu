@@ -485,6 +485,7 @@ int mdg_count_submit(mdg_ctx *ctx, const mdg_batch *host)
     if (!ctx) return MDG_ERR_ARGUMENT;
     int rc = check_batch(ctx, host);
     if (rc) return rc;
+    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before counting");
     if (ctx->slots.empty() || !ctx->slots[0].stream)
         return fail(ctx, MDG_ERR_STATE, "context was created without staging slots (max_reads = 0)");
     MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
