@@ -15,7 +15,7 @@
 
 #include "../../include/mapdamage_b200.h"
 #include "mdg_count.cuh"
-#include "mdg_fast.cuh"
+#include "mdg_swar.cuh"
 #include "mdg_rescale.cuh"
 #include "mdg_synth.cuh"
 
@@ -80,6 +80,14 @@ struct Slot {
 
 }  // namespace
 
+// Work list of one launch stream: reads the bit-sliced kernel hands to the general kernel.
+struct WorkList {
+    cudaStream_t stream = nullptr;
+    uint32_t *reads = nullptr;
+    unsigned long long *count = nullptr;
+    int64_t cap = 0;
+};
+
 struct mdg_dev_batch {
     DeviceArrays arrays;
 };
@@ -110,7 +118,11 @@ struct mdg_ctx {
     bool shared_slab = false;
     size_t slab_bytes = 0;
     int general_grid = 0;
-    mdg::FastPlan fast{};
+    // bit-sliced kernel for gap-free reads; complex reads go through a per-stream work list
+    bool swar_enabled = false, force_general = false;
+    mdg::SwarGeom swar{};
+    size_t swar_smem = 0;
+    std::vector<WorkList> worklists;
     // measurement
     cudaEvent_t ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> kernel_events;  // pairs
@@ -241,6 +253,29 @@ int next_kernel_events(mdg_ctx *ctx, cudaEvent_t *start, cudaEvent_t *stop)
     return MDG_OK;
 }
 
+int worklist_for(mdg_ctx *ctx, cudaStream_t stream, int64_t n_reads, WorkList **out)
+{
+    WorkList *wl = nullptr;
+    for (auto &w : ctx->worklists)
+        if (w.stream == stream) wl = &w;
+    if (!wl) {
+        ctx->worklists.emplace_back();
+        wl = &ctx->worklists.back();
+        wl->stream = stream;
+        MDG_CUDA(ctx, cudaMalloc(&wl->count, 8));
+    }
+    if (wl->cap < n_reads) {
+        MDG_CUDA(ctx, cudaStreamSynchronize(stream));
+        cudaFree(wl->reads);
+        wl->reads = nullptr;
+        wl->cap = 0;
+        MDG_CUDA(ctx, cudaMalloc(&wl->reads, (size_t)n_reads * 4));
+        wl->cap = n_reads;
+    }
+    *out = wl;
+    return MDG_OK;
+}
+
 // The counting kernels over one device batch.
 int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStream_t stream)
 {
@@ -253,17 +288,37 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
     int rc = next_kernel_events(ctx, &e0, &e1);
     if (rc) return rc;
     MDG_CUDA(ctx, cudaEventRecord(e0, stream));
-    if (ctx->fast.enabled) {
-        rc = mdg::launch_fast(ctx->fast, b, ctx->ref, p, ctx->count_tables, stream, &ctx->launches);
-        if (rc) return fail(ctx, MDG_ERR_CUDA, "fast-path launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    if (ctx->swar_enabled && !ctx->force_general) {
+        WorkList *wl = nullptr;
+        rc = worklist_for(ctx, stream, b.n_reads, &wl);
+        if (rc) return rc;
+        MDG_CUDA(ctx, cudaMemsetAsync(wl->count, 0, 8, stream));
+        const int64_t n_tiles = (b.n_reads + ctx->swar.tile - 1) / ctx->swar.tile;
+        const int grid = (int)std::min<int64_t>(ctx->sm_count, n_tiles);
+        if (b.qual && p.min_qual > 0)
+            mdg::count_swar_kernel<true><<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables,
+                                                                                             ctx->swar, wl->reads, wl->count);
+        else
+            mdg::count_swar_kernel<false><<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables,
+                                                                                              ctx->swar, wl->reads, wl->count);
+        MDG_CUDA(ctx, cudaGetLastError());
+        // reads with indels / skips: the general kernel over the work list (returns at once when it is empty)
+        const int ggrid = (int)std::min<int64_t>(ctx->general_grid, (b.n_reads + 7) / 8);
+        if (ctx->shared_slab)
+            mdg::count_general_kernel<true><<<ggrid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, ctx->count_tables,
+                                                                                     wl->reads, wl->count);
+        else
+            mdg::count_general_kernel<false><<<ggrid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables, wl->reads,
+                                                                        wl->count);
+        MDG_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 2;
     } else {
-        int64_t warps = (b.n_reads + 0) ;
-        int grid = (int)std::min<int64_t>(ctx->general_grid, (warps + 7) / 8);
+        int grid = (int)std::min<int64_t>(ctx->general_grid, (b.n_reads + 7) / 8);
         if (grid < 1) grid = 1;
         if (ctx->shared_slab)
-            mdg::count_general_kernel<true><<<grid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, ctx->count_tables);
+            mdg::count_general_kernel<true><<<grid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, ctx->count_tables, nullptr, nullptr);
         else
-            mdg::count_general_kernel<false><<<grid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables);
+            mdg::count_general_kernel<false><<<grid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables, nullptr, nullptr);
         ctx->launches += 1;
         MDG_CUDA(ctx, cudaGetLastError());
     }
@@ -390,12 +445,34 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
     }
     if (per_sm < 1) per_sm = 1;
     ctx->general_grid = ctx->sm_count * per_sm;
+    // bit-sliced kernel: one library, a shared-memory general slab for its work list, geometry that fits a block
     {
-        cudaError_t fe = mdg::plan_fast(ctx->fast, *cfg, ctx->sm_count, ctx->smem_optin);
-        if (fe != cudaSuccess) {
-            fail(ctx, MDG_ERR_CUDA, "fast-path setup failed: %s", cudaGetErrorString(fe));
-            return bail(MDG_ERR_CUDA);
+        mdg::SwarGeom &g = ctx->swar;
+        g.w_a = (cfg->around + 7) / 8;
+        g.w_l = (cfg->length + 7) / 8;
+        const int jobs = 2 * (g.w_a + g.w_l);
+        g.slots = (mdg::SWAR_MAX_THREADS / jobs) & ~1;
+        if (nl == 1 && g.slots >= 2 && cfg->around <= 64 && cfg->length < 32768) {
+            g.work_threads = jobs * g.slots;
+            g.threads = (g.work_threads + 31) / 32 * 32;
+            for (int tile : {2048, 1024, 512}) {
+                const size_t bytes = ((size_t)mdg::SWAR_L2_WORDS * g.threads + (size_t)tile * 5 + 4 * MDG_LG_SMEM_BINS + 4 * L + 4) * 4;
+                if (bytes <= ctx->smem_optin) {
+                    g.tile = tile;
+                    ctx->swar_smem = bytes;
+                    break;
+                }
+            }
+            if (g.tile) {
+                MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_swar_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)ctx->swar_smem));
+                MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_swar_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)ctx->swar_smem));
+                ctx->swar_enabled = true;
+            }
         }
+        const char *env = getenv("MDG_FORCE_GENERAL");
+        ctx->force_general = env && env[0] == '1';
     }
 
     // staging slots
@@ -428,7 +505,10 @@ void mdg_destroy(mdg_ctx *ctx)
         cudaFree(slot.mr_out);
         cudaFree(slot.status_out);
     }
-    mdg::free_fast(ctx->fast);
+    for (auto &w : ctx->worklists) {
+        cudaFree(w.reads);
+        cudaFree(w.count);
+    }
     for (cudaEvent_t e : ctx->kernel_events) cudaEventDestroy(e);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -458,13 +538,20 @@ int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, cons
     cudaFree(ctx->ref_block);
     ctx->ref_block = nullptr;
     ctx->ref = mdg::DevRef{};
-    size_t words_bytes = align_up((size_t)n_bytes + 16);
+    // 256 bytes of "not a base" on both sides: the kernels read whole words around an alignment
+    const size_t pad = 256;
+    size_t words_bytes = align_up((size_t)n_bytes + pad);
     size_t off_bytes = align_up((size_t)n_contigs * 8);
     size_t len_bytes = align_up((size_t)n_contigs * 4);
-    MDG_CUDA(ctx, cudaMalloc(&ctx->ref_block, words_bytes + off_bytes + len_bytes));
-    char *p = (char *)ctx->ref_block;
-    MDG_CUDA(ctx, cudaMemset(p, 0x77, words_bytes));
+    MDG_CUDA(ctx, cudaMalloc(&ctx->ref_block, pad + words_bytes + off_bytes + len_bytes));
+    char *p = (char *)ctx->ref_block + pad;
+    MDG_CUDA(ctx, cudaMemset(ctx->ref_block, 0x77, pad + words_bytes));
     MDG_CUDA(ctx, cudaMemcpy(p, packed, (size_t)n_bytes, cudaMemcpyHostToDevice));
+    // device image: one-hot nibbles (A,C,G,T = 1,2,4,8 as in BAM; 0 = anything else)
+    mdg::ref_to_one_hot_kernel<<<ctx->sm_count * 8, 256, 0, ctx->compute>>>((uint32_t *)ctx->ref_block,
+                                                                             (int64_t)((pad + words_bytes) / 4));
+    MDG_CUDA(ctx, cudaGetLastError());
+    MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     MDG_CUDA(ctx, cudaMemcpy(p + words_bytes, contig_off, (size_t)n_contigs * 8, cudaMemcpyHostToDevice));
     MDG_CUDA(ctx, cudaMemcpy(p + words_bytes + off_bytes, contig_len, (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
     ctx->ref.words = (const uint32_t *)p;

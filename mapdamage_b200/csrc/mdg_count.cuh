@@ -242,9 +242,14 @@ __device__ void count_read(const DevBatch &b, const DevRef &ref, const CountPara
 }
 
 // Launch: blockDim = 256; dynamic shared memory = slab_words * 4 when kShared.
+// With a work list (made by count_swar_kernel) only the listed reads are counted.
 template <bool kShared>
-__global__ void __launch_bounds__(256) count_general_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t)
+__global__ void __launch_bounds__(256) count_general_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t,
+                                                            const uint32_t *__restrict__ worklist,
+                                                            const unsigned long long *__restrict__ work_count)
 {
+    const int64_t n_work = worklist ? (int64_t)*work_count : b.n_reads;
+    if ((int64_t)blockIdx.x * (blockDim.x >> 5) >= n_work) return;  // nothing for this block (uniform)
     extern __shared__ uint32_t smem[];
     const int L = p.L, LA = p.L + p.A;
     const int mis_words = 4 * MDG_N_CLASSES * L, comp_words = 16 * LA, lg_words = 4 * MDG_LG_SMEM_BINS;
@@ -263,8 +268,8 @@ __global__ void __launch_bounds__(256) count_general_kernel(DevBatch b, DevRef r
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * warps_per_block;
-    for (int64_t r = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < b.n_reads; r += stride)
-        count_read<kShared>(b, ref, p, t, sink, r, lane);
+    for (int64_t w = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < n_work; w += stride)
+        count_read<kShared>(b, ref, p, t, sink, worklist ? (int64_t)worklist[w] : w, lane);
     if (kShared) {
         // flush the block's slab into the 64-bit tables of library 0
         __syncthreads();

@@ -37,7 +37,7 @@ struct DevBatch {
 };
 
 struct DevRef {
-    const uint32_t *words;       // 8 bases per word, low nibble first
+    const uint32_t *words;       // 8 bases per word, low nibble first, one-hot
     const uint64_t *contig_off;  // first base of each contig in the packed stream
     const uint32_t *contig_len;
     int32_t n_contigs;
@@ -76,9 +76,10 @@ __device__ __forceinline__ uint32_t read_nibble(const uint8_t *__restrict__ seq4
     return (base_index & 1) ? (byte & 0xF) : (byte >> 4);
 }
 
+// the device genome is one-hot (1,2,4,8 = A,C,G,T; 0 = anything else), the BAM code of the same base
 __device__ __forceinline__ uint32_t ref_code(const uint32_t *__restrict__ words, uint64_t base_index)
 {
-    return (__ldg(words + (base_index >> 3)) >> ((uint32_t)(base_index & 7) * 4)) & 0xFu;
+    return code_of_nibble((__ldg(words + (base_index >> 3)) >> ((uint32_t)(base_index & 7) * 4)) & 0xFu);
 }
 
 __device__ __forceinline__ bool op_in_columns(uint32_t op)  // align.py:82: M, I, D, =, X

@@ -1,0 +1,494 @@
+// Counting pass, bit-sliced kernel for gap-free reads ([H][S] M/=/X+ [S][H]).
+//
+// Same outputs as count_general_kernel (reference main.py:165-217: the read
+// filter reader.py:121-132, FragmentLengths.update statistics.py:117-126,
+// get_around align.py:22-35, align / align_with_qual align.py:38-73, revcomp
+// main.py:200-205, update_soft_clipping statistics.py:37-51, both
+// MisincorporationRates.update walks statistics.py:22-35 and
+// DNAComposition.update_read / update_reference statistics.py:75-93), but
+// organised the other way round: instead of a warp walking the columns of one
+// read and firing one atomic per table cell, a THREAD owns eight consecutive
+// table positions of one (anchor, strand) and the reads are its loop.
+//
+//   anchor 0 (left):  position p = alignment column           -> 5' table of forward reads, 3' of reverse reads
+//   anchor 1 (right): position p = columns from the right end -> 3' table of forward reads, 5' of reverse reads
+//   p < 0: flanking reference base at distance -p (DNAComposition.update_reference)
+//
+// For a gap-free read, column == query index == reference offset, so the
+// eight (read, reference) pairs a thread needs are one 32-bit word of the BAM
+// 4-bit sequence and one word of the one-hot genome, both shifted into place
+// with a funnel shift.  Every table class becomes a bit mask with one bit per
+// nibble:
+//     R_g  = reference base g         (4 classes)   -> misincorporation columns A,C,G,T / flank composition
+//     H_b  = read base b              (4 classes)   -> read composition
+//     P_gb = reference g, read b != g (12 classes)  -> substitution columns
+// and is added, eight positions at a time, into 4-bit counters (registers),
+// spilled every 15 reads into 8-bit counters (registers) and every 255 reads
+// into the thread's private 16-bit counters in shared memory.  There is no
+// atomic in the loop; the block reduces its private counters once, at the
+// end, into the 64-bit tables.  Reads whose CIGAR has I/D/N/P (or anything
+// else this layout cannot express) are appended to a work list for
+// count_general_kernel.
+#pragma once
+#include "mdg_device.cuh"
+
+namespace mdg {
+
+constexpr int SWAR_CLASSES = 20;
+constexpr int SWAR_L2_WORDS = 4 * SWAR_CLASSES;  // 16-bit counters: 20 classes x 8 positions
+constexpr int SWAR_MAX_THREADS = 512;
+constexpr uint32_t K1 = 0x11111111u;
+
+struct SwarGeom {
+    int32_t w_a, w_l;      // flank / aligned words per anchor
+    int32_t slots;         // read slots per block (even: half per strand)
+    int32_t threads;       // blockDim.x
+    int32_t work_threads;  // 2 * (w_a + w_l) * slots
+    int32_t tile;          // reads staged per iteration of the block
+};
+
+struct __align__(16) SwarRecord {  // one staged read, 16 bytes
+    uint32_t nib0;       // first aligned base, in batch base coordinates (base_off + leading clip)
+    uint32_t c_flanks;   // columns | left flank bases << 16 | right flank bases << 24 | has_qual << 15
+    uint32_t ref_lo, ref_hi;  // genome base index of the first aligned column
+};
+
+__device__ __forceinline__ uint32_t nibble_mask_below(int n)  // nibbles [0, n)
+{
+    return n >= 8 ? 0xffffffffu : n <= 0 ? 0u : (1u << (4 * n)) - 1u;
+}
+
+// BAM packs the first base of a byte in the high nibble; make nibble i of the word base i
+__device__ __forceinline__ uint32_t natural_order(uint32_t w)
+{
+    return ((w & 0x0F0F0F0Fu) << 4) | ((w >> 4) & 0x0F0F0F0Fu);
+}
+
+// bit 4i set iff nibble i has exactly one bit set (A, C, G or T in BAM code)
+__device__ __forceinline__ uint32_t one_hot_nibbles(uint32_t x)
+{
+    const uint32_t b = x >> 1, c = x >> 2, d = x >> 3;
+    const uint32_t exactly_one = (x ^ b ^ c) & ~(x & b & c);  // of bits 0..2
+    const uint32_t none = ~(x | b | c);
+    return ((exactly_one & ~d) | (none & d)) & K1;
+}
+
+// thread -> (anchor, word, slot): flank threads first so that whole warps share a code path
+struct SwarJob {
+    int anchor, word, slot;
+    bool flank, active;
+};
+
+__device__ __forceinline__ SwarJob swar_job(const SwarGeom &g, int t)
+{
+    SwarJob j;
+    const int n_flank = 2 * g.w_a * g.slots;
+    j.active = t < g.work_threads;
+    j.flank = t < n_flank;
+    if (j.flank) {
+        const int f = t % (2 * g.w_a);
+        j.slot = t / (2 * g.w_a);
+        j.anchor = f / g.w_a;
+        j.word = f % g.w_a;
+    } else {
+        const int u = t - n_flank, per = 2 * g.w_l;
+        const int f = u % per;
+        j.slot = u / per;
+        j.anchor = f / g.w_l;
+        j.word = g.w_a + f % g.w_l;
+    }
+    return j;
+}
+
+__device__ __forceinline__ int swar_thread_of(const SwarGeom &g, int anchor, int word, int slot)
+{
+    if (word < g.w_a) return slot * 2 * g.w_a + anchor * g.w_a + word;
+    return 2 * g.w_a * g.slots + slot * 2 * g.w_l + anchor * g.w_l + (word - g.w_a);
+}
+
+// class index of the pair (reference g, read b), g != b
+__device__ __forceinline__ int swar_pair_class(int g, int b) { return 8 + g * 3 + b - (b > g ? 1 : 0); }
+
+template <bool kQual>
+__global__ void __launch_bounds__(SWAR_MAX_THREADS, 1)
+count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom g, uint32_t *__restrict__ worklist,
+                  unsigned long long *__restrict__ work_count)
+{
+    extern __shared__ uint32_t smem[];
+    const int nthreads = g.threads, T = g.tile, L = p.L, A = p.A;
+    uint32_t *const s_l2 = smem;                                     // [SWAR_L2_WORDS][nthreads]
+    SwarRecord *const s_rec = (SwarRecord *)(s_l2 + SWAR_L2_WORDS * nthreads);  // [T]: forward from the front, reverse from the back
+    uint32_t *const s_cx = (uint32_t *)(s_rec + T);                  // [T] complex reads of the tile
+    uint32_t *const s_lg = s_cx + T;                                 // [kind][strand][MDG_LG_SMEM_BINS]
+    uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;            // [end][strand][L]
+    uint32_t *const s_ctl = s_clip + 4 * L;                          // n_fwd, n_rev, n_cx
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < SWAR_L2_WORDS * nthreads; i += nthreads) s_l2[i] = 0;
+    for (int i = tid; i < 4 * MDG_LG_SMEM_BINS + 4 * L; i += nthreads) s_lg[i] = 0;
+
+    const SwarJob job = swar_job(g, tid);
+    const int strand = job.slot & 1;
+    const int pbase = 8 * (job.word - g.w_a);  // window position of nibble 0 (left anchor) / nibble 7 (right anchor)
+    const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
+    const uint32_t *__restrict__ ref32 = ref.words;
+
+    uint32_t acc0[SWAR_CLASSES];      // 8 x 4-bit counters per class
+    uint32_t acc1[2 * SWAR_CLASSES];  // 2 x (4 x 8-bit) counters per class: even / odd nibbles
+#pragma unroll
+    for (int c = 0; c < SWAR_CLASSES; ++c) acc0[c] = acc1[2 * c] = acc1[2 * c + 1] = 0;
+    int n0 = 0, n1 = 0;
+
+    auto spill1 = [&]() {  // 8-bit -> private 16-bit counters in shared memory
+#pragma unroll
+        for (int w = 0; w < 2 * SWAR_CLASSES; ++w) {
+            const uint32_t v = acc1[w];
+            s_l2[(2 * w) * nthreads + tid] += v & 0x00FF00FFu;
+            s_l2[(2 * w + 1) * nthreads + tid] += (v >> 8) & 0x00FF00FFu;
+            acc1[w] = 0;
+        }
+        n1 = 0;
+    };
+    auto spill0 = [&]() {  // 4-bit -> 8-bit counters
+#pragma unroll
+        for (int c = 0; c < SWAR_CLASSES; ++c) {
+            acc1[2 * c] += acc0[c] & 0x0F0F0F0Fu;
+            acc1[2 * c + 1] += (acc0[c] >> 4) & 0x0F0F0F0Fu;
+            acc0[c] = 0;
+        }
+        n0 = 0;
+        if (++n1 == 17) spill1();
+    };
+
+    // reduces the block's private counters into the 64-bit tables (end of the kernel, and before a
+    // thread's 16-bit counters could overflow)
+    const int jobs_per_anchor = g.w_a + g.w_l;
+    const int n_cells = 2 * jobs_per_anchor * 2 * SWAR_CLASSES * 8;  // anchor, word, strand, class, nibble
+    const int LA = L + A;
+    auto flush_block = [&]() {
+        if (n0) spill0();
+        if (n1) spill1();
+        __syncthreads();
+        for (int cell = tid; cell < n_cells; cell += nthreads) {
+            int rest = cell;
+            const int nib = rest & 7; rest >>= 3;
+            const int cls = rest % SWAR_CLASSES; rest /= SWAR_CLASSES;
+            const int cstrand = rest & 1; rest >>= 1;
+            const int word = rest % jobs_per_anchor;
+            const int anchor = rest / jobs_per_anchor;
+            if (word < g.w_a && cls >= 4) continue;  // flank words only count reference bases
+            // 16-bit lane holding (cls, nib): 8-bit lane bl = nib >> 1 of acc1[2 * cls + (nib & 1)]
+            const int w1 = 2 * cls + (nib & 1), bl = nib >> 1;
+            const int w2 = 2 * w1 + (bl & 1), half = bl >> 1;
+            unsigned long long sum = 0;
+            for (int slot = cstrand; slot < g.slots; slot += 2) {
+                const uint32_t v = s_l2[w2 * nthreads + swar_thread_of(g, anchor, word, slot)];
+                sum += half ? v >> 16 : v & 0xFFFFu;
+            }
+            if (!sum) continue;
+            const int pb = 8 * (word - g.w_a);
+            const int pos = anchor ? pb + 7 - nib : pb + nib;
+            const int end = anchor ^ cstrand;
+            const int es = end * 2 + cstrand;
+            if (pos >= 0) {
+                if (pos >= L) continue;
+                if (cls < 4) {
+                    const int gb = cstrand ? 3 - cls : cls;
+                    atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + gb) * L + pos, sum);
+                } else if (cls < 8) {
+                    const int rb = cstrand ? 3 - (cls - 4) : cls - 4;
+                    atomicAdd(t.dnacomp + ((size_t)es * 4 + rb) * LA + pos, sum);
+                } else {
+                    int gb = (cls - 8) / 3, rb = (cls - 8) % 3;
+                    rb += rb >= gb ? 1 : 0;
+                    if (cstrand) { gb = 3 - gb; rb = 3 - rb; }
+                    atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + 4 + 5 * gb + rb) * L + pos, sum);
+                }
+            } else {
+                const int d = -pos;
+                if (d > A) continue;
+                const int gb = cstrand ? 3 - cls : cls;
+                atomicAdd(t.dnacomp + ((size_t)es * 4 + gb) * LA + L + d - 1, sum);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < SWAR_L2_WORDS * nthreads; i += nthreads) s_l2[i] = 0;
+        __syncthreads();
+    };
+    // worst case every read of a tile lands on one strand: T / (slots / 2) reads per thread per tile
+    const int flush_period = max(1, 60000 / ((T + (g.slots >> 1) - 1) / (g.slots >> 1)));
+    int tiles_since_flush = 0;
+
+    const int64_t n_tiles = (b.n_reads + T - 1) / T;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tid < 3) s_ctl[tid] = 0;
+        __syncthreads();
+
+        // ---- stage the tile: filter, classify, per-read events ----
+        const int64_t tile_start = tile * T;
+        for (int q0 = 0; q0 < T; q0 += nthreads) {
+            const int q = q0 + tid;
+            const int64_t r = tile_start + q;
+            int kind = 0;  // 0 nothing, 1 gap-free, 2 for the general kernel
+            SwarRecord rec{};
+            int rstrand = 0;
+            if (q < T && r < b.n_reads) {
+                const uint32_t flag = b.flag[r];
+                if (!(flag & FILTERED_FLAGS)) {
+                    const int tid_ref = b.tid[r];
+                    if (b.lib[r] >= p.n_lib) {
+                        atomicCAS(t.error_flag, 0, DATA_ERR_LIB);
+                    } else if (tid_ref < 0 || tid_ref >= ref.n_contigs) {
+                        atomicCAS(t.error_flag, 0, DATA_ERR_TID);
+                    } else {
+                        rstrand = (flag >> 4) & 1;
+                        const uint32_t c0 = b.cigar_off[r], c1 = b.cigar_off[r + 1];
+                        uint32_t lead = 0, trail = 0, cols = 0;
+                        int state = 0, n_lead = 0, n_trail = 0;
+                        bool simple = c1 > c0;
+                        for (uint32_t k = c0; k < c1 && simple; ++k) {
+                            const uint32_t w = __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
+                            const bool match = op == OP_M || op == OP_EQ || op == OP_X;
+                            if (state == 0) {
+                                if (op == OP_H) simple = n_lead == 0;
+                                else if (op == OP_S) { lead += len; ++n_lead; }
+                                else if (match) { cols += len; state = 1; }
+                                else simple = false;
+                            } else if (state == 1) {
+                                if (match) cols += len;
+                                else if (op == OP_S) { trail += len; ++n_trail; state = 2; }
+                                else if (op == OP_H) state = 3;
+                                else simple = false;
+                            } else if (state == 2) {
+                                if (op == OP_S) { trail += len; ++n_trail; }
+                                else if (op == OP_H) state = 3;
+                                else simple = false;
+                            } else {
+                                simple = op == OP_H;
+                            }
+                        }
+                        const uint32_t l_seq = b.l_seq[r];
+                        const int64_t pos = b.pos[r];
+                        const int64_t contig_len = ref.contig_len[tid_ref];
+                        simple = simple && state >= 1 && cols > 0 && cols < 32768 && n_lead <= 1 && n_trail <= 1 &&
+                                 (uint64_t)lead + cols + trail == l_seq && pos >= 0 && pos + (int64_t)cols <= contig_len;
+                        kind = simple ? 1 : 2;
+                        if (simple) {
+                            const int64_t aend = pos + cols;
+                            const uint64_t boff = b.base_off[r];
+                            const uint64_t ref0 = ref.contig_off[tid_ref] + (uint64_t)pos;
+                            const uint32_t lf = (uint32_t)min((int64_t)A, pos);
+                            const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
+                            uint32_t has_qual = 0;
+                            if (kQual) has_qual = b.qual[boff] != 0xFF;
+                            rec.nib0 = (uint32_t)(boff + lead);
+                            rec.c_flanks = cols | (has_qual << 15) | (lf << 16) | (rf << 24);
+                            rec.ref_lo = (uint32_t)ref0;
+                            rec.ref_hi = (uint32_t)(ref0 >> 32);
+                            // FragmentLengths.update, statistics.py:117-126
+                            int64_t length = -1;
+                            int lkind = 0;
+                            if (flag & 0x1) {
+                                if ((flag & 0x40) && (flag & 0x2)) {
+                                    const int64_t tl = b.tlen[r];
+                                    length = tl < 0 ? -tl : tl;
+                                }
+                            } else {
+                                lkind = 1;
+                                length = cols;
+                            }
+                            if (length >= 0) {
+                                if (length < MDG_LG_SMEM_BINS && length < p.lg_bins) {
+                                    atomicAdd(s_lg + (lkind * 2 + rstrand) * MDG_LG_SMEM_BINS + length, 1u);
+                                } else if (length < p.lg_bins) {
+                                    atomicAdd(t.lghist + (size_t)(lkind * 2 + rstrand) * p.lg_bins + length, 1ull);
+                                } else {
+                                    const unsigned long long at = atomicAdd(t.lg_overflow_count, 1ull);
+                                    if ((int64_t)at < t.lg_overflow_cap) {
+                                        int32_t *row = t.lg_overflow_rows + at * 4;
+                                        row[0] = 0; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
+                                    }
+                                }
+                            }
+                            // update_soft_clipping, statistics.py:37-51
+                            if (lead) {
+                                const int end = rstrand ? 1 : 0, lim = (int)min(lead, (uint32_t)L);
+                                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
+                            }
+                            if (trail) {
+                                const int end = rstrand ? 0 : 1, lim = (int)min(trail, (uint32_t)L);
+                                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
+                            }
+                        }
+                    }
+                }
+            }
+            // warp-aggregated appends to the three lists
+            const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int which = 0; which < 3; ++which) {
+                const bool mine = which == 2 ? kind == 2 : (kind == 1 && rstrand == which);
+                const uint32_t m = __ballot_sync(0xffffffffu, mine);
+                if (m) {
+                    uint32_t base = 0;
+                    if (lane == __ffs(m) - 1) base = atomicAdd(s_ctl + which, (uint32_t)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                    if (mine) {
+                        const uint32_t at = base + __popc(m & lt);
+                        if (which == 0) s_rec[at] = rec;
+                        else if (which == 1) s_rec[T - 1 - at] = rec;
+                        else s_cx[at] = (uint32_t)(tile_start + q);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- complex reads go to the general kernel's work list ----
+        if (tid < 32 && s_ctl[2]) {
+            const uint32_t n_cx = s_ctl[2];
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(work_count, (unsigned long long)n_cx);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t i = lane; i < n_cx; i += 32) worklist[base + i] = s_cx[i];
+        }
+
+        // ---- the counting loop ----
+        if (job.active) {
+            const int n_mine = (int)s_ctl[strand];
+            const int stride = g.slots >> 1;
+            for (int i = job.slot >> 1; i < n_mine; i += stride) {
+                const SwarRecord rec = s_rec[strand ? T - 1 - i : i];
+                const int C = (int)(rec.c_flanks & 0x7FFF);
+                const uint64_t ref0 = ((uint64_t)rec.ref_hi << 32) | rec.ref_lo;
+                if (job.flank) {
+                    // DNAComposition.update_reference: up to A reference bases outside the alignment
+                    const int avail = job.anchor ? (int)(rec.c_flanks >> 24) : (int)((rec.c_flanks >> 16) & 0xFF);
+                    // nibble i is at distance d: left anchor d = -(pbase + i), right anchor d = -(pbase + 7 - i)
+                    // valid iff 1 <= d <= avail
+                    uint32_t mask;
+                    int64_t g0;
+                    if (job.anchor == 0) {
+                        mask = ~nibble_mask_below(-pbase - avail);  // i >= -pbase - avail  (all i have d >= 1)
+                        g0 = (int64_t)ref0 + pbase;
+                    } else {
+                        mask = nibble_mask_below(pbase + 8 + avail);  // i <= pbase + 7 + avail - 1
+                        g0 = (int64_t)ref0 + C - 8 - pbase;
+                    }
+                    if (mask) {
+                        const int64_t wi = g0 >> 3;
+                        const uint32_t y = __funnelshift_r(__ldg(ref32 + wi), __ldg(ref32 + wi + 1), 4 * (int)(g0 & 7)) & mask;
+                        acc0[0] += y & K1;
+                        acc0[1] += (y >> 1) & K1;
+                        acc0[2] += (y >> 2) & K1;
+                        acc0[3] += (y >> 3) & K1;
+                        if (++n0 == 15) spill0();
+                    }
+                } else {
+                    // positions [0, min(L, C)) of this anchor
+                    const int phi = min(L, C);
+                    uint32_t mask;
+                    int col0;
+                    if (job.anchor == 0) {
+                        mask = nibble_mask_below(phi - pbase);
+                        col0 = pbase;
+                    } else {
+                        mask = ~nibble_mask_below(pbase + 8 - phi);
+                        col0 = C - 8 - pbase;
+                    }
+                    if (mask) {
+                        const int64_t q0 = (int64_t)rec.nib0 + col0;
+                        const int64_t qi = q0 >> 3;
+                        uint32_t x = __funnelshift_r(natural_order(__ldg(seq32 + qi)), natural_order(__ldg(seq32 + qi + 1)),
+                                                     4 * (int)(q0 & 7));
+                        const int64_t g0 = (int64_t)ref0 + col0;
+                        const int64_t wi = g0 >> 3;
+                        uint32_t y = __funnelshift_r(__ldg(ref32 + wi), __ldg(ref32 + wi + 1), 4 * (int)(g0 & 7));
+                        // a column counts only when the read base is A/C/G/T (statistics.py:27); the
+                        // reference side is already 0 for anything that is not A/C/G/T
+                        const uint32_t valid = (one_hot_nibbles(x) * 15u) & mask;
+                        x &= valid;
+                        y &= valid;
+                        // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
+                        acc0[4] += x & K1;
+                        acc0[5] += (x >> 1) & K1;
+                        acc0[6] += (x >> 2) & K1;
+                        acc0[7] += (x >> 3) & K1;
+                        if (kQual) {
+                            if (rec.c_flanks & 0x8000u) {
+                                // align_with_qual, align.py:67-71: bases below --min-basequal become N on both sides
+                                const int64_t qb = q0;  // byte index of the first quality
+                                const uint32_t *q32 = (const uint32_t *)(b.qual + (qb & ~3ll));
+                                const uint32_t qa = __ldg(q32), qm = __ldg(q32 + 1), qz = __ldg(q32 + 2);
+                                const int sh = 8 * (int)(qb & 3);
+                                const uint32_t lo = __funnelshift_r(qa, qm, sh), hi = __funnelshift_r(qm, qz, sh);
+                                const uint32_t mq = (uint32_t)p.min_qual * 0x01010101u;
+                                // bit 7 of a byte of ((q | 0x80) - min_qual) is clear iff q < min_qual
+                                uint32_t zl = (~((lo | 0x80808080u) - mq) & 0x80808080u) >> 7;
+                                uint32_t zh = (~((hi | 0x80808080u) - mq) & 0x80808080u) >> 7;
+                                zl |= zl >> 4;
+                                zh |= zh >> 4;
+                                const uint32_t low = ((zl & 0x11u) | ((zl >> 8) & 0x1100u)) |
+                                                     (((zh & 0x11u) | ((zh >> 8) & 0x1100u)) << 16);
+                                const uint32_t keep = ~(low * 15u);
+                                x &= keep;
+                                y &= keep;
+                            }
+                        }
+                        const uint32_t y1 = y >> 1, y2 = y >> 2, y3 = y >> 3;
+                        const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+                        acc0[0] += y & K1;
+                        acc0[1] += y1 & K1;
+                        acc0[2] += y2 & K1;
+                        acc0[3] += y3 & K1;
+                        acc0[8] += y & x1 & K1;    // A>C
+                        acc0[9] += y & x2 & K1;    // A>G
+                        acc0[10] += y & x3 & K1;   // A>T
+                        acc0[11] += y1 & x & K1;   // C>A
+                        acc0[12] += y1 & x2 & K1;  // C>G
+                        acc0[13] += y1 & x3 & K1;  // C>T
+                        acc0[14] += y2 & x & K1;   // G>A
+                        acc0[15] += y2 & x1 & K1;  // G>C
+                        acc0[16] += y2 & x3 & K1;  // G>T
+                        acc0[17] += y3 & x & K1;   // T>A
+                        acc0[18] += y3 & x1 & K1;  // T>C
+                        acc0[19] += y3 & x2 & K1;  // T>G
+                        if (++n0 == 15) spill0();
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (++tiles_since_flush == flush_period) {
+            flush_block();
+            tiles_since_flush = 0;
+        }
+    }
+
+    flush_block();
+    for (int i = tid; i < 4 * MDG_LG_SMEM_BINS; i += nthreads) {
+        const uint32_t v = s_lg[i];
+        if (v) atomicAdd(t.lghist + (size_t)(i / MDG_LG_SMEM_BINS) * p.lg_bins + i % MDG_LG_SMEM_BINS, (unsigned long long)v);
+    }
+    for (int i = tid; i < 4 * L; i += nthreads) {
+        const uint32_t v = s_clip[i];
+        if (v) atomicAdd(t.misincorp + ((size_t)(i / L) * MDG_N_CLASSES + MDG_CLASS_SOFTCLIP) * L + i % L, (unsigned long long)v);
+    }
+}
+
+// Genome as uploaded (0..3 = A,C,G,T, anything else) -> one-hot nibbles (1,2,4,8; 0 = not a base), in place.
+__global__ void ref_to_one_hot_kernel(uint32_t *words, int64_t n_words)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = words[i];
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t c = (w >> (4 * k)) & 0xF;
+            out |= (c < 4 ? 1u << c : 0u) << (4 * k);
+        }
+        words[i] = out;
+    }
+}
+
+}  // namespace mdg

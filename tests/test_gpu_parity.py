@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 def run_engine(batch, reference, n_lib=1, length=70, around=10, min_qual=0, lg_bins=8192, chunks=1,
                resident=False):
     with DamageEngine(length=length, around=around, min_qual=min_qual, n_libraries=n_lib,
-                      lg_bins=lg_bins, max_reads=max(1024, batch.n)) as engine:
+                      lg_bins=lg_bins, max_reads=max(1024, batch.n),
+                      max_cigar_ops=max(4096, batch.cigar.shape[0])) as engine:
         engine.set_reference(reference)
         if resident:
             dev = engine.upload(batch)
@@ -131,7 +132,7 @@ def test_rescale_golden(case_dir, params):
     batch, reference, _, records = load_rescale_case(case_dir)
     model = RescaleModel.from_csv(case_dir / "Stats_out_MCMC_correct_prob.csv",
                                   params["length_5p"], params["length_3p"])
-    with DamageEngine(max_reads=max(1024, batch.n)) as engine:
+    with DamageEngine(max_reads=max(1024, batch.n), max_cigar_ops=max(4096, batch.cigar.shape[0])) as engine:
         engine.set_reference(reference)
         engine.set_rescale_model(model)
         qual, mr, status = engine.rescale(batch)
