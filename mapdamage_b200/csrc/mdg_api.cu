@@ -120,6 +120,7 @@ struct mdg_ctx {
     int general_grid = 0;
     // bit-sliced kernel for gap-free reads; complex reads go through a per-stream work list
     bool swar_enabled = false, force_general = false;
+    int swar_max_threads = 384;
     mdg::SwarGeom swar{};
     size_t swar_smem = 0;
     std::vector<WorkList> worklists;
@@ -253,6 +254,16 @@ int next_kernel_events(mdg_ctx *ctx, cudaEvent_t *start, cudaEvent_t *stop)
     return MDG_OK;
 }
 
+typedef void (*SwarKernel)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::SwarGeom, uint32_t *,
+                           unsigned long long *);
+
+// variants: with / without the quality mask, compiled for blocks of up to 384 (150 registers) or 512 threads
+SwarKernel swar_kernel(bool qual, int max_threads)
+{
+    if (max_threads <= 384) return qual ? mdg::count_swar_kernel<true, 384> : mdg::count_swar_kernel<false, 384>;
+    return qual ? mdg::count_swar_kernel<true, 512> : mdg::count_swar_kernel<false, 512>;
+}
+
 int worklist_for(mdg_ctx *ctx, cudaStream_t stream, int64_t n_reads, WorkList **out)
 {
     WorkList *wl = nullptr;
@@ -295,12 +306,11 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         MDG_CUDA(ctx, cudaMemsetAsync(wl->count, 0, 8, stream));
         const int64_t n_tiles = (b.n_reads + ctx->swar.tile - 1) / ctx->swar.tile;
         const int grid = (int)std::min<int64_t>(ctx->sm_count, n_tiles);
-        if (b.qual && p.min_qual > 0)
-            mdg::count_swar_kernel<true><<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables,
-                                                                                             ctx->swar, wl->reads, wl->count);
-        else
-            mdg::count_swar_kernel<false><<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables,
-                                                                                              ctx->swar, wl->reads, wl->count);
+        const bool q = b.qual && p.min_qual > 0;
+        void (*kernel)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::SwarGeom, uint32_t *,
+                       unsigned long long *) = swar_kernel(q, ctx->swar_max_threads);
+        kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables, ctx->swar, wl->reads,
+                                                                     wl->count);
         MDG_CUDA(ctx, cudaGetLastError());
         // reads with indels / skips: the general kernel over the work list (returns at once when it is empty)
         const int ggrid = (int)std::min<int64_t>(ctx->general_grid, (b.n_reads + 7) / 8);
@@ -451,7 +461,9 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
         g.w_a = (cfg->around + 7) / 8;
         g.w_l = (cfg->length + 7) / 8;
         const int jobs = 2 * (g.w_a + g.w_l);
-        g.slots = (mdg::SWAR_MAX_THREADS / jobs) & ~1;
+        const char *tenv = getenv("MDG_SWAR_THREADS");
+        ctx->swar_max_threads = tenv && atoi(tenv) > 384 ? 512 : 384;
+        g.slots = (ctx->swar_max_threads / jobs) & ~1;
         if (nl == 1 && g.slots >= 2 && cfg->around <= 64 && cfg->length < 32768) {
             g.work_threads = jobs * g.slots;
             g.threads = (g.work_threads + 31) / 32 * 32;
@@ -464,10 +476,9 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 }
             }
             if (g.tile) {
-                MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_swar_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)ctx->swar_smem));
-                MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_swar_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)ctx->swar_smem));
+                for (bool q : {false, true})
+                    MDG_CREATE_CUDA(cudaFuncSetAttribute(swar_kernel(q, ctx->swar_max_threads),
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->swar_smem));
                 ctx->swar_enabled = true;
             }
         }

@@ -36,7 +36,7 @@ namespace mdg {
 
 constexpr int SWAR_CLASSES = 20;
 constexpr int SWAR_L2_WORDS = 4 * SWAR_CLASSES;  // 16-bit counters: 20 classes x 8 positions
-constexpr int SWAR_MAX_THREADS = 512;
+constexpr int SWAR_MAX_THREADS = 512;  // largest block any variant is compiled for
 constexpr uint32_t K1 = 0x11111111u;
 
 struct SwarGeom {
@@ -72,6 +72,8 @@ __device__ __forceinline__ uint32_t one_hot_nibbles(uint32_t x)
     const uint32_t none = ~(x | b | c);
     return ((exactly_one & ~d) | (none & d)) & K1;
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 // thread -> (anchor, word, slot): flank threads first so that whole warps share a code path
 struct SwarJob {
@@ -109,8 +111,8 @@ __device__ __forceinline__ int swar_thread_of(const SwarGeom &g, int anchor, int
 // class index of the pair (reference g, read b), g != b
 __device__ __forceinline__ int swar_pair_class(int g, int b) { return 8 + g * 3 + b - (b > g ? 1 : 0); }
 
-template <bool kQual>
-__global__ void __launch_bounds__(SWAR_MAX_THREADS, 1)
+template <bool kQual, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, 1)
 count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom g, uint32_t *__restrict__ worklist,
                   unsigned long long *__restrict__ work_count)
 {
@@ -219,125 +221,270 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
     const int flush_period = max(1, 60000 / ((T + (g.slots >> 1) - 1) / (g.slots >> 1)));
     int tiles_since_flush = 0;
 
+    // ---- per-thread stages of the software pipeline: loads of read i+1 fly while read i is counted ----
+    struct Stage {
+        uint32_t w0, w1, r0, r1, mask;
+        uint32_t qa, qm, qz;
+        int sx, sy, sq;
+    };
+    auto fetch = [&](int i, Stage &st) {
+        const SwarRecord rec = s_rec[strand ? T - 1 - i : i];
+        const int C = (int)(rec.c_flanks & 0x7FFF);
+        const int64_t ref0 = (int64_t)(((uint64_t)rec.ref_hi << 32) | rec.ref_lo);
+        int64_t g0;
+        if (job.flank) {
+            // DNAComposition.update_reference: up to A reference bases outside the alignment.  Nibble i is
+            // at distance d = -(pbase + i) (left anchor) or -(pbase + 7 - i) (right anchor); it counts iff
+            // d <= min(A, bases before / after the alignment on the contig)
+            const int avail = job.anchor ? (int)(rec.c_flanks >> 24) : (int)((rec.c_flanks >> 16) & 0xFF);
+            if (job.anchor == 0) {
+                st.mask = ~nibble_mask_below(-pbase - avail);
+                g0 = ref0 + pbase;
+            } else {
+                st.mask = nibble_mask_below(pbase + 8 + avail);
+                g0 = ref0 + C - 8 - pbase;
+            }
+        } else {
+            // positions [0, min(L, C)) of this anchor; column == query index == reference offset
+            const int phi = min(L, C);
+            int col0;
+            if (job.anchor == 0) {
+                st.mask = nibble_mask_below(phi - pbase);
+                col0 = pbase;
+            } else {
+                st.mask = ~nibble_mask_below(pbase + 8 - phi);
+                col0 = C - 8 - pbase;
+            }
+            g0 = ref0 + col0;
+            if (st.mask) {
+                const int64_t q0 = (int64_t)rec.nib0 + col0;
+                const int64_t qi = q0 >> 3;
+                st.w0 = __ldg(seq32 + qi);
+                st.w1 = __ldg(seq32 + qi + 1);
+                st.sx = 4 * (int)(q0 & 7);
+                if (kQual) {
+                    st.sq = -1;
+                    if (rec.c_flanks & 0x8000u) {
+                        const uint32_t *q32 = (const uint32_t *)(b.qual + (q0 & ~3ll));
+                        st.qa = __ldg(q32);
+                        st.qm = __ldg(q32 + 1);
+                        st.qz = __ldg(q32 + 2);
+                        st.sq = 8 * (int)(q0 & 3);
+                    }
+                }
+            }
+        }
+        if (st.mask) {
+            const int64_t wi = g0 >> 3;
+            st.r0 = __ldg(ref32 + wi);
+            st.r1 = __ldg(ref32 + wi + 1);
+            st.sy = 4 * (int)(g0 & 7);
+        }
+    };
+    auto count = [&](const Stage &st) {
+        if (!st.mask) return;
+        uint32_t y = __funnelshift_r(st.r0, st.r1, st.sy);
+        if (job.flank) {
+            y &= st.mask;
+            acc0[0] += y & K1;
+            acc0[1] += (y >> 1) & K1;
+            acc0[2] += (y >> 2) & K1;
+            acc0[3] += (y >> 3) & K1;
+        } else {
+            uint32_t x = __funnelshift_r(natural_order(st.w0), natural_order(st.w1), st.sx);
+            // a column counts only when the read base is A/C/G/T (statistics.py:27); the reference
+            // side is already 0 for anything that is not A/C/G/T
+            const uint32_t valid = (one_hot_nibbles(x) * 15u) & st.mask;
+            x &= valid;
+            y &= valid;
+            // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
+            acc0[4] += x & K1;
+            acc0[5] += (x >> 1) & K1;
+            acc0[6] += (x >> 2) & K1;
+            acc0[7] += (x >> 3) & K1;
+            if (kQual) {
+                if (st.sq >= 0) {
+                    // align_with_qual, align.py:67-71: bases below --min-basequal become N on both sides
+                    const uint32_t lo = __funnelshift_r(st.qa, st.qm, st.sq), hi = __funnelshift_r(st.qm, st.qz, st.sq);
+                    const uint32_t mq = (uint32_t)p.min_qual * 0x01010101u;
+                    // bit 7 of a byte of ((q | 0x80) - min_qual) is clear iff q < min_qual
+                    uint32_t zl = (~((lo | 0x80808080u) - mq) & 0x80808080u) >> 7;
+                    uint32_t zh = (~((hi | 0x80808080u) - mq) & 0x80808080u) >> 7;
+                    zl |= zl >> 4;
+                    zh |= zh >> 4;
+                    const uint32_t low = ((zl & 0x11u) | ((zl >> 8) & 0x1100u)) |
+                                         (((zh & 0x11u) | ((zh >> 8) & 0x1100u)) << 16);
+                    const uint32_t keep = ~(low * 15u);
+                    x &= keep;
+                    y &= keep;
+                }
+            }
+            const uint32_t y1 = y >> 1, y2 = y >> 2, y3 = y >> 3;
+            const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+            acc0[0] += y & K1;
+            acc0[1] += y1 & K1;
+            acc0[2] += y2 & K1;
+            acc0[3] += y3 & K1;
+            acc0[8] += y & x1 & K1;    // A>C
+            acc0[9] += y & x2 & K1;    // A>G
+            acc0[10] += y & x3 & K1;   // A>T
+            acc0[11] += y1 & x & K1;   // C>A
+            acc0[12] += y1 & x2 & K1;  // C>G
+            acc0[13] += y1 & x3 & K1;  // C>T
+            acc0[14] += y2 & x & K1;   // G>A
+            acc0[15] += y2 & x1 & K1;  // G>C
+            acc0[16] += y2 & x3 & K1;  // G>T
+            acc0[17] += y3 & x & K1;   // T>A
+            acc0[18] += y3 & x1 & K1;  // T>C
+            acc0[19] += y3 & x2 & K1;  // T>G
+        }
+        if (++n0 == 15) spill0();
+    };
+
+    // ---- staging of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
+    struct Header {
+        uint32_t flag, lib, l_seq, boff, c0, c1, cig0;
+        int32_t tid_ref, pos;
+        bool live;
+    };
+    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, SwarRecord &rec) {
+        kind = 0;
+        rstrand = 0;
+        if (!h.live || (h.flag & FILTERED_FLAGS)) return;
+        if (h.lib >= (uint32_t)p.n_lib) {
+            atomicCAS(t.error_flag, 0, DATA_ERR_LIB);
+            return;
+        }
+        if (h.tid_ref < 0 || h.tid_ref >= ref.n_contigs) {
+            atomicCAS(t.error_flag, 0, DATA_ERR_TID);
+            return;
+        }
+        rstrand = (h.flag >> 4) & 1;
+        uint32_t lead = 0, trail = 0, cols = 0;
+        int state = 0, n_lead = 0, n_trail = 0;
+        bool simple = h.c1 > h.c0;
+        for (uint32_t k = h.c0; k < h.c1 && simple; ++k) {
+            const uint32_t w = k == h.c0 ? h.cig0 : __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
+            const bool match = op == OP_M || op == OP_EQ || op == OP_X;
+            if (state == 0) {
+                if (op == OP_H) simple = n_lead == 0;
+                else if (op == OP_S) { lead += len; ++n_lead; }
+                else if (match) { cols += len; state = 1; }
+                else simple = false;
+            } else if (state == 1) {
+                if (match) cols += len;
+                else if (op == OP_S) { trail += len; ++n_trail; state = 2; }
+                else if (op == OP_H) state = 3;
+                else simple = false;
+            } else if (state == 2) {
+                if (op == OP_S) { trail += len; ++n_trail; }
+                else if (op == OP_H) state = 3;
+                else simple = false;
+            } else {
+                simple = op == OP_H;
+            }
+        }
+        const int64_t pos = h.pos;
+        const int64_t contig_len = ref.contig_len[h.tid_ref];
+        simple = simple && state >= 1 && cols > 0 && cols < 32768 && n_lead <= 1 && n_trail <= 1 &&
+                 (uint64_t)lead + cols + trail == h.l_seq && pos >= 0 && pos + (int64_t)cols <= contig_len;
+        kind = simple ? 1 : 2;
+        if (!simple) return;
+        const int64_t aend = pos + cols;
+        const uint64_t ref0 = ref.contig_off[h.tid_ref] + (uint64_t)pos;
+        const uint32_t lf = (uint32_t)min((int64_t)A, pos);
+        const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
+        uint32_t has_qual = 0;
+        if (kQual) has_qual = b.qual[h.boff] != 0xFF;
+        rec.nib0 = h.boff + lead;
+        rec.c_flanks = cols | (has_qual << 15) | (lf << 16) | (rf << 24);
+        rec.ref_lo = (uint32_t)ref0;
+        rec.ref_hi = (uint32_t)(ref0 >> 32);
+        // FragmentLengths.update, statistics.py:117-126
+        int64_t length = -1;
+        int lkind = 0;
+        if (h.flag & 0x1) {
+            if ((h.flag & 0x40) && (h.flag & 0x2)) {
+                const int64_t tl = b.tlen[r];
+                length = tl < 0 ? -tl : tl;
+            }
+        } else {
+            lkind = 1;
+            length = cols;
+        }
+        if (length >= 0) {
+            if (length < MDG_LG_SMEM_BINS && length < p.lg_bins) {
+                atomicAdd(s_lg + (lkind * 2 + rstrand) * MDG_LG_SMEM_BINS + length, 1u);
+            } else if (length < p.lg_bins) {
+                atomicAdd(t.lghist + (size_t)(lkind * 2 + rstrand) * p.lg_bins + length, 1ull);
+            } else {
+                const unsigned long long at = atomicAdd(t.lg_overflow_count, 1ull);
+                if ((int64_t)at < t.lg_overflow_cap) {
+                    int32_t *row = t.lg_overflow_rows + at * 4;
+                    row[0] = 0; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
+                }
+            }
+        }
+        // update_soft_clipping, statistics.py:37-51
+        if (lead) {
+            const int end = rstrand ? 1 : 0, lim = (int)min(lead, (uint32_t)L);
+            for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
+        }
+        if (trail) {
+            const int end = rstrand ? 0 : 1, lim = (int)min(trail, (uint32_t)L);
+            for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
+        }
+    };
+
+    constexpr int PREP = 4;  // reads staged per thread with their loads in flight together
     const int64_t n_tiles = (b.n_reads + T - 1) / T;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (tid < 3) s_ctl[tid] = 0;
         __syncthreads();
 
-        // ---- stage the tile: filter, classify, per-read events ----
         const int64_t tile_start = tile * T;
-        for (int q0 = 0; q0 < T; q0 += nthreads) {
-            const int q = q0 + tid;
-            const int64_t r = tile_start + q;
-            int kind = 0;  // 0 nothing, 1 gap-free, 2 for the general kernel
-            SwarRecord rec{};
-            int rstrand = 0;
-            if (q < T && r < b.n_reads) {
-                const uint32_t flag = b.flag[r];
-                if (!(flag & FILTERED_FLAGS)) {
-                    const int tid_ref = b.tid[r];
-                    if (b.lib[r] >= p.n_lib) {
-                        atomicCAS(t.error_flag, 0, DATA_ERR_LIB);
-                    } else if (tid_ref < 0 || tid_ref >= ref.n_contigs) {
-                        atomicCAS(t.error_flag, 0, DATA_ERR_TID);
-                    } else {
-                        rstrand = (flag >> 4) & 1;
-                        const uint32_t c0 = b.cigar_off[r], c1 = b.cigar_off[r + 1];
-                        uint32_t lead = 0, trail = 0, cols = 0;
-                        int state = 0, n_lead = 0, n_trail = 0;
-                        bool simple = c1 > c0;
-                        for (uint32_t k = c0; k < c1 && simple; ++k) {
-                            const uint32_t w = __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
-                            const bool match = op == OP_M || op == OP_EQ || op == OP_X;
-                            if (state == 0) {
-                                if (op == OP_H) simple = n_lead == 0;
-                                else if (op == OP_S) { lead += len; ++n_lead; }
-                                else if (match) { cols += len; state = 1; }
-                                else simple = false;
-                            } else if (state == 1) {
-                                if (match) cols += len;
-                                else if (op == OP_S) { trail += len; ++n_trail; state = 2; }
-                                else if (op == OP_H) state = 3;
-                                else simple = false;
-                            } else if (state == 2) {
-                                if (op == OP_S) { trail += len; ++n_trail; }
-                                else if (op == OP_H) state = 3;
-                                else simple = false;
-                            } else {
-                                simple = op == OP_H;
-                            }
-                        }
-                        const uint32_t l_seq = b.l_seq[r];
-                        const int64_t pos = b.pos[r];
-                        const int64_t contig_len = ref.contig_len[tid_ref];
-                        simple = simple && state >= 1 && cols > 0 && cols < 32768 && n_lead <= 1 && n_trail <= 1 &&
-                                 (uint64_t)lead + cols + trail == l_seq && pos >= 0 && pos + (int64_t)cols <= contig_len;
-                        kind = simple ? 1 : 2;
-                        if (simple) {
-                            const int64_t aend = pos + cols;
-                            const uint64_t boff = b.base_off[r];
-                            const uint64_t ref0 = ref.contig_off[tid_ref] + (uint64_t)pos;
-                            const uint32_t lf = (uint32_t)min((int64_t)A, pos);
-                            const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
-                            uint32_t has_qual = 0;
-                            if (kQual) has_qual = b.qual[boff] != 0xFF;
-                            rec.nib0 = (uint32_t)(boff + lead);
-                            rec.c_flanks = cols | (has_qual << 15) | (lf << 16) | (rf << 24);
-                            rec.ref_lo = (uint32_t)ref0;
-                            rec.ref_hi = (uint32_t)(ref0 >> 32);
-                            // FragmentLengths.update, statistics.py:117-126
-                            int64_t length = -1;
-                            int lkind = 0;
-                            if (flag & 0x1) {
-                                if ((flag & 0x40) && (flag & 0x2)) {
-                                    const int64_t tl = b.tlen[r];
-                                    length = tl < 0 ? -tl : tl;
-                                }
-                            } else {
-                                lkind = 1;
-                                length = cols;
-                            }
-                            if (length >= 0) {
-                                if (length < MDG_LG_SMEM_BINS && length < p.lg_bins) {
-                                    atomicAdd(s_lg + (lkind * 2 + rstrand) * MDG_LG_SMEM_BINS + length, 1u);
-                                } else if (length < p.lg_bins) {
-                                    atomicAdd(t.lghist + (size_t)(lkind * 2 + rstrand) * p.lg_bins + length, 1ull);
-                                } else {
-                                    const unsigned long long at = atomicAdd(t.lg_overflow_count, 1ull);
-                                    if ((int64_t)at < t.lg_overflow_cap) {
-                                        int32_t *row = t.lg_overflow_rows + at * 4;
-                                        row[0] = 0; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
-                                    }
-                                }
-                            }
-                            // update_soft_clipping, statistics.py:37-51
-                            if (lead) {
-                                const int end = rstrand ? 1 : 0, lim = (int)min(lead, (uint32_t)L);
-                                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
-                            }
-                            if (trail) {
-                                const int end = rstrand ? 0 : 1, lim = (int)min(trail, (uint32_t)L);
-                                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
-                            }
-                        }
-                    }
+        for (int q0 = 0; q0 < T; q0 += nthreads * PREP) {
+            Header h[PREP];
+#pragma unroll
+            for (int u = 0; u < PREP; ++u) {
+                const int q = q0 + u * nthreads + tid;
+                const int64_t r = tile_start + q;
+                h[u].live = q < T && r < b.n_reads;
+                if (h[u].live) {
+                    h[u].flag = b.flag[r];
+                    h[u].lib = b.lib[r];
+                    h[u].tid_ref = b.tid[r];
+                    h[u].pos = b.pos[r];
+                    h[u].l_seq = b.l_seq[r];
+                    h[u].boff = b.base_off[r];
+                    h[u].c0 = b.cigar_off[r];
+                    h[u].c1 = b.cigar_off[r + 1];
                 }
             }
-            // warp-aggregated appends to the three lists
-            const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-            for (int which = 0; which < 3; ++which) {
-                const bool mine = which == 2 ? kind == 2 : (kind == 1 && rstrand == which);
-                const uint32_t m = __ballot_sync(0xffffffffu, mine);
-                if (m) {
-                    uint32_t base = 0;
-                    if (lane == __ffs(m) - 1) base = atomicAdd(s_ctl + which, (uint32_t)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                    if (mine) {
-                        const uint32_t at = base + __popc(m & lt);
-                        if (which == 0) s_rec[at] = rec;
-                        else if (which == 1) s_rec[T - 1 - at] = rec;
-                        else s_cx[at] = (uint32_t)(tile_start + q);
+            for (int u = 0; u < PREP; ++u) h[u].cig0 = h[u].live && h[u].c1 > h[u].c0 ? __ldg(b.cigar + h[u].c0) : 0;
+#pragma unroll
+            for (int u = 0; u < PREP; ++u) {
+                const int q = q0 + u * nthreads + tid;
+                int kind, rstrand;
+                SwarRecord rec{};
+                stage_read(h[u], tile_start + q, kind, rstrand, rec);
+                // warp-aggregated appends to the three lists
+                const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int which = 0; which < 3; ++which) {
+                    const bool mine = which == 2 ? kind == 2 : (kind == 1 && rstrand == which);
+                    const uint32_t m = __ballot_sync(0xffffffffu, mine);
+                    if (m) {
+                        uint32_t base = 0;
+                        if (lane == __ffs(m) - 1) base = atomicAdd(s_ctl + which, (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                        if (mine) {
+                            const uint32_t at = base + __popc(m & lt);
+                            if (which == 0) s_rec[at] = rec;
+                            else if (which == 1) s_rec[T - 1 - at] = rec;
+                            else s_cx[at] = (uint32_t)(tile_start + q);
+                        }
                     }
                 }
             }
@@ -353,109 +500,60 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             for (uint32_t i = lane; i < n_cx; i += 32) worklist[base + i] = s_cx[i];
         }
 
+        // ---- pull the block's next tile towards L2 while this one is counted ----
+        const int64_t next_start = (tile + gridDim.x) * T;
+        uint32_t next_boff = 0, next_coff = 0;
+        bool next_live = false;
+        {
+            const int64_t rn = next_start + (int64_t)tid * ((T + nthreads - 1) / nthreads);
+            next_live = tid * ((T + nthreads - 1) / nthreads) < T && rn < b.n_reads;
+            if (next_live) {
+                next_boff = b.base_off[rn];
+                next_coff = b.cigar_off[rn];
+            }
+            // header arrays: T entries each, one 128-byte line per 32 (u32) or 64 (u16) entries
+            const int64_t r4 = next_start + (int64_t)tid * 32;
+            if (tid * 32 < T && r4 < b.n_reads) {
+                prefetch_l2(b.tid + r4);
+                prefetch_l2(b.pos + r4);
+                prefetch_l2(b.l_seq + r4);
+                prefetch_l2(b.tlen + r4);
+                if (!(tid & 1)) {
+                    prefetch_l2(b.flag + r4);
+                    prefetch_l2(b.lib + r4);
+                }
+            }
+        }
+
         // ---- the counting loop ----
         if (job.active) {
             const int n_mine = (int)s_ctl[strand];
             const int stride = g.slots >> 1;
-            for (int i = job.slot >> 1; i < n_mine; i += stride) {
-                const SwarRecord rec = s_rec[strand ? T - 1 - i : i];
-                const int C = (int)(rec.c_flanks & 0x7FFF);
-                const uint64_t ref0 = ((uint64_t)rec.ref_hi << 32) | rec.ref_lo;
-                if (job.flank) {
-                    // DNAComposition.update_reference: up to A reference bases outside the alignment
-                    const int avail = job.anchor ? (int)(rec.c_flanks >> 24) : (int)((rec.c_flanks >> 16) & 0xFF);
-                    // nibble i is at distance d: left anchor d = -(pbase + i), right anchor d = -(pbase + 7 - i)
-                    // valid iff 1 <= d <= avail
-                    uint32_t mask;
-                    int64_t g0;
-                    if (job.anchor == 0) {
-                        mask = ~nibble_mask_below(-pbase - avail);  // i >= -pbase - avail  (all i have d >= 1)
-                        g0 = (int64_t)ref0 + pbase;
-                    } else {
-                        mask = nibble_mask_below(pbase + 8 + avail);  // i <= pbase + 7 + avail - 1
-                        g0 = (int64_t)ref0 + C - 8 - pbase;
-                    }
-                    if (mask) {
-                        const int64_t wi = g0 >> 3;
-                        const uint32_t y = __funnelshift_r(__ldg(ref32 + wi), __ldg(ref32 + wi + 1), 4 * (int)(g0 & 7)) & mask;
-                        acc0[0] += y & K1;
-                        acc0[1] += (y >> 1) & K1;
-                        acc0[2] += (y >> 2) & K1;
-                        acc0[3] += (y >> 3) & K1;
-                        if (++n0 == 15) spill0();
-                    }
-                } else {
-                    // positions [0, min(L, C)) of this anchor
-                    const int phi = min(L, C);
-                    uint32_t mask;
-                    int col0;
-                    if (job.anchor == 0) {
-                        mask = nibble_mask_below(phi - pbase);
-                        col0 = pbase;
-                    } else {
-                        mask = ~nibble_mask_below(pbase + 8 - phi);
-                        col0 = C - 8 - pbase;
-                    }
-                    if (mask) {
-                        const int64_t q0 = (int64_t)rec.nib0 + col0;
-                        const int64_t qi = q0 >> 3;
-                        uint32_t x = __funnelshift_r(natural_order(__ldg(seq32 + qi)), natural_order(__ldg(seq32 + qi + 1)),
-                                                     4 * (int)(q0 & 7));
-                        const int64_t g0 = (int64_t)ref0 + col0;
-                        const int64_t wi = g0 >> 3;
-                        uint32_t y = __funnelshift_r(__ldg(ref32 + wi), __ldg(ref32 + wi + 1), 4 * (int)(g0 & 7));
-                        // a column counts only when the read base is A/C/G/T (statistics.py:27); the
-                        // reference side is already 0 for anything that is not A/C/G/T
-                        const uint32_t valid = (one_hot_nibbles(x) * 15u) & mask;
-                        x &= valid;
-                        y &= valid;
-                        // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
-                        acc0[4] += x & K1;
-                        acc0[5] += (x >> 1) & K1;
-                        acc0[6] += (x >> 2) & K1;
-                        acc0[7] += (x >> 3) & K1;
-                        if (kQual) {
-                            if (rec.c_flanks & 0x8000u) {
-                                // align_with_qual, align.py:67-71: bases below --min-basequal become N on both sides
-                                const int64_t qb = q0;  // byte index of the first quality
-                                const uint32_t *q32 = (const uint32_t *)(b.qual + (qb & ~3ll));
-                                const uint32_t qa = __ldg(q32), qm = __ldg(q32 + 1), qz = __ldg(q32 + 2);
-                                const int sh = 8 * (int)(qb & 3);
-                                const uint32_t lo = __funnelshift_r(qa, qm, sh), hi = __funnelshift_r(qm, qz, sh);
-                                const uint32_t mq = (uint32_t)p.min_qual * 0x01010101u;
-                                // bit 7 of a byte of ((q | 0x80) - min_qual) is clear iff q < min_qual
-                                uint32_t zl = (~((lo | 0x80808080u) - mq) & 0x80808080u) >> 7;
-                                uint32_t zh = (~((hi | 0x80808080u) - mq) & 0x80808080u) >> 7;
-                                zl |= zl >> 4;
-                                zh |= zh >> 4;
-                                const uint32_t low = ((zl & 0x11u) | ((zl >> 8) & 0x1100u)) |
-                                                     (((zh & 0x11u) | ((zh >> 8) & 0x1100u)) << 16);
-                                const uint32_t keep = ~(low * 15u);
-                                x &= keep;
-                                y &= keep;
-                            }
-                        }
-                        const uint32_t y1 = y >> 1, y2 = y >> 2, y3 = y >> 3;
-                        const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
-                        acc0[0] += y & K1;
-                        acc0[1] += y1 & K1;
-                        acc0[2] += y2 & K1;
-                        acc0[3] += y3 & K1;
-                        acc0[8] += y & x1 & K1;    // A>C
-                        acc0[9] += y & x2 & K1;    // A>G
-                        acc0[10] += y & x3 & K1;   // A>T
-                        acc0[11] += y1 & x & K1;   // C>A
-                        acc0[12] += y1 & x2 & K1;  // C>G
-                        acc0[13] += y1 & x3 & K1;  // C>T
-                        acc0[14] += y2 & x & K1;   // G>A
-                        acc0[15] += y2 & x1 & K1;  // G>C
-                        acc0[16] += y2 & x3 & K1;  // G>T
-                        acc0[17] += y3 & x & K1;   // T>A
-                        acc0[18] += y3 & x1 & K1;  // T>C
-                        acc0[19] += y3 & x2 & K1;  // T>G
-                        if (++n0 == 15) spill0();
-                    }
-                }
+            // two stages that swap roles, so that no register copy waits on a load at the loop edge
+            int i = job.slot >> 1;
+            Stage sa{}, sb{};
+            if (i < n_mine) fetch(i, sa);
+            while (i < n_mine) {
+                sb.mask = 0;
+                if (i + stride < n_mine) fetch(i + stride, sb);
+                count(sa);
+                i += stride;
+                if (i >= n_mine) break;
+                sa.mask = 0;
+                if (i + stride < n_mine) fetch(i + stride, sa);
+                count(sb);
+                i += stride;
+            }
+        }
+        if (next_live) {
+            // each thread covers (T / nthreads) consecutive reads of the next tile: a few hundred bytes
+            const int per = (T + nthreads - 1) / nthreads;
+            const char *seq_at = (const char *)b.seq4 + (next_boff >> 1);
+            for (int off = 0; off < per * 80; off += 128) prefetch_l2(seq_at + off);
+            prefetch_l2(b.cigar + next_coff);
+            if (kQual) {
+                const char *q_at = (const char *)b.qual + next_boff;
+                for (int off = 0; off < per * 160; off += 128) prefetch_l2(q_at + off);
             }
         }
         __syncthreads();

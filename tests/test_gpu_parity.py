@@ -18,7 +18,8 @@ def run_engine(batch, reference, n_lib=1, length=70, around=10, min_qual=0, lg_b
                resident=False):
     with DamageEngine(length=length, around=around, min_qual=min_qual, n_libraries=n_lib,
                       lg_bins=lg_bins, max_reads=max(1024, batch.n),
-                      max_cigar_ops=max(4096, batch.cigar.shape[0])) as engine:
+                      max_cigar_ops=max(4096, batch.cigar.shape[0]),
+                      max_bases=max(1 << 16, batch.total_bases)) as engine:
         engine.set_reference(reference)
         if resident:
             dev = engine.upload(batch)
@@ -170,7 +171,7 @@ def test_rescale_vs_oracle(name, l5, l3):
     model = RescaleModel(corr, l5, l3)
     want_qual, want_mr, want_status, subs, rc = oracle.rescale(batch, reference, corr)
     assert rc == 0
-    with DamageEngine(max_reads=batch.n) as engine:
+    with DamageEngine(max_reads=batch.n, max_cigar_ops=batch.cigar.shape[0], max_bases=batch.total_bases) as engine:
         engine.set_reference(reference)
         engine.set_rescale_model(model)
         qual, mr, status = engine.rescale(batch)
@@ -180,9 +181,8 @@ def test_rescale_vs_oracle(name, l5, l3):
     assert np.array_equal(mr[status == 1], want_mr[want_status == 1])
     # compare the quality bytes of real bases only (pad slots are unspecified)
     mask = np.zeros(qual.shape[0], dtype=bool)
-    starts = batch.base_off.astype(np.int64)
-    idx = np.repeat(starts, batch.l_seq) + (np.arange(int(batch.l_seq.sum())) -
-                                             np.repeat(np.cumsum(batch.l_seq) - batch.l_seq, batch.l_seq))
+    starts, lens = batch.base_off.astype(np.int64), batch.l_seq.astype(np.int64)
+    idx = np.repeat(starts, lens) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens) - lens, lens))
     mask[idx] = True
     assert np.array_equal(qual[mask], want_qual[:qual.shape[0]][mask])
     assert (qual[mask] != batch.qual[:qual.shape[0]][mask]).sum() > 100
