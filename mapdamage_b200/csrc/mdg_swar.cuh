@@ -41,22 +41,24 @@ constexpr uint32_t K1 = 0x11111111u;
 
 struct SwarGeom {
     int32_t w_a, w_l;      // flank / aligned words per anchor
-    int32_t slots;         // read slots per block (even: half per strand)
+    int32_t slots;         // read slots of the aligned words (even: half per strand)
+    int32_t slots_f;       // read slots of the flank words: fewer, a flank word is ~4x cheaper to count
     int32_t threads;       // blockDim.x
-    int32_t work_threads;  // 2 * (w_a + w_l) * slots
+    int32_t work_threads;  // 2 * w_a * slots_f + 2 * w_l * slots
     int32_t tile;          // reads staged per iteration of the block
 };
 
-struct __align__(16) SwarRecord {  // one staged read, 16 bytes
-    uint32_t nib0;       // first aligned base, in batch base coordinates (base_off + leading clip)
-    uint32_t c_flanks;   // columns | left flank bases << 16 | right flank bases << 24 | has_qual << 15
-    uint32_t ref_lo, ref_hi;  // genome base index of the first aligned column
+// One staged read as one anchor sees it (16 bytes): where its words start and how far to shift them.
+//   left anchor:  word 0 of the window starts at the first aligned base / its reference base
+//   right anchor: word 0 ends at the last aligned base (indices of base "one past the end")
+struct __align__(16) SwarRecord {
+    int32_t qi;     // 32-bit word of seq4 holding that base
+    int32_t ri;     // 32-bit word of the genome holding that base
+    uint32_t sh;    // funnel shifts in bits: read | reference << 8
+    uint32_t meta;  // min(L, columns) | has_qual << 15 | left flank bases << 16 | right flank bases << 24
 };
 
-__device__ __forceinline__ uint32_t nibble_mask_below(int n)  // nibbles [0, n)
-{
-    return n >= 8 ? 0xffffffffu : n <= 0 ? 0u : (1u << (4 * n)) - 1u;
-}
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 // BAM packs the first base of a byte in the high nibble; make nibble i of the word base i
 __device__ __forceinline__ uint32_t natural_order(uint32_t w)
@@ -73,8 +75,6 @@ __device__ __forceinline__ uint32_t one_hot_nibbles(uint32_t x)
     return ((exactly_one & ~d) | (none & d)) & K1;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
 // thread -> (anchor, word, slot): flank threads first so that whole warps share a code path
 struct SwarJob {
     int anchor, word, slot;
@@ -84,7 +84,7 @@ struct SwarJob {
 __device__ __forceinline__ SwarJob swar_job(const SwarGeom &g, int t)
 {
     SwarJob j;
-    const int n_flank = 2 * g.w_a * g.slots;
+    const int n_flank = 2 * g.w_a * g.slots_f;
     j.active = t < g.work_threads;
     j.flank = t < n_flank;
     if (j.flank) {
@@ -105,11 +105,15 @@ __device__ __forceinline__ SwarJob swar_job(const SwarGeom &g, int t)
 __device__ __forceinline__ int swar_thread_of(const SwarGeom &g, int anchor, int word, int slot)
 {
     if (word < g.w_a) return slot * 2 * g.w_a + anchor * g.w_a + word;
-    return 2 * g.w_a * g.slots + slot * 2 * g.w_l + anchor * g.w_l + (word - g.w_a);
+    return 2 * g.w_a * g.slots_f + slot * 2 * g.w_l + anchor * g.w_l + (word - g.w_a);
 }
 
-// class index of the pair (reference g, read b), g != b
-__device__ __forceinline__ int swar_pair_class(int g, int b) { return 8 + g * 3 + b - (b > g ? 1 : 0); }
+// Private 16-bit counters: word w of thread t.  Flank threads (the first n_flank) only ever touch the
+// reference-base classes, words 0..15; the other 64 words exist for the aligned threads only.
+__device__ __forceinline__ int swar_l2_index(int w, int t, int nthreads, int n_flank)
+{
+    return w < 16 ? w * nthreads + t : 16 * nthreads + (w - 16) * (nthreads - n_flank) + (t - n_flank);
+}
 
 template <bool kQual, int kMaxThreads>
 __global__ void __launch_bounds__(kMaxThreads, 1)
@@ -118,45 +122,85 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 {
     extern __shared__ uint32_t smem[];
     const int nthreads = g.threads, T = g.tile, L = p.L, A = p.A;
-    uint32_t *const s_l2 = smem;                                     // [SWAR_L2_WORDS][nthreads]
-    SwarRecord *const s_rec = (SwarRecord *)(s_l2 + SWAR_L2_WORDS * nthreads);  // [T]: forward from the front, reverse from the back
-    uint32_t *const s_cx = (uint32_t *)(s_rec + T);                  // [T] complex reads of the tile
-    uint32_t *const s_lg = s_cx + T;                                 // [kind][strand][MDG_LG_SMEM_BINS]
-    uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;            // [end][strand][L]
-    uint32_t *const s_ctl = s_clip + 4 * L;                          // n_fwd, n_rev, n_cx
+    const int n_flank = 2 * g.w_a * g.slots_f;
+    const int l2_words = 16 * nthreads + 64 * (nthreads - n_flank);
+    uint32_t *const s_l2 = smem;
+    SwarRecord *const s_rec = (SwarRecord *)(s_l2 + ((l2_words + 3) & ~3));  // [anchor][T]: forward reads from the front, reverse from the back
+    uint32_t *const s_cx = (uint32_t *)(s_rec + 2 * T);    // [T] complex reads of the tile
+    uint32_t *const s_lg = s_cx + T;                       // [kind][strand][MDG_LG_SMEM_BINS]
+    uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;  // [end][strand][L]
+    uint32_t *const s_ctl = s_clip + 4 * L;                // n_fwd, n_rev, n_cx
 
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < SWAR_L2_WORDS * nthreads; i += nthreads) s_l2[i] = 0;
+    for (int i = tid; i < l2_words; i += nthreads) s_l2[i] = 0;
     for (int i = tid; i < 4 * MDG_LG_SMEM_BINS + 4 * L; i += nthreads) s_lg[i] = 0;
 
     const SwarJob job = swar_job(g, tid);
     const int strand = job.slot & 1;
-    const int pbase = 8 * (job.word - g.w_a);  // window position of nibble 0 (left anchor) / nibble 7 (right anchor)
     const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
     const uint32_t *__restrict__ ref32 = ref.words;
 
-    uint32_t acc0[SWAR_CLASSES];      // 8 x 4-bit counters per class
-    uint32_t acc1[2 * SWAR_CLASSES];  // 2 x (4 x 8-bit) counters per class: even / odd nibbles
+    // Thread constants.  Window position of nibble i: p = pbase + i (left anchor) or pbase + 7 - i (right).
+    //   aligned words: nibble counts iff 0 <= p < v, v = min(L, columns)
+    //   flank words (pbase < 0): nibble at distance d = -p counts iff d <= v, v = flank bases on the contig
+    // Both are "the low n nibbles" or the complement of that, with 4 n = c4 + s4 * v clamped to [0, 32].
+    const int pbase = 8 * (job.word - g.w_a);
+    const int koff = job.anchor ? -(1 + job.word - g.w_a) : job.word - g.w_a;  // word offset from the record's index
+    const bool low_side = (job.anchor != 0) == job.flank;                       // counted nibbles are the low ones
+    const int s4 = low_side ? 4 : -4;
+    const int c4 = job.anchor ? 4 * pbase + 32 : -4 * pbase;
+    const uint32_t flip = low_side ? 0u : 0xffffffffu;
+    const int vshift = job.flank ? (job.anchor ? 24 : 16) : 0;
+    const uint32_t vmask = job.flank ? 0xFFu : 0x7FFFu;
+    const SwarRecord *const my_recs = s_rec + job.anchor * T;
+
+    uint32_t acc0[SWAR_CLASSES];  // 8 x 4-bit counters per class
+    uint32_t acc1[16];            // classes 0..7 (reference / read bases): 2 x (4 x 8-bit) counters, even / odd nibbles
 #pragma unroll
-    for (int c = 0; c < SWAR_CLASSES; ++c) acc0[c] = acc1[2 * c] = acc1[2 * c + 1] = 0;
+    for (int c = 0; c < SWAR_CLASSES; ++c) acc0[c] = 0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) acc1[w] = 0;
     int n0 = 0, n1 = 0;
+    uint32_t *const my_l2 = s_l2 + 16 * nthreads + (tid - n_flank);  // words 16.. of an aligned thread, stride l2_stride
+    const int l2_stride = nthreads - n_flank;
 
     auto spill1 = [&]() {  // 8-bit -> private 16-bit counters in shared memory
 #pragma unroll
-        for (int w = 0; w < 2 * SWAR_CLASSES; ++w) {
+        for (int w = 0; w < 16; ++w) {
             const uint32_t v = acc1[w];
-            s_l2[(2 * w) * nthreads + tid] += v & 0x00FF00FFu;
-            s_l2[(2 * w + 1) * nthreads + tid] += (v >> 8) & 0x00FF00FFu;
+            if (w < 8) {
+                s_l2[(2 * w) * nthreads + tid] += v & 0x00FF00FFu;
+                s_l2[(2 * w + 1) * nthreads + tid] += (v >> 8) & 0x00FF00FFu;
+            } else if (!job.flank) {
+                my_l2[(2 * w - 16) * l2_stride] += v & 0x00FF00FFu;
+                my_l2[(2 * w - 15) * l2_stride] += (v >> 8) & 0x00FF00FFu;
+            }
             acc1[w] = 0;
         }
         n1 = 0;
     };
-    auto spill0 = [&]() {  // 4-bit -> 8-bit counters
+    auto spill0 = [&]() {  // 4-bit counters: base classes -> 8-bit registers; substitution classes (mostly
+                           // zero) straight into the 16-bit counters
 #pragma unroll
-        for (int c = 0; c < SWAR_CLASSES; ++c) {
+        for (int c = 0; c < 8; ++c) {
             acc1[2 * c] += acc0[c] & 0x0F0F0F0Fu;
             acc1[2 * c + 1] += (acc0[c] >> 4) & 0x0F0F0F0Fu;
             acc0[c] = 0;
+        }
+        if (!job.flank) {
+#pragma unroll
+            for (int c = 8; c < SWAR_CLASSES; ++c) {
+                const uint32_t v = acc0[c];
+                if (v) {
+                    // 16-bit lane of (class, nibble): word 4 c + 2 (nibble & 1) + ((nibble >> 1) & 1), half nibble >> 2
+                    uint32_t *at = my_l2 + (4 * c - 16) * l2_stride;
+                    at[0] += v & 0x000F000Fu;
+                    at[l2_stride] += (v >> 8) & 0x000F000Fu;
+                    at[2 * l2_stride] += (v >> 4) & 0x000F000Fu;
+                    at[3 * l2_stride] += (v >> 12) & 0x000F000Fu;
+                    acc0[c] = 0;
+                }
+            }
         }
         n0 = 0;
         if (++n1 == 17) spill1();
@@ -183,8 +227,9 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             const int w1 = 2 * cls + (nib & 1), bl = nib >> 1;
             const int w2 = 2 * w1 + (bl & 1), half = bl >> 1;
             unsigned long long sum = 0;
-            for (int slot = cstrand; slot < g.slots; slot += 2) {
-                const uint32_t v = s_l2[w2 * nthreads + swar_thread_of(g, anchor, word, slot)];
+            const int n_slots = word < g.w_a ? g.slots_f : g.slots;
+            for (int slot = cstrand; slot < n_slots; slot += 2) {
+                const uint32_t v = s_l2[swar_l2_index(w2, swar_thread_of(g, anchor, word, slot), nthreads, n_flank)];
                 sum += half ? v >> 16 : v & 0xFFFFu;
             }
             if (!sum) continue;
@@ -214,130 +259,106 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             }
         }
         __syncthreads();
-        for (int i = tid; i < SWAR_L2_WORDS * nthreads; i += nthreads) s_l2[i] = 0;
+        for (int i = tid; i < l2_words; i += nthreads) s_l2[i] = 0;
         __syncthreads();
     };
     // worst case every read of a tile lands on one strand: T / (slots / 2) reads per thread per tile
-    const int flush_period = max(1, 60000 / ((T + (g.slots >> 1) - 1) / (g.slots >> 1)));
+    const int min_slots = g.w_a ? min(g.slots, g.slots_f) : g.slots;
+    const int flush_period = max(1, 60000 / ((T + (min_slots >> 1) - 1) / (min_slots >> 1)));
     int tiles_since_flush = 0;
 
     // ---- per-thread stages of the software pipeline: loads of read i+1 fly while read i is counted ----
     struct Stage {
-        uint32_t w0, w1, r0, r1, mask;
+        uint32_t w0, w1, r0, r1, mask, sh;
         uint32_t qa, qm, qz;
-        int sx, sy, sq;
+        int sq;
     };
-    auto fetch = [&](int i, Stage &st) {
-        const SwarRecord rec = s_rec[strand ? T - 1 - i : i];
-        const int C = (int)(rec.c_flanks & 0x7FFF);
-        const int64_t ref0 = (int64_t)(((uint64_t)rec.ref_hi << 32) | rec.ref_lo);
-        int64_t g0;
-        if (job.flank) {
-            // DNAComposition.update_reference: up to A reference bases outside the alignment.  Nibble i is
-            // at distance d = -(pbase + i) (left anchor) or -(pbase + 7 - i) (right anchor); it counts iff
-            // d <= min(A, bases before / after the alignment on the contig)
-            const int avail = job.anchor ? (int)(rec.c_flanks >> 24) : (int)((rec.c_flanks >> 16) & 0xFF);
-            if (job.anchor == 0) {
-                st.mask = ~nibble_mask_below(-pbase - avail);
-                g0 = ref0 + pbase;
-            } else {
-                st.mask = nibble_mask_below(pbase + 8 + avail);
-                g0 = ref0 + C - 8 - pbase;
-            }
-        } else {
-            // positions [0, min(L, C)) of this anchor; column == query index == reference offset
-            const int phi = min(L, C);
-            int col0;
-            if (job.anchor == 0) {
-                st.mask = nibble_mask_below(phi - pbase);
-                col0 = pbase;
-            } else {
-                st.mask = ~nibble_mask_below(pbase + 8 - phi);
-                col0 = C - 8 - pbase;
-            }
-            g0 = ref0 + col0;
-            if (st.mask) {
-                const int64_t q0 = (int64_t)rec.nib0 + col0;
-                const int64_t qi = q0 >> 3;
-                st.w0 = __ldg(seq32 + qi);
-                st.w1 = __ldg(seq32 + qi + 1);
-                st.sx = 4 * (int)(q0 & 7);
+    auto fetch = [&](int i, Stage &st, bool with_read) {
+        const SwarRecord rec = my_recs[strand ? T - 1 - i : i];
+        const int v = (int)((rec.meta >> vshift) & vmask);
+        st.mask = __funnelshift_lc(0xffffffffu, 0u, max(c4 + s4 * v, 0)) ^ flip;
+        st.sh = rec.sh;
+        if (st.mask) {
+            const uint32_t *rp = ref32 + (rec.ri + koff);
+            st.r0 = __ldg(rp);
+            st.r1 = __ldg(rp + 1);
+            if (with_read) {
+                const uint32_t *qp = seq32 + (rec.qi + koff);
+                st.w0 = __ldg(qp);
+                st.w1 = __ldg(qp + 1);
                 if (kQual) {
                     st.sq = -1;
-                    if (rec.c_flanks & 0x8000u) {
-                        const uint32_t *q32 = (const uint32_t *)(b.qual + (q0 & ~3ll));
+                    if (rec.meta & 0x8000u) {
+                        // qualities of the window's eight bases start at byte 8 * word + read shift / 4;
+                        // three words from the aligned word below cover them
+                        const uint32_t *q32 = (const uint32_t *)b.qual + 2 * (int64_t)(rec.qi + koff) + ((rec.sh >> 4) & 1);
                         st.qa = __ldg(q32);
                         st.qm = __ldg(q32 + 1);
                         st.qz = __ldg(q32 + 2);
-                        st.sq = 8 * (int)(q0 & 3);
+                        st.sq = (int)(rec.sh * 2) & 24;
                     }
                 }
             }
         }
-        if (st.mask) {
-            const int64_t wi = g0 >> 3;
-            st.r0 = __ldg(ref32 + wi);
-            st.r1 = __ldg(ref32 + wi + 1);
-            st.sy = 4 * (int)(g0 & 7);
-        }
     };
-    auto count = [&](const Stage &st) {
+    auto count_flank = [&](const Stage &st) {
         if (!st.mask) return;
-        uint32_t y = __funnelshift_r(st.r0, st.r1, st.sy);
-        if (job.flank) {
-            y &= st.mask;
-            acc0[0] += y & K1;
-            acc0[1] += (y >> 1) & K1;
-            acc0[2] += (y >> 2) & K1;
-            acc0[3] += (y >> 3) & K1;
-        } else {
-            uint32_t x = __funnelshift_r(natural_order(st.w0), natural_order(st.w1), st.sx);
-            // a column counts only when the read base is A/C/G/T (statistics.py:27); the reference
-            // side is already 0 for anything that is not A/C/G/T
-            const uint32_t valid = (one_hot_nibbles(x) * 15u) & st.mask;
-            x &= valid;
-            y &= valid;
-            // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
-            acc0[4] += x & K1;
-            acc0[5] += (x >> 1) & K1;
-            acc0[6] += (x >> 2) & K1;
-            acc0[7] += (x >> 3) & K1;
-            if (kQual) {
-                if (st.sq >= 0) {
-                    // align_with_qual, align.py:67-71: bases below --min-basequal become N on both sides
-                    const uint32_t lo = __funnelshift_r(st.qa, st.qm, st.sq), hi = __funnelshift_r(st.qm, st.qz, st.sq);
-                    const uint32_t mq = (uint32_t)p.min_qual * 0x01010101u;
-                    // bit 7 of a byte of ((q | 0x80) - min_qual) is clear iff q < min_qual
-                    uint32_t zl = (~((lo | 0x80808080u) - mq) & 0x80808080u) >> 7;
-                    uint32_t zh = (~((hi | 0x80808080u) - mq) & 0x80808080u) >> 7;
-                    zl |= zl >> 4;
-                    zh |= zh >> 4;
-                    const uint32_t low = ((zl & 0x11u) | ((zl >> 8) & 0x1100u)) |
-                                         (((zh & 0x11u) | ((zh >> 8) & 0x1100u)) << 16);
-                    const uint32_t keep = ~(low * 15u);
-                    x &= keep;
-                    y &= keep;
-                }
+        // DNAComposition.update_reference: reference bases just outside the alignment
+        const uint32_t y = __funnelshift_r(st.r0, st.r1, st.sh >> 8) & st.mask;
+        acc0[0] += y & K1;
+        acc0[1] += (y >> 1) & K1;
+        acc0[2] += (y >> 2) & K1;
+        acc0[3] += (y >> 3) & K1;
+        if (++n0 == 15) spill0();
+    };
+    auto count_aligned = [&](const Stage &st) {
+        if (!st.mask) return;
+        uint32_t y = __funnelshift_r(st.r0, st.r1, st.sh >> 8);
+        uint32_t x = __funnelshift_r(natural_order(st.w0), natural_order(st.w1), st.sh);
+        // a column counts only when the read base is A/C/G/T (statistics.py:27); the reference
+        // side is already 0 for anything that is not A/C/G/T
+        const uint32_t valid = (one_hot_nibbles(x) * 15u) & st.mask;
+        x &= valid;
+        y &= valid;
+        // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
+        acc0[4] += x & K1;
+        acc0[5] += (x >> 1) & K1;
+        acc0[6] += (x >> 2) & K1;
+        acc0[7] += (x >> 3) & K1;
+        if (kQual) {
+            if (st.sq >= 0) {
+                // align_with_qual, align.py:67-71: bases below --min-basequal become N on both sides
+                const uint32_t lo = __funnelshift_r(st.qa, st.qm, st.sq), hi = __funnelshift_r(st.qm, st.qz, st.sq);
+                const uint32_t mq = (uint32_t)p.min_qual * 0x01010101u;
+                // bit 7 of a byte of ((q | 0x80) - min_qual) is clear iff q < min_qual
+                uint32_t zl = (~((lo | 0x80808080u) - mq) & 0x80808080u) >> 7;
+                uint32_t zh = (~((hi | 0x80808080u) - mq) & 0x80808080u) >> 7;
+                zl |= zl >> 4;
+                zh |= zh >> 4;
+                const uint32_t low = ((zl & 0x11u) | ((zl >> 8) & 0x1100u)) | (((zh & 0x11u) | ((zh >> 8) & 0x1100u)) << 16);
+                const uint32_t keep = ~(low * 15u);
+                x &= keep;
+                y &= keep;
             }
-            const uint32_t y1 = y >> 1, y2 = y >> 2, y3 = y >> 3;
-            const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
-            acc0[0] += y & K1;
-            acc0[1] += y1 & K1;
-            acc0[2] += y2 & K1;
-            acc0[3] += y3 & K1;
-            acc0[8] += y & x1 & K1;    // A>C
-            acc0[9] += y & x2 & K1;    // A>G
-            acc0[10] += y & x3 & K1;   // A>T
-            acc0[11] += y1 & x & K1;   // C>A
-            acc0[12] += y1 & x2 & K1;  // C>G
-            acc0[13] += y1 & x3 & K1;  // C>T
-            acc0[14] += y2 & x & K1;   // G>A
-            acc0[15] += y2 & x1 & K1;  // G>C
-            acc0[16] += y2 & x3 & K1;  // G>T
-            acc0[17] += y3 & x & K1;   // T>A
-            acc0[18] += y3 & x1 & K1;  // T>C
-            acc0[19] += y3 & x2 & K1;  // T>G
         }
+        const uint32_t y1 = y >> 1, y2 = y >> 2, y3 = y >> 3;
+        const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+        acc0[0] += y & K1;
+        acc0[1] += y1 & K1;
+        acc0[2] += y2 & K1;
+        acc0[3] += y3 & K1;
+        acc0[8] += y & x1 & K1;    // A>C
+        acc0[9] += y & x2 & K1;    // A>G
+        acc0[10] += y & x3 & K1;   // A>T
+        acc0[11] += y1 & x & K1;   // C>A
+        acc0[12] += y1 & x2 & K1;  // C>G
+        acc0[13] += y1 & x3 & K1;  // C>T
+        acc0[14] += y2 & x & K1;   // G>A
+        acc0[15] += y2 & x1 & K1;  // G>C
+        acc0[16] += y2 & x3 & K1;  // G>T
+        acc0[17] += y3 & x & K1;   // T>A
+        acc0[18] += y3 & x1 & K1;  // T>C
+        acc0[19] += y3 & x2 & K1;  // T>G
         if (++n0 == 15) spill0();
     };
 
@@ -347,7 +368,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         int32_t tid_ref, pos;
         bool live;
     };
-    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, SwarRecord &rec) {
+    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, SwarRecord &left, SwarRecord &right) {
         kind = 0;
         rstrand = 0;
         if (!h.live || (h.flag & FILTERED_FLAGS)) return;
@@ -392,14 +413,19 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         if (!simple) return;
         const int64_t aend = pos + cols;
         const uint64_t ref0 = ref.contig_off[h.tid_ref] + (uint64_t)pos;
+        const uint64_t q0 = (uint64_t)h.boff + lead;
         const uint32_t lf = (uint32_t)min((int64_t)A, pos);
         const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
         uint32_t has_qual = 0;
         if (kQual) has_qual = b.qual[h.boff] != 0xFF;
-        rec.nib0 = h.boff + lead;
-        rec.c_flanks = cols | (has_qual << 15) | (lf << 16) | (rf << 24);
-        rec.ref_lo = (uint32_t)ref0;
-        rec.ref_hi = (uint32_t)(ref0 >> 32);
+        left.qi = (int32_t)(q0 >> 3);
+        left.ri = (int32_t)(ref0 >> 3);
+        left.sh = 4 * (uint32_t)(q0 & 7) | (4 * (uint32_t)(ref0 & 7)) << 8;
+        left.meta = min(cols, (uint32_t)L) | (has_qual << 15) | (lf << 16) | (rf << 24);
+        right.qi = (int32_t)((q0 + cols) >> 3);
+        right.ri = (int32_t)((ref0 + cols) >> 3);
+        right.sh = 4 * (uint32_t)((q0 + cols) & 7) | (4 * (uint32_t)((ref0 + cols) & 7)) << 8;
+        right.meta = left.meta;
         // FragmentLengths.update, statistics.py:117-126
         int64_t length = -1;
         int lkind = 0;
@@ -436,8 +462,50 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         }
     };
 
+    // L2 prefetch of one tile, split over the block: the record arrays directly, the sequence (and
+    // qualities) through base_off, which is itself a load -- so callers issue the two halves far apart
+    const int per = (T + nthreads - 1) / nthreads;  // consecutive reads of a tile covered by one thread
+    auto prefetch_headers = [&](int64_t tile_index, uint32_t &boff, uint32_t &coff) {
+        const int64_t start = tile_index * T;
+        const int64_t rn = start + (int64_t)tid * per;
+        const bool live = tid * per < T && rn < b.n_reads;
+        if (live) {
+            boff = b.base_off[rn];
+            coff = b.cigar_off[rn];
+        }
+        // T entries per array, one 128-byte line per 32 (u32) or 64 (u16) entries
+        const int64_t r4 = start + (int64_t)tid * 32;
+        if (tid * 32 < T && r4 < b.n_reads) {
+            prefetch_l2(b.tid + r4);
+            prefetch_l2(b.pos + r4);
+            prefetch_l2(b.l_seq + r4);
+            prefetch_l2(b.tlen + r4);
+            if (!(tid & 1)) {
+                prefetch_l2(b.flag + r4);
+                prefetch_l2(b.lib + r4);
+            }
+        }
+        return live;
+    };
+    auto prefetch_bases = [&](uint32_t boff, uint32_t coff) {
+        const char *seq_at = (const char *)b.seq4 + (boff >> 1);
+        for (int off = 0; off < per * 80; off += 128) prefetch_l2(seq_at + off);
+        prefetch_l2(b.cigar + coff);
+        if (kQual) {
+            const char *q_at = (const char *)b.qual + boff;
+            for (int off = 0; off < per * 160; off += 128) prefetch_l2(q_at + off);
+        }
+    };
+
     constexpr int PREP = 4;  // reads staged per thread with their loads in flight together
     const int64_t n_tiles = (b.n_reads + T - 1) / T;
+    {   // the block's first two tiles have nobody to prefetch them
+        uint32_t boff0 = 0, coff0 = 0, boff1 = 0, coff1 = 0;
+        const bool live0 = prefetch_headers(blockIdx.x, boff0, coff0);
+        const bool live1 = prefetch_headers(blockIdx.x + (int64_t)gridDim.x, boff1, coff1);
+        if (live0) prefetch_bases(boff0, coff0);
+        if (live1) prefetch_bases(boff1, coff1);
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (tid < 3) s_ctl[tid] = 0;
         __syncthreads();
@@ -467,8 +535,8 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             for (int u = 0; u < PREP; ++u) {
                 const int q = q0 + u * nthreads + tid;
                 int kind, rstrand;
-                SwarRecord rec{};
-                stage_read(h[u], tile_start + q, kind, rstrand, rec);
+                SwarRecord left{}, right{};
+                stage_read(h[u], tile_start + q, kind, rstrand, left, right);
                 // warp-aggregated appends to the three lists
                 const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
@@ -481,9 +549,13 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
                         if (mine) {
                             const uint32_t at = base + __popc(m & lt);
-                            if (which == 0) s_rec[at] = rec;
-                            else if (which == 1) s_rec[T - 1 - at] = rec;
-                            else s_cx[at] = (uint32_t)(tile_start + q);
+                            if (which == 2) {
+                                s_cx[at] = (uint32_t)(tile_start + q);
+                            } else {
+                                const uint32_t where = which == 0 ? at : T - 1 - at;
+                                s_rec[where] = left;
+                                s_rec[T + where] = right;
+                            }
                         }
                     }
                 }
@@ -500,62 +572,45 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             for (uint32_t i = lane; i < n_cx; i += 32) worklist[base + i] = s_cx[i];
         }
 
-        // ---- pull the block's next tile towards L2 while this one is counted ----
-        const int64_t next_start = (tile + gridDim.x) * T;
-        uint32_t next_boff = 0, next_coff = 0;
-        bool next_live = false;
-        {
-            const int64_t rn = next_start + (int64_t)tid * ((T + nthreads - 1) / nthreads);
-            next_live = tid * ((T + nthreads - 1) / nthreads) < T && rn < b.n_reads;
-            if (next_live) {
-                next_boff = b.base_off[rn];
-                next_coff = b.cigar_off[rn];
-            }
-            // header arrays: T entries each, one 128-byte line per 32 (u32) or 64 (u16) entries
-            const int64_t r4 = next_start + (int64_t)tid * 32;
-            if (tid * 32 < T && r4 < b.n_reads) {
-                prefetch_l2(b.tid + r4);
-                prefetch_l2(b.pos + r4);
-                prefetch_l2(b.l_seq + r4);
-                prefetch_l2(b.tlen + r4);
-                if (!(tid & 1)) {
-                    prefetch_l2(b.flag + r4);
-                    prefetch_l2(b.lib + r4);
+        // ---- pull the tile after next towards L2 while this one is counted ----
+        uint32_t ahead_boff = 0, ahead_coff = 0;
+        const bool ahead_live = prefetch_headers(tile + 2 * (int64_t)gridDim.x, ahead_boff, ahead_coff);
+
+        // ---- the counting loop: two stages that swap roles, so no register copy waits on a load ----
+        if (job.active) {
+            const int n_mine = (int)s_ctl[strand];
+            const int stride = (job.flank ? g.slots_f : g.slots) >> 1;
+            int i = job.slot >> 1;
+            Stage sa{}, sb{};
+            if (job.flank) {
+                if (i < n_mine) fetch(i, sa, false);
+                while (i < n_mine) {
+                    sb.mask = 0;
+                    if (i + stride < n_mine) fetch(i + stride, sb, false);
+                    count_flank(sa);
+                    i += stride;
+                    if (i >= n_mine) break;
+                    sa.mask = 0;
+                    if (i + stride < n_mine) fetch(i + stride, sa, false);
+                    count_flank(sb);
+                    i += stride;
+                }
+            } else {
+                if (i < n_mine) fetch(i, sa, true);
+                while (i < n_mine) {
+                    sb.mask = 0;
+                    if (i + stride < n_mine) fetch(i + stride, sb, true);
+                    count_aligned(sa);
+                    i += stride;
+                    if (i >= n_mine) break;
+                    sa.mask = 0;
+                    if (i + stride < n_mine) fetch(i + stride, sa, true);
+                    count_aligned(sb);
+                    i += stride;
                 }
             }
         }
-
-        // ---- the counting loop ----
-        if (job.active) {
-            const int n_mine = (int)s_ctl[strand];
-            const int stride = g.slots >> 1;
-            // two stages that swap roles, so that no register copy waits on a load at the loop edge
-            int i = job.slot >> 1;
-            Stage sa{}, sb{};
-            if (i < n_mine) fetch(i, sa);
-            while (i < n_mine) {
-                sb.mask = 0;
-                if (i + stride < n_mine) fetch(i + stride, sb);
-                count(sa);
-                i += stride;
-                if (i >= n_mine) break;
-                sa.mask = 0;
-                if (i + stride < n_mine) fetch(i + stride, sa);
-                count(sb);
-                i += stride;
-            }
-        }
-        if (next_live) {
-            // each thread covers (T / nthreads) consecutive reads of the next tile: a few hundred bytes
-            const int per = (T + nthreads - 1) / nthreads;
-            const char *seq_at = (const char *)b.seq4 + (next_boff >> 1);
-            for (int off = 0; off < per * 80; off += 128) prefetch_l2(seq_at + off);
-            prefetch_l2(b.cigar + next_coff);
-            if (kQual) {
-                const char *q_at = (const char *)b.qual + next_boff;
-                for (int off = 0; off < per * 160; off += 128) prefetch_l2(q_at + off);
-            }
-        }
+        if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
         __syncthreads();
         if (++tiles_since_flush == flush_period) {
             flush_block();
