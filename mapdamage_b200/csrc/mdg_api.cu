@@ -458,25 +458,15 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
     // bit-sliced kernel: one library, a shared-memory general slab for its work list, geometry that fits a block
     {
         mdg::SwarGeom &g = ctx->swar;
-        g.w_a = (cfg->around + 7) / 8;
-        g.w_l = (cfg->length + 7) / 8;
+        g.words = (cfg->around + cfg->length + 7) / 8;
         const char *tenv = getenv("MDG_SWAR_THREADS");
-        ctx->swar_max_threads = tenv && atoi(tenv) > 384 ? 512 : 384;
-        // a flank word costs about a quarter of an aligned word: give it a quarter of the read slots
-        g.slots = 0;
-        for (int slots = 2; slots <= ctx->swar_max_threads; slots += 2) {
-            const int slots_f = g.w_a ? std::max(2, (slots / 4 + 1) & ~1) : 0;
-            if (2 * g.w_a * slots_f + 2 * g.w_l * slots > ctx->swar_max_threads) break;
-            g.slots = slots;
-            g.slots_f = slots_f;
-        }
+        ctx->swar_max_threads = tenv && atoi(tenv) <= 384 ? 384 : 512;
+        g.slots = (ctx->swar_max_threads / (2 * g.words)) & ~1;
         if (nl == 1 && g.slots >= 2 && cfg->around <= 64 && cfg->length < 32768) {
-            g.work_threads = 2 * g.w_a * g.slots_f + 2 * g.w_l * g.slots;
+            g.work_threads = 2 * g.words * g.slots;
             g.threads = (g.work_threads + 31) / 32 * 32;
-            const int n_flank = 2 * g.w_a * g.slots_f;
-            const size_t l2_words = ((size_t)16 * g.threads + (size_t)64 * (g.threads - n_flank) + 3) & ~(size_t)3;
             for (int tile : {2048, 1024, 512}) {
-                const size_t bytes = (l2_words + (size_t)tile * 9 + 4 * MDG_LG_SMEM_BINS + 4 * L + 4) * 4;
+                const size_t bytes = ((size_t)mdg::SWAR_L2_WORDS * g.threads + (size_t)tile * 5 + 4 * MDG_LG_SMEM_BINS + 4 * L + 4) * 4;
                 if (bytes <= ctx->smem_optin) {
                     g.tile = tile;
                     ctx->swar_smem = bytes;

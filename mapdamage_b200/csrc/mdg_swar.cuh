@@ -13,6 +13,7 @@
 //   anchor 0 (left):  position p = alignment column           -> 5' table of forward reads, 3' of reverse reads
 //   anchor 1 (right): position p = columns from the right end -> 3' table of forward reads, 5' of reverse reads
 //   p < 0: flanking reference base at distance -p (DNAComposition.update_reference)
+// The window of an anchor is positions [-A, L), cut into words of eight; every thread runs the same code.
 //
 // For a gap-free read, column == query index == reference offset, so the
 // eight (read, reference) pairs a thread needs are one 32-bit word of the BAM
@@ -40,22 +41,19 @@ constexpr int SWAR_MAX_THREADS = 512;  // largest block any variant is compiled 
 constexpr uint32_t K1 = 0x11111111u;
 
 struct SwarGeom {
-    int32_t w_a, w_l;      // flank / aligned words per anchor
-    int32_t slots;         // read slots of the aligned words (even: half per strand)
-    int32_t slots_f;       // read slots of the flank words: fewer, a flank word is ~4x cheaper to count
+    int32_t words;         // 32-bit words per anchor window: ceil((A + L) / 8), window positions [-A, 8 words - A)
+    int32_t slots;         // read slots per block (even: half per strand)
     int32_t threads;       // blockDim.x
-    int32_t work_threads;  // 2 * w_a * slots_f + 2 * w_l * slots
+    int32_t work_threads;  // 2 * words * slots
     int32_t tile;          // reads staged per iteration of the block
 };
 
-// One staged read as one anchor sees it (16 bytes): where its words start and how far to shift them.
-//   left anchor:  word 0 of the window starts at the first aligned base / its reference base
-//   right anchor: word 0 ends at the last aligned base (indices of base "one past the end")
+// One staged read (16 bytes), shared by both anchors.
 struct __align__(16) SwarRecord {
-    int32_t qi;     // 32-bit word of seq4 holding that base
-    int32_t ri;     // 32-bit word of the genome holding that base
-    uint32_t sh;    // funnel shifts in bits: read | reference << 8
-    uint32_t meta;  // min(L, columns) | has_qual << 15 | left flank bases << 16 | right flank bases << 24
+    uint32_t q0;      // first aligned base, in batch base coordinates (base_off + leading clip)
+    uint32_t ref_lo;  // genome base index of the first aligned column, low 32 bits
+    uint32_t cols;    // columns (15 bits) | has_qual << 15 | left flank bases << 16 | right flank bases << 24
+    uint32_t hi_phi;  // min(L, columns) | genome base index high bits << 16
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
@@ -75,84 +73,48 @@ __device__ __forceinline__ uint32_t one_hot_nibbles(uint32_t x)
     return ((exactly_one & ~d) | (none & d)) & K1;
 }
 
-// thread -> (anchor, word, slot): flank threads first so that whole warps share a code path
-struct SwarJob {
-    int anchor, word, slot;
-    bool flank, active;
-};
+// the low n nibbles, n = bits / 4 clamped to [0, 8]
+__device__ __forceinline__ uint32_t low_nibbles(int bits) { return __funnelshift_lc(0xffffffffu, 0u, max(bits, 0)); }
 
-__device__ __forceinline__ SwarJob swar_job(const SwarGeom &g, int t)
-{
-    SwarJob j;
-    const int n_flank = 2 * g.w_a * g.slots_f;
-    j.active = t < g.work_threads;
-    j.flank = t < n_flank;
-    if (j.flank) {
-        const int f = t % (2 * g.w_a);
-        j.slot = t / (2 * g.w_a);
-        j.anchor = f / g.w_a;
-        j.word = f % g.w_a;
-    } else {
-        const int u = t - n_flank, per = 2 * g.w_l;
-        const int f = u % per;
-        j.slot = u / per;
-        j.anchor = f / g.w_l;
-        j.word = g.w_a + f % g.w_l;
-    }
-    return j;
-}
-
-__device__ __forceinline__ int swar_thread_of(const SwarGeom &g, int anchor, int word, int slot)
-{
-    if (word < g.w_a) return slot * 2 * g.w_a + anchor * g.w_a + word;
-    return 2 * g.w_a * g.slots_f + slot * 2 * g.w_l + anchor * g.w_l + (word - g.w_a);
-}
-
-// Private 16-bit counters: word w of thread t.  Flank threads (the first n_flank) only ever touch the
-// reference-base classes, words 0..15; the other 64 words exist for the aligned threads only.
-__device__ __forceinline__ int swar_l2_index(int w, int t, int nthreads, int n_flank)
-{
-    return w < 16 ? w * nthreads + t : 16 * nthreads + (w - 16) * (nthreads - n_flank) + (t - n_flank);
-}
-
+// thread t = ((slot * 2) + anchor) * words + word
 template <bool kQual, int kMaxThreads>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom g, uint32_t *__restrict__ worklist,
                   unsigned long long *__restrict__ work_count)
 {
     extern __shared__ uint32_t smem[];
-    const int nthreads = g.threads, T = g.tile, L = p.L, A = p.A;
-    const int n_flank = 2 * g.w_a * g.slots_f;
-    const int l2_words = 16 * nthreads + 64 * (nthreads - n_flank);
-    uint32_t *const s_l2 = smem;
-    SwarRecord *const s_rec = (SwarRecord *)(s_l2 + ((l2_words + 3) & ~3));  // [anchor][T]: forward reads from the front, reverse from the back
-    uint32_t *const s_cx = (uint32_t *)(s_rec + 2 * T);    // [T] complex reads of the tile
-    uint32_t *const s_lg = s_cx + T;                       // [kind][strand][MDG_LG_SMEM_BINS]
-    uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;  // [end][strand][L]
-    uint32_t *const s_ctl = s_clip + 4 * L;                // n_fwd, n_rev, n_cx
+    const int nthreads = g.threads, T = g.tile, L = p.L, A = p.A, W = g.words;
+    const int l2_words = SWAR_L2_WORDS * nthreads;
+    uint32_t *const s_l2 = smem;                                // [SWAR_L2_WORDS][nthreads] private 16-bit counters
+    SwarRecord *const s_rec = (SwarRecord *)(s_l2 + l2_words);  // [T]: forward reads from the front, reverse from the back
+    uint32_t *const s_cx = (uint32_t *)(s_rec + T);             // [T] complex reads of the tile
+    uint32_t *const s_lg = s_cx + T;                            // [kind][strand][MDG_LG_SMEM_BINS]
+    uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;       // [end][strand][L]
+    uint32_t *const s_ctl = s_clip + 4 * L;                     // n_fwd, n_rev, n_cx
 
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < l2_words; i += nthreads) s_l2[i] = 0;
     for (int i = tid; i < 4 * MDG_LG_SMEM_BINS + 4 * L; i += nthreads) s_lg[i] = 0;
 
-    const SwarJob job = swar_job(g, tid);
-    const int strand = job.slot & 1;
+    const bool active = tid < g.work_threads;
+    const int word = tid % W, anchor = (tid / W) & 1, slot = tid / (2 * W);
+    const int strand = slot & 1;
     const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
     const uint32_t *__restrict__ ref32 = ref.words;
 
-    // Thread constants.  Window position of nibble i: p = pbase + i (left anchor) or pbase + 7 - i (right).
-    //   aligned words: nibble counts iff 0 <= p < v, v = min(L, columns)
-    //   flank words (pbase < 0): nibble at distance d = -p counts iff d <= v, v = flank bases on the contig
-    // Both are "the low n nibbles" or the complement of that, with 4 n = c4 + s4 * v clamped to [0, 32].
-    const int pbase = 8 * (job.word - g.w_a);
-    const int koff = job.anchor ? -(1 + job.word - g.w_a) : job.word - g.w_a;  // word offset from the record's index
-    const bool low_side = (job.anchor != 0) == job.flank;                       // counted nibbles are the low ones
-    const int s4 = low_side ? 4 : -4;
-    const int c4 = job.anchor ? 4 * pbase + 32 : -4 * pbase;
-    const uint32_t flip = low_side ? 0u : 0xffffffffu;
-    const int vshift = job.flank ? (job.anchor ? 24 : 16) : 0;
-    const uint32_t vmask = job.flank ? 0xFFu : 0x7FFFu;
-    const SwarRecord *const my_recs = s_rec + job.anchor * T;
+    // Thread constants.  The window word covers positions pbase .. pbase + 7, pbase = 8 word - A; nibble i
+    // holds position pbase + i (left anchor) or pbase + 7 - i (right anchor: memory order runs towards the end).
+    // With z = the nibble index of position 0 (left) / one past it (right):
+    //   left:  aligned nibbles [z, z + v),  flank nibbles [z - f, z)      v = min(L, columns)
+    //   right: aligned nibbles [z - v, z),  flank nibbles [z, z + f)      f = flank bases on the contig
+    const int pbase = 8 * word - A;
+    const int z4 = 4 * (anchor ? pbase + 8 : -pbase);
+    const int s4 = anchor ? -4 : 4;
+    const uint32_t flip_a = anchor ? 0xffffffffu : 0u;
+    const uint32_t side_a = anchor ? low_nibbles(z4) : ~low_nibbles(z4);  // the side of z aligned nibbles are on
+    const int fshift = anchor ? 24 : 16;
+    // base offset of nibble 0 from the first aligned base: left pbase; right columns - 8 - pbase
+    const int cbase = anchor ? -8 - pbase : pbase;
 
     uint32_t acc0[SWAR_CLASSES];  // 8 x 4-bit counters per class
     uint32_t acc1[16];            // classes 0..7 (reference / read bases): 2 x (4 x 8-bit) counters, even / odd nibbles
@@ -161,20 +123,14 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 #pragma unroll
     for (int w = 0; w < 16; ++w) acc1[w] = 0;
     int n0 = 0, n1 = 0;
-    uint32_t *const my_l2 = s_l2 + 16 * nthreads + (tid - n_flank);  // words 16.. of an aligned thread, stride l2_stride
-    const int l2_stride = nthreads - n_flank;
+    uint32_t *const my_l2 = s_l2 + tid;  // word w at my_l2[w * nthreads]
 
     auto spill1 = [&]() {  // 8-bit -> private 16-bit counters in shared memory
 #pragma unroll
         for (int w = 0; w < 16; ++w) {
             const uint32_t v = acc1[w];
-            if (w < 8) {
-                s_l2[(2 * w) * nthreads + tid] += v & 0x00FF00FFu;
-                s_l2[(2 * w + 1) * nthreads + tid] += (v >> 8) & 0x00FF00FFu;
-            } else if (!job.flank) {
-                my_l2[(2 * w - 16) * l2_stride] += v & 0x00FF00FFu;
-                my_l2[(2 * w - 15) * l2_stride] += (v >> 8) & 0x00FF00FFu;
-            }
+            my_l2[(2 * w) * nthreads] += v & 0x00FF00FFu;
+            my_l2[(2 * w + 1) * nthreads] += (v >> 8) & 0x00FF00FFu;
             acc1[w] = 0;
         }
         n1 = 0;
@@ -187,19 +143,17 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             acc1[2 * c + 1] += (acc0[c] >> 4) & 0x0F0F0F0Fu;
             acc0[c] = 0;
         }
-        if (!job.flank) {
 #pragma unroll
-            for (int c = 8; c < SWAR_CLASSES; ++c) {
-                const uint32_t v = acc0[c];
-                if (v) {
-                    // 16-bit lane of (class, nibble): word 4 c + 2 (nibble & 1) + ((nibble >> 1) & 1), half nibble >> 2
-                    uint32_t *at = my_l2 + (4 * c - 16) * l2_stride;
-                    at[0] += v & 0x000F000Fu;
-                    at[l2_stride] += (v >> 8) & 0x000F000Fu;
-                    at[2 * l2_stride] += (v >> 4) & 0x000F000Fu;
-                    at[3 * l2_stride] += (v >> 12) & 0x000F000Fu;
-                    acc0[c] = 0;
-                }
+        for (int c = 8; c < SWAR_CLASSES; ++c) {
+            const uint32_t v = acc0[c];
+            if (v) {
+                // 16-bit lane of (class, nibble): word 4 c + 2 (nibble & 1) + ((nibble >> 1) & 1), half nibble >> 2
+                uint32_t *at = my_l2 + (4 * c) * nthreads;
+                at[0] += v & 0x000F000Fu;
+                at[nthreads] += (v >> 8) & 0x000F000Fu;
+                at[2 * nthreads] += (v >> 4) & 0x000F000Fu;
+                at[3 * nthreads] += (v >> 12) & 0x000F000Fu;
+                acc0[c] = 0;
             }
         }
         n0 = 0;
@@ -208,8 +162,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 
     // reduces the block's private counters into the 64-bit tables (end of the kernel, and before a
     // thread's 16-bit counters could overflow)
-    const int jobs_per_anchor = g.w_a + g.w_l;
-    const int n_cells = 2 * jobs_per_anchor * 2 * SWAR_CLASSES * 8;  // anchor, word, strand, class, nibble
+    const int n_cells = 2 * W * 2 * SWAR_CLASSES * 8;  // anchor, word, strand, class, nibble
     const int LA = L + A;
     auto flush_block = [&]() {
         if (n0) spill0();
@@ -220,25 +173,23 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             const int nib = rest & 7; rest >>= 3;
             const int cls = rest % SWAR_CLASSES; rest /= SWAR_CLASSES;
             const int cstrand = rest & 1; rest >>= 1;
-            const int word = rest % jobs_per_anchor;
-            const int anchor = rest / jobs_per_anchor;
-            if (word < g.w_a && cls >= 4) continue;  // flank words only count reference bases
+            const int cword = rest % W;
+            const int canchor = rest / W;
+            const int pb = 8 * cword - A;
+            const int pos = canchor ? pb + 7 - nib : pb + nib;
+            if (pos >= L || pos < -A || (pos < 0 && cls >= 4)) continue;
             // 16-bit lane holding (cls, nib): 8-bit lane bl = nib >> 1 of acc1[2 * cls + (nib & 1)]
             const int w1 = 2 * cls + (nib & 1), bl = nib >> 1;
             const int w2 = 2 * w1 + (bl & 1), half = bl >> 1;
             unsigned long long sum = 0;
-            const int n_slots = word < g.w_a ? g.slots_f : g.slots;
-            for (int slot = cstrand; slot < n_slots; slot += 2) {
-                const uint32_t v = s_l2[swar_l2_index(w2, swar_thread_of(g, anchor, word, slot), nthreads, n_flank)];
+            for (int cslot = cstrand; cslot < g.slots; cslot += 2) {
+                const uint32_t v = s_l2[w2 * nthreads + (cslot * 2 + canchor) * W + cword];
                 sum += half ? v >> 16 : v & 0xFFFFu;
             }
             if (!sum) continue;
-            const int pb = 8 * (word - g.w_a);
-            const int pos = anchor ? pb + 7 - nib : pb + nib;
-            const int end = anchor ^ cstrand;
+            const int end = canchor ^ cstrand;
             const int es = end * 2 + cstrand;
             if (pos >= 0) {
-                if (pos >= L) continue;
                 if (cls < 4) {
                     const int gb = cstrand ? 3 - cls : cls;
                     atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + gb) * L + pos, sum);
@@ -252,10 +203,8 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                     atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + 4 + 5 * gb + rb) * L + pos, sum);
                 }
             } else {
-                const int d = -pos;
-                if (d > A) continue;
                 const int gb = cstrand ? 3 - cls : cls;
-                atomicAdd(t.dnacomp + ((size_t)es * 4 + gb) * LA + L + d - 1, sum);
+                atomicAdd(t.dnacomp + ((size_t)es * 4 + gb) * LA + L - pos - 1, sum);
             }
         }
         __syncthreads();
@@ -263,72 +212,68 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         __syncthreads();
     };
     // worst case every read of a tile lands on one strand: T / (slots / 2) reads per thread per tile
-    const int min_slots = g.w_a ? min(g.slots, g.slots_f) : g.slots;
-    const int flush_period = max(1, 60000 / ((T + (min_slots >> 1) - 1) / (min_slots >> 1)));
+    const int flush_period = max(1, 60000 / ((T + (g.slots >> 1) - 1) / (g.slots >> 1)));
     int tiles_since_flush = 0;
 
     // ---- per-thread stages of the software pipeline: loads of read i+1 fly while read i is counted ----
     struct Stage {
-        uint32_t w0, w1, r0, r1, mask, sh;
+        uint32_t w0, w1, r0, r1, aligned, flank, sh;
         uint32_t qa, qm, qz;
-        int sq;
     };
-    auto fetch = [&](int i, Stage &st, bool with_read) {
-        const SwarRecord rec = my_recs[strand ? T - 1 - i : i];
-        const int v = (int)((rec.meta >> vshift) & vmask);
-        st.mask = __funnelshift_lc(0xffffffffu, 0u, max(c4 + s4 * v, 0)) ^ flip;
-        st.sh = rec.sh;
-        if (st.mask) {
-            const uint32_t *rp = ref32 + (rec.ri + koff);
+    auto fetch = [&](int i, Stage &st) {
+        const SwarRecord rec = s_rec[strand ? T - 1 - i : i];
+        const int v = (int)(rec.hi_phi & 0xFFFF), f = (int)((rec.cols >> fshift) & 0xFF);
+        st.aligned = (low_nibbles(z4 + s4 * v) ^ flip_a) & side_a;
+        st.flank = (low_nibbles(z4 - s4 * f) ^ ~flip_a) & ~side_a;
+        if (st.aligned | st.flank) {
+            const int off = cbase + (anchor ? (int)(rec.cols & 0x7FFF) : 0);
+            const int64_t gn = (int64_t)(((uint64_t)(rec.hi_phi >> 16) << 32) | rec.ref_lo) + off;
+            const uint32_t *rp = ref32 + (gn >> 3);
             st.r0 = __ldg(rp);
             st.r1 = __ldg(rp + 1);
-            if (with_read) {
-                const uint32_t *qp = seq32 + (rec.qi + koff);
+            const int64_t qn = (int64_t)rec.q0 + off;
+            st.sh = 4 * (uint32_t)(qn & 7) | (4 * (uint32_t)(gn & 7)) << 8 | 0x10000u;
+            if (st.aligned) {
+                const uint32_t *qp = seq32 + (qn >> 3);
                 st.w0 = __ldg(qp);
                 st.w1 = __ldg(qp + 1);
                 if (kQual) {
-                    st.sq = -1;
-                    if (rec.meta & 0x8000u) {
-                        // qualities of the window's eight bases start at byte 8 * word + read shift / 4;
-                        // three words from the aligned word below cover them
-                        const uint32_t *q32 = (const uint32_t *)b.qual + 2 * (int64_t)(rec.qi + koff) + ((rec.sh >> 4) & 1);
+                    if (rec.cols & 0x8000u) {
+                        // qualities of the window's eight bases: three words from the aligned word below cover them
+                        const uint32_t *q32 = (const uint32_t *)b.qual + (qn >> 2);
                         st.qa = __ldg(q32);
                         st.qm = __ldg(q32 + 1);
                         st.qz = __ldg(q32 + 2);
-                        st.sq = (int)(rec.sh * 2) & 24;
+                        st.sh |= 0x20000u | (8 * (uint32_t)(qn & 3)) << 24;
                     }
                 }
+            } else {
+                st.w0 = st.w1 = 0;
             }
+        } else {
+            st.sh = 0;
         }
     };
-    auto count_flank = [&](const Stage &st) {
-        if (!st.mask) return;
-        // DNAComposition.update_reference: reference bases just outside the alignment
-        const uint32_t y = __funnelshift_r(st.r0, st.r1, st.sh >> 8) & st.mask;
-        acc0[0] += y & K1;
-        acc0[1] += (y >> 1) & K1;
-        acc0[2] += (y >> 2) & K1;
-        acc0[3] += (y >> 3) & K1;
-        if (++n0 == 15) spill0();
-    };
-    auto count_aligned = [&](const Stage &st) {
-        if (!st.mask) return;
+    auto count = [&](const Stage &st) {
+        if (!st.sh) return;  // no nibble of this word counts for this read
         uint32_t y = __funnelshift_r(st.r0, st.r1, st.sh >> 8);
         uint32_t x = __funnelshift_r(natural_order(st.w0), natural_order(st.w1), st.sh);
-        // a column counts only when the read base is A/C/G/T (statistics.py:27); the reference
-        // side is already 0 for anything that is not A/C/G/T
-        const uint32_t valid = (one_hot_nibbles(x) * 15u) & st.mask;
+        // a column counts only when the read base is A/C/G/T (statistics.py:27); the reference side is
+        // already 0 for anything that is not A/C/G/T.  Flank nibbles carry the reference base alone
+        // (DNAComposition.update_reference, statistics.py:85-93).
+        const uint32_t valid = (one_hot_nibbles(x) * 15u) & st.aligned;
         x &= valid;
-        y &= valid;
+        y &= valid | st.flank;
         // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
         acc0[4] += x & K1;
         acc0[5] += (x >> 1) & K1;
         acc0[6] += (x >> 2) & K1;
         acc0[7] += (x >> 3) & K1;
         if (kQual) {
-            if (st.sq >= 0) {
+            if (st.sh & 0x20000u) {
                 // align_with_qual, align.py:67-71: bases below --min-basequal become N on both sides
-                const uint32_t lo = __funnelshift_r(st.qa, st.qm, st.sq), hi = __funnelshift_r(st.qm, st.qz, st.sq);
+                const int sq = (int)(st.sh >> 24);
+                const uint32_t lo = __funnelshift_r(st.qa, st.qm, sq), hi = __funnelshift_r(st.qm, st.qz, sq);
                 const uint32_t mq = (uint32_t)p.min_qual * 0x01010101u;
                 // bit 7 of a byte of ((q | 0x80) - min_qual) is clear iff q < min_qual
                 uint32_t zl = (~((lo | 0x80808080u) - mq) & 0x80808080u) >> 7;
@@ -336,7 +281,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                 zl |= zl >> 4;
                 zh |= zh >> 4;
                 const uint32_t low = ((zl & 0x11u) | ((zl >> 8) & 0x1100u)) | (((zh & 0x11u) | ((zh >> 8) & 0x1100u)) << 16);
-                const uint32_t keep = ~(low * 15u);
+                const uint32_t keep = ~(low * 15u) | st.flank;  // there is no read base, hence no quality, on a flank
                 x &= keep;
                 y &= keep;
             }
@@ -368,7 +313,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         int32_t tid_ref, pos;
         bool live;
     };
-    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, SwarRecord &left, SwarRecord &right) {
+    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, SwarRecord &rec) {
         kind = 0;
         rstrand = 0;
         if (!h.live || (h.flag & FILTERED_FLAGS)) return;
@@ -407,25 +352,21 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         }
         const int64_t pos = h.pos;
         const int64_t contig_len = ref.contig_len[h.tid_ref];
+        const uint64_t ref0 = ref.contig_off[h.tid_ref] + (uint64_t)(pos > 0 ? pos : 0);
         simple = simple && state >= 1 && cols > 0 && cols < 32768 && n_lead <= 1 && n_trail <= 1 &&
-                 (uint64_t)lead + cols + trail == h.l_seq && pos >= 0 && pos + (int64_t)cols <= contig_len;
+                 (uint64_t)lead + cols + trail == h.l_seq && pos >= 0 && pos + (int64_t)cols <= contig_len &&
+                 ref0 < (1ull << 47);
         kind = simple ? 1 : 2;
         if (!simple) return;
         const int64_t aend = pos + cols;
-        const uint64_t ref0 = ref.contig_off[h.tid_ref] + (uint64_t)pos;
-        const uint64_t q0 = (uint64_t)h.boff + lead;
         const uint32_t lf = (uint32_t)min((int64_t)A, pos);
         const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
         uint32_t has_qual = 0;
         if (kQual) has_qual = b.qual[h.boff] != 0xFF;
-        left.qi = (int32_t)(q0 >> 3);
-        left.ri = (int32_t)(ref0 >> 3);
-        left.sh = 4 * (uint32_t)(q0 & 7) | (4 * (uint32_t)(ref0 & 7)) << 8;
-        left.meta = min(cols, (uint32_t)L) | (has_qual << 15) | (lf << 16) | (rf << 24);
-        right.qi = (int32_t)((q0 + cols) >> 3);
-        right.ri = (int32_t)((ref0 + cols) >> 3);
-        right.sh = 4 * (uint32_t)((q0 + cols) & 7) | (4 * (uint32_t)((ref0 + cols) & 7)) << 8;
-        right.meta = left.meta;
+        rec.q0 = h.boff + lead;
+        rec.ref_lo = (uint32_t)ref0;
+        rec.cols = cols | (has_qual << 15) | (lf << 16) | (rf << 24);
+        rec.hi_phi = min(cols, (uint32_t)L) | (uint32_t)(ref0 >> 32) << 16;
         // FragmentLengths.update, statistics.py:117-126
         int64_t length = -1;
         int lkind = 0;
@@ -535,8 +476,8 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             for (int u = 0; u < PREP; ++u) {
                 const int q = q0 + u * nthreads + tid;
                 int kind, rstrand;
-                SwarRecord left{}, right{};
-                stage_read(h[u], tile_start + q, kind, rstrand, left, right);
+                SwarRecord rec{};
+                stage_read(h[u], tile_start + q, kind, rstrand, rec);
                 // warp-aggregated appends to the three lists
                 const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
@@ -549,13 +490,8 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
                         if (mine) {
                             const uint32_t at = base + __popc(m & lt);
-                            if (which == 2) {
-                                s_cx[at] = (uint32_t)(tile_start + q);
-                            } else {
-                                const uint32_t where = which == 0 ? at : T - 1 - at;
-                                s_rec[where] = left;
-                                s_rec[T + where] = right;
-                            }
+                            if (which == 2) s_cx[at] = (uint32_t)(tile_start + q);
+                            else s_rec[which == 0 ? at : T - 1 - at] = rec;
                         }
                     }
                 }
@@ -577,37 +513,22 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         const bool ahead_live = prefetch_headers(tile + 2 * (int64_t)gridDim.x, ahead_boff, ahead_coff);
 
         // ---- the counting loop: two stages that swap roles, so no register copy waits on a load ----
-        if (job.active) {
+        if (active) {
             const int n_mine = (int)s_ctl[strand];
-            const int stride = (job.flank ? g.slots_f : g.slots) >> 1;
-            int i = job.slot >> 1;
+            const int stride = g.slots >> 1;
+            int i = slot >> 1;
             Stage sa{}, sb{};
-            if (job.flank) {
-                if (i < n_mine) fetch(i, sa, false);
-                while (i < n_mine) {
-                    sb.mask = 0;
-                    if (i + stride < n_mine) fetch(i + stride, sb, false);
-                    count_flank(sa);
-                    i += stride;
-                    if (i >= n_mine) break;
-                    sa.mask = 0;
-                    if (i + stride < n_mine) fetch(i + stride, sa, false);
-                    count_flank(sb);
-                    i += stride;
-                }
-            } else {
-                if (i < n_mine) fetch(i, sa, true);
-                while (i < n_mine) {
-                    sb.mask = 0;
-                    if (i + stride < n_mine) fetch(i + stride, sb, true);
-                    count_aligned(sa);
-                    i += stride;
-                    if (i >= n_mine) break;
-                    sa.mask = 0;
-                    if (i + stride < n_mine) fetch(i + stride, sa, true);
-                    count_aligned(sb);
-                    i += stride;
-                }
+            if (i < n_mine) fetch(i, sa);
+            while (i < n_mine) {
+                sb.sh = 0;
+                if (i + stride < n_mine) fetch(i + stride, sb);
+                count(sa);
+                i += stride;
+                if (i >= n_mine) break;
+                sa.sh = 0;
+                if (i + stride < n_mine) fetch(i + stride, sa);
+                count(sb);
+                i += stride;
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
