@@ -176,6 +176,17 @@ int mdg_set_rescale_model(mdg_ctx *ctx, const uint8_t *lut, const double *inc, i
 int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, float *mr_out,
                        uint8_t *status_out);
 int mdg_fetch_rescale_stats(mdg_ctx *ctx, uint64_t *stats8);
+/*
+ * Integer part of the substitution bookkeeping of rescale._record_subs
+ * (rescale.py:106-139), accumulated over every rescale submit since
+ * mdg_set_rescale_model; the host derives the log summary of
+ * _qual_summary_subs / _print_subs (rescale.py:142-192) from it:
+ *   sub [type C>T, G>A][1 + len5p + len3p][94]: rescaled columns by model slot and old Phred
+ *   rev [type T>C, A>G][94]: the reverse transitions by Phred (their qualities never change)
+ *   ref_count [A, C, G, T]: reference bases over all walked alignment columns
+ * Any pointer may be NULL.
+ */
+int mdg_fetch_rescale_hist(mdg_ctx *ctx, uint64_t *sub, uint64_t *rev, uint64_t *ref_count);
 
 /* ---- multi-GPU: one context per rank, tables summed over ranks ---------- */
 

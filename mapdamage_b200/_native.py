@@ -70,6 +70,7 @@ SYMBOLS = {
     "mdg_set_rescale_model": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "mdg_rescale_submit": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdg_fetch_rescale_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdg_fetch_rescale_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdg_synth_batch": (C.c_int, [C.c_void_p, C.POINTER(SynthParams), C.POINTER(C.c_void_p)]),
     "mdg_batch_sizes": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),

@@ -1,0 +1,100 @@
+"""Host-side mirror of the reference's counting pass (``main.py:126-231``).
+
+The reference builds three accumulators (``main.py:147-155``), feeds them one
+read at a time (``main.py:165-217``) and writes ``misincorporation.txt``,
+``dnacomp.txt`` and ``lgdistribution.txt`` (``main.py:229-231``).  Here the
+loop body is the CUDA counting pass: alignments are decoded on the host into
+SoA batches, streamed through :class:`~mapdamage_b200.engine.DamageEngine`
+(double-buffered ``mdg_count_submit``), and the accumulators are filled from
+the device's count slabs.  The three classes keep the reference's constructor
+arguments, ``.data`` layout and ``.write()`` bytes, so everything downstream
+(the R plotting / Bayesian stage) reads the same files.
+
+Only SAM text is decoded here: pysam/htslib are absent from this image and
+BGZF/BAM decode is the "next" row f2 of SURVEY.md section 8.
+"""
+import logging
+from pathlib import Path
+
+from . import statistics
+from .batch import BatchBuilder
+from .engine import DamageEngine
+from .refgenome import Reference
+from .samtext import iter_sam
+
+TABLE_FILES = ("misincorporation.txt", "dnacomp.txt", "lgdistribution.txt")
+
+
+def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_libraries=False,
+                     folder=None, batch_reads=1 << 20, device=0, lg_bins=1 << 16, engine=None):
+    """Counting pass over one alignment file.
+
+    ``ref`` is a FASTA path or a :class:`Reference`.  Returns
+    ``(misincorp, dnacomp, lgdistrib)`` -- mirrors of the reference's
+    ``MisincorporationRates`` / ``DNAComposition`` / ``FragmentLengths`` -- and,
+    when ``folder`` is given, writes the three tables into it the way
+    ``main.py:229-231`` does.  Raises :class:`~mapdamage_b200.batch.BAMError`
+    where the reference does (read without a known read group, ``reader.py:63-81``).
+    """
+    log = logging.getLogger(__name__)
+    filename = Path(filename)
+    if filename.suffix.lower() in (".bam", ".cram"):
+        raise NotImplementedError("only SAM text is decoded here; BAM/CRAM decode is SURVEY.md row f2")
+    header, records = iter_sam(filename)
+    reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
+    reference = reference.reordered(header.references)
+    builder = BatchBuilder(readgroups=None if merge_libraries else header.libraries(),
+                           merge_libraries=merge_libraries, apply_filter=True)
+    libraries = builder.libraries
+    own_engine = engine is None
+    if own_engine:
+        engine = DamageEngine(length=length, around=around, min_qual=min_basequal,
+                              n_libraries=max(1, len(libraries)), lg_bins=lg_bins, device=device,
+                              max_reads=batch_reads, max_cigar_ops=8 * batch_reads, max_bases=512 * batch_reads)
+    try:
+        engine.set_reference(reference)
+        n_kept = 0
+        for record in records:
+            if builder.add(record):
+                n_kept += 1
+            if n_kept and n_kept % batch_reads == 0:
+                _submit(engine, builder)
+        _submit(engine, builder)
+        mis, comp, lg = engine.tables()
+        overflow = engine.lg_overflow()
+    finally:
+        if own_engine:
+            engine.close()
+    log.debug("Counted %d of %d alignments", n_kept, builder.n_seen)
+    misincorp = statistics.MisincorporationRates(libraries, length).load(mis)
+    dnacomp = statistics.DNAComposition(libraries, around, length).load(comp)
+    lgdistrib = statistics.FragmentLengths(libraries).load(lg, overflow)
+    if folder is not None:
+        folder = Path(folder)
+        folder.mkdir(parents=True, exist_ok=True)
+        misincorp.write(folder / TABLE_FILES[0])
+        dnacomp.write(folder / TABLE_FILES[1])
+        lgdistrib.write(folder / TABLE_FILES[2])
+    return misincorp, dnacomp, lgdistrib
+
+
+def _submit(engine, builder):
+    batch = builder.finish()
+    if not batch.n:
+        return
+    if not engine.fits(batch):
+        # long reads / long CIGARs: halve until the staging slot takes it
+        for part in batch.split(2):
+            _submit_batch(engine, part)
+        return
+    engine.count(batch)
+
+
+def _submit_batch(engine, batch):
+    if not batch.n:
+        return
+    if engine.fits(batch) or batch.n == 1:
+        engine.count(batch)
+    else:
+        for part in batch.split(2):
+            _submit_batch(engine, part)

@@ -114,6 +114,8 @@ struct mdg_ctx {
     // rescale model
     void *model_block = nullptr;
     mdg::RescaleModel model{};
+    unsigned long long *rescale_hist = nullptr;  // [2][n_slots][94] | [2][94] | [4], see mdg_fetch_rescale_hist
+    size_t n_hist = 0;
     // launch geometry
     bool shared_slab = false;
     size_t slab_bytes = 0;
@@ -692,9 +694,12 @@ int mdg_set_rescale_model(mdg_ctx *ctx, const uint8_t *lut, const double *inc, i
     cudaFree(ctx->model_block);
     ctx->model_block = nullptr;
     const int n_slots = 1 + len5p + len3p;
-    const size_t inc_bytes = align_up((size_t)2 * n_slots * 8), lut_bytes = (size_t)2 * n_slots * 94;
-    MDG_CUDA(ctx, cudaMalloc(&ctx->model_block, inc_bytes + lut_bytes));
+    const size_t inc_bytes = align_up((size_t)2 * n_slots * 8), lut_bytes = align_up((size_t)2 * n_slots * 94);
+    ctx->n_hist = (size_t)2 * n_slots * 94 + 2 * 94 + 4;
+    MDG_CUDA(ctx, cudaMalloc(&ctx->model_block, inc_bytes + lut_bytes + ctx->n_hist * 8));
     char *p = (char *)ctx->model_block;
+    ctx->rescale_hist = (unsigned long long *)(p + inc_bytes + lut_bytes);
+    MDG_CUDA(ctx, cudaMemset(ctx->rescale_hist, 0, ctx->n_hist * 8));
     MDG_CUDA(ctx, cudaMemcpy(p, inc, (size_t)2 * n_slots * 8, cudaMemcpyHostToDevice));
     MDG_CUDA(ctx, cudaMemcpy(p + inc_bytes, lut, lut_bytes, cudaMemcpyHostToDevice));
     ctx->model.inc = (const double *)p;
@@ -724,7 +729,9 @@ int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, f
     if (rc) return rc;
     const int64_t n = host->n_reads;
     if (n == 0) return MDG_OK;
-    mdg::RescaleOut out{slot.qual_out, slot.mr_out, slot.status_out, ctx->rescale_stats, ctx->count_tables.error_flag};
+    const size_t n_sub = (size_t)2 * ctx->model.n_slots * 94;
+    mdg::RescaleOut out{slot.qual_out, slot.mr_out, slot.status_out, ctx->rescale_stats, ctx->count_tables.error_flag,
+                        ctx->rescale_hist, ctx->rescale_hist + n_sub, ctx->rescale_hist + n_sub + 2 * 94};
     int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 7) / 8);
     cudaEvent_t e0, e1;
     rc = next_kernel_events(ctx, &e0, &e1);
@@ -746,6 +753,19 @@ int mdg_fetch_rescale_stats(mdg_ctx *ctx, uint64_t *stats8)
     int rc = mdg_sync(ctx);
     if (rc) return rc;
     MDG_CUDA(ctx, cudaMemcpy(stats8, ctx->rescale_stats, 64, cudaMemcpyDeviceToHost));
+    return MDG_OK;
+}
+
+int mdg_fetch_rescale_hist(mdg_ctx *ctx, uint64_t *sub, uint64_t *rev, uint64_t *ref_count)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    if (!ctx->rescale_hist) return fail(ctx, MDG_ERR_STATE, "mdg_set_rescale_model must be called first");
+    int rc = mdg_sync(ctx);
+    if (rc) return rc;
+    const size_t n_sub = (size_t)2 * ctx->model.n_slots * 94;
+    if (sub) MDG_CUDA(ctx, cudaMemcpy(sub, ctx->rescale_hist, n_sub * 8, cudaMemcpyDeviceToHost));
+    if (rev) MDG_CUDA(ctx, cudaMemcpy(rev, ctx->rescale_hist + n_sub, 2 * 94 * 8, cudaMemcpyDeviceToHost));
+    if (ref_count) MDG_CUDA(ctx, cudaMemcpy(ref_count, ctx->rescale_hist + n_sub + 2 * 94, 4 * 8, cudaMemcpyDeviceToHost));
     return MDG_OK;
 }
 

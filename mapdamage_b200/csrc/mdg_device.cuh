@@ -202,7 +202,7 @@ __device__ __forceinline__ ColumnSite locate_column(const uint32_t *__restrict__
             if (col < c + len) {
                 ColumnSite s;
                 s.op = op;
-                s.query = q + (col - c);
+                s.query = op_has_read(op) ? q + (col - c) : q;  // D: read bases before the deletion
                 s.refidx = col - ins;
                 return s;
             }

@@ -25,6 +25,10 @@ struct RescaleOut {
     uint8_t *status;
     unsigned long long *stats;  // pairs, improper, without quals, rescaled, too long
     int32_t *error_flag;
+    // rescale._record_subs (rescale.py:106-139), integer part: the host turns these into the log summary
+    unsigned long long *hist_sub;   // [type C>T, G>A][slot][94]: rescaled columns by position slot and old Phred
+    unsigned long long *hist_rev;   // [type T>C, A>G][94]: the reverse transitions by Phred (never rescaled)
+    unsigned long long *ref_count;  // [A, C, G, T]: reference bases over all walked columns
 };
 
 // float(("%.5f" % x)) narrowed to float32: exact decimal rounding, half to even.
@@ -52,7 +56,7 @@ __device__ inline float round_5_decimals(double x)
 }
 
 __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const RescaleModel &m, const RescaleOut &out,
-                             int64_t r, int lane)
+                             int64_t r, int lane, uint32_t (&ref_seen)[4])
 {
     const uint32_t flag = b.flag[r];
     const uint32_t l_seq = b.l_seq[r];
@@ -113,14 +117,20 @@ __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const Rescale
         const uint32_t i = base + lane;
         double add = 0.0;
         bool contributes = false;
+        uint32_t ref_here = CODE_OTHER;
         if (i < C) {
             const uint32_t col = strand ? C - 1 - i : i;
             uint32_t op = OP_M, j = col, refidx = col;
-            if (n_cig > 1) {
+            if (n_cig > 1 || !(ct.first_op == OP_M || ct.first_op == OP_EQ || ct.first_op == OP_X)) {
                 ColumnSite s = locate_column(cigar, n_cig, col);
                 op = s.op; j = s.query; refidx = s.refidx;
             }
-            if (op_has_read(op) && j < n) {
+            uint32_t gb_counted = CODE_OTHER;  // reference base of this column, if _record_subs sees the column
+            const bool read_col = op_has_read(op) && j < n;
+            // a deletion column is walked (and its reference base recorded) as long as read bases remain
+            // after it in 5'->3' order (rescale.py:249-261); j = read bases to its left
+            const bool del_col = op == OP_D && (strand ? j > 0 : j < n);
+            if (read_col || del_col) {
                 // reference character paired with this column: the reverse-strand zip is
                 // anchored at the right end, `skipped` columns further on
                 uint32_t gb = CODE_GAP;
@@ -134,31 +144,42 @@ __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const Rescale
                     int64_t gpos = pos + (int64_t)refidx;
                     gb = (gpos >= 0 && gpos < contig_len) ? ref_code(ref.words, contig_off + gpos) : CODE_OTHER;
                 }
-                uint32_t rb = code_of_nibble(read_nibble(b.seq4, qbase + j));
-                if (strand) { rb = complement(rb); gb = complement(gb); }
-                int type = -1;
-                if (rb == 3 && gb == 1) type = 0;       // read T on reference C
-                else if (rb == 0 && gb == 2) type = 1;  // read A on reference G
-                if (type >= 0) {
-                    // _corr_this_base, rescale.py:49-79
-                    const int64_t p5 = (int64_t)(strand ? n - 1 - j : j) + 1;
-                    const int64_t back = p5 - (int64_t)n - 1;
-                    int64_t p = p5;
-                    if (both_ends && p5 >= -back) p = back;
-                    int slot = 0;
-                    if (p > 0 && p <= m.len5p) slot = (int)p;
-                    else if (p < 0 && -p <= m.len3p) slot = m.len5p + (int)(-p);
+                if (strand) gb = complement(gb);
+                gb_counted = gb;
+                if (read_col) {
+                    uint32_t rb = code_of_nibble(read_nibble(b.seq4, qbase + j));
+                    if (strand) rb = complement(rb);
+                    int type = -1;
+                    if (rb == 3 && gb == 1) type = 0;       // read T on reference C
+                    else if (rb == 0 && gb == 2) type = 1;  // read A on reference G
                     const uint32_t q = b.qual[qbase + j];
-                    if (q > 93) {
-                        atomicCAS(out.error_flag, 0, DATA_ERR_QUAL);
-                    } else {
-                        out.qual[qbase + j] = m.lut[((size_t)type * m.n_slots + slot) * 94 + q];
-                        add = m.inc[type * m.n_slots + slot];
-                        contributes = slot != 0;  // slot 0 adds exactly 0.0
+                    if (type >= 0) {
+                        // _corr_this_base, rescale.py:49-79
+                        const int64_t p5 = (int64_t)(strand ? n - 1 - j : j) + 1;
+                        const int64_t back = p5 - (int64_t)n - 1;
+                        int64_t p = p5;
+                        if (both_ends && p5 >= -back) p = back;
+                        int slot = 0;
+                        if (p > 0 && p <= m.len5p) slot = (int)p;
+                        else if (p < 0 && -p <= m.len3p) slot = m.len5p + (int)(-p);
+                        if (q > 93) {
+                            atomicCAS(out.error_flag, 0, DATA_ERR_QUAL);
+                        } else {
+                            out.qual[qbase + j] = m.lut[((size_t)type * m.n_slots + slot) * 94 + q];
+                            add = m.inc[type * m.n_slots + slot];
+                            contributes = slot != 0;  // slot 0 adds exactly 0.0
+                            atomicAdd(out.hist_sub + ((size_t)type * m.n_slots + slot) * 94 + q, 1ull);
+                        }
+                    } else if (q <= 93) {
+                        if (rb == 1 && gb == 3) atomicAdd(out.hist_rev + q, 1ull);            // read C on reference T
+                        else if (rb == 2 && gb == 0) atomicAdd(out.hist_rev + 94 + q, 1ull);  // read G on reference A
                     }
                 }
             }
+            if (gb_counted < 4) ref_here = gb_counted;
         }
+#pragma unroll
+        for (uint32_t g = 0; g < 4; ++g) ref_seen[g] += __popc(__ballot_sync(0xffffffffu, ref_here == g));
         uint32_t mask = __ballot_sync(0xffffffffu, contributes);
         while (mask) {  // sequential fp64 sum in read order (rescale.py:244)
             int src = __ffs(mask) - 1;
@@ -183,8 +204,11 @@ __global__ void __launch_bounds__(256) rescale_kernel(DevBatch b, DevRef ref, Re
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * warps_per_block;
+    uint32_t ref_seen[4] = {0, 0, 0, 0};  // identical in every lane (ballot counts)
     for (int64_t r = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < b.n_reads; r += stride)
-        rescale_read(b, ref, m, out, r, lane);
+        rescale_read(b, ref, m, out, r, lane, ref_seen);
+    const uint32_t mine = lane == 0 ? ref_seen[0] : lane == 1 ? ref_seen[1] : lane == 2 ? ref_seen[2] : ref_seen[3];
+    if (lane < 4 && mine) atomicAdd(out.ref_count + lane, (unsigned long long)mine);
 }
 
 }  // namespace mdg

@@ -259,6 +259,15 @@ class DamageEngine:
         keys = ("pairs", "improper_pairs", "without_quals", "rescaled", "alignment_longer_than_read")
         return {k: int(v) for k, v in zip(keys, stats)}
 
+    def rescale_hist(self, n_slots):
+        """``(sub[2][n_slots][94], rev[2][94], ref_count[4])`` -- integer substitution bookkeeping."""
+        sub = np.zeros((2, n_slots, 94), dtype=np.uint64)
+        rev = np.zeros((2, 94), dtype=np.uint64)
+        ref_count = np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.mdg_fetch_rescale_hist(self._ctx, sub.ctypes.data, rev.ctypes.data,
+                                                     ref_count.ctypes.data))
+        return sub, rev, ref_count
+
     # -- multi-GPU -------------------------------------------------------
     @staticmethod
     def nccl_unique_id():

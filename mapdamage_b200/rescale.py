@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference's rescale pass (``rescale.py:285-383``).
+
+``rescale_qual(ref, options)`` keeps the reference's signature, log messages
+and return code; the per-read work (``_rescale_qual_read``, ``rescale.py:195-282``)
+runs in ``rescale_kernel``.  Every record of the input is written to the
+output in input order (``rescale.py:300,344``); rescaled reads get their new
+qualities and the ``MR:f`` tag.  The substitution summary the reference logs
+(``_record_subs`` / ``_qual_summary_subs`` / ``_print_subs``, ``rescale.py:106-192``)
+is rebuilt on the host from integer histograms the kernel accumulates.
+
+Only SAM text is read and written here (BAM encode/decode: SURVEY.md row f2).
+"""
+import logging
+import struct
+import time
+from pathlib import Path
+
+import numpy as np
+
+from .batch import BatchBuilder
+from .engine import DamageEngine
+from .refgenome import Reference
+from .rescale_model import RescaleError, RescaleModel, get_corr_prob
+from .samtext import format_record, iter_sam
+
+__all__ = ["rescale_qual", "RescaleError", "SubstitutionSummary"]
+
+
+def _phred_pval(qual):
+    """``_phred_char_to_pval`` (``rescale.py:18-20``) of Phred score ``qual``."""
+    return 10 ** (-(float(qual + 33) - float(33)) / 10)
+
+
+class SubstitutionSummary:
+    """``subs`` of the reference (``rescale.py:82-105``) from the device histograms.
+
+    ``sub[type][slot][Q]`` counts rescaled C>T / G>A columns, ``rev[type][Q]``
+    the T>C / A>G columns, ``ref_count`` the reference bases seen.  The float
+    sums are formed per histogram cell instead of per base, so they can differ
+    from the reference's running sums in the last bits; they are only ever
+    printed with four decimals.
+    """
+
+    def __init__(self, model, sub, rev, ref_count):
+        self.data = {}
+        names = ("CT", "GA")
+        for t, name in enumerate(names):
+            before = np.zeros(130, dtype=np.int64)
+            after = np.zeros(130, dtype=np.int64)
+            pvals = pvals_before = 0.0
+            for slot in range(model.n_slots):
+                corr = model.prob[t, slot]
+                for qual in np.flatnonzero(sub[t, slot]):
+                    count = int(sub[t, slot, qual])
+                    before[qual] += count
+                    after[int(model.lut[t, slot, qual])] += count
+                    pseq = 1 - _phred_pval(int(qual))
+                    pvals += count * ((1 - corr) * pseq)
+                    pvals_before += count * pseq
+            self.data[name + "-before"] = before
+            self.data[name + "-after"] = after
+            self.data[name + "-pvals"] = pvals
+            self.data[name + "-pvals_before"] = pvals_before
+        for t, name in enumerate(("TC", "AG")):
+            hist = np.zeros(130, dtype=np.int64)
+            hist[:94] = rev[t]
+            self.data[name + "-before"] = hist
+            self.data[name + "-after"] = hist.copy()
+            self.data[name + "-pvals"] = float(sum(int(rev[t, q]) * (1 - _phred_pval(int(q)))
+                                                   for q in np.flatnonzero(rev[t])))
+        for code, base in enumerate("ACGT"):
+            self.data[base] = int(ref_count[code])
+
+    def at_least(self, key, level):
+        """``subs[key + "-Q%d"]`` of ``_qual_summary_subs`` (``rescale.py:142-161``)."""
+        return int(self.data[key][level:].sum())
+
+    def log_lines(self):
+        """The lines ``_print_subs`` logs (``rescale.py:164-192``)."""
+        lines = ["Expected substition frequencies before and after rescaling:"]
+        for sub in ("CT", "TC", "GA", "AG"):
+            base_count = self.data[sub[0]]
+            if base_count:
+                pvals = self.data[sub + "-pvals"]
+                pvals_before = self.data.get(sub + "-pvals_before", pvals)
+                lines.append("    %s>%s    %.4f    %.4f"
+                             % (sub[0], sub[1], pvals_before / base_count, pvals / base_count))
+            else:
+                lines.append("\t%s\tNA\t\tNA" % sub)
+        lines.append("Quality metrics before and after scaling:")
+        for sub in ("CT", "GA"):
+            for qual in (0, 10, 20, 30, 40):
+                lines.append("    %s-Q%02i% 10i% 10i" % (sub, qual, self.at_least(sub + "-before", qual),
+                                                           self.at_least(sub + "-after", qual)))
+        return lines
+
+
+def _walk_ends_in_deletion(record):
+    """True when the 5'->3' walk of the alignment ends on deletion columns (``rescale.py:255-261``)."""
+    columns = [op for op, n in record.cigar if op in (0, 1, 2, 7, 8) and n > 0]
+    if not columns:
+        return False
+    return (columns[0] if record.flag & 0x10 else columns[-1]) == 2
+
+
+def _mr_text(value):
+    """``MR:f`` as a SAM writer prints the float32 a BAM ``f`` tag would store."""
+    return "MR:f:%r" % struct.unpack("<f", struct.pack("<f", float(value)))[0]
+
+
+def _rescale_qual_core(ref, options, engine=None, batch_reads=1 << 18):
+    log = logging.getLogger(__name__)
+    corr_prob = get_corr_prob(Path(options.folder) / "Stats_out_MCMC_correct_prob.csv",
+                              rescale_length_5p=options.rescale_length_5p,
+                              rescale_length_3p=options.rescale_length_3p)
+    model = RescaleModel(corr_prob, options.rescale_length_5p, options.rescale_length_3p)
+    filename = Path(options.filename)
+    if filename.suffix.lower() in (".bam", ".cram"):
+        raise RescaleError("only SAM text is decoded here; BAM/CRAM decode is SURVEY.md row f2")
+    header, records = iter_sam(filename)
+    reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
+    reference = reference.reordered(header.references)
+
+    own_engine = engine is None
+    if own_engine:
+        engine = DamageEngine(max_reads=batch_reads, max_cigar_ops=8 * batch_reads, max_bases=512 * batch_reads,
+                              device=getattr(options, "device", 0))
+    try:
+        engine.set_reference(reference)
+        engine.set_rescale_model(model)
+        with open(options.rescale_out, "wt") as out:
+            for line in header.lines:
+                out.write(line + "\n")
+            chunk = []
+            for record in records:
+                if "MR" in record.tags and not (record.flag & 0x4) and record.qual is not None \
+                        and _would_rescale(record):
+                    # rescale.py:277-278
+                    raise SystemExit("Read: %s already has a MR tag, can't rescale"
+                                     % format_record(record, header))
+                chunk.append(record)
+                if len(chunk) == batch_reads:
+                    _rescale_chunk(engine, header, chunk, out, log)
+                    chunk = []
+            _rescale_chunk(engine, header, chunk, out, log)
+        stats = engine.rescale_stats()
+        summary = SubstitutionSummary(model, *engine.rescale_hist(model.n_slots))
+    finally:
+        if own_engine:
+            engine.close()
+
+    if stats["pairs"]:
+        log.warning(
+            "Processed %i paired reads, assumed to be non-overlapping, facing inwards "
+            "and correctly paired; %i of these were excluded as improperly paired.",
+            stats["pairs"], stats["improper_pairs"])
+    if stats["without_quals"]:
+        log.warning("Skipped %i reads without quality scores", stats["without_quals"])
+    if not (np.array_equal(summary.data["TC-before"], summary.data["TC-after"])
+            and np.array_equal(summary.data["AG-before"], summary.data["AG-after"])):
+        raise RescaleError("Qualities for T.C and A.G transitions should not change in the rescaling. "
+                           "Please file a bug on github.")
+    for line in summary.log_lines():
+        log.info("%s", line)
+    return summary
+
+
+def _would_rescale(record):
+    """The pairing rule of ``rescale.py:305-342``: does the reference rescale this mapped read?"""
+    if not (record.flag & 0x1):
+        return True
+    reverse, mate_reverse = bool(record.flag & 0x10), bool(record.flag & 0x20)
+    same = record.tid == record.mtid
+    return ((not reverse and mate_reverse and record.mpos > record.pos and same)
+            or (reverse and not mate_reverse and record.mpos < record.pos and same))
+
+
+def _rescale_chunk(engine, header, chunk, out, log):
+    if not chunk:
+        return
+    builder = BatchBuilder(merge_libraries=True, apply_filter=False)
+    for record in chunk:
+        builder.add(record)
+    batch = builder.finish(with_qual=True)
+    qual, mr, status = engine.rescale(batch)
+    engine.sync()  # raises the "quality and sequence mismatch" data error (rescale.py:266-273)
+    for i, record in enumerate(chunk):
+        if status[i] & 1:
+            if _walk_ends_in_deletion(record):
+                log.warning("The aligment of the read is longer than the actual read %s", record.qname)
+            off, n = int(batch.base_off[i]), int(batch.l_seq[i])
+            text = (qual[off:off + n] + 33).astype(np.uint8).tobytes().decode("latin-1")
+            out.write(format_record(record, header, qual=text, extra_tags=(_mr_text(mr[i]),)) + "\n")
+        else:
+            out.write(format_record(record, header) + "\n")
+
+
+def rescale_qual(ref, options):
+    """``rescale.rescale_qual`` (``rescale.py:368-383``): 0 on success, 1 on failure."""
+    from ._native import NativeError
+
+    log = logging.getLogger(__name__)
+    log.info("Rescaling BAM: '%s' -> '%s'", options.filename, options.rescale_out)
+    start_time = time.time()
+    try:
+        _rescale_qual_core(ref, options)
+    except RescaleError as error:
+        log.error("%s", error)
+        return 1
+    except NativeError as error:
+        # the device reports what the reference raises as exceptions inside its loop
+        log.error("Unhandled exception: %s", error.message)
+        return 1
+    except Exception as error:
+        log.error("Unhandled exception: %s", error)
+        return 1
+    log.debug("Rescaling completed in %f seconds", time.time() - start_time)
+    return 0

@@ -116,3 +116,45 @@ def read_fasta(path):
     if name is not None:
         seqs[name] = "".join(chunks)
     return seqs
+
+
+def iter_sam(path):
+    """``(header, record iterator)``: the header is complete on return, records stream."""
+    header = SamHeader()
+    handle = open(Path(path), "rt")
+    first = None
+    for line in handle:
+        if line.startswith("@"):
+            header.add(line.rstrip("\n"))
+        elif line.strip():
+            first = line
+            break
+
+    def records():
+        try:
+            if first is not None:
+                yield parse_record(first, header)
+                for line in handle:
+                    if line.strip():
+                        yield parse_record(line, header)
+        finally:
+            handle.close()
+
+    return header, records()
+
+
+def format_record(record, header, qual=None, extra_tags=()):
+    """SAM text line of ``record``, optionally with new qualities / appended tags."""
+    if record.mtid is None or record.mtid < 0:
+        rnext = "*"
+    else:
+        rnext = "=" if record.mtid == record.tid else header.references[record.mtid]
+    fields = [
+        record.qname, str(record.flag), record.rname, str(record.pos + 1), str(record.mapq),
+        format_cigar(record.cigar), rnext, str(record.mpos + 1), str(record.tlen),
+        record.seq if record.seq is not None else "*",
+        (qual if qual is not None else record.qual) or "*",
+    ]
+    fields.extend(record.tag_text)
+    fields.extend(extra_tags)
+    return "\t".join(fields)
