@@ -185,7 +185,7 @@ def reference_arm(args, rank, world):
 def gpu_arm(args, rank, local_rank, world):
     import torch
 
-    from mapdamage_b200 import synth
+    from mapdamage_b200 import multigpu, synth
     from mapdamage_b200.engine import DamageEngine
 
     dist = None
@@ -216,9 +216,7 @@ def gpu_arm(args, rank, local_rank, world):
     reference = synth.make_reference([REF_BASES], seed=args.seed)
     engine.set_reference(reference)
     if world > 1:
-        box = [DamageEngine.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        engine.nccl_init(box[0], rank, world)
+        multigpu.connect(engine, dist, rank, world)
 
     resident = [engine.synth_batch(n, seed=args.seed + 1000 * rank + i, length=(READ_LEN, READ_LEN),
                                    with_qual=False) for i, n in enumerate(sizes)]
