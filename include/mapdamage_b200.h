@@ -71,6 +71,15 @@ typedef struct {
  * Phred bytes starting at byte base_off[i] of qual.  base_off[i] is even.
  * qual may be NULL (no read has qualities); a read whose first quality byte
  * is 0xFF has none (BAM convention).  lib[i] indexes the library axis.
+ *
+ * Optional arrays -- a NULL pointer stands for the common case and saves its
+ * bytes on the host->device link (the pass is PCIe-bound end to end):
+ *   lib       NULL: every read is in library 0
+ *   tlen      NULL: 0 (only read for proper-pair first mates, statistics.py:121-124)
+ *   mtid/mpos NULL: -1 (only read by the rescale pairing rule, rescale.py:318-337)
+ *   cigar_off NULL: every read has exactly one CIGAR op, cigar[i] (n_cigar == n_reads)
+ *   base_off  NULL: reads are packed back to back, each starting on an even base:
+ *                   base_off[i] = sum over k < i of (l_seq[k] rounded up to even)
  */
 typedef struct {
     int64_t n_reads;

@@ -82,6 +82,33 @@ class ReadBatch:
             if self.qual is not None and self.qual.shape[0] < end:
                 raise ValueError("qual is shorter than base_off/l_seq imply")
 
+    def droppable(self):
+        """Names of the optional ``mdg_batch`` arrays that hold exactly what a NULL pointer stands for
+        (``include/mapdamage_b200.h``), so they need not cross PCIe.  Computed once and cached."""
+        if getattr(self, "_droppable", None) is None:
+            n = self.n
+            drop = set()
+            if n:
+                if not self.lib.any():
+                    drop.add("lib")
+                if not (self.flag & 1).any():
+                    drop.add("tlen")
+                if (self.mtid == -1).all() and (self.mpos == -1).all():
+                    drop.update(("mtid", "mpos"))
+                if self.cigar.shape[0] == n and np.array_equal(self.cigar_off, np.arange(n + 1, dtype=np.uint32)):
+                    drop.add("cigar_off")
+                padded = (self.l_seq.astype(np.int64) + 1) & ~1
+                packed = np.zeros(n, dtype=np.int64)
+                np.cumsum(padded[:-1], out=packed[1:])
+                if np.array_equal(self.base_off, packed):
+                    drop.add("base_off")
+            self._droppable = frozenset(drop)
+        return self._droppable
+
+    def invalidate(self):
+        """Call after editing the arrays in place: forgets what :meth:`droppable` cached."""
+        self._droppable = None
+
     @property
     def total_bases(self):
         """Base slots spanned by the batch (incl. odd-length pad slots)."""

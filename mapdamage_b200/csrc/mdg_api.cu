@@ -65,6 +65,7 @@ struct DeviceArrays {
     size_t bytes = 0;
     int64_t cap_reads = 0, cap_cigar = 0, cap_bases = 0;
     int64_t n_cigar = 0, n_bases = 0;
+    unsigned long long *scan_tmp = nullptr;  // inside `block`: per-256-read totals for the layout scan
     bool has_qual = false;
     mdg::DevBatch view{};
 };
@@ -172,6 +173,7 @@ int alloc_arrays(mdg_ctx *ctx, DeviceArrays &a, int64_t reads, int64_t cigar, in
     size_t o_lseq = take(reads * 4), o_boff = take(reads * 4), o_coff = take((reads + 1) * 4);
     size_t o_cig = take(cigar * 4), o_seq = take(bases / 2 + 8), o_qual = with_qual ? take(bases + 8) : 0;
     size_t o_tlen = take(reads * 4), o_mtid = take(reads * 4), o_mpos = take(reads * 4);
+    size_t o_scan = take(((size_t)(reads + 255) / 256 + 2) * 16);
     MDG_CUDA(ctx, cudaMalloc(&a.block, off));
     a.bytes = off;
     a.cap_reads = reads; a.cap_cigar = cigar; a.cap_bases = bases; a.has_qual = with_qual;
@@ -189,6 +191,7 @@ int alloc_arrays(mdg_ctx *ctx, DeviceArrays &a, int64_t reads, int64_t cigar, in
     a.view.tlen = (const int32_t *)(p + o_tlen);
     a.view.mtid = (const int32_t *)(p + o_mtid);
     a.view.mpos = (const int32_t *)(p + o_mpos);
+    a.scan_tmp = (unsigned long long *)(p + o_scan);
     return MDG_OK;
 }
 
@@ -199,10 +202,10 @@ int check_batch(mdg_ctx *ctx, const mdg_batch *h)
         return fail(ctx, MDG_ERR_ARGUMENT, "batch sizes must be non-negative and n_bases even");
     if (h->n_reads >= (1ll << 31) || h->n_cigar >= (1ll << 32) || h->n_bases >= (1ll << 32))
         return fail(ctx, MDG_ERR_ARGUMENT, "batch too large: split it (offsets are 32-bit)");
-    if (h->n_reads &&
-        (!h->flag || !h->tid || !h->pos || !h->lib || !h->l_seq || !h->base_off || !h->cigar_off || !h->tlen ||
-         !h->mtid || !h->mpos || (h->n_cigar && !h->cigar) || (h->n_bases && !h->seq4)))
-        return fail(ctx, MDG_ERR_ARGUMENT, "batch has a NULL array");
+    if (h->n_reads && (!h->flag || !h->tid || !h->pos || !h->l_seq || (h->n_cigar && !h->cigar) || (h->n_bases && !h->seq4)))
+        return fail(ctx, MDG_ERR_ARGUMENT, "batch lacks a required array (flag, tid, pos, l_seq, cigar, seq4)");
+    if (h->n_reads && !h->cigar_off && h->n_cigar != h->n_reads)
+        return fail(ctx, MDG_ERR_ARGUMENT, "cigar_off may only be NULL when every read has exactly one CIGAR op");
     return MDG_OK;
 }
 
@@ -222,21 +225,39 @@ int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t s
     if (!n) return MDG_OK;
 #define MDG_H2D(field, bytes) \
     MDG_CUDA(ctx, cudaMemcpyAsync((void *)a.view.field, h->field, (size_t)(bytes), cudaMemcpyHostToDevice, stream))
+#define MDG_FILL(field, byte, bytes) \
+    MDG_CUDA(ctx, cudaMemsetAsync((void *)a.view.field, byte, (size_t)(bytes), stream))
     MDG_H2D(flag, n * 2);
     MDG_H2D(tid, n * 4);
     MDG_H2D(pos, n * 4);
-    MDG_H2D(lib, n * 2);
     MDG_H2D(l_seq, n * 4);
-    MDG_H2D(base_off, n * 4);
-    MDG_H2D(cigar_off, (n + 1) * 4);
     MDG_H2D(cigar, h->n_cigar * 4);
     MDG_H2D(seq4, h->n_bases / 2);
-    MDG_H2D(tlen, n * 4);
+    // optional arrays: what a NULL pointer stands for is made on the device instead of crossing PCIe
+    if (h->lib) MDG_H2D(lib, n * 2);
+    else MDG_FILL(lib, 0, n * 2);
+    if (h->tlen) MDG_H2D(tlen, n * 4);
+    else MDG_FILL(tlen, 0, n * 4);
     if (mates) {
-        MDG_H2D(mtid, n * 4);
-        MDG_H2D(mpos, n * 4);
+        if (h->mtid) MDG_H2D(mtid, n * 4);
+        else MDG_FILL(mtid, 0xFF, n * 4);
+        if (h->mpos) MDG_H2D(mpos, n * 4);
+        else MDG_FILL(mpos, 0xFF, n * 4);
+    }
+    if (h->cigar_off) MDG_H2D(cigar_off, (n + 1) * 4);
+    if (h->base_off) MDG_H2D(base_off, n * 4);
+    if (!h->cigar_off || !h->base_off) {
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        mdg::layout_block_totals<<<blocks, 256, 0, stream>>>(a.view.l_seq, n, a.scan_tmp);
+        mdg::synth_scan_totals<<<1, 1024, 0, stream>>>(a.scan_tmp, (int64_t)blocks);
+        mdg::layout_fill<<<blocks, 256, 0, stream>>>(a.view.l_seq, n, a.scan_tmp, h->base_off ? nullptr : (uint32_t *)a.view.base_off,
+                                                     h->cigar_off ? nullptr : (uint32_t *)a.view.cigar_off,
+                                                     (uint64_t)h->n_bases, ctx->count_tables.error_flag);
+        MDG_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 3;
     }
 #undef MDG_H2D
+#undef MDG_FILL
     if (quals && a.has_qual && h->qual)
         MDG_CUDA(ctx, cudaMemcpyAsync((void *)a.view.qual, h->qual, (size_t)h->n_bases, cudaMemcpyHostToDevice, stream));
     return MDG_OK;
@@ -349,6 +370,7 @@ int check_device_errors(mdg_ctx *ctx)
         case mdg::DATA_ERR_LIB: return fail(ctx, MDG_ERR_DATA, "a read's library index is >= n_libraries");
         case mdg::DATA_ERR_TID: return fail(ctx, MDG_ERR_DATA, "a mapped read has no CIGAR or a reference id outside the genome");
         case mdg::DATA_ERR_QUAL: return fail(ctx, MDG_ERR_DATA, "a base quality above 93 cannot be rescaled");
+        case mdg::DATA_ERR_LAYOUT: return fail(ctx, MDG_ERR_DATA, "n_bases does not match the read lengths of a batch passed without base_off");
         case mdg::DATA_ERR_CLIP: return fail(ctx, MDG_ERR_DATA, "quality and sequence mismatch: soft clip behind a hard clip (reference rescale.py:266-273 fails the same way)");
         default: return fail(ctx, MDG_ERR_DATA, "device reported data error %d", flag);
         }
@@ -870,7 +892,7 @@ int mdg_batch_download(mdg_ctx *ctx, const mdg_dev_batch *batch, const mdg_batch
     MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
 #define MDG_D2H(field, bytes) \
-    MDG_CUDA(ctx, cudaMemcpy((void *)h->field, a.view.field, (size_t)(bytes), cudaMemcpyDeviceToHost))
+    if (h->field) MDG_CUDA(ctx, cudaMemcpy((void *)h->field, a.view.field, (size_t)(bytes), cudaMemcpyDeviceToHost))
     MDG_D2H(flag, n * 2);
     MDG_D2H(tid, n * 4);
     MDG_D2H(pos, n * 4);

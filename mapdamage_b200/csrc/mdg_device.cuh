@@ -58,7 +58,7 @@ struct CountParams {
 };
 
 // data-error codes written to CountTables::error_flag
-enum : int32_t { DATA_ERR_LIB = 1, DATA_ERR_TID = 2, DATA_ERR_QUAL = 3, DATA_ERR_CLIP = 4 };
+enum : int32_t { DATA_ERR_LIB = 1, DATA_ERR_TID = 2, DATA_ERR_QUAL = 3, DATA_ERR_CLIP = 4, DATA_ERR_LAYOUT = 5 };
 
 // BAM 4-bit nucleotide code (=ACMGRSVTWYHKDBN) -> device base code; only
 // A,C,G,T (one bit set) are bases (statistics.py:27)

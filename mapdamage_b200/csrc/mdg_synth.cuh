@@ -153,6 +153,41 @@ __global__ void __launch_bounds__(1024) synth_scan_totals(unsigned long long *to
     if (threadIdx.x < 2) totals[2 * n_blocks + threadIdx.x] = carry[threadIdx.x];
 }
 
+// ---- default layout of a batch passed without base_off / cigar_off (mdg_batch: optional arrays) ----
+// base_off[i] = sum over k < i of l_seq[k] rounded up to even; cigar_off[i] = i (one op per read)
+__global__ void __launch_bounds__(256) layout_block_totals(const uint32_t *__restrict__ l_seq, int64_t n, unsigned long long *totals)
+{
+    __shared__ uint2 total;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t bases = i < n ? (l_seq[i] + 1) & ~1u : 0;
+    block_exclusive_scan2(bases, 0, &total);
+    if (threadIdx.x == 0) {
+        totals[2 * (size_t)blockIdx.x] = total.x;
+        totals[2 * (size_t)blockIdx.x + 1] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) layout_fill(const uint32_t *__restrict__ l_seq, int64_t n, const unsigned long long *block_off,
+                                                   uint32_t *base_off, uint32_t *cigar_off, uint64_t n_bases, int32_t *error_flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t len = i < n ? l_seq[i] : 0;
+    const uint2 off = block_exclusive_scan2((len + 1) & ~1u, 0, nullptr);
+    if (i >= n) return;
+    if (cigar_off) {
+        cigar_off[i] = (uint32_t)i;
+        if (i == n - 1) cigar_off[n] = (uint32_t)n;
+    }
+    if (base_off) {
+        uint64_t at = block_off[2 * (size_t)blockIdx.x] + off.x;
+        if (at + len > n_bases) {
+            atomicCAS(error_flag, 0, DATA_ERR_LAYOUT);
+            at = 0;
+        }
+        base_off[i] = (uint32_t)at;
+    }
+}
+
 __device__ __forceinline__ void place_read(const SynthDev &p, const DevRef &ref, uint64_t h, int32_t rspan,
                                            int32_t *tid, int64_t *pos)
 {

@@ -17,8 +17,9 @@ _FIELDS = ("flag", "tid", "pos", "lib", "l_seq", "base_off", "cigar_off", "cigar
            "tlen", "mtid", "mpos")
 
 
-def batch_struct(batch):
-    """``mdg_batch`` view of a :class:`ReadBatch` (no copies)."""
+def batch_struct(batch, compact=False):
+    """``mdg_batch`` view of a :class:`ReadBatch` (no copies).  ``compact`` passes NULL for the
+    optional arrays that only hold their default (``ReadBatch.droppable``)."""
     n_bases = batch.total_bases
     if batch.seq4.shape[0] * 2 < n_bases:
         raise ValueError("seq4 shorter than the batch's base span")
@@ -31,8 +32,9 @@ def batch_struct(batch):
     s.n_reads = batch.n
     s.n_cigar = int(batch.cigar.shape[0])
     s.n_bases = n_bases
+    drop = batch.droppable() if compact else ()
     for name in _FIELDS:
-        setattr(s, name, getattr(batch, name).ctypes.data)
+        setattr(s, name, None if name in drop else getattr(batch, name).ctypes.data)
     s.qual = None if qual is None else qual.ctypes.data
     return s
 
@@ -179,10 +181,13 @@ class DamageEngine:
         self._check(self._lib.mdg_batch_download(self._ctx, device_batch.handle, C.byref(s)))
         return ReadBatch(**arrays)
 
-    def h2d_bytes(self, batch, rescale=False):
+    def h2d_bytes(self, batch, rescale=False, compact=True):
         """Bytes ``count`` (or ``rescale``) copies to the device for ``batch`` (see ``copy_batch``)."""
         n = batch.n
-        total = n * (2 + 4 + 4 + 2 + 4 + 4 + 4) + (n + 1) * 4 + batch.cigar.nbytes + batch.total_bases // 2
+        drop = batch.droppable() if compact and not rescale else ()
+        total = n * (2 + 4 + 4 + 4) + batch.cigar.nbytes + batch.total_bases // 2  # flag, tid, pos, l_seq, cigar, seq4
+        total += sum(size for name, size in (("lib", 2 * n), ("tlen", 4 * n), ("base_off", 4 * n),
+                                             ("cigar_off", 4 * (n + 1))) if name not in drop)
         if rescale:
             total += 8 * n
         if batch.qual is not None and (rescale or self.min_qual > 0):
@@ -194,9 +199,10 @@ class DamageEngine:
                 and batch.total_bases <= self.max_bases)
 
     # -- counting pass ---------------------------------------------------
-    def count(self, batch):
-        """Queues one host batch (async copy + kernels); see :meth:`sync`."""
-        s = batch_struct(batch)
+    def count(self, batch, compact=True):
+        """Queues one host batch (async copy + kernels); see :meth:`sync`.  With ``compact`` the optional
+        arrays that only hold their default value stay on the host (``ReadBatch.droppable``)."""
+        s = batch_struct(batch, compact)
         self._keepalive.append((batch, s))
         self._check(self._lib.mdg_count_submit(self._ctx, C.byref(s)))
 

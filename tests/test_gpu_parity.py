@@ -121,6 +121,7 @@ def test_errors_are_loud():
     with DamageEngine(max_reads=2048) as engine:
         engine.set_reference(reference)
         batch.lib[5] = 3
+        batch.invalidate()
         engine.count(batch)
         with pytest.raises(_native.NativeError) as info:
             engine.sync()
@@ -226,3 +227,34 @@ def test_device_generated_batches(name, min_qual):
     assert 0.2 < c_to_t < 0.4 and 0.2 < g_to_a < 0.4  # the injected 5' C>T / 3' G>A damage is there
     if kw.get("paired"):
         assert want[2][:, 0].sum() > 0 and np.all(host.flag & 1)
+
+
+@pytest.mark.parametrize("name", ["se100_noqual", "pe_mixed", "short"])
+def test_optional_arrays_default_on_device(name):
+    """NULL lib / tlen / base_off / cigar_off (mdg_batch optional arrays) count like the explicit arrays."""
+    reference = synth.make_reference([300_000, 150_000, 4_000], seed=5)
+    batch = synth.simulate_reads(reference, 30_000, seed=21, **SYNTH[name])
+    assert "base_off" in batch.droppable() and "lib" in batch.droppable()
+    if name == "se100_noqual":
+        assert {"cigar_off", "tlen"} <= batch.droppable()
+    tables = []
+    for compact in (False, True):
+        with DamageEngine(max_reads=batch.n, max_cigar_ops=batch.cigar.shape[0], max_bases=batch.total_bases) as engine:
+            engine.set_reference(reference)
+            assert engine.h2d_bytes(batch, compact=True) < engine.h2d_bytes(batch, compact=False)
+            engine.count(batch, compact=compact)
+            tables.append(engine.tables())
+    want = oracle.count(batch, reference, lg_bins=8192, threads=4)
+    for a, b, c in zip(tables[0], tables[1], want):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    # a batch that lies about its size is refused, not read out of bounds
+    import ctypes as C
+    from mapdamage_b200.engine import batch_struct
+    with DamageEngine(max_reads=batch.n, max_cigar_ops=batch.cigar.shape[0], max_bases=batch.total_bases) as engine:
+        engine.set_reference(reference)
+        s = batch_struct(batch, compact=True)
+        s.n_bases = (s.n_bases // 4) & ~1
+        engine._check(engine._lib.mdg_count_submit(engine._ctx, C.byref(s)))
+        with pytest.raises(_native.NativeError) as info:
+            engine.sync()
+        assert info.value.code == _native.ERR_DATA
