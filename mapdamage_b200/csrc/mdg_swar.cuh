@@ -48,12 +48,13 @@ struct SwarGeom {
     int32_t tile;          // reads staged per iteration of the block
 };
 
-// One staged read (16 bytes), shared by both anchors.
+// One staged read (16 bytes), shared by both anchors.  Base indices are kept as (32-bit word, nibble)
+// so that the loop needs no 64-bit arithmetic.
 struct __align__(16) SwarRecord {
-    uint32_t q0;      // first aligned base, in batch base coordinates (base_off + leading clip)
-    uint32_t ref_lo;  // genome base index of the first aligned column, low 32 bits
-    uint32_t cols;    // columns (15 bits) | has_qual << 15 | left flank bases << 16 | right flank bases << 24
-    uint32_t hi_phi;  // min(L, columns) | genome base index high bits << 16
+    uint32_t qi;    // 32-bit word of seq4 holding the first aligned base (base_off + leading clip)
+    uint32_t ri;    // 32-bit word of the genome holding the first aligned column
+    uint32_t cols;  // columns (15 bits) | has_qual << 15 | left flank bases << 16 | right flank bases << 24
+    uint32_t misc;  // min(L, columns) | nibble of the genome word << 16 | nibble of the seq4 word << 20
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
@@ -220,38 +221,39 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         uint32_t w0, w1, r0, r1, aligned, flank, sh;
         uint32_t qa, qm, qz;
     };
-    auto fetch = [&](int i, Stage &st) {
-        const SwarRecord rec = s_rec[strand ? T - 1 - i : i];
-        const int v = (int)(rec.hi_phi & 0xFFFF), f = (int)((rec.cols >> fshift) & 0xFF);
+    const int amul = anchor ? 1 : 0;
+    auto fetch = [&](const SwarRecord *at, Stage &st) {
+        const SwarRecord rec = *at;
+        const int v = (int)(rec.misc & 0xFFFF), f = (int)((rec.cols >> fshift) & 0xFF);
         st.aligned = (low_nibbles(z4 + s4 * v) ^ flip_a) & side_a;
         st.flank = (low_nibbles(z4 - s4 * f) ^ ~flip_a) & ~side_a;
+        st.sh = 0;
         if (st.aligned | st.flank) {
-            const int off = cbase + (anchor ? (int)(rec.cols & 0x7FFF) : 0);
-            const int64_t gn = (int64_t)(((uint64_t)(rec.hi_phi >> 16) << 32) | rec.ref_lo) + off;
-            const uint32_t *rp = ref32 + (gn >> 3);
+            // nibble 0 of this word, relative to the first aligned base
+            const int off = cbase + amul * (int)(rec.cols & 0x7FFF);
+            const int tr = (int)((rec.misc >> 16) & 7) + off, tq = (int)(rec.misc >> 20) + off;
+            const uint32_t *rp = ref32 + ((int)rec.ri + (tr >> 3));
             st.r0 = __ldg(rp);
             st.r1 = __ldg(rp + 1);
-            const int64_t qn = (int64_t)rec.q0 + off;
-            st.sh = 4 * (uint32_t)(qn & 7) | (4 * (uint32_t)(gn & 7)) << 8 | 0x10000u;
+            st.sh = ((uint32_t)(tq & 7) << 2) | ((uint32_t)(tr & 7) << 10) | 0x10000u;
+            const int qw = (int)rec.qi + (tq >> 3);
             if (st.aligned) {
-                const uint32_t *qp = seq32 + (qn >> 3);
+                const uint32_t *qp = seq32 + qw;
                 st.w0 = __ldg(qp);
                 st.w1 = __ldg(qp + 1);
                 if (kQual) {
                     if (rec.cols & 0x8000u) {
                         // qualities of the window's eight bases: three words from the aligned word below cover them
-                        const uint32_t *q32 = (const uint32_t *)b.qual + (qn >> 2);
+                        const uint32_t *q32 = (const uint32_t *)b.qual + 2 * (int64_t)qw + ((tq >> 2) & 1);
                         st.qa = __ldg(q32);
                         st.qm = __ldg(q32 + 1);
                         st.qz = __ldg(q32 + 2);
-                        st.sh |= 0x20000u | (8 * (uint32_t)(qn & 3)) << 24;
+                        st.sh |= 0x20000u | ((uint32_t)(tq & 3) << 27);
                     }
                 }
             } else {
                 st.w0 = st.w1 = 0;
             }
-        } else {
-            st.sh = 0;
         }
     };
     auto count = [&](const Stage &st) {
@@ -355,7 +357,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         const uint64_t ref0 = ref.contig_off[h.tid_ref] + (uint64_t)(pos > 0 ? pos : 0);
         simple = simple && state >= 1 && cols > 0 && cols < 32768 && n_lead <= 1 && n_trail <= 1 &&
                  (uint64_t)lead + cols + trail == h.l_seq && pos >= 0 && pos + (int64_t)cols <= contig_len &&
-                 ref0 < (1ull << 47);
+                 ref0 < (1ull << 33);
         kind = simple ? 1 : 2;
         if (!simple) return;
         const int64_t aend = pos + cols;
@@ -363,10 +365,11 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
         uint32_t has_qual = 0;
         if (kQual) has_qual = b.qual[h.boff] != 0xFF;
-        rec.q0 = h.boff + lead;
-        rec.ref_lo = (uint32_t)ref0;
+        const uint64_t q0 = (uint64_t)h.boff + lead;
+        rec.qi = (uint32_t)(q0 >> 3);
+        rec.ri = (uint32_t)(ref0 >> 3);
         rec.cols = cols | (has_qual << 15) | (lf << 16) | (rf << 24);
-        rec.hi_phi = min(cols, (uint32_t)L) | (uint32_t)(ref0 >> 32) << 16;
+        rec.misc = min(cols, (uint32_t)L) | (uint32_t)(ref0 & 7) << 16 | (uint32_t)(q0 & 7) << 20;
         // FragmentLengths.update, statistics.py:117-126
         int64_t length = -1;
         int lkind = 0;
@@ -514,21 +517,27 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 
         // ---- the counting loop: two stages that swap roles, so no register copy waits on a load ----
         if (active) {
+            // this thread's reads: every stride-th record of its strand's list (forward reads from the
+            // front of s_rec, reverse reads from the back).  Two stages swap roles, so that the loads of
+            // the next read are in flight while this one is counted and no register copy waits on a load.
             const int n_mine = (int)s_ctl[strand];
             const int stride = g.slots >> 1;
-            int i = slot >> 1;
+            int left = n_mine > (slot >> 1) ? (n_mine - (slot >> 1) + stride - 1) / stride : 0;
+            const SwarRecord *at = strand ? s_rec + (T - 1 - (slot >> 1)) : s_rec + (slot >> 1);
+            const int step = strand ? -stride : stride;
             Stage sa{}, sb{};
-            if (i < n_mine) fetch(i, sa);
-            while (i < n_mine) {
+            if (left > 0) fetch(at, sa);
+            while (left > 0) {
+                at += step;
                 sb.sh = 0;
-                if (i + stride < n_mine) fetch(i + stride, sb);
+                if (left > 1) fetch(at, sb);
                 count(sa);
-                i += stride;
-                if (i >= n_mine) break;
+                if (--left == 0) break;
+                at += step;
                 sa.sh = 0;
-                if (i + stride < n_mine) fetch(i + stride, sa);
+                if (left > 1) fetch(at, sa);
                 count(sb);
-                i += stride;
+                --left;
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
