@@ -123,7 +123,7 @@ struct mdg_ctx {
     int general_grid = 0;
     // bit-sliced kernel for gap-free reads; complex reads go through a per-stream work list
     bool swar_enabled = false, force_general = false;
-    int swar_max_threads = 384;
+    int swar_max_threads = 512, swar_reads = 1, swar_blocks_per_sm = 1;
     mdg::SwarGeom swar{};
     size_t swar_smem = 0;
     std::vector<WorkList> worklists;
@@ -280,11 +280,22 @@ int next_kernel_events(mdg_ctx *ctx, cudaEvent_t *start, cudaEvent_t *stop)
 typedef void (*SwarKernel)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::SwarGeom, uint32_t *,
                            unsigned long long *);
 
-// variants: with / without the quality mask, compiled for blocks of up to 384 (150 registers) or 512 threads
-SwarKernel swar_kernel(bool qual, int max_threads)
+// variants: with / without the quality mask; blocks of up to `max_threads` threads, each counting `reads`
+// reads per loop iteration (fewer threads leave more registers for more reads in flight)
+SwarKernel swar_kernel(bool qual, int max_threads, int reads)
 {
-    if (max_threads <= 384) return qual ? mdg::count_swar_kernel<true, 384> : mdg::count_swar_kernel<false, 384>;
-    return qual ? mdg::count_swar_kernel<true, 512> : mdg::count_swar_kernel<false, 512>;
+#define MDG_VARIANT(T, R) \
+    if (max_threads == T && reads == R) return qual ? mdg::count_swar_kernel<true, T, R> : mdg::count_swar_kernel<false, T, R>;
+    MDG_VARIANT(512, 1)
+    MDG_VARIANT(512, 2)
+    MDG_VARIANT(384, 2)
+    MDG_VARIANT(384, 3)
+    MDG_VARIANT(256, 3)
+#undef MDG_VARIANT
+    // two co-resident blocks per SM: one stages its tile while the other counts
+    if (max_threads == 256 && reads == 1) return qual ? mdg::count_swar_kernel<true, 256, 1, 2> : mdg::count_swar_kernel<false, 256, 1, 2>;
+    if (max_threads == 256 && reads == 2) return qual ? mdg::count_swar_kernel<true, 256, 2, 2> : mdg::count_swar_kernel<false, 256, 2, 2>;
+    return nullptr;
 }
 
 int worklist_for(mdg_ctx *ctx, cudaStream_t stream, int64_t n_reads, WorkList **out)
@@ -328,10 +339,10 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         if (rc) return rc;
         MDG_CUDA(ctx, cudaMemsetAsync(wl->count, 0, 8, stream));
         const int64_t n_tiles = (b.n_reads + ctx->swar.tile - 1) / ctx->swar.tile;
-        const int grid = (int)std::min<int64_t>(ctx->sm_count, n_tiles);
+        const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->swar_blocks_per_sm, n_tiles);
         const bool q = b.qual && p.min_qual > 0;
         void (*kernel)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::SwarGeom, uint32_t *,
-                       unsigned long long *) = swar_kernel(q, ctx->swar_max_threads);
+                       unsigned long long *) = swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads);
         kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables, ctx->swar, wl->reads,
                                                                      wl->count);
         MDG_CUDA(ctx, cudaGetLastError());
@@ -483,15 +494,28 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
     {
         mdg::SwarGeom &g = ctx->swar;
         g.words = (cfg->around + cfg->length + 7) / 8;
-        const char *tenv = getenv("MDG_SWAR_THREADS");
-        ctx->swar_max_threads = tenv && atoi(tenv) <= 384 ? 384 : 512;
+        // block size / reads per iteration; MDG_SWAR_VARIANT="threads,reads" picks another compiled variant
+        ctx->swar_max_threads = 512;
+        ctx->swar_reads = 1;
+        if (const char *venv = getenv("MDG_SWAR_VARIANT")) {
+            int vt = 0, vr = 0;
+            if (sscanf(venv, "%d,%d", &vt, &vr) == 2 && swar_kernel(false, vt, vr)) {
+                ctx->swar_max_threads = vt;
+                ctx->swar_reads = vr;
+            }
+        }
         g.slots = (ctx->swar_max_threads / (2 * g.words)) & ~1;
         if (nl == 1 && g.slots >= 2 && cfg->around <= 64 && cfg->length < 32768) {
             g.work_threads = 2 * g.words * g.slots;
             g.threads = (g.work_threads + 31) / 32 * 32;
+            const char *tile_env = getenv("MDG_SWAR_TILE");
+            const int tile_max = tile_env ? atoi(tile_env) : 2048;
+            const int blocks_per_sm = ctx->swar_max_threads == 256 && ctx->swar_reads <= 2 ? 2 : 1;
+            ctx->swar_blocks_per_sm = blocks_per_sm;
             for (int tile : {2048, 1024, 512}) {
+                if (tile > tile_max) continue;
                 const size_t bytes = ((size_t)mdg::SWAR_L2_WORDS * g.threads + (size_t)tile * 5 + 4 * MDG_LG_SMEM_BINS + 4 * L + 4) * 4;
-                if (bytes <= ctx->smem_optin) {
+                if (bytes * blocks_per_sm + 1024 * blocks_per_sm <= ctx->smem_optin + (blocks_per_sm > 1 ? 1024 : 0)) {
                     g.tile = tile;
                     ctx->swar_smem = bytes;
                     break;
@@ -499,7 +523,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             }
             if (g.tile) {
                 for (bool q : {false, true})
-                    MDG_CREATE_CUDA(cudaFuncSetAttribute(swar_kernel(q, ctx->swar_max_threads),
+                    MDG_CREATE_CUDA(cudaFuncSetAttribute(swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads),
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->swar_smem));
                 ctx->swar_enabled = true;
             }

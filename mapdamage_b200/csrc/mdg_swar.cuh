@@ -78,8 +78,10 @@ __device__ __forceinline__ uint32_t one_hot_nibbles(uint32_t x)
 __device__ __forceinline__ uint32_t low_nibbles(int bits) { return __funnelshift_lc(0xffffffffu, 0u, max(bits, 0)); }
 
 // thread t = ((slot * 2) + anchor) * words + word
-template <bool kQual, int kMaxThreads>
-__global__ void __launch_bounds__(kMaxThreads, 1)
+// kReads = reads a thread counts per loop iteration: their instruction streams interleave (ILP) and their
+// class masks are summed before they touch the counters (one 3-input add per class and pair of reads).
+template <bool kQual, int kMaxThreads, int kReads, int kBlocksPerSm = 1>
+__global__ void __launch_bounds__(kMaxThreads, kBlocksPerSm)
 count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom g, uint32_t *__restrict__ worklist,
                   unsigned long long *__restrict__ work_count)
 {
@@ -228,6 +230,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         st.aligned = (low_nibbles(z4 + s4 * v) ^ flip_a) & side_a;
         st.flank = (low_nibbles(z4 - s4 * f) ^ ~flip_a) & ~side_a;
         st.sh = 0;
+        st.w0 = st.w1 = st.r0 = st.r1 = 0;
         if (st.aligned | st.flank) {
             // nibble 0 of this word, relative to the first aligned base
             const int off = cbase + amul * (int)(rec.cols & 0x7FFF);
@@ -256,21 +259,17 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             }
         }
     };
-    auto count = [&](const Stage &st) {
-        if (!st.sh) return;  // no nibble of this word counts for this read
-        uint32_t y = __funnelshift_r(st.r0, st.r1, st.sh >> 8);
-        uint32_t x = __funnelshift_r(natural_order(st.w0), natural_order(st.w1), st.sh);
+    // the read / reference words of one staged read, masked down to the nibbles that count
+    auto masked_words = [&](const Stage &st, uint32_t &x, uint32_t &xc, uint32_t &y) {
+        y = __funnelshift_r(st.r0, st.r1, st.sh >> 8);
+        x = __funnelshift_r(natural_order(st.w0), natural_order(st.w1), st.sh);
         // a column counts only when the read base is A/C/G/T (statistics.py:27); the reference side is
         // already 0 for anything that is not A/C/G/T.  Flank nibbles carry the reference base alone
         // (DNAComposition.update_reference, statistics.py:85-93).
         const uint32_t valid = (one_hot_nibbles(x) * 15u) & st.aligned;
         x &= valid;
         y &= valid | st.flank;
-        // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
-        acc0[4] += x & K1;
-        acc0[5] += (x >> 1) & K1;
-        acc0[6] += (x >> 2) & K1;
-        acc0[7] += (x >> 3) & K1;
+        xc = x;  // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
         if (kQual) {
             if (st.sh & 0x20000u) {
                 // align_with_qual, align.py:67-71: bases below --min-basequal become N on both sides
@@ -288,25 +287,50 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                 y &= keep;
             }
         }
-        const uint32_t y1 = y >> 1, y2 = y >> 2, y3 = y >> 3;
-        const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
-        acc0[0] += y & K1;
-        acc0[1] += y1 & K1;
-        acc0[2] += y2 & K1;
-        acc0[3] += y3 & K1;
-        acc0[8] += y & x1 & K1;    // A>C
-        acc0[9] += y & x2 & K1;    // A>G
-        acc0[10] += y & x3 & K1;   // A>T
-        acc0[11] += y1 & x & K1;   // C>A
-        acc0[12] += y1 & x2 & K1;  // C>G
-        acc0[13] += y1 & x3 & K1;  // C>T
-        acc0[14] += y2 & x & K1;   // G>A
-        acc0[15] += y2 & x1 & K1;  // G>C
-        acc0[16] += y2 & x3 & K1;  // G>T
-        acc0[17] += y3 & x & K1;   // T>A
-        acc0[18] += y3 & x1 & K1;  // T>C
-        acc0[19] += y3 & x2 & K1;  // T>G
-        if (++n0 == 15) spill0();
+    };
+    auto count = [&](const Stage (&st)[kReads]) {
+        uint32_t x[kReads], xc[kReads], y[kReads];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < kReads; ++r) {
+            any = any || st[r].sh != 0;
+            masked_words(st[r], x[r], xc[r], y[r]);  // a stage with sh == 0 holds zero words and zero masks
+        }
+        if (!any) return;  // no nibble of this word counts for these reads
+#define MDG_CLASS(c, expr)                                     \
+        {                                                      \
+            uint32_t sum = 0;                                  \
+            _Pragma("unroll") for (int r = 0; r < kReads; ++r) \
+            {                                                  \
+                const uint32_t X = x[r], Y = y[r], XC = xc[r]; \
+                (void)X; (void)Y; (void)XC;                    \
+                sum += (expr) & K1;                            \
+            }                                                  \
+            acc0[c] += sum;                                    \
+        }
+        MDG_CLASS(4, XC)
+        MDG_CLASS(5, XC >> 1)
+        MDG_CLASS(6, XC >> 2)
+        MDG_CLASS(7, XC >> 3)
+        MDG_CLASS(0, Y)
+        MDG_CLASS(1, Y >> 1)
+        MDG_CLASS(2, Y >> 2)
+        MDG_CLASS(3, Y >> 3)
+        MDG_CLASS(8, Y & (X >> 1))          // A>C
+        MDG_CLASS(9, Y & (X >> 2))          // A>G
+        MDG_CLASS(10, Y & (X >> 3))         // A>T
+        MDG_CLASS(11, (Y >> 1) & X)         // C>A
+        MDG_CLASS(12, (Y >> 1) & (X >> 2))  // C>G
+        MDG_CLASS(13, (Y >> 1) & (X >> 3))  // C>T
+        MDG_CLASS(14, (Y >> 2) & X)         // G>A
+        MDG_CLASS(15, (Y >> 2) & (X >> 1))  // G>C
+        MDG_CLASS(16, (Y >> 2) & (X >> 3))  // G>T
+        MDG_CLASS(17, (Y >> 3) & X)         // T>A
+        MDG_CLASS(18, (Y >> 3) & (X >> 1))  // T>C
+        MDG_CLASS(19, (Y >> 3) & (X >> 2))  // T>G
+#undef MDG_CLASS
+        n0 += kReads;
+        if (n0 > 15 - kReads) spill0();
     };
 
     // ---- staging of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
@@ -525,19 +549,25 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             int left = n_mine > (slot >> 1) ? (n_mine - (slot >> 1) + stride - 1) / stride : 0;
             const SwarRecord *at = strand ? s_rec + (T - 1 - (slot >> 1)) : s_rec + (slot >> 1);
             const int step = strand ? -stride : stride;
-            Stage sa{}, sb{};
-            if (left > 0) fetch(at, sa);
+            const Stage nothing{};
+            auto fetch_group = [&](Stage (&st)[kReads], int have) {
+#pragma unroll
+                for (int r = 0; r < kReads; ++r) {
+                    if (r < have) fetch(at + r * step, st[r]);
+                    else st[r] = nothing;
+                }
+                at += kReads * step;
+            };
+            Stage sa[kReads], sb[kReads];
+            fetch_group(sa, left);
             while (left > 0) {
-                at += step;
-                sb.sh = 0;
-                if (left > 1) fetch(at, sb);
+                fetch_group(sb, left - kReads);
                 count(sa);
-                if (--left == 0) break;
-                at += step;
-                sa.sh = 0;
-                if (left > 1) fetch(at, sa);
+                left -= kReads;
+                if (left <= 0) break;
+                fetch_group(sa, left - kReads);
                 count(sb);
-                --left;
+                left -= kReads;
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
