@@ -123,7 +123,7 @@ struct mdg_ctx {
     int general_grid = 0;
     // bit-sliced kernel for gap-free reads; complex reads go through a per-stream work list
     bool swar_enabled = false, force_general = false;
-    int swar_max_threads = 512, swar_reads = 1, swar_blocks_per_sm = 1;
+    int swar_max_threads = 256, swar_reads = 1, swar_blocks_per_sm = 2;
     mdg::SwarGeom swar{};
     size_t swar_smem = 0;
     std::vector<WorkList> worklists;
@@ -495,7 +495,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
         mdg::SwarGeom &g = ctx->swar;
         g.words = (cfg->around + cfg->length + 7) / 8;
         // block size / reads per iteration; MDG_SWAR_VARIANT="threads,reads" picks another compiled variant
-        ctx->swar_max_threads = 512;
+        ctx->swar_max_threads = 256;  // two co-resident blocks per SM
         ctx->swar_reads = 1;
         if (const char *venv = getenv("MDG_SWAR_VARIANT")) {
             int vt = 0, vr = 0;
@@ -514,13 +514,15 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             ctx->swar_blocks_per_sm = blocks_per_sm;
             for (int tile : {2048, 1024, 512}) {
                 if (tile > tile_max) continue;
-                const size_t bytes = ((size_t)mdg::SWAR_L2_WORDS * g.threads + (size_t)tile * 5 + 4 * MDG_LG_SMEM_BINS + 4 * L + 4) * 4;
+                const size_t bytes = ((size_t)mdg::SWAR_L2_WORDS * g.threads + (size_t)tile * 5 + 4 * MDG_LG_SMEM_BINS + 4 * L + 8) * 4;
                 if (bytes * blocks_per_sm + 1024 * blocks_per_sm <= ctx->smem_optin + (blocks_per_sm > 1 ? 1024 : 0)) {
                     g.tile = tile;
                     ctx->swar_smem = bytes;
                     break;
                 }
             }
+            const char *uenv = getenv("MDG_SWAR_UNIFORM");
+            g.uniform = !(uenv && uenv[0] == '0');
             if (g.tile) {
                 for (bool q : {false, true})
                     MDG_CREATE_CUDA(cudaFuncSetAttribute(swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads),

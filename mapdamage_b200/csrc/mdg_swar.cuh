@@ -46,6 +46,7 @@ struct SwarGeom {
     int32_t threads;       // blockDim.x
     int32_t work_threads;  // 2 * words * slots
     int32_t tile;          // reads staged per iteration of the block
+    int32_t uniform;       // 1: tiles whose gap-free reads all have the same length are counted in one window per read
 };
 
 // One staged read (16 bytes), shared by both anchors.  Base indices are kept as (32-bit word, nibble)
@@ -93,31 +94,57 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
     uint32_t *const s_cx = (uint32_t *)(s_rec + T);             // [T] complex reads of the tile
     uint32_t *const s_lg = s_cx + T;                            // [kind][strand][MDG_LG_SMEM_BINS]
     uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;       // [end][strand][L]
-    uint32_t *const s_ctl = s_clip + 4 * L;                     // n_fwd, n_rev, n_cx
+    uint32_t *const s_ctl = s_clip + 4 * L;                     // n_fwd, n_rev, n_cx, min / max columns
 
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < l2_words; i += nthreads) s_l2[i] = 0;
     for (int i = tid; i < 4 * MDG_LG_SMEM_BINS + 4 * L; i += nthreads) s_lg[i] = 0;
 
-    const bool active = tid < g.work_threads;
-    const int word = tid % W, anchor = (tid / W) & 1, slot = tid / (2 * W);
-    const int strand = slot & 1;
     const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
     const uint32_t *__restrict__ ref32 = ref.words;
 
-    // Thread constants.  The window word covers positions pbase .. pbase + 7, pbase = 8 word - A; nibble i
-    // holds position pbase + i (left anchor) or pbase + 7 - i (right anchor: memory order runs towards the end).
-    // With z = the nibble index of position 0 (left) / one past it (right):
-    //   left:  aligned nibbles [z, z + v),  flank nibbles [z - f, z)      v = min(L, columns)
-    //   right: aligned nibbles [z - v, z),  flank nibbles [z, z + f)      f = flank bases on the contig
-    const int pbase = 8 * word - A;
-    const int z4 = 4 * (anchor ? pbase + 8 : -pbase);
-    const int s4 = anchor ? -4 : 4;
-    const uint32_t flip_a = anchor ? 0xffffffffu : 0u;
-    const uint32_t side_a = anchor ? low_nibbles(z4) : ~low_nibbles(z4);  // the side of z aligned nibbles are on
-    const int fshift = anchor ? 24 : 16;
-    // base offset of nibble 0 from the first aligned base: left pbase; right columns - 8 - pbase
-    const int cbase = anchor ? -8 - pbase : pbase;
+    // Thread geometry, a function of the block's mode (set_mode):
+    //   mode 0 (two anchors): thread = ((slot * 2) + anchor) * W + word.  The window word covers positions
+    //     pbase .. pbase + 7, pbase = 8 word - A; nibble i holds position pbase + i (left anchor) or
+    //     pbase + 7 - i (right anchor: memory order runs towards the end).  With z = the nibble index of
+    //     position 0 (left) / one past it (right):
+    //       left:  aligned nibbles [z, z + v),  flank nibbles [z - f, z)      v = min(L, columns)
+    //       right: aligned nibbles [z - v, z),  flank nibbles [z, z + f)      f = flank bases on the contig
+    //   mode C > 0 (every gap-free read of the tile has C columns): one window [-A, C + A) per read, thread =
+    //     slot * Wu + word; a column feeds the left-anchored table at p = column and the right-anchored one at
+    //     p = C - 1 - column when the counters are reduced, so each base is visited once instead of twice.
+    int mode = 0;
+    auto words_of = [&](int columns) { return columns ? (columns + 2 * A + 7) / 8 : W; };
+    auto slots_of = [&](int columns) { return columns ? (nthreads / words_of(columns)) & ~1 : g.slots; };
+    bool active;
+    int word, anchor, slot, strand, z4, s4, fshift, cbase, amul;
+    uint32_t flip_a, side_a;
+    auto set_mode = [&](int columns) {
+        mode = columns;
+        if (columns == 0) {
+            active = tid < g.work_threads;
+            word = tid % W;
+            anchor = (tid / W) & 1;
+            slot = tid / (2 * W);
+        } else {
+            const int mode_words = words_of(columns);
+            active = tid < mode_words * slots_of(columns);
+            word = tid % mode_words;
+            anchor = 0;
+            slot = tid / mode_words;
+        }
+        strand = slot & 1;
+        const int pbase = 8 * word - A;
+        z4 = 4 * (anchor ? pbase + 8 : -pbase);
+        s4 = anchor ? -4 : 4;
+        flip_a = anchor ? 0xffffffffu : 0u;
+        side_a = anchor ? low_nibbles(z4) : ~low_nibbles(z4);  // the side of z aligned nibbles are on
+        fshift = anchor ? 24 : 16;
+        // base offset of nibble 0 from the first aligned base: left pbase; right columns - 8 - pbase
+        cbase = anchor ? -8 - pbase : pbase;
+        amul = anchor ? 1 : 0;
+    };
+    set_mode(0);
 
     uint32_t acc0[SWAR_CLASSES];  // 8 x 4-bit counters per class
     uint32_t acc1[16];            // classes 0..7 (reference / read bases): 2 x (4 x 8-bit) counters, even / odd nibbles
@@ -165,49 +192,63 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 
     // reduces the block's private counters into the 64-bit tables (end of the kernel, and before a
     // thread's 16-bit counters could overflow)
-    const int n_cells = 2 * W * 2 * SWAR_CLASSES * 8;  // anchor, word, strand, class, nibble
     const int LA = L + A;
+    auto add_cell = [&](int canchor, int cstrand, int cls, int pos, unsigned long long sum) {
+        // window position `pos` of an anchor -> table cell; classes are complemented on the reverse strand
+        const int es = (canchor ^ cstrand) * 2 + cstrand;
+        if (pos >= 0) {
+            if (cls < 4) {
+                const int gb = cstrand ? 3 - cls : cls;
+                atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + gb) * L + pos, sum);
+            } else if (cls < 8) {
+                const int rb = cstrand ? 3 - (cls - 4) : cls - 4;
+                atomicAdd(t.dnacomp + ((size_t)es * 4 + rb) * LA + pos, sum);
+            } else {
+                int gb = (cls - 8) / 3, rb = (cls - 8) % 3;
+                rb += rb >= gb ? 1 : 0;
+                if (cstrand) { gb = 3 - gb; rb = 3 - rb; }
+                atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + 4 + 5 * gb + rb) * L + pos, sum);
+            }
+        } else if (cls < 4) {
+            const int gb = cstrand ? 3 - cls : cls;
+            atomicAdd(t.dnacomp + ((size_t)es * 4 + gb) * LA + L - pos - 1, sum);
+        }
+    };
     auto flush_block = [&]() {
         if (n0) spill0();
         if (n1) spill1();
         __syncthreads();
+        const int n_anchors = mode ? 1 : 2, mode_words = words_of(mode), mode_slots = slots_of(mode);
+        const int n_cells = n_anchors * mode_words * 2 * SWAR_CLASSES * 8;  // anchor, word, strand, class, nibble
         for (int cell = tid; cell < n_cells; cell += nthreads) {
             int rest = cell;
             const int nib = rest & 7; rest >>= 3;
             const int cls = rest % SWAR_CLASSES; rest /= SWAR_CLASSES;
             const int cstrand = rest & 1; rest >>= 1;
-            const int cword = rest % W;
-            const int canchor = rest / W;
+            const int cword = rest % mode_words;
+            const int canchor = rest / mode_words;
             const int pb = 8 * cword - A;
             const int pos = canchor ? pb + 7 - nib : pb + nib;
-            if (pos >= L || pos < -A || (pos < 0 && cls >= 4)) continue;
+            if (pos < -A || (pos < 0 && cls >= 4)) continue;
+            if (mode ? pos >= mode + A || (pos >= mode && cls >= 4) : pos >= L) continue;
             // 16-bit lane holding (cls, nib): 8-bit lane bl = nib >> 1 of acc1[2 * cls + (nib & 1)]
             const int w1 = 2 * cls + (nib & 1), bl = nib >> 1;
             const int w2 = 2 * w1 + (bl & 1), half = bl >> 1;
             unsigned long long sum = 0;
-            for (int cslot = cstrand; cslot < g.slots; cslot += 2) {
-                const uint32_t v = s_l2[w2 * nthreads + (cslot * 2 + canchor) * W + cword];
+            for (int cslot = cstrand; cslot < mode_slots; cslot += 2) {
+                const uint32_t v = s_l2[w2 * nthreads + (cslot * n_anchors + canchor) * mode_words + cword];
                 sum += half ? v >> 16 : v & 0xFFFFu;
             }
             if (!sum) continue;
-            const int end = canchor ^ cstrand;
-            const int es = end * 2 + cstrand;
-            if (pos >= 0) {
-                if (cls < 4) {
-                    const int gb = cstrand ? 3 - cls : cls;
-                    atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + gb) * L + pos, sum);
-                } else if (cls < 8) {
-                    const int rb = cstrand ? 3 - (cls - 4) : cls - 4;
-                    atomicAdd(t.dnacomp + ((size_t)es * 4 + rb) * LA + pos, sum);
-                } else {
-                    int gb = (cls - 8) / 3, rb = (cls - 8) % 3;
-                    rb += rb >= gb ? 1 : 0;
-                    if (cstrand) { gb = 3 - gb; rb = 3 - rb; }
-                    atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + 4 + 5 * gb + rb) * L + pos, sum);
-                }
+            if (!mode) {
+                add_cell(canchor, cstrand, cls, pos, sum);
+            } else if (pos < 0) {
+                add_cell(0, cstrand, cls, pos, sum);  // left flank
+            } else if (pos >= mode) {
+                add_cell(1, cstrand, cls, mode - 1 - pos, sum);  // right flank at distance pos - C + 1
             } else {
-                const int gb = cstrand ? 3 - cls : cls;
-                atomicAdd(t.dnacomp + ((size_t)es * 4 + gb) * LA + L - pos - 1, sum);
+                if (pos < L) add_cell(0, cstrand, cls, pos, sum);
+                if (mode - 1 - pos < L) add_cell(1, cstrand, cls, mode - 1 - pos, sum);
             }
         }
         __syncthreads();
@@ -215,20 +256,29 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         __syncthreads();
     };
     // worst case every read of a tile lands on one strand: T / (slots / 2) reads per thread per tile
+    // (the uniform mode never has fewer slots than the two-anchor mode it replaces)
     const int flush_period = max(1, 60000 / ((T + (g.slots >> 1) - 1) / (g.slots >> 1)));
     int tiles_since_flush = 0;
+    bool dirty = false;  // counters hold counts of the current mode
 
     // ---- per-thread stages of the software pipeline: loads of read i+1 fly while read i is counted ----
     struct Stage {
         uint32_t w0, w1, r0, r1, aligned, flank, sh;
         uint32_t qa, qm, qz;
     };
-    const int amul = anchor ? 1 : 0;
     auto fetch = [&](const SwarRecord *at, Stage &st) {
         const SwarRecord rec = *at;
         const int v = (int)(rec.misc & 0xFFFF), f = (int)((rec.cols >> fshift) & 0xFF);
-        st.aligned = (low_nibbles(z4 + s4 * v) ^ flip_a) & side_a;
-        st.flank = (low_nibbles(z4 - s4 * f) ^ ~flip_a) & ~side_a;
+        if (mode) {
+            // aligned nibbles [z, zr), zr = z + C; left flank nibbles [z - lf, z); right flank nibbles [zr, zr + rf)
+            const int zr4 = z4 + 4 * mode;
+            const uint32_t below_z = low_nibbles(z4), below_zr = low_nibbles(zr4);
+            st.aligned = below_zr & ~below_z;
+            st.flank = (below_z & ~low_nibbles(z4 - 4 * f)) | (low_nibbles(zr4 + 4 * (int)(rec.cols >> 24)) & ~below_zr);
+        } else {
+            st.aligned = (low_nibbles(z4 + s4 * v) ^ flip_a) & side_a;
+            st.flank = (low_nibbles(z4 - s4 * f) ^ ~flip_a) & ~side_a;
+        }
         st.sh = 0;
         st.w0 = st.w1 = st.r0 = st.r1 = 0;
         if (st.aligned | st.flank) {
@@ -339,9 +389,10 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         int32_t tid_ref, pos;
         bool live;
     };
-    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, SwarRecord &rec) {
+    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, uint32_t &columns, SwarRecord &rec) {
         kind = 0;
         rstrand = 0;
+        columns = 0;
         if (!h.live || (h.flag & FILTERED_FLAGS)) return;
         if (h.lib >= (uint32_t)p.n_lib) {
             atomicCAS(t.error_flag, 0, DATA_ERR_LIB);
@@ -384,6 +435,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                  ref0 < (1ull << 33);
         kind = simple ? 1 : 2;
         if (!simple) return;
+        columns = cols;
         const int64_t aend = pos + cols;
         const uint32_t lf = (uint32_t)min((int64_t)A, pos);
         const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
@@ -475,7 +527,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         if (live1) prefetch_bases(boff1, coff1);
     }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (tid < 3) s_ctl[tid] = 0;
+        if (tid < 5) s_ctl[tid] = tid == 3 ? 0xffffffffu : 0u;  // n_fwd, n_rev, n_cx, min columns, max columns
         __syncthreads();
 
         const int64_t tile_start = tile * T;
@@ -503,8 +555,17 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             for (int u = 0; u < PREP; ++u) {
                 const int q = q0 + u * nthreads + tid;
                 int kind, rstrand;
+                uint32_t columns;
                 SwarRecord rec{};
-                stage_read(h[u], tile_start + q, kind, rstrand, rec);
+                stage_read(h[u], tile_start + q, kind, rstrand, columns, rec);
+                if (g.uniform) {
+                    const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
+                    const uint32_t hi = __reduce_max_sync(0xffffffffu, kind == 1 ? columns : 0u);
+                    if (lane == 0 && hi) {
+                        atomicMin(s_ctl + 3, lo);
+                        atomicMax(s_ctl + 4, hi);
+                    }
+                }
                 // warp-aggregated appends to the three lists
                 const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
@@ -535,6 +596,23 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             for (uint32_t i = lane; i < n_cx; i += 32) worklist[base + i] = s_cx[i];
         }
 
+        // ---- one window per read when every gap-free read of the tile has the same length ----
+        {
+            int want = 0;
+            const uint32_t lo = s_ctl[3], hi = s_ctl[4];
+            if (g.uniform && lo == hi && hi > 0) {
+                const int words = ((int)hi + 2 * A + 7) / 8;
+                if (words < 2 * W && nthreads / words >= 2) want = (int)hi;
+            }
+            if (want != mode) {
+                if (dirty) flush_block();  // the counters are laid out by mode
+                set_mode(want);
+                dirty = false;
+                tiles_since_flush = 0;
+            }
+            dirty = dirty || s_ctl[0] + s_ctl[1] > 0;
+        }
+
         // ---- pull the tile after next towards L2 while this one is counted ----
         uint32_t ahead_boff = 0, ahead_coff = 0;
         const bool ahead_live = prefetch_headers(tile + 2 * (int64_t)gridDim.x, ahead_boff, ahead_coff);
@@ -545,7 +623,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             // front of s_rec, reverse reads from the back).  Two stages swap roles, so that the loads of
             // the next read are in flight while this one is counted and no register copy waits on a load.
             const int n_mine = (int)s_ctl[strand];
-            const int stride = g.slots >> 1;
+            const int stride = slots_of(mode) >> 1;
             int left = n_mine > (slot >> 1) ? (n_mine - (slot >> 1) + stride - 1) / stride : 0;
             const SwarRecord *at = strand ? s_rec + (T - 1 - (slot >> 1)) : s_rec + (slot >> 1);
             const int step = strand ? -stride : stride;
@@ -575,6 +653,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         if (++tiles_since_flush == flush_period) {
             flush_block();
             tiles_since_flush = 0;
+            dirty = false;
         }
     }
 
