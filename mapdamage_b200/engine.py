@@ -184,12 +184,12 @@ class DamageEngine:
     def h2d_bytes(self, batch, rescale=False, compact=True):
         """Bytes ``count`` (or ``rescale``) copies to the device for ``batch`` (see ``copy_batch``)."""
         n = batch.n
-        drop = batch.droppable() if compact and not rescale else ()
+        drop = batch.droppable() if compact else ()
         total = n * (2 + 4 + 4 + 4) + batch.cigar.nbytes + batch.total_bases // 2  # flag, tid, pos, l_seq, cigar, seq4
         total += sum(size for name, size in (("lib", 2 * n), ("tlen", 4 * n), ("base_off", 4 * n),
                                              ("cigar_off", 4 * (n + 1))) if name not in drop)
         if rescale:
-            total += 8 * n
+            total += sum(4 * n for name in ("mtid", "mpos") if name not in drop)
         if batch.qual is not None and (rescale or self.min_qual > 0):
             total += batch.total_bases
         return total
@@ -246,10 +246,10 @@ class DamageEngine:
         self._check(self._lib.mdg_set_rescale_model(
             self._ctx, lut.ctypes.data, inc.ctypes.data, model.len5p, model.len3p))
 
-    def rescale(self, batch, out=None):
+    def rescale(self, batch, out=None, compact=True):
         """Queues the rescale of one batch; returns ``(qual_out, mr, status)`` arrays
         that are valid after :meth:`sync`."""
-        s = batch_struct(batch)
+        s = batch_struct(batch, compact)
         if out is None:
             out = (np.empty(max(1, s.n_bases), dtype=np.uint8), np.empty(max(1, batch.n), dtype=np.float32),
                    np.empty(max(1, batch.n), dtype=np.uint8))
