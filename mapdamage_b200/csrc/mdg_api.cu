@@ -87,6 +87,9 @@ struct WorkList {
     uint32_t *reads = nullptr;
     unsigned long long *count = nullptr;
     int64_t cap = 0;
+    // several libraries: reads grouped by library
+    uint32_t *by_library = nullptr;         // [cap]
+    unsigned long long *lib_scratch = nullptr;  // counts [n_lib] | offsets [n_lib + 1] | cursors [n_lib]
 };
 
 struct mdg_dev_batch {
@@ -278,7 +281,7 @@ int next_kernel_events(mdg_ctx *ctx, cudaEvent_t *start, cudaEvent_t *stop)
 }
 
 typedef void (*SwarKernel)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::SwarGeom, uint32_t *,
-                           unsigned long long *);
+                           unsigned long long *, mdg::SwarSubset);
 
 // variants: with / without the quality mask; blocks of up to `max_threads` threads, each counting `reads`
 // reads per loop iteration (fewer threads leave more registers for more reads in flight)
@@ -308,6 +311,8 @@ int worklist_for(mdg_ctx *ctx, cudaStream_t stream, int64_t n_reads, WorkList **
         wl = &ctx->worklists.back();
         wl->stream = stream;
         MDG_CUDA(ctx, cudaMalloc(&wl->count, 8));
+        if (ctx->cfg.n_libraries > 1)
+            MDG_CUDA(ctx, cudaMalloc(&wl->lib_scratch, ((size_t)3 * ctx->cfg.n_libraries + 1) * 8));
     }
     if (wl->cap < n_reads) {
         MDG_CUDA(ctx, cudaStreamSynchronize(stream));
@@ -315,6 +320,11 @@ int worklist_for(mdg_ctx *ctx, cudaStream_t stream, int64_t n_reads, WorkList **
         wl->reads = nullptr;
         wl->cap = 0;
         MDG_CUDA(ctx, cudaMalloc(&wl->reads, (size_t)n_reads * 4));
+        if (ctx->cfg.n_libraries > 1) {
+            cudaFree(wl->by_library);
+            wl->by_library = nullptr;
+            MDG_CUDA(ctx, cudaMalloc(&wl->by_library, (size_t)n_reads * 4));
+        }
         wl->cap = n_reads;
     }
     *out = wl;
@@ -341,10 +351,34 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         const int64_t n_tiles = (b.n_reads + ctx->swar.tile - 1) / ctx->swar.tile;
         const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->swar_blocks_per_sm, n_tiles);
         const bool q = b.qual && p.min_qual > 0;
-        void (*kernel)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::SwarGeom, uint32_t *,
-                       unsigned long long *) = swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads);
-        kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables, ctx->swar, wl->reads,
-                                                                     wl->count);
+        SwarKernel kernel = swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads);
+        const int nl = ctx->cfg.n_libraries;
+        if (nl == 1) {
+            kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables, ctx->swar, wl->reads,
+                                                                         wl->count, mdg::SwarSubset{nullptr, nullptr, 0});
+            ctx->launches += 1;
+        } else {
+            // group the reads by library, then one pass per library into that library's tables
+            unsigned long long *counts = wl->lib_scratch, *offsets = counts + nl, *cursors = offsets + nl + 1;
+            MDG_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)nl * 8, stream));
+            const int pgrid = (int)std::min<int64_t>((b.n_reads + 1023) / 1024, (int64_t)ctx->sm_count * 8);
+            mdg::library_count_kernel<<<pgrid, 256, (size_t)nl * 4, stream>>>(b, nl, counts, ctx->count_tables.error_flag);
+            mdg::library_offsets_kernel<<<1, 256, 0, stream>>>(counts, nl, offsets, cursors);
+            mdg::library_scatter_kernel<<<(unsigned)((b.n_reads + 1023) / 1024), 256, (size_t)nl * 8, stream>>>(b, nl, cursors,
+                                                                                                                wl->by_library);
+            MDG_CUDA(ctx, cudaGetLastError());
+            const size_t L = ctx->cfg.length, A = ctx->cfg.around;
+            for (int lib = 0; lib < nl; ++lib) {
+                mdg::CountTables tl = ctx->count_tables;
+                tl.misincorp += (size_t)lib * 4 * MDG_N_CLASSES * L;
+                tl.dnacomp += (size_t)lib * 16 * (L + A);
+                tl.lghist += (size_t)lib * 4 * ctx->cfg.lg_bins;
+                mdg::CountParams pl = p;
+                kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, pl, tl, ctx->swar, wl->reads, wl->count,
+                                                                             mdg::SwarSubset{wl->by_library, offsets, lib});
+            }
+            ctx->launches += 3 + nl;
+        }
         MDG_CUDA(ctx, cudaGetLastError());
         // reads with indels / skips: the general kernel over the work list (returns at once when it is empty)
         const int ggrid = (int)std::min<int64_t>(ctx->general_grid, (b.n_reads + 7) / 8);
@@ -355,7 +389,7 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             mdg::count_general_kernel<false><<<ggrid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables, wl->reads,
                                                                         wl->count);
         MDG_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 2;
+        ctx->launches += 1;
     } else {
         int grid = (int)std::min<int64_t>(ctx->general_grid, (b.n_reads + 7) / 8);
         if (grid < 1) grid = 1;
@@ -505,7 +539,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             }
         }
         g.slots = (ctx->swar_max_threads / (2 * g.words)) & ~1;
-        if (nl == 1 && g.slots >= 2 && cfg->around <= 64 && cfg->length < 32768) {
+        if (nl <= mdg::PARTITION_MAX_LIBS && g.slots >= 2 && cfg->around <= 64 && cfg->length < 32768) {
             g.work_threads = 2 * g.words * g.slots;
             g.threads = (g.work_threads + 31) / 32 * 32;
             const char *tile_env = getenv("MDG_SWAR_TILE");
@@ -567,6 +601,8 @@ void mdg_destroy(mdg_ctx *ctx)
     for (auto &w : ctx->worklists) {
         cudaFree(w.reads);
         cudaFree(w.count);
+        cudaFree(w.by_library);
+        cudaFree(w.lib_scratch);
     }
     for (cudaEvent_t e : ctx->kernel_events) cudaEventDestroy(e);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);

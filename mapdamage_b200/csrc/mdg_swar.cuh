@@ -78,13 +78,21 @@ __device__ __forceinline__ uint32_t one_hot_nibbles(uint32_t x)
 // the low n nibbles, n = bits / 4 clamped to [0, 8]
 __device__ __forceinline__ uint32_t low_nibbles(int bits) { return __funnelshift_lc(0xffffffffu, 0u, max(bits, 0)); }
 
+// With several libraries the kernel runs once per library over that library's reads (partition_by_library):
+// the thread-private counters know nothing of libraries, the tables `t` points at are that library's.
+struct SwarSubset {
+    const uint32_t *list;               // read indices grouped by library, or null: every read of the batch
+    const unsigned long long *offsets;  // [n_lib + 1] into list
+    int32_t lib;
+};
+
 // thread t = ((slot * 2) + anchor) * words + word
 // kReads = reads a thread counts per loop iteration: their instruction streams interleave (ILP) and their
 // class masks are summed before they touch the counters (one 3-input add per class and pair of reads).
 template <bool kQual, int kMaxThreads, int kReads, int kBlocksPerSm = 1>
 __global__ void __launch_bounds__(kMaxThreads, kBlocksPerSm)
 count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom g, uint32_t *__restrict__ worklist,
-                  unsigned long long *__restrict__ work_count)
+                  unsigned long long *__restrict__ work_count, SwarSubset sub)
 {
     extern __shared__ uint32_t smem[];
     const int nthreads = g.threads, T = g.tile, L = p.L, A = p.A, W = g.words;
@@ -102,6 +110,8 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 
     const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
     const uint32_t *__restrict__ ref32 = ref.words;
+    const uint32_t *const subset = sub.list ? sub.list + sub.offsets[sub.lib] : nullptr;
+    const int64_t n_todo = sub.list ? (int64_t)(sub.offsets[sub.lib + 1] - sub.offsets[sub.lib]) : b.n_reads;
 
     // Thread geometry, a function of the block's mode (set_mode):
     //   mode 0 (two anchors): thread = ((slot * 2) + anchor) * W + word.  The window word covers positions
@@ -385,7 +395,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 
     // ---- staging of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
     struct Header {
-        uint32_t flag, lib, l_seq, boff, c0, c1, cig0;
+        uint32_t index, flag, lib, l_seq, boff, c0, c1, cig0;
         int32_t tid_ref, pos;
         bool live;
     };
@@ -398,6 +408,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             atomicCAS(t.error_flag, 0, DATA_ERR_LIB);
             return;
         }
+        if (subset && h.lib != (uint32_t)sub.lib) return;  // cannot happen: the list is grouped by library
         if (h.tid_ref < 0 || h.tid_ref >= ref.n_contigs) {
             atomicCAS(t.error_flag, 0, DATA_ERR_TID);
             return;
@@ -467,7 +478,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                 const unsigned long long at = atomicAdd(t.lg_overflow_count, 1ull);
                 if ((int64_t)at < t.lg_overflow_cap) {
                     int32_t *row = t.lg_overflow_rows + at * 4;
-                    row[0] = 0; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
+                    row[0] = sub.list ? sub.lib : 0; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
                 }
             }
         }
@@ -518,8 +529,8 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
     };
 
     constexpr int PREP = 4;  // reads staged per thread with their loads in flight together
-    const int64_t n_tiles = (b.n_reads + T - 1) / T;
-    {   // the block's first two tiles have nobody to prefetch them
+    const int64_t n_tiles = (n_todo + T - 1) / T;
+    if (!subset) {  // the block's first two tiles have nobody to prefetch them
         uint32_t boff0 = 0, coff0 = 0, boff1 = 0, coff1 = 0;
         const bool live0 = prefetch_headers(blockIdx.x, boff0, coff0);
         const bool live1 = prefetch_headers(blockIdx.x + (int64_t)gridDim.x, boff1, coff1);
@@ -536,8 +547,9 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 #pragma unroll
             for (int u = 0; u < PREP; ++u) {
                 const int q = q0 + u * nthreads + tid;
-                const int64_t r = tile_start + q;
-                h[u].live = q < T && r < b.n_reads;
+                h[u].live = q < T && tile_start + q < n_todo;
+                const int64_t r = !h[u].live ? 0 : subset ? (int64_t)subset[tile_start + q] : tile_start + q;
+                h[u].index = (uint32_t)r;
                 if (h[u].live) {
                     h[u].flag = b.flag[r];
                     h[u].lib = b.lib[r];
@@ -557,7 +569,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                 int kind, rstrand;
                 uint32_t columns;
                 SwarRecord rec{};
-                stage_read(h[u], tile_start + q, kind, rstrand, columns, rec);
+                stage_read(h[u], h[u].index, kind, rstrand, columns, rec);
                 if (g.uniform) {
                     const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
                     const uint32_t hi = __reduce_max_sync(0xffffffffu, kind == 1 ? columns : 0u);
@@ -578,7 +590,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
                         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
                         if (mine) {
                             const uint32_t at = base + __popc(m & lt);
-                            if (which == 2) s_cx[at] = (uint32_t)(tile_start + q);
+                            if (which == 2) s_cx[at] = h[u].index;
                             else s_rec[which == 0 ? at : T - 1 - at] = rec;
                         }
                     }
@@ -615,7 +627,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
 
         // ---- pull the tile after next towards L2 while this one is counted ----
         uint32_t ahead_boff = 0, ahead_coff = 0;
-        const bool ahead_live = prefetch_headers(tile + 2 * (int64_t)gridDim.x, ahead_boff, ahead_coff);
+        const bool ahead_live = !subset && prefetch_headers(tile + 2 * (int64_t)gridDim.x, ahead_boff, ahead_coff);
 
         // ---- the counting loop: two stages that swap roles, so no register copy waits on a load ----
         if (active) {
@@ -666,6 +678,68 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         const uint32_t v = s_clip[i];
         if (v) atomicAdd(t.misincorp + ((size_t)(i / L) * MDG_N_CLASSES + MDG_CLASS_SOFTCLIP) * L + i % L, (unsigned long long)v);
     }
+}
+
+// ---- reads grouped by library: list[offsets[l] .. offsets[l + 1]) = indices of the reads of library l ----
+constexpr int PARTITION_MAX_LIBS = 2048;
+
+__global__ void __launch_bounds__(256) library_count_kernel(DevBatch b, int n_lib, unsigned long long *counts, int32_t *error_flag)
+{
+    extern __shared__ uint32_t s_hist[];
+    for (int i = threadIdx.x; i < n_lib; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t lib = b.lib[r];
+        if (lib < (uint32_t)n_lib) atomicAdd(s_hist + lib, 1u);
+        else atomicCAS(error_flag, 0, DATA_ERR_LIB);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_lib; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(counts + i, (unsigned long long)s_hist[i]);
+}
+
+// offsets = exclusive scan of counts; cursors start at the offsets.  One block.
+__global__ void __launch_bounds__(256) library_offsets_kernel(const unsigned long long *counts, int n_lib, unsigned long long *offsets,
+                                                              unsigned long long *cursors)
+{
+    if (threadIdx.x == 0) {
+        unsigned long long at = 0;
+        for (int i = 0; i < n_lib; ++i) {
+            offsets[i] = cursors[i] = at;
+            at += counts[i];
+        }
+        offsets[n_lib] = at;
+    }
+}
+
+// each block reserves one range per library for its 1024 reads, then hands out places within it
+__global__ void __launch_bounds__(256) library_scatter_kernel(DevBatch b, int n_lib, unsigned long long *cursors, uint32_t *list)
+{
+    extern __shared__ uint32_t s_part[];  // [n_lib] counts, then [n_lib] bases (low 32 bits suffice: list < 2^31 entries)
+    uint32_t *s_count = s_part, *s_base = s_part + n_lib;
+    const int64_t first = (int64_t)blockIdx.x * 1024;
+    for (int i = threadIdx.x; i < n_lib; i += blockDim.x) s_count[i] = 0;
+    __syncthreads();
+    uint32_t my_lib[4], my_rank[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int64_t r = first + u * 256 + threadIdx.x;
+        my_lib[u] = 0xffffffffu;
+        if (r < b.n_reads) {
+            const uint32_t lib = b.lib[r];
+            if (lib < (uint32_t)n_lib) {
+                my_lib[u] = lib;
+                my_rank[u] = atomicAdd(s_count + lib, 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_lib; i += blockDim.x)
+        s_base[i] = s_count[i] ? (uint32_t)atomicAdd(cursors + i, (unsigned long long)s_count[i]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (my_lib[u] != 0xffffffffu) list[s_base[my_lib[u]] + my_rank[u]] = (uint32_t)(first + u * 256 + threadIdx.x);
 }
 
 // Genome as uploaded (0..3 = A,C,G,T, anything else) -> one-hot nibbles (1,2,4,8; 0 = not a base), in place.
