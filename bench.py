@@ -44,6 +44,7 @@ UNIT = "reads/s"
 LENGTH, AROUND = 70, 10
 READ_LEN = 100
 REF_BASES = 1_000_000
+N_LIBS_C3 = 2
 # 15 B of record fields + 4 B per CIGAR op + packed read + packed reference span with flanks
 ALGO_BYTES_PER_READ = 15 + 4 * 1 + (READ_LEN + 1) // 2 + (READ_LEN + 2 * AROUND + 1) // 2  # = 129
 
@@ -60,6 +61,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="reads timed on the CPU oracle")
     ap.add_argument("--check-sample", type=int, default=200_000, help="reads checked against the oracle")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", choices=("c2", "c3"), default="c2",
+                    help="c2 = configs[1] (the headline); c3 = configs[2]: 50-150 bp pairs, mixed CIGARs, two libraries")
     return ap.parse_args()
 
 
@@ -210,16 +213,23 @@ def gpu_arm(args, rank, local_rank, world):
     n_batches = max(1, -(-args.reads // args.batch_reads))
     sizes = [args.reads // n_batches + (1 if i < args.reads % n_batches else 0) for i in range(n_batches)]
     cap = max(sizes)
-    engine = DamageEngine(length=LENGTH, around=AROUND, min_qual=0, n_libraries=1, lg_bins=8192,
-                          device=local_rank, n_slots=2, max_reads=cap, max_cigar_ops=cap,
-                          max_bases=cap * (READ_LEN + (READ_LEN & 1)))
+    c3 = args.workload == "c3"
+    n_lib = N_LIBS_C3 if c3 else 1
+    engine = DamageEngine(length=LENGTH, around=AROUND, min_qual=0, n_libraries=n_lib, lg_bins=8192,
+                          device=local_rank, n_slots=2, max_reads=cap + 1, max_cigar_ops=3 * cap + 3 if c3 else cap,
+                          max_bases=(cap + 1) * (152 if c3 else READ_LEN + (READ_LEN & 1)))
     reference = synth.make_reference([REF_BASES], seed=args.seed)
     engine.set_reference(reference)
     if world > 1:
         multigpu.connect(engine, dist, rank, world)
 
-    resident = [engine.synth_batch(n, seed=args.seed + 1000 * rank + i, length=(READ_LEN, READ_LEN),
-                                   with_qual=False) for i, n in enumerate(sizes)]
+    if args.workload == "c3":
+        shape = dict(length=(50, 150), mix=(7, 1, 1, 1), paired=True, n_libs=N_LIBS_C3)
+        sizes = [n + (n & 1) for n in sizes]
+    else:
+        shape = dict(length=(READ_LEN, READ_LEN))
+    resident = [engine.synth_batch(n, seed=args.seed + 1000 * rank + i, with_qual=False, **shape)
+                for i, n in enumerate(sizes)]
 
     def one_pass():
         for dev in resident:
@@ -234,7 +244,7 @@ def gpu_arm(args, rank, local_rank, world):
         import oracle
 
         sample = host0.slice(0, min(args.check_sample, host0.n))
-        want = oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192,
+        want = oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, n_lib=n_lib,
                             threads=min(8, os.cpu_count() or 1))
         engine.reset()
         engine.count(sample)
@@ -249,11 +259,17 @@ def gpu_arm(args, rank, local_rank, world):
     mis, comp, lg = engine.tables()
     total = sum(sizes)
     # every read is 100M on an N-free genome: each end/position sees every read exactly once
-    per_pos = mis[0, :, :, 0:4, :].sum(axis=(1, 2))
-    if not (np.all(per_pos == total) and int(lg.sum()) == total and int(lg[0, 1, :, READ_LEN].sum()) == total):
-        raise SystemExit("bench: full-size invariants failed (reference-base totals / length histogram)")
-    if not np.all(comp[0, :, :, :, :LENGTH].sum(axis=(1, 2)) == total):
-        raise SystemExit("bench: full-size invariants failed (read composition totals)")
+    if not c3:
+        per_pos = mis[0, :, :, 0:4, :].sum(axis=(1, 2))
+        if not (np.all(per_pos == total) and int(lg.sum()) == total and int(lg[0, 1, :, READ_LEN].sum()) == total):
+            raise SystemExit("bench: full-size invariants failed (reference-base totals / length histogram)")
+        if not np.all(comp[0, :, :, :, :LENGTH].sum(axis=(1, 2)) == total):
+            raise SystemExit("bench: full-size invariants failed (read composition totals)")
+    else:
+        # every record is a proper pair: one histogram entry per first mate; reads of >= 50 bp fill position 1 of
+        # both ends with a read base
+        if int(lg.sum()) != total // 2 or int(comp[:, :, :, :, 0].sum()) != 2 * total:
+            raise SystemExit("bench: full-size invariants failed (pair histogram mass / read composition totals)")
     check["full_size_invariants"] = "ok"
 
     # ---- value: resident batches, CUDA events on the compute stream ----
@@ -316,7 +332,7 @@ def gpu_arm(args, rank, local_rank, world):
 
         sample = host0.slice(0, min(args.cpu_sample, host0.n))
         t0 = time.perf_counter()
-        oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, threads=1)
+        oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, n_lib=n_lib, threads=1)
         dt = time.perf_counter() - t0
         cpu = {"value": sample.n / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "first %d reads of batch 0 of this workload, one thread, %.1f s" % (sample.n, dt)}
@@ -324,7 +340,11 @@ def gpu_arm(args, rank, local_rank, world):
     if rank == 0:
         peak, peak_source = measured_peak()
         launch_ms = kernel_ms / n_count_launch_groups
-        bytes_per_launch = ALGO_BYTES_PER_READ * total / n_batches
+        algo = ALGO_BYTES_PER_READ
+        if c3:  # SURVEY 8(d) formula, averaged over batch 0
+            algo = float(15 + 4 * host0.cigar.shape[0] / host0.n + (host0.l_seq.mean() + 1) / 2
+                         + (host0.l_seq.mean() + 2 * AROUND + 1) / 2)
+        bytes_per_launch = algo * total / n_batches
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
         traffic = recorded_traffic()
         line = {
@@ -332,7 +352,9 @@ def gpu_arm(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
             "config": {
-                "workload": "configs[1]: 50M x 100bp SE aDNA reads (C->T/G->A damage), 1 Mb reference, -l 70 -a 10 -Q 0",
+                "workload": "configs[2]: 50M x 50-150bp PE aDNA reads, mixed CIGARs (70% match, 10% each insertion / deletion / "
+                            "soft clips), 2 libraries, 1 Mb reference, -l 70 -a 10 -Q 0" if c3 else
+                            "configs[1]: 50M x 100bp SE aDNA reads (C->T/G->A damage), 1 Mb reference, -l 70 -a 10 -Q 0",
                 "reads_per_gpu_per_step": total, "batches_per_step": n_batches, "seed": args.seed,
                 "l2": "inputs larger than L2 (%.1f GB of resident batches per pass vs 126 MB)" % (
                     total * 90 / 1e9),
@@ -345,7 +367,7 @@ def gpu_arm(args, rank, local_rank, world):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
-                "peak_source": peak_source, "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ,
+                "peak_source": peak_source, "algorithmic_bytes_per_read": algo,
                 "reads_per_launch": total / n_batches, "kernel_ms_per_launch": launch_ms,
                 "kernel_share_of_step": kernel_ms / ms,
                 "frac_of_nominal_8TBps": achieved / 8000.0,

@@ -310,7 +310,7 @@ int worklist_for(mdg_ctx *ctx, cudaStream_t stream, int64_t n_reads, WorkList **
         ctx->worklists.emplace_back();
         wl = &ctx->worklists.back();
         wl->stream = stream;
-        MDG_CUDA(ctx, cudaMalloc(&wl->count, 8));
+        MDG_CUDA(ctx, cudaMalloc(&wl->count, (size_t)ctx->cfg.n_libraries * 8));
         if (ctx->cfg.n_libraries > 1)
             MDG_CUDA(ctx, cudaMalloc(&wl->lib_scratch, ((size_t)3 * ctx->cfg.n_libraries + 1) * 8));
     }
@@ -331,6 +331,17 @@ int worklist_for(mdg_ctx *ctx, cudaStream_t stream, int64_t n_reads, WorkList **
     return MDG_OK;
 }
 
+// The count tables as library `lib` sees them: its own slabs at index 0 of the library axis.
+mdg::CountTables lib_tables(const mdg_ctx *ctx, int lib)
+{
+    mdg::CountTables t = ctx->count_tables;
+    const size_t L = ctx->cfg.length, A = ctx->cfg.around;
+    t.misincorp += (size_t)lib * 4 * MDG_N_CLASSES * L;
+    t.dnacomp += (size_t)lib * 16 * (L + A);
+    t.lghist += (size_t)lib * 4 * ctx->cfg.lg_bins;
+    return t;
+}
+
 // The counting kernels over one device batch.
 int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStream_t stream)
 {
@@ -347,7 +358,7 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         WorkList *wl = nullptr;
         rc = worklist_for(ctx, stream, b.n_reads, &wl);
         if (rc) return rc;
-        MDG_CUDA(ctx, cudaMemsetAsync(wl->count, 0, 8, stream));
+        MDG_CUDA(ctx, cudaMemsetAsync(wl->count, 0, (size_t)ctx->cfg.n_libraries * 8, stream));
         const int64_t n_tiles = (b.n_reads + ctx->swar.tile - 1) / ctx->swar.tile;
         const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->swar_blocks_per_sm, n_tiles);
         const bool q = b.qual && p.min_qual > 0;
@@ -367,36 +378,48 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             mdg::library_scatter_kernel<<<(unsigned)((b.n_reads + 1023) / 1024), 256, (size_t)nl * 8, stream>>>(b, nl, cursors,
                                                                                                                 wl->by_library);
             MDG_CUDA(ctx, cudaGetLastError());
-            const size_t L = ctx->cfg.length, A = ctx->cfg.around;
-            for (int lib = 0; lib < nl; ++lib) {
-                mdg::CountTables tl = ctx->count_tables;
-                tl.misincorp += (size_t)lib * 4 * MDG_N_CLASSES * L;
-                tl.dnacomp += (size_t)lib * 16 * (L + A);
-                tl.lghist += (size_t)lib * 4 * ctx->cfg.lg_bins;
-                mdg::CountParams pl = p;
-                kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, pl, tl, ctx->swar, wl->reads, wl->count,
-                                                                             mdg::SwarSubset{wl->by_library, offsets, lib});
-            }
+            for (int lib = 0; lib < nl; ++lib)
+                kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, lib_tables(ctx, lib), ctx->swar, wl->reads,
+                                                                             wl->count, mdg::SwarSubset{wl->by_library, offsets, lib});
             ctx->launches += 3 + nl;
         }
         MDG_CUDA(ctx, cudaGetLastError());
-        // reads with indels / skips: the general kernel over the work list (returns at once when it is empty)
+        // reads with indels / skips: the general kernel over the work list(s) (returns at once when empty)
         const int ggrid = (int)std::min<int64_t>(ctx->general_grid, (b.n_reads + 7) / 8);
-        if (ctx->shared_slab)
-            mdg::count_general_kernel<true><<<ggrid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, ctx->count_tables,
-                                                                                     wl->reads, wl->count);
-        else
-            mdg::count_general_kernel<false><<<ggrid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables, wl->reads,
-                                                                        wl->count);
+        if (nl == 1 || !ctx->shared_slab) {
+            const unsigned long long *offsets = nl == 1 ? nullptr : wl->lib_scratch + nl;
+            if (nl > 1) {
+                // no room for a shared-memory slab: one launch per library all the same, into the global tables
+                for (int lib = 0; lib < nl; ++lib)
+                    mdg::count_general_kernel<false><<<ggrid, 256, 0, stream>>>(b, ctx->ref, p, lib_tables(ctx, lib), wl->reads,
+                                                                                wl->count, offsets, lib);
+                ctx->launches += nl;
+            } else if (ctx->shared_slab) {
+                mdg::count_general_kernel<true><<<ggrid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, ctx->count_tables,
+                                                                                         wl->reads, wl->count, nullptr, 0);
+                ctx->launches += 1;
+            } else {
+                mdg::count_general_kernel<false><<<ggrid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables, wl->reads,
+                                                                            wl->count, nullptr, 0);
+                ctx->launches += 1;
+            }
+        } else {
+            for (int lib = 0; lib < nl; ++lib)
+                mdg::count_general_kernel<true><<<ggrid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, lib_tables(ctx, lib),
+                                                                                         wl->reads, wl->count,
+                                                                                         wl->lib_scratch + nl, lib);
+            ctx->launches += nl;
+        }
         MDG_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 1;
     } else {
         int grid = (int)std::min<int64_t>(ctx->general_grid, (b.n_reads + 7) / 8);
         if (grid < 1) grid = 1;
-        if (ctx->shared_slab)
-            mdg::count_general_kernel<true><<<grid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, ctx->count_tables, nullptr, nullptr);
+        if (ctx->shared_slab && ctx->cfg.n_libraries == 1)
+            mdg::count_general_kernel<true><<<grid, 256, ctx->slab_bytes, stream>>>(b, ctx->ref, p, ctx->count_tables, nullptr, nullptr,
+                                                                                    nullptr, 0);
         else
-            mdg::count_general_kernel<false><<<grid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables, nullptr, nullptr);
+            mdg::count_general_kernel<false><<<grid, 256, 0, stream>>>(b, ctx->ref, p, ctx->count_tables, nullptr, nullptr,
+                                                                       nullptr, 0);
         ctx->launches += 1;
         MDG_CUDA(ctx, cudaGetLastError());
     }
@@ -511,7 +534,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
 
     // general kernel: shared-memory slab when there is one library and it fits
     ctx->slab_bytes = (4 * MDG_N_CLASSES * L + 16 * (L + A) + 4 * MDG_LG_SMEM_BINS) * 4;
-    ctx->shared_slab = nl == 1 && ctx->slab_bytes + 1024 <= ctx->smem_optin;
+    ctx->shared_slab = ctx->slab_bytes + 1024 <= ctx->smem_optin;  // one library's slab fits a block
     int per_sm = 0;
     if (ctx->shared_slab) {
         MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_general_kernel<true>,

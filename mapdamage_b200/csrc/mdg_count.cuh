@@ -54,18 +54,20 @@ __device__ __forceinline__ void count_pair(const Sink<kShared> &sink, int lib, i
     }
 }
 
+// own_lib >= 0: the tables `t` points at are those of library own_lib and every read handed in belongs to it
 template <bool kShared>
 __device__ void count_read(const DevBatch &b, const DevRef &ref, const CountParams &p, const CountTables &t,
-                           const Sink<kShared> &sink, int64_t r, int lane)
+                           const Sink<kShared> &sink, int64_t r, int lane, int own_lib)
 {
     const uint32_t flag = b.flag[r];
     if (flag & FILTERED_FLAGS) return;
-    const int lib = b.lib[r];
+    const int read_lib = b.lib[r];
     const int tid = b.tid[r];
-    if (lib >= p.n_lib) {
+    if (read_lib >= p.n_lib) {
         if (lane == 0) atomicCAS(t.error_flag, 0, DATA_ERR_LIB);
         return;
     }
+    const int lib = own_lib >= 0 ? 0 : read_lib;  // index on the library axis of `t`
     if (tid < 0 || tid >= ref.n_contigs) {
         if (lane == 0) atomicCAS(t.error_flag, 0, DATA_ERR_TID);
         return;
@@ -112,7 +114,7 @@ __device__ void count_read(const DevBatch &b, const DevRef &ref, const CountPara
                 unsigned long long slot = atomicAdd(t.lg_overflow_count, 1ull);
                 if ((int64_t)slot < t.lg_overflow_cap) {
                     int32_t *row = t.lg_overflow_rows + slot * 4;
-                    row[0] = lib; row[1] = kind; row[2] = strand; row[3] = (int32_t)length;
+                    row[0] = read_lib; row[1] = kind; row[2] = strand; row[3] = (int32_t)length;
                 }
             }
         }
@@ -246,8 +248,15 @@ __device__ void count_read(const DevBatch &b, const DevRef &ref, const CountPara
 template <bool kShared>
 __global__ void __launch_bounds__(256) count_general_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t,
                                                             const uint32_t *__restrict__ worklist,
-                                                            const unsigned long long *__restrict__ work_count)
+                                                            const unsigned long long *__restrict__ work_count,
+                                                            const unsigned long long *__restrict__ lib_offsets, int own_lib)
 {
+    // per-library work list: the reads of library own_lib start at worklist + lib_offsets[own_lib], their number
+    // is work_count[own_lib]
+    if (lib_offsets) {
+        worklist += lib_offsets[own_lib];
+        work_count += own_lib;
+    }
     const int64_t n_work = worklist ? (int64_t)*work_count : b.n_reads;
     if ((int64_t)blockIdx.x * (blockDim.x >> 5) >= n_work) return;  // nothing for this block (uniform)
     extern __shared__ uint32_t smem[];
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(256) count_general_kernel(DevBatch b, DevRef r
     const int warps_per_block = blockDim.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * warps_per_block;
     for (int64_t w = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < n_work; w += stride)
-        count_read<kShared>(b, ref, p, t, sink, worklist ? (int64_t)worklist[w] : w, lane);
+        count_read<kShared>(b, ref, p, t, sink, worklist ? (int64_t)worklist[w] : w, lane, lib_offsets ? own_lib : -1);
     if (kShared) {
         // flush the block's slab into the 64-bit tables of library 0
         __syncthreads();
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(256) count_general_kernel(DevBatch b, DevRef r
                         unsigned long long slot = atomicAdd(t.lg_overflow_count, 1ull);
                         if ((int64_t)slot < t.lg_overflow_cap) {
                             int32_t *row = t.lg_overflow_rows + slot * 4;
-                            row[0] = 0; row[1] = ks >> 1; row[2] = ks & 1; row[3] = bin;
+                            row[0] = lib_offsets ? own_lib : 0; row[1] = ks >> 1; row[2] = ks & 1; row[3] = bin;
                         }
                     }
                 }

@@ -603,9 +603,11 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
         if (tid < 32 && s_ctl[2]) {
             const uint32_t n_cx = s_ctl[2];
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(work_count, (unsigned long long)n_cx);
+            // several libraries: library l appends at worklist + offsets[l], counted in work_count[l]
+            uint32_t *const wl = sub.list ? worklist + sub.offsets[sub.lib] : worklist;
+            if (lane == 0) base = atomicAdd(work_count + (sub.list ? sub.lib : 0), (unsigned long long)n_cx);
             base = __shfl_sync(0xffffffffu, base, 0);
-            for (uint32_t i = lane; i < n_cx; i += 32) worklist[base + i] = s_cx[i];
+            for (uint32_t i = lane; i < n_cx; i += 32) wl[base + i] = s_cx[i];
         }
 
         // ---- one window per read when every gap-free read of the tile has the same length ----
