@@ -125,6 +125,13 @@ void mdg_host_free(void *ptr);
 int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, const uint64_t *contig_off,
                       const uint32_t *contig_len, int32_t n_contigs);
 
+/*
+ * A, C, G, T counts over the whole uploaded genome: replaces seqtk.comp
+ * (seqtk/seqtk.c:56-143) under composition.write_base_comp
+ * (composition.py:6-25), whose dnacomp_genome.csv feeds the Bayesian stage.
+ */
+int mdg_genome_composition(mdg_ctx *ctx, uint64_t *counts4);
+
 /* ---- counting pass: replaces the loop body main.py:165-217 ------------- */
 
 /*

@@ -108,6 +108,7 @@ struct mdg_ctx {
     mdg::DevRef ref{};
     void *ref_block = nullptr;
     uint64_t ref_total_bases = 0;
+    int64_t ref_words = 0;  // 32-bit words of the genome image (without the padding around it)
     uint32_t ref_min_contig = 0;
     // tables: one allocation [misincorp | dnacomp | lghist]
     unsigned long long *tables = nullptr;
@@ -676,12 +677,33 @@ int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, cons
     ctx->ref.contig_off = (const uint64_t *)(p + words_bytes);
     ctx->ref.contig_len = (const uint32_t *)(p + words_bytes + off_bytes);
     ctx->ref.n_contigs = n_contigs;
+    ctx->ref_words = (int64_t)((n_bytes + 3) / 4);
     ctx->ref_total_bases = 0;
     ctx->ref_min_contig = 0xffffffffu;
     for (int c = 0; c < n_contigs; ++c) {
         ctx->ref_total_bases += contig_len[c];
         ctx->ref_min_contig = std::min(ctx->ref_min_contig, contig_len[c]);
     }
+    return MDG_OK;
+}
+
+int mdg_genome_composition(mdg_ctx *ctx, uint64_t *counts4)
+{
+    if (!ctx || !counts4) return MDG_ERR_ARGUMENT;
+    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before mdg_genome_composition");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    unsigned long long *dev = nullptr;
+    MDG_CUDA(ctx, cudaMalloc(&dev, 32));
+    cudaError_t e = cudaMemsetAsync(dev, 0, 32, ctx->compute);
+    if (e == cudaSuccess) {
+        mdg::genome_composition_kernel<<<ctx->sm_count * 8, 256, 0, ctx->compute>>>(ctx->ref.words, ctx->ref_words, dev);
+        ctx->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts4, dev, 32, cudaMemcpyDeviceToHost, ctx->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->compute);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(ctx, MDG_ERR_CUDA, "mdg_genome_composition failed: %s", cudaGetErrorString(e));
     return MDG_OK;
 }
 

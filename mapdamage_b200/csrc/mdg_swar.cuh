@@ -744,6 +744,33 @@ __global__ void __launch_bounds__(256) library_scatter_kernel(DevBatch b, int n_
         if (my_lib[u] != 0xffffffffu) list[s_base[my_lib[u]] + my_rank[u]] = (uint32_t)(first + u * 256 + threadIdx.x);
 }
 
+// Base composition of the whole genome (reference composition.py:6-25 over seqtk.comp, seqtk/seqtk.c:92-110):
+// the one-hot image holds one bit per A/C/G/T base and nothing else, so the counts are population counts.
+__global__ void __launch_bounds__(256) genome_composition_kernel(const uint32_t *__restrict__ words, int64_t n_words,
+                                                                 unsigned long long *counts)
+{
+    unsigned long long mine[4] = {0, 0, 0, 0};
+    const uint4 *quads = (const uint4 *)words;
+    const int64_t n_quads = n_words / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(quads + i);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            mine[g] += __popc((q.x >> g) & K1) + __popc((q.y >> g) & K1) + __popc((q.z >> g) & K1) + __popc((q.w >> g) & K1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n_words - 4 * n_quads) {
+        const uint32_t w = words[4 * n_quads + threadIdx.x];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) mine[g] += __popc((w >> g) & K1);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        unsigned long long v = mine[g];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(counts + g, v);
+    }
+}
+
 // Genome as uploaded (0..3 = A,C,G,T, anything else) -> one-hot nibbles (1,2,4,8; 0 = not a base), in place.
 __global__ void ref_to_one_hot_kernel(uint32_t *words, int64_t n_words)
 {

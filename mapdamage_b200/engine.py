@@ -142,6 +142,12 @@ class DamageEngine:
             self._ctx, packed.ctypes.data, packed.shape[0], offsets.ctypes.data,
             lengths.ctypes.data, len(reference.names)))
 
+    def genome_composition(self):
+        """``[A, C, G, T]`` counts over the uploaded genome (``mdg_genome_composition``)."""
+        counts = np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.mdg_genome_composition(self._ctx, counts.ctypes.data))
+        return [int(x) for x in counts]
+
     def upload(self, batch):
         handle = C.c_void_p()
         s = batch_struct(batch)

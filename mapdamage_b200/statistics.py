@@ -16,6 +16,10 @@ Slab layouts (shared with the kernels and the oracle):
   reference base at distance ``d`` (1..A)
 * fragment lengths ``[lib][kind pe,se][strand][lg_bins]``
 """
+import csv
+import logging
+import os
+
 import numpy as np
 
 from . import seq as _seq
@@ -182,3 +186,46 @@ class FragmentLengths:
                             "%s\t%s\t%s\t%s\t%d\t%d\n"
                             % (sample, library, strand, pe_or_se, length, count)
                         )
+
+
+def _first_position_counts(path):
+    """Sums, over libraries and strands, the ``Pos == 1`` rows of a misincorporation table:
+    ``{"5p": (C, C>T), "3p": (G, G>A)}``; ``None`` for a file without a header."""
+    wanted = {"5p": ("C", "C>T"), "3p": ("G", "G>A")}
+    sums = {end: [0, 0] for end in wanted}
+    with open(path, newline="") as handle:
+        rows = csv.DictReader(handle, delimiter="\t")
+        if not rows.fieldnames:
+            return None
+        for row in rows:
+            if int(row["Pos"]) != 1:
+                continue
+            base, mutation = wanted[row["End"]]
+            sums[row["End"]][0] += int(row[base])
+            sums[row["End"]][1] += int(row[mutation])
+    return {end: tuple(v) for end, v in sums.items()}
+
+
+def check_table_and_warn_if_dmg_freq_is_low(folder):
+    """Host mirror of the reference's pre-flight check for the Bayesian stage (``statistics.py:140-184``):
+    ``True`` when ``misincorporation.txt`` in ``folder`` has C (5') and G (3') counts at the first position;
+    warns when C>T + G>A there is below 1 %.  Messages and return values are the reference's."""
+    log = logging.getLogger(__name__)
+    name = "misincorporation.txt"
+    try:
+        counts = _first_position_counts(os.path.join(folder, name))
+    except (csv.Error, IOError, OSError, KeyError) as error:
+        log.error("Error reading misincorporation table: %s", error)
+        return False
+    if counts is None:
+        log.error("%r is empty; please re-run mapDamage", name)
+        return False
+    (c_total, c_to_t), (g_total, g_to_a) = counts["5p"], counts["3p"]
+    if not (c_total and g_total):
+        log.error("Insufficient data in %r; cannot perform Bayesian computation", name)
+        return False
+    damage = 0.0 + c_to_t / c_total + g_to_a / g_total
+    if damage < 0.01:
+        log.warning("DNA damage levels are too low, the Bayesian computation should not be "
+                    "performed (%f < 0.01)", damage)
+    return True
