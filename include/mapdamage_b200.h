@@ -245,6 +245,62 @@ int mdg_batch_sizes(mdg_ctx *ctx, const mdg_dev_batch *batch, int64_t *n_reads, 
  * the const pointers of mdg_batch. */
 int mdg_batch_download(mdg_ctx *ctx, const mdg_dev_batch *batch, const mdg_batch *host);
 
+/* ---- host input / output path: BGZF + BAM --------------- */
+
+/*
+ * What the reference gets from pysam / htslib: iteration over a BAM file
+ * (reader.py:38,121-132; rescale.py:298,300) and a BAM writer
+ * (rescale.py:299,344).  Decoding is done on n_threads host threads (0 = all)
+ * straight into the struct-of-arrays batch; no CUDA call is made here.
+ */
+typedef struct mdg_bam_reader mdg_bam_reader;
+typedef struct mdg_bam_writer mdg_bam_writer;
+
+int mdg_bam_open(const char *path, int32_t n_threads, mdg_bam_reader **out);
+void mdg_bam_close(mdg_bam_reader *reader);
+/* Message of the last failure (reader may be NULL for mdg_bam_open failures). */
+const char *mdg_bam_error(const mdg_bam_reader *reader);
+/* SAM header text; returns its length (copies at most cap - 1 bytes when buf is given). */
+int64_t mdg_bam_header_text(const mdg_bam_reader *reader, char *buf, int64_t cap);
+int32_t mdg_bam_n_references(const mdg_bam_reader *reader);
+int mdg_bam_reference(const mdg_bam_reader *reader, int32_t index, char *name, int32_t cap, uint32_t *length);
+/*
+ * Read group -> library index (reader.py:63-81,98-118).  n = 0 merges all
+ * libraries (--merge-libraries); otherwise a read without a listed read group
+ * fails the batch with MDG_ERR_DATA, as the reference raises BAMError.
+ */
+int mdg_bam_set_libraries(mdg_bam_reader *reader, const char *const *read_groups, const uint16_t *library, int32_t n);
+/*
+ * Decodes up to max_reads records whose flag has none of drop_flags (0xF04 for
+ * the counting pass, reader.py:9-13; 0 for the rescale pass) into the caller's
+ * arrays (every array of *out but qual is required; written through the const
+ * pointers; cigar_off gets n + 1 entries).  Stops early when max_cigar words or
+ * max_bases base slots would overflow.  Optionally keeps the records verbatim
+ * for mdg_bam_write_batch: raw (raw_cap bytes) and raw_off (n + 1 entries), and
+ * flags records that already carry an MR tag (rescale.py:277-278).  Returns the
+ * number of records decoded (0 at the end of the file) or a negative status.
+ */
+int64_t mdg_bam_read_batch(mdg_bam_reader *reader, const mdg_batch *out, int64_t max_reads, int64_t max_cigar,
+                           int64_t max_bases, uint32_t drop_flags, uint8_t *raw, int64_t raw_cap, uint64_t *raw_off,
+                           uint8_t *has_mr, int64_t *n_cigar, int64_t *n_bases);
+/* Records walked so far, dropped ones included. */
+int64_t mdg_bam_records_seen(const mdg_bam_reader *reader);
+
+/* BAM writer: header as given, BGZF blocks deflated at `level` (0-9, < 0 = 1) on n_threads threads. */
+int mdg_bam_create(const char *path, const char *header_text, const char *const *ref_names, const uint32_t *ref_lengths,
+                   int32_t n_refs, int32_t n_threads, int32_t level, mdg_bam_writer **out);
+const char *mdg_bam_writer_error(const mdg_bam_writer *writer);
+/*
+ * Appends n records kept by mdg_bam_read_batch, in order (rescale.py:344).
+ * Where status[i] & 1, the qualities become qual[base_off[i] .. + l_seq) and
+ * an MR:f tag with mr[i] is appended (rescale.py:273-280).
+ */
+int mdg_bam_write_batch(mdg_bam_writer *writer, const uint8_t *raw, const uint64_t *raw_off, int64_t n, const uint8_t *status,
+                        const uint8_t *qual, const uint32_t *base_off, const float *mr);
+/* Flushes, writes the BGZF end-of-file block and closes the file. */
+int mdg_bam_finish(mdg_bam_writer *writer);
+void mdg_bam_writer_free(mdg_bam_writer *writer);
+
 /* ---- measurement helpers (bench.py) ------------------------------------ */
 
 /* CUDA events on the context's compute stream: which = 0 start, 1 stop. */

@@ -76,6 +76,24 @@ SYMBOLS = {
     "mdg_batch_sizes": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.POINTER(C.c_int64)]),
     "mdg_batch_download": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Batch)]),
+    "mdg_bam_open": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "mdg_bam_close": (None, [C.c_void_p]),
+    "mdg_bam_error": (C.c_char_p, [C.c_void_p]),
+    "mdg_bam_header_text": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "mdg_bam_n_references": (C.c_int32, [C.c_void_p]),
+    "mdg_bam_reference": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_uint32)]),
+    "mdg_bam_set_libraries": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32]),
+    "mdg_bam_read_batch": (C.c_int64, [C.c_void_p, C.POINTER(Batch), C.c_int64, C.c_int64, C.c_int64, C.c_uint32,
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64)]),
+    "mdg_bam_records_seen": (C.c_int64, [C.c_void_p]),
+    "mdg_bam_create": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_int32, C.POINTER(C.c_void_p)]),
+    "mdg_bam_writer_error": (C.c_char_p, [C.c_void_p]),
+    "mdg_bam_write_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "mdg_bam_finish": (C.c_int, [C.c_void_p]),
+    "mdg_bam_writer_free": (None, [C.c_void_p]),
     "mdg_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mdg_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "mdg_allreduce_tables": (C.c_int, [C.c_void_p]),

@@ -1,0 +1,181 @@
+"""BAM input / output through the native decoder (``csrc/mdg_bamio.cpp``).
+
+The reference iterates ``pysam.AlignmentFile`` objects (``reader.py:38,121-132``;
+``rescale.py:298-300``) and writes one (``rescale.py:299,344``).  Here a
+:class:`BamReader` yields whole struct-of-arrays batches -- BGZF inflate and the
+record copies run on host threads inside the library -- and a :class:`BamWriter`
+re-emits the records of a batch with rescaled qualities and ``MR`` tags.  Only
+the header is handled in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .batch import BAMError, FILTERED_FLAGS, ReadBatch
+from .samtext import SamHeader
+
+
+class BamReader:
+    """Iterates a BAM file as :class:`ReadBatch` objects.
+
+    ``merge_libraries`` / read groups follow ``reader.BAMReader`` (``reader.py:44-50,63-81``):
+    ``libraries`` is the sorted ``(sample, library)`` list indexing the count slabs.
+    """
+
+    def __init__(self, path, threads=0, merge_libraries=False, apply_filter=True):
+        self._lib = _native.load()
+        self._reader = C.c_void_p()
+        code = self._lib.mdg_bam_open(str(path).encode(), threads, C.byref(self._reader))
+        if code < 0:
+            raise BAMError((self._lib.mdg_bam_error(None) or b"").decode())
+        text = C.create_string_buffer(int(self._lib.mdg_bam_header_text(self._reader, None, 0)) + 1)
+        self._lib.mdg_bam_header_text(self._reader, text, len(text))
+        self.header = SamHeader()
+        for line in text.value.decode("utf-8", "replace").splitlines():
+            if line:
+                self.header.add(line)
+        # the binary reference list is authoritative (a BAM may lack @SQ lines)
+        names, lengths = [], []
+        for i in range(self._lib.mdg_bam_n_references(self._reader)):
+            name = C.create_string_buffer(1024)
+            length = C.c_uint32()
+            self._lib.mdg_bam_reference(self._reader, i, name, len(name), C.byref(length))
+            names.append(name.value.decode())
+            lengths.append(int(length.value))
+        self.header.set_references(names, lengths)
+        self.apply_filter = apply_filter
+        self.merge_libraries = merge_libraries
+        if merge_libraries:
+            self.libraries = [("*", "*")]
+            self._lib.mdg_bam_set_libraries(self._reader, None, None, 0)
+        else:
+            groups = self.header.libraries()
+            self.libraries = sorted(set(groups.values()))
+            index = {key: i for i, key in enumerate(self.libraries)}
+            ids = (C.c_char_p * max(1, len(groups)))(*[rg.encode() for rg in groups])
+            libs = np.array([index[groups[rg]] for rg in groups], dtype=np.uint16)
+            if groups:
+                self._lib.mdg_bam_set_libraries(self._reader, ids, libs.ctypes.data, len(groups))
+            else:
+                # no read groups in the header: every read fails, as in the reference (reader.py:67-73)
+                ids = (C.c_char_p * 1)(b"\x00")
+                self._lib.mdg_bam_set_libraries(self._reader, ids, np.zeros(1, np.uint16).ctypes.data, 1)
+
+    def close(self):
+        if self._reader:
+            self._lib.mdg_bam_close(self._reader)
+            self._reader = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    @property
+    def records_seen(self):
+        return int(self._lib.mdg_bam_records_seen(self._reader))
+
+    @staticmethod
+    def buffers(max_reads=1 << 20, max_cigar=None, max_bases=None, with_qual=True, empty=np.empty):
+        """Arrays one batch is decoded into; ``empty(shape, dtype)`` allocates (pinned: ``engine.arena.empty``).
+        Reusing a set of buffers for several ``read_batch`` calls saves the allocations."""
+        max_cigar = max_cigar or 4 * max_reads
+        max_bases = max_bases or 160 * max_reads
+        arrays = {name: empty(max_reads, dtype) for name, dtype in ReadBatch.FIELDS if name != "cigar_off"}
+        arrays["cigar_off"] = empty(max_reads + 1, np.uint32)
+        arrays["cigar"] = empty(max_cigar, np.uint32)
+        arrays["seq4"] = empty(max_bases // 2, np.uint8)
+        arrays["qual"] = empty(max_bases, np.uint8) if with_qual else None
+        return arrays
+
+    def read_batch(self, max_reads=1 << 20, max_cigar=None, max_bases=None, with_qual=True, keep_raw=False,
+                   buffers=None):
+        """Next batch, or ``None`` at the end of the file.  ``keep_raw`` attaches ``raw`` / ``raw_off`` /
+        ``has_mr`` (what :class:`BamWriter` needs).  ``buffers`` (from :meth:`buffers`) are decoded into in place:
+        the batch returned is a view of them."""
+        arrays = buffers if buffers is not None else self.buffers(max_reads, max_cigar, max_bases, with_qual)
+        max_reads = arrays["flag"].shape[0]
+        max_cigar = arrays["cigar"].shape[0]
+        max_bases = arrays["seq4"].shape[0] * 2
+        s = _native.Batch()
+        for name, array in arrays.items():
+            setattr(s, name, None if array is None else array.ctypes.data)
+        raw = raw_off = has_mr = None
+        raw_cap = 0
+        if keep_raw:
+            raw_cap = max_bases * 2 + 256 * max_reads
+            raw = np.empty(raw_cap, dtype=np.uint8)
+            raw_off = np.empty(max_reads + 1, dtype=np.uint64)
+            has_mr = np.empty(max_reads, dtype=np.uint8)
+        n_cigar, n_bases = C.c_int64(), C.c_int64()
+        n = self._lib.mdg_bam_read_batch(
+            self._reader, C.byref(s), max_reads, max_cigar, max_bases, FILTERED_FLAGS if self.apply_filter else 0,
+            None if raw is None else raw.ctypes.data, raw_cap, None if raw_off is None else raw_off.ctypes.data,
+            None if has_mr is None else has_mr.ctypes.data, C.byref(n_cigar), C.byref(n_bases))
+        if n < 0:
+            message = (self._lib.mdg_bam_error(self._reader) or b"").decode()
+            if n == _native.ERR_DATA and "read-group" in message:
+                raise BAMError(message[0].upper() + message[1:])
+            raise BAMError(message)
+        if n == 0:
+            return None
+        trimmed = {name: arrays[name][:n] for name, _ in ReadBatch.FIELDS if name != "cigar_off"}
+        trimmed["cigar_off"] = arrays["cigar_off"][:n + 1]
+        trimmed["cigar"] = arrays["cigar"][:n_cigar.value]
+        trimmed["seq4"] = arrays["seq4"][:n_bases.value // 2]
+        trimmed["qual"] = None if arrays["qual"] is None else arrays["qual"][:n_bases.value]
+        batch = ReadBatch(**trimmed)
+        if keep_raw:
+            batch.raw, batch.raw_off, batch.has_mr = raw, raw_off[:n + 1], has_mr[:n]
+        return batch
+
+    def __iter__(self):
+        while True:
+            batch = self.read_batch()
+            if batch is None:
+                return
+            yield batch
+
+
+class BamWriter:
+    """Writes the records of batches read with ``keep_raw`` (``rescale.py:299,344``)."""
+
+    def __init__(self, path, header, threads=0, level=1):
+        self._lib = _native.load()
+        self._writer = C.c_void_p()
+        text = "".join(line + "\n" for line in header.lines).encode()
+        names = (C.c_char_p * max(1, len(header.references)))(*[n.encode() for n in header.references])
+        lengths = np.array(header.lengths, dtype=np.uint32)
+        code = self._lib.mdg_bam_create(str(path).encode(), text, names, lengths.ctypes.data, len(header.references),
+                                        threads, level, C.byref(self._writer))
+        if code < 0:
+            raise OSError((self._lib.mdg_bam_writer_error(None) or b"").decode())
+
+    def write(self, batch, status=None, qual=None, mr=None):
+        """Appends every record of ``batch``; where ``status`` is set the record gets ``qual`` and ``MR``."""
+        code = self._lib.mdg_bam_write_batch(
+            self._writer, batch.raw.ctypes.data, batch.raw_off.ctypes.data, batch.n,
+            None if status is None else np.ascontiguousarray(status, np.uint8).ctypes.data,
+            None if qual is None else qual.ctypes.data, batch.base_off.ctypes.data,
+            None if mr is None else np.ascontiguousarray(mr, np.float32).ctypes.data)
+        if code < 0:
+            raise OSError((self._lib.mdg_bam_writer_error(self._writer) or b"").decode())
+
+    def close(self):
+        if self._writer:
+            code = self._lib.mdg_bam_finish(self._writer)
+            message = (self._lib.mdg_bam_writer_error(self._writer) or b"").decode()
+            self._lib.mdg_bam_writer_free(self._writer)
+            self._writer = C.c_void_p()
+            if code < 0:
+                raise OSError(message)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -26,7 +26,7 @@ def find_nvcc():
 
 
 def sources():
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [PACKAGE.parent / "include" / "mapdamage_b200.h"]
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.cpp")) + [PACKAGE.parent / "include" / "mapdamage_b200.h"]
 
 
 def is_stale():
@@ -42,7 +42,7 @@ def build_library(force=False, verbose=False):
     cmd = [find_nvcc(), *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIBRARY), str(CSRC / "mdg_api.cu"), "-lcudart", "-ldl"]
+    cmd += ["-o", str(LIBRARY), str(CSRC / "mdg_api.cu"), str(CSRC / "mdg_bamio.cpp"), "-lcudart", "-ldl", "-lz", "-lpthread"]
     env = dict(os.environ)
     result = subprocess.run(cmd, env=env, capture_output=True, text=True)
     if result.returncode != 0:

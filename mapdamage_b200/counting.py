@@ -10,8 +10,8 @@ the device's count slabs.  The three classes keep the reference's constructor
 arguments, ``.data`` layout and ``.write()`` bytes, so everything downstream
 (the R plotting / Bayesian stage) reads the same files.
 
-Only SAM text is decoded here: pysam/htslib are absent from this image and
-BGZF/BAM decode is the "next" row f2 of SURVEY.md section 8.
+Input is BAM (decoded natively on host threads, ``bamio.BamReader``: pysam/htslib are absent from this
+image) or SAM text (per-record Python, for small files and tests).
 """
 import logging
 from pathlib import Path
@@ -38,8 +38,9 @@ def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_
     """
     log = logging.getLogger(__name__)
     filename = Path(filename)
-    if filename.suffix.lower() in (".bam", ".cram"):
-        raise NotImplementedError("only SAM text is decoded here; BAM/CRAM decode is SURVEY.md row f2")
+    if filename.suffix.lower() == ".bam":
+        return _count_bam(filename, ref, length, around, min_basequal, merge_libraries, folder, batch_reads, device,
+                          lg_bins, engine)
     header, records = iter_sam(filename)
     reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
     reference = reference.reordered(header.references)
@@ -66,6 +67,47 @@ def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_
         if own_engine:
             engine.close()
     log.debug("Counted %d of %d alignments", n_kept, builder.n_seen)
+    return _finish(libraries, length, around, mis, comp, lg, overflow, folder)
+
+
+def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, folder, batch_reads, device, lg_bins, engine):
+    """BAM input: batches come straight out of the native decoder (``bamio.BamReader``) into pinned buffers."""
+    from .bamio import BamReader
+
+    log = logging.getLogger(__name__)
+    with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True) as reader:
+        reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
+        reference = reference.reordered(reader.header.references)
+        libraries = reader.libraries
+        own_engine = engine is None
+        if own_engine:
+            engine = DamageEngine(length=length, around=around, min_qual=min_basequal,
+                                  n_libraries=max(1, len(libraries)), lg_bins=lg_bins, device=device,
+                                  max_reads=batch_reads)
+        try:
+            engine.set_reference(reference)
+            # one more set of host buffers than staging slots: a set is reused only after its copy has drained
+            sets = [reader.buffers(engine.max_reads, engine.max_cigar_ops, engine.max_bases,
+                                   with_qual=min_basequal > 0, empty=engine.arena.empty) for _ in range(3)]
+            n_kept = turn = 0
+            while True:
+                batch = reader.read_batch(buffers=sets[turn % 3])
+                if batch is None:
+                    break
+                engine.count(batch, compact=False)
+                n_kept += batch.n
+                turn += 1
+            mis, comp, lg = engine.tables()
+            overflow = engine.lg_overflow()
+            n_seen = reader.records_seen
+        finally:
+            if own_engine:
+                engine.close()
+    log.debug("Counted %d of %d alignments", n_kept, n_seen)
+    return _finish(libraries, length, around, mis, comp, lg, overflow, folder)
+
+
+def _finish(libraries, length, around, mis, comp, lg, overflow, folder):
     misincorp = statistics.MisincorporationRates(libraries, length).load(mis)
     dnacomp = statistics.DNAComposition(libraries, around, length).load(comp)
     lgdistrib = statistics.FragmentLengths(libraries).load(lg, overflow)

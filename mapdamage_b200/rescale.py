@@ -8,7 +8,7 @@ qualities and the ``MR:f`` tag.  The substitution summary the reference logs
 (``_record_subs`` / ``_qual_summary_subs`` / ``_print_subs``, ``rescale.py:106-192``)
 is rebuilt on the host from integer histograms the kernel accumulates.
 
-Only SAM text is read and written here (BAM encode/decode: SURVEY.md row f2).
+Input / output is BAM (native decode and encode, ``bamio``) or, for small files and tests, SAM text.
 """
 import logging
 import struct
@@ -115,8 +115,8 @@ def _rescale_qual_core(ref, options, engine=None, batch_reads=1 << 18):
                               rescale_length_3p=options.rescale_length_3p)
     model = RescaleModel(corr_prob, options.rescale_length_5p, options.rescale_length_3p)
     filename = Path(options.filename)
-    if filename.suffix.lower() in (".bam", ".cram"):
-        raise RescaleError("only SAM text is decoded here; BAM/CRAM decode is SURVEY.md row f2")
+    if filename.suffix.lower() == ".bam":
+        return _rescale_bam(ref, options, model, engine, batch_reads, log)
     header, records = iter_sam(filename)
     reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
     reference = reference.reordered(header.references)
@@ -149,6 +149,60 @@ def _rescale_qual_core(ref, options, engine=None, batch_reads=1 << 18):
         if own_engine:
             engine.close()
 
+    return _report(log, stats, summary)
+
+
+def _rescale_bam(ref, options, model, engine, batch_reads, log):
+    """BAM in, BAM out: batches from the native decoder, records re-emitted by the native encoder."""
+    from .bamio import BamReader, BamWriter
+
+    with BamReader(options.filename, merge_libraries=True, apply_filter=False) as reader:
+        reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
+        reference = reference.reordered(reader.header.references)
+        own_engine = engine is None
+        if own_engine:
+            engine = DamageEngine(max_reads=batch_reads, device=getattr(options, "device", 0))
+        try:
+            engine.set_reference(reference)
+            engine.set_rescale_model(model)
+            buffers = reader.buffers(engine.max_reads, engine.max_cigar_ops, engine.max_bases, with_qual=True,
+                                     empty=engine.arena.empty)
+            too_long = 0
+            with BamWriter(options.rescale_out, reader.header) as writer:
+                while True:
+                    batch = reader.read_batch(buffers=buffers, keep_raw=True)
+                    if batch is None:
+                        break
+                    qual, mr, status = engine.rescale(batch, compact=False)
+                    engine.sync()
+                    clash = np.flatnonzero(batch.has_mr & (status & 1))
+                    if clash.size:  # rescale.py:277-278
+                        raise SystemExit("Read: %s already has a MR tag, can't rescale" % _record_name(batch, clash[0]))
+                    now = engine.rescale_stats()["alignment_longer_than_read"]
+                    if now != too_long:  # rescale.py:255-261; rare, so the names are dug out per record
+                        for i in np.flatnonzero(status & 1):
+                            cigar = batch.cigar_of(int(i))
+                            columns = [op for op, n in cigar if op in (0, 1, 2, 7, 8) and n > 0]
+                            if columns and (columns[0] if batch.flag[i] & 0x10 else columns[-1]) == 2:
+                                log.warning("The aligment of the read is longer than the actual read %s",
+                                            _record_name(batch, int(i)))
+                        too_long = now
+                    writer.write(batch, status=status, qual=qual, mr=mr)
+            stats = engine.rescale_stats()
+            summary = SubstitutionSummary(model, *engine.rescale_hist(model.n_slots))
+        finally:
+            if own_engine:
+                engine.close()
+    return _report(log, stats, summary)
+
+
+def _record_name(batch, i):
+    start = int(batch.raw_off[i])
+    l_name = int(batch.raw[start + 12])
+    return batch.raw[start + 36:start + 36 + l_name - 1].tobytes().decode("latin-1")
+
+
+def _report(log, stats, summary):
     if stats["pairs"]:
         log.warning(
             "Processed %i paired reads, assumed to be non-overlapping, facing inwards "

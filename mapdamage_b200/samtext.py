@@ -57,6 +57,12 @@ class SamHeader:
     def tid(self, name):
         return -1 if name == "*" else self._tid[name]
 
+    def set_references(self, names, lengths):
+        """Replaces the reference list (BAM: the binary list wins over the @SQ lines)."""
+        self.references = list(names)
+        self.lengths = list(lengths)
+        self._tid = {name: i for i, name in enumerate(self.references)}
+
     def libraries(self):
         """Read-group ID -> (sample, library); KeyError text as reader.py:107-116."""
         out = {}

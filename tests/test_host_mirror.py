@@ -93,3 +93,56 @@ def test_substitution_summary_vs_oracle(name, kw):
                           pvals):
         assert summary.data[key] == pytest.approx(value, rel=1e-9), key
     assert want[0, 0].sum() > 100 and want[2, 0].sum() > 100
+
+
+# ---- the same two call sites fed with BAM (native decode / encode) ----
+def _as_bam(sam, path, block_bytes=0xff00):
+    import bam_py
+    from mapdamage_b200.samtext import read_sam
+
+    header, records = read_sam(sam)
+    bam_py.write_bam(path, header, records, block_bytes=block_bytes)
+    return header, records
+
+
+@pytest.mark.parametrize("case_dir,params", [c for c in golden_cases("counting") if not c.values[1]["exception"]])
+def test_count_alignments_from_bam(case_dir, params, tmp_path):
+    sam, fasta = materialise_inputs(case_dir, params, tmp_path)
+    _as_bam(sam, tmp_path / "input.bam", block_bytes=4096)
+    counting.count_alignments(tmp_path / "input.bam", fasta, length=params["length"], around=params["around"],
+                              min_basequal=params["minqual"], merge_libraries=params["merge_libraries"],
+                              folder=tmp_path / "out", batch_reads=1024)
+    assert_tables_equal(tmp_path / "out", case_dir)
+
+
+@pytest.mark.parametrize("case_dir,params", [c for c in golden_cases("rescale")])
+def test_rescale_qual_bam_to_bam(case_dir, params, tmp_path, caplog):
+    import bam_py
+    from mapdamage_b200.samtext import read_sam
+
+    _as_bam(case_dir / "input.sam", tmp_path / "input.bam", block_bytes=2048)
+    options = argparse.Namespace(folder=case_dir, filename=tmp_path / "input.bam", rescale_out=tmp_path / "rescaled.bam",
+                                 rescale_length_5p=params["length_5p"], rescale_length_3p=params["length_3p"])
+    caplog.set_level(logging.INFO, logger="mapdamage_b200.rescale")
+    if params["exception"]:
+        with pytest.raises(SystemExit) as info:
+            rescale.rescale_qual(case_dir / "ref.fa", options)
+        assert str(info.value).startswith(params["exception"].split(": ", 1)[1])
+        return
+    rc = rescale.rescale_qual(case_dir / "ref.fa", options)
+    assert rc == params["rc"]
+    if rc != 0:
+        return
+    _, want = read_sam(case_dir / "expected.sam")
+    text, refs, got = bam_py.read_bam(tmp_path / "rescaled.bam")
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert (g["qname"], g["flag"], g["pos"], g["cigar"], g["seq"], g["qual"]) == \
+               (w.qname, w.flag, w.pos, w.cigar, w.seq, w.qual)
+        if "MR" in w.tags:
+            assert g["tags"]["MR"] == ("f", float(np.float32(w.tags["MR"])))
+        else:
+            assert "MR" not in g["tags"]
+    messages = [r.getMessage() for r in caplog.records if r.name == "mapdamage_b200.rescale"]
+    assert [m for m in messages if not m.startswith("Rescaling BAM")] == \
+           [m for m in params["log"] if not m.startswith("Rescaling BAM")]
