@@ -297,6 +297,13 @@ const char *mdg_bam_writer_error(const mdg_bam_writer *writer);
  */
 int mdg_bam_write_batch(mdg_bam_writer *writer, const uint8_t *raw, const uint64_t *raw_off, int64_t n, const uint8_t *status,
                         const uint8_t *qual, const uint32_t *base_off, const float *mr);
+/*
+ * Encodes a struct-of-arrays batch as BAM records (synthetic data, format
+ * conversion): names are "<name_prefix><first_index + i>", MAPQ 37, and an
+ * RG:Z tag read_group_of_library[lib[i]] when that table is given.
+ */
+int mdg_bam_write_soa(mdg_bam_writer *writer, const mdg_batch *batch, int64_t first_index, const char *name_prefix,
+                      const char *const *read_group_of_library, int32_t n_libraries);
 /* Flushes, writes the BGZF end-of-file block and closes the file. */
 int mdg_bam_finish(mdg_bam_writer *writer);
 void mdg_bam_writer_free(mdg_bam_writer *writer);

@@ -92,6 +92,8 @@ SYMBOLS = {
     "mdg_bam_writer_error": (C.c_char_p, [C.c_void_p]),
     "mdg_bam_write_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "mdg_bam_write_soa": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int64, C.c_char_p, C.POINTER(C.c_char_p),
+                                    C.c_int32]),
     "mdg_bam_finish": (C.c_int, [C.c_void_p]),
     "mdg_bam_writer_free": (None, [C.c_void_p]),
     "mdg_nccl_unique_id": (C.c_int, [C.c_void_p]),

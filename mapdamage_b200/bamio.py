@@ -164,6 +164,19 @@ class BamWriter:
         if code < 0:
             raise OSError((self._lib.mdg_bam_writer_error(self._writer) or b"").decode())
 
+    def write_soa(self, batch, first_index=0, name_prefix="r", read_groups=None):
+        """Encodes ``batch`` (a :class:`ReadBatch`) as records; ``read_groups[lib]`` becomes the ``RG`` tag."""
+        from .engine import batch_struct
+
+        s = batch_struct(batch)
+        groups = None
+        if read_groups:
+            groups = (C.c_char_p * len(read_groups))(*[g.encode() for g in read_groups])
+        code = self._lib.mdg_bam_write_soa(self._writer, C.byref(s), first_index, name_prefix.encode(), groups,
+                                           len(read_groups) if read_groups else 0)
+        if code < 0:
+            raise OSError((self._lib.mdg_bam_writer_error(self._writer) or b"").decode())
+
     def close(self):
         if self._writer:
             code = self._lib.mdg_bam_finish(self._writer)

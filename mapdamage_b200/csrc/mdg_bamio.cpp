@@ -589,6 +589,75 @@ int mdg_bam_write_batch(mdg_bam_writer *w, const uint8_t *raw, const uint64_t *r
     return flush_blocks(w, false);
 }
 
+// Encodes the records of a struct-of-arrays batch (synthetic data, format conversion): names are
+// "<prefix><first_index + i>", MAPQ 37, optional RG:Z tag per library index.
+int mdg_bam_write_soa(mdg_bam_writer *w, const mdg_batch *b, int64_t first_index, const char *name_prefix,
+                      const char *const *read_group_of_library, int32_t n_libraries)
+{
+    if (!w || !b || b->n_reads < 0) return wfail(w, MDG_ERR_ARGUMENT, "mdg_bam_write_soa: bad argument");
+    if (b->n_reads && (!b->flag || !b->tid || !b->pos || !b->l_seq || !b->base_off || !b->cigar_off || !b->cigar || !b->seq4))
+        return wfail(w, MDG_ERR_ARGUMENT, "mdg_bam_write_soa: flag, tid, pos, l_seq, base_off, cigar_off, cigar and seq4 are required");
+    const char *prefix = name_prefix ? name_prefix : "r";
+    const int64_t chunk = 1 << 16;
+    for (int64_t start = 0; start < b->n_reads; start += chunk) {
+        const int64_t stop = std::min(b->n_reads, start + chunk);
+        for (int64_t i = start; i < stop; ++i) {
+            char name[64];
+            const int l_name = snprintf(name, sizeof name, "%s%lld", prefix, (long long)(first_index + i)) + 1;
+            const uint32_t c0 = b->cigar_off[i], n_cig = b->cigar_off[i + 1] - c0, l_seq = b->l_seq[i];
+            const char *rg = nullptr;
+            if (read_group_of_library && b->lib && b->lib[i] < n_libraries) rg = read_group_of_library[b->lib[i]];
+            const size_t l_rg = rg ? 3 + strlen(rg) + 1 : 0;
+            const size_t size = 32 + (size_t)l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq + l_rg;
+            const size_t at = w->pending.size();
+            w->pending.resize(at + 4 + size);
+            uint8_t *p = w->pending.data() + at;
+            put32(p, (uint32_t)size);
+            p += 4;
+            uint32_t span = 0;
+            for (uint32_t k = 0; k < n_cig; ++k) {
+                const uint32_t op = b->cigar[c0 + k] & 0xF;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += b->cigar[c0 + k] >> 4;
+            }
+            const int64_t beg = std::max<int64_t>(b->pos[i], 0), end = beg + (span ? span : 1) - 1;
+            uint32_t bin = 0;  // reg2bin, SAM specification 5.3
+            if (beg >> 14 == end >> 14) bin = (uint32_t)(4681 + (beg >> 14));
+            else if (beg >> 17 == end >> 17) bin = (uint32_t)(585 + (beg >> 17));
+            else if (beg >> 20 == end >> 20) bin = (uint32_t)(73 + (beg >> 20));
+            else if (beg >> 23 == end >> 23) bin = (uint32_t)(9 + (beg >> 23));
+            else if (beg >> 26 == end >> 26) bin = (uint32_t)(1 + (beg >> 26));
+            put32(p, (uint32_t)b->tid[i]);
+            put32(p + 4, (uint32_t)b->pos[i]);
+            p[8] = (uint8_t)l_name;
+            p[9] = 37;
+            put16(p + 10, bin);
+            put16(p + 12, n_cig);
+            put16(p + 14, b->flag[i]);
+            put32(p + 16, l_seq);
+            put32(p + 20, (uint32_t)(b->mtid ? b->mtid[i] : -1));
+            put32(p + 24, (uint32_t)(b->mpos ? b->mpos[i] : -1));
+            put32(p + 28, (uint32_t)(b->tlen ? b->tlen[i] : 0));
+            memcpy(p + 32, name, (size_t)l_name);
+            uint8_t *q = p + 32 + l_name;
+            memcpy(q, b->cigar + c0, 4ull * n_cig);
+            q += 4ull * n_cig;
+            memcpy(q, b->seq4 + b->base_off[i] / 2, (l_seq + 1) / 2);
+            if (l_seq & 1) q[l_seq / 2] &= 0xF0;
+            q += (l_seq + 1) / 2;
+            if (b->qual) memcpy(q, b->qual + b->base_off[i], l_seq);
+            else memset(q, 0xFF, l_seq);
+            q += l_seq;
+            if (rg) {
+                q[0] = 'R'; q[1] = 'G'; q[2] = 'Z';
+                memcpy(q + 3, rg, strlen(rg) + 1);
+            }
+        }
+        int rc = flush_blocks(w, false);
+        if (rc) return rc;
+    }
+    return MDG_OK;
+}
+
 int mdg_bam_finish(mdg_bam_writer *w)
 {
     if (!w) return MDG_ERR_ARGUMENT;

@@ -125,3 +125,29 @@ def test_large_file_round_trip(tmp_path):
     with BamReader(out, threads=2, merge_libraries=True, apply_filter=False) as reader:
         again = reader.read_batch(max_reads=50_000, keep_raw=True)
         assert again.n == want.n and np.array_equal(again.has_mr, np.arange(want.n) % 3 == 0)
+
+
+def test_soa_encoder(tmp_path):
+    """A batch written with write_soa decodes (Python codec and C decoder) to the same batch."""
+    from mapdamage_b200.samtext import SamHeader
+
+    reference = synth.make_reference([100_000, 5_000], seed=3)
+    batch = synth.simulate_reads(reference, 5_001, seed=8, length=(31, 99), mix=(6, 1, 1, 2), paired=False, n_libs=2)
+    header = SamHeader()
+    header.add("@HD\tVN:1.6\tSO:unsorted")
+    for name, length in zip(reference.names, reference.lengths):
+        header.add("@SQ\tSN:%s\tLN:%d" % (name, length))
+    header.add("@RG\tID:rgA\tSM:s\tLB:libA")
+    header.add("@RG\tID:rgB\tSM:s\tLB:libB")
+    with BamWriter(tmp_path / "soa.bam", header, threads=2) as writer:
+        writer.write_soa(batch.slice(0, 3000), first_index=0, read_groups=["rgA", "rgB"])
+        writer.write_soa(batch.slice(3000, batch.n), first_index=3000, read_groups=["rgA", "rgB"])
+    _, _, decoded = bam_py.read_bam(tmp_path / "soa.bam")
+    assert [d["qname"] for d in decoded[:2] + decoded[-1:]] == ["r0", "r1", "r%d" % (batch.n - 1)]
+    for i in (0, 17, 3000, batch.n - 1):
+        assert decoded[i]["seq"] == batch.sequence_of(i) and decoded[i]["qual"] == batch.qualities_of(i)
+        assert decoded[i]["cigar"] == batch.cigar_of(i) and decoded[i]["tags"]["RG"][1] == ("rgA", "rgB")[batch.lib[i]]
+    with BamReader(tmp_path / "soa.bam", merge_libraries=False, apply_filter=False) as reader:
+        assert reader.libraries == [("s", "libA"), ("s", "libB")]
+        got = reader.read_batch(max_reads=6000)
+    assert_same_batch(got, batch)
