@@ -10,9 +10,12 @@
 // Format: SAM/BAM specification v1.6, sections 4.1 (BGZF) and 4.2 (BAM).
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -56,6 +59,40 @@ struct Block {
 
 }  // namespace
 
+// growable byte buffer without value-initialisation (a vector would zero every refill)
+struct Bytes {
+    uint8_t *p = nullptr;
+    size_t len = 0, cap = 0;
+    ~Bytes() { free(p); }
+    uint8_t *data() { return p; }
+    const uint8_t *data() const { return p; }
+    size_t size() const { return len; }
+    bool reserve(size_t want)
+    {
+        if (want <= cap) return true;
+        size_t grown = std::max(want, cap + cap / 2 + (1 << 20));
+        uint8_t *q = (uint8_t *)realloc(p, grown);
+        if (!q) return false;
+        p = q;
+        cap = grown;
+        return true;
+    }
+    void drop_front(size_t n)
+    {
+        memmove(p, p + n, len - n);
+        len -= n;
+    }
+};
+
+// One unit of read-ahead: a slab of the file, its BGZF blocks, and their inflated bytes.
+struct Chunk {
+    Bytes compressed, inflated;
+    std::vector<Block> blocks;
+    bool last = false;  // the file ended in this chunk
+    int error = 0;
+    std::string message;
+};
+
 struct mdg_bam_reader {
     FILE *fp = nullptr;
     int n_threads = 1;
@@ -66,13 +103,21 @@ struct mdg_bam_reader {
     std::unordered_map<std::string, int32_t> library_of;  // read group id -> library index
     bool merge_libraries = true;
     // decompressed bytes not yet consumed
-    std::vector<uint8_t> stream;
+    Bytes stream;
     size_t stream_pos = 0;  // next unread byte
     size_t keep_from = 0;   // bytes before this may be dropped by the next refill (a batch under construction
                             // keeps its first record here; offsets relative to keep_from survive refills)
     bool eof = false;
-    std::vector<uint8_t> compressed;
     int64_t records_seen = 0;
+    // read-ahead: a producer thread reads and inflates the next chunk while the caller works on this one
+    Chunk chunks[2];
+    std::thread producer;
+    std::mutex mutex;
+    std::condition_variable cond;
+    int ready[2] = {0, 0};  // 1 = filled by the producer, waiting for the consumer
+    int produce_at = 0, consume_at = 0;
+    bool stop = false, producer_done = false;
+    Bytes carry;  // bytes of a BGZF block cut by the end of a slab
 };
 
 struct mdg_bam_writer {
@@ -99,59 +144,91 @@ int rfail(mdg_bam_reader *r, int code, const char *fmt, ...)
     return code;
 }
 
-// Reads up to `want_blocks` BGZF blocks from the file and inflates them onto the end of r->stream.
-int refill(mdg_bam_reader *r, int want_blocks)
+constexpr size_t SLAB_BYTES = 32u << 20;
+
+// Producer side: reads one slab of the file, cuts it into BGZF blocks and inflates them in parallel.
+void fill_chunk(mdg_bam_reader *r, Chunk &c)
 {
-    if (r->eof) return MDG_OK;
-    // drop what nobody needs any more
-    if (r->keep_from) {
-        r->stream.erase(r->stream.begin(), r->stream.begin() + (ptrdiff_t)r->keep_from);
-        r->stream_pos -= r->keep_from;
-        r->keep_from = 0;
+    c.blocks.clear();
+    c.error = 0;
+    c.last = false;
+    c.compressed.len = 0;
+    if (!c.compressed.reserve(r->carry.len + SLAB_BYTES)) {
+        c.error = MDG_ERR_ARGUMENT;
+        c.message = "out of host memory";
+        return;
     }
-    r->compressed.clear();
-    std::vector<Block> blocks;
-    size_t out_off = r->stream.size();
-    for (int k = 0; k < want_blocks; ++k) {
-        uint8_t head[18];
-        size_t got = fread(head, 1, 18, r->fp);
-        if (got == 0) {
-            r->eof = true;
-            break;
+    memcpy(c.compressed.p, r->carry.p, r->carry.len);
+    const size_t got = fread(c.compressed.p + r->carry.len, 1, SLAB_BYTES, r->fp);
+    c.compressed.len = r->carry.len + got;
+    r->carry.len = 0;
+    const bool file_done = got < SLAB_BYTES;
+    size_t at = 0, out_off = 0;
+    const uint8_t *in = c.compressed.p;
+    while (true) {
+        const size_t left = c.compressed.len - at;
+        if (left == 0) break;
+        int64_t total = -1;  // whole block size, when its header is complete
+        if (left >= 18) {
+            if (in[at] != 31 || in[at + 1] != 139 || in[at + 2] != 8 || !(in[at + 3] & 4)) {
+                c.error = MDG_ERR_DATA;
+                c.message = "not a BGZF block (bad gzip member header)";
+                return;
+            }
+            const uint32_t xlen = le16(in + at + 10);
+            if (left >= 12 + (size_t)xlen) {
+                int64_t bsize = -1;
+                for (size_t x = 0; x + 4 <= xlen;) {
+                    const uint32_t slen = le16(in + at + 12 + x + 2);
+                    if (in[at + 12 + x] == 'B' && in[at + 12 + x + 1] == 'C' && slen == 2 && x + 6 <= xlen)
+                        bsize = le16(in + at + 12 + x + 4);
+                    x += 4 + slen;
+                }
+                if (bsize < 0) {
+                    c.error = MDG_ERR_DATA;
+                    c.message = "BGZF block without a BC subfield";
+                    return;
+                }
+                total = bsize + 1;
+                if (total < 12 + (int64_t)xlen + 8) {
+                    c.error = MDG_ERR_DATA;
+                    c.message = "BGZF block with an impossible size";
+                    return;
+                }
+                if (left >= (size_t)total) {
+                    Block b;
+                    b.in_off = at + 12 + xlen;
+                    b.in_len = (size_t)total - 12 - xlen - 8;
+                    b.isize = le32(in + at + total - 4);
+                    b.out_off = out_off;
+                    out_off += b.isize;
+                    c.blocks.push_back(b);
+                    at += (size_t)total;
+                    continue;
+                }
+            }
         }
-        if (got != 18 || head[0] != 31 || head[1] != 139 || head[2] != 8 || !(head[3] & 4))
-            return rfail(r, MDG_ERR_DATA, "not a BGZF block (bad gzip member header)");
-        const uint32_t xlen = le16(head + 10);
-        // the BC subfield is first in every BGZF writer's output; search it all the same
-        std::vector<uint8_t> extra(xlen);
-        memcpy(extra.data(), head + 12, std::min<size_t>(6, xlen));
-        if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, r->fp) != xlen - 6)
-            return rfail(r, MDG_ERR_DATA, "truncated BGZF block header");
-        int64_t bsize = -1;
-        for (size_t at = 0; at + 4 <= xlen;) {
-            const uint32_t slen = le16(extra.data() + at + 2);
-            if (extra[at] == 'B' && extra[at + 1] == 'C' && slen == 2 && at + 6 <= xlen) bsize = le16(extra.data() + at + 4);
-            at += 4 + slen;
+        // an incomplete block at the end of the slab: carry it into the next one
+        if (file_done) {
+            c.error = MDG_ERR_DATA;
+            c.message = "truncated BGZF block";
+            return;
         }
-        if (bsize < 0) return rfail(r, MDG_ERR_DATA, "BGZF block without a BC subfield");
-        const int64_t payload = bsize + 1 - 12 - (int64_t)xlen - 8;  // minus header, extra, CRC32 + ISIZE
-        if (payload < 0) return rfail(r, MDG_ERR_DATA, "BGZF block with an impossible size");
-        const size_t at = r->compressed.size();
-        r->compressed.resize(at + (size_t)payload + 8);
-        if (fread(r->compressed.data() + at, 1, (size_t)payload + 8, r->fp) != (size_t)payload + 8)
-            return rfail(r, MDG_ERR_DATA, "truncated BGZF block");
-        Block b;
-        b.in_off = at;
-        b.in_len = (size_t)payload;
-        b.isize = le32(r->compressed.data() + at + payload + 4);
-        b.out_off = out_off;
-        out_off += b.isize;
-        blocks.push_back(b);
+        r->carry.reserve(left);
+        memcpy(r->carry.p, in + at, left);
+        r->carry.len = left;
+        break;
     }
-    r->stream.resize(out_off);
+    c.last = file_done;
+    if (!c.inflated.reserve(out_off + 8)) {
+        c.error = MDG_ERR_ARGUMENT;
+        c.message = "out of host memory";
+        return;
+    }
+    c.inflated.len = out_off;
     std::atomic<int> bad{0};
-    parallel_for((int64_t)blocks.size(), r->n_threads, [&](int64_t i) {
-        const Block &b = blocks[(size_t)i];
+    parallel_for((int64_t)c.blocks.size(), r->n_threads, [&](int64_t i) {
+        const Block &b = c.blocks[(size_t)i];
         if (!b.isize) return;
         z_stream z;
         memset(&z, 0, sizeof z);
@@ -159,19 +236,84 @@ int refill(mdg_bam_reader *r, int want_blocks)
             bad = 1;
             return;
         }
-        z.next_in = r->compressed.data() + b.in_off;
+        z.next_in = c.compressed.p + b.in_off;
         z.avail_in = (uInt)b.in_len;
-        z.next_out = r->stream.data() + b.out_off;
+        z.next_out = c.inflated.p + b.out_off;
         z.avail_out = b.isize;
         const int rc = inflate(&z, Z_FINISH);
         if (rc != Z_STREAM_END || z.avail_out != 0) bad = 1;
-        else if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), r->stream.data() + b.out_off, b.isize) !=
-                 le32(r->compressed.data() + b.in_off + b.in_len))
+        else if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), c.inflated.p + b.out_off, b.isize) != le32(c.compressed.p + b.in_off + b.in_len))
             bad = 2;
         inflateEnd(&z);
     });
-    if (bad) return rfail(r, MDG_ERR_DATA, bad == 2 ? "BGZF block fails its CRC32" : "BGZF block does not inflate");
-    return MDG_OK;
+    if (bad) {
+        c.error = MDG_ERR_DATA;
+        c.message = bad == 2 ? "BGZF block fails its CRC32" : "BGZF block does not inflate";
+    }
+}
+
+void producer_loop(mdg_bam_reader *r)
+{
+    while (true) {
+        Chunk *c;
+        {
+            std::unique_lock<std::mutex> lock(r->mutex);
+            r->cond.wait(lock, [&] { return r->stop || !r->ready[r->produce_at]; });
+            if (r->stop) break;
+            c = &r->chunks[r->produce_at];
+        }
+        fill_chunk(r, *c);
+        const bool done = c->last || c->error;
+        {
+            std::lock_guard<std::mutex> lock(r->mutex);
+            r->ready[r->produce_at] = 1;
+            r->produce_at ^= 1;
+            if (done) r->producer_done = true;
+        }
+        r->cond.notify_all();
+        if (done) break;
+    }
+}
+
+// Consumer side: appends the next inflated chunk to r->stream.
+int refill(mdg_bam_reader *r)
+{
+    if (r->eof) return MDG_OK;
+    // drop what nobody needs any more
+    if (r->keep_from) {
+        r->stream.drop_front(r->keep_from);
+        r->stream_pos -= r->keep_from;
+        r->keep_from = 0;
+    }
+    Chunk *c;
+    {
+        std::unique_lock<std::mutex> lock(r->mutex);
+        r->cond.wait(lock, [&] { return r->ready[r->consume_at] != 0; });
+        c = &r->chunks[r->consume_at];
+    }
+    int rc = MDG_OK;
+    if (c->error) {
+        rc = rfail(r, c->error, "%s", c->message.c_str());
+        r->eof = true;
+    } else {
+        if (!r->stream.reserve(r->stream.len + c->inflated.len + 8)) return rfail(r, MDG_ERR_ARGUMENT, "out of host memory");
+        // the copy is the only serial touch of the decompressed bytes; spread it over the pool
+        const size_t piece = 4u << 20, n_pieces = (c->inflated.len + piece - 1) / piece;
+        uint8_t *dst = r->stream.p + r->stream.len;
+        parallel_for((int64_t)n_pieces, std::min(r->n_threads, 8), [&](int64_t i) {
+            const size_t at = (size_t)i * piece;
+            memcpy(dst + at, c->inflated.p + at, std::min(piece, c->inflated.len - at));
+        });
+        r->stream.len += c->inflated.len;
+        if (c->last) r->eof = true;
+    }
+    {
+        std::lock_guard<std::mutex> lock(r->mutex);
+        r->ready[r->consume_at] = 0;
+        r->consume_at ^= 1;
+    }
+    r->cond.notify_all();
+    return rc;
 }
 
 // makes at least `need` unread bytes available; returns false at a clean end of file
@@ -182,11 +324,21 @@ int ensure(mdg_bam_reader *r, size_t need, bool *ok)
             *ok = false;
             return r->stream.size() == r->stream_pos ? MDG_OK : rfail(r, MDG_ERR_DATA, "BAM stream ends inside a record");
         }
-        int rc = refill(r, 64 * r->n_threads);
+        int rc = refill(r);
         if (rc) return rc;
     }
     *ok = true;
     return MDG_OK;
+}
+
+void stop_producer(mdg_bam_reader *r)
+{
+    {
+        std::lock_guard<std::mutex> lock(r->mutex);
+        r->stop = true;
+    }
+    r->cond.notify_all();
+    if (r->producer.joinable()) r->producer.join();
 }
 
 int read_header(mdg_bam_reader *r)
@@ -302,10 +454,12 @@ int mdg_bam_open(const char *path, int32_t n_threads, mdg_bam_reader **out)
         delete r;
         return MDG_ERR_ARGUMENT;
     }
-    setvbuf(r->fp, nullptr, _IOFBF, 1 << 22);
+    setvbuf(r->fp, nullptr, _IONBF, 0);  // slabs are read whole
+    r->producer = std::thread(producer_loop, r);
     int rc = read_header(r);
     if (rc) {
         g_open_error = r->error;
+        stop_producer(r);
         fclose(r->fp);
         delete r;
         return rc;
@@ -317,6 +471,7 @@ int mdg_bam_open(const char *path, int32_t n_threads, mdg_bam_reader **out)
 void mdg_bam_close(mdg_bam_reader *r)
 {
     if (!r) return;
+    stop_producer(r);
     if (r->fp) fclose(r->fp);
     delete r;
 }
