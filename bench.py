@@ -94,7 +94,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
+
+    def wait_for_samples(self, n=1, timeout=4.0):
+        """nvidia-smi takes a moment to print its first line; the load loop should not start before it."""
+        end = time.perf_counter() + timeout
+        while len(self.rows) < n and time.perf_counter() < end and self.proc is not None:
+            time.sleep(0.02)
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -107,23 +113,28 @@ class ClockSampler:
             self.thread.join(timeout=5)
         return False
 
-    def summary(self):
-        sm, mx, reasons = [], [], set()
+    def summary(self, t0=None, t1=None):
+        """Median SM clock and the throttle reasons seen while the load ran (``t0``..``t1``: the part of the
+        samples inside the timed region is reported separately; the load before it is the same loop)."""
+        sm, mx, reasons, inside = [], [], set(), 0
         for row in self.rows:
-            if len(row) < 7:
+            if len(row) < 8:
                 continue
             try:
-                sm.append(float(row[0]))
-                mx.append(float(row[1]))
+                sm.append(float(row[1]))
+                mx.append(float(row[2]))
             except ValueError:
                 continue
-            for name, state in zip(self.REASONS, row[3:7]):
+            if t0 is not None and t0 <= row[0] <= t1 + 0.1:
+                inside += 1
+            for name, state in zip(self.REASONS, row[4:8]):
                 if state.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_in_timed_region": inside,
+                "window": "sampled every 100 ms over the same counting loop: >= 1 s of untimed passes, then the timed steps"}
 
 
 def measured_peak():
@@ -189,8 +200,9 @@ def gpu_arm(args, rank, local_rank, world):
     import torch
 
     from mapdamage_b200 import multigpu, synth
-    from mapdamage_b200.engine import DamageEngine
+    from mapdamage_b200.engine import DamageEngine, bind_host_to_device
 
+    cpus = bind_host_to_device(local_rank)  # pinned batches on the GPU's own NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -273,19 +285,33 @@ def gpu_arm(args, rank, local_rank, world):
     check["full_size_invariants"] = "ok"
 
     # ---- value: resident batches, CUDA events on the compute stream ----
+    t_warm = time.perf_counter()
     for _ in range(args.warmup):
         one_pass()
     engine.sync()
-    engine.kernel_ms()
-    launches0 = engine.launch_count()
+    # the same number of extra passes on every rank (each pass ends in a collective): about one second of load
+    t_pass = max_over_ranks((time.perf_counter() - t_warm) / max(1, args.warmup))
+    n_sustain = int(min(2000, max(1, np.ceil(1.0 / max(t_pass, 1e-4)))))
     barrier()
     with ClockSampler(local_rank) as clocks:
+        # the timed region is tens of milliseconds, shorter than one nvidia-smi period: keep the same load
+        # running untimed until the sampler has seen it, then time the K steps without a gap
+        clocks.wait_for_samples(1)
+        for _ in range(n_sustain):
+            one_pass()
+        engine.sync()
+        engine.kernel_ms()
+        launches0 = engine.launch_count()
+        barrier()
+        t_start = time.perf_counter()
         engine.event_record(0)
         for _ in range(args.steps):
             one_pass()
         engine.event_record(1)
         ms = engine.event_elapsed_ms()
+        t_stop = time.perf_counter()
         barrier()
+    clock_summary = clocks.summary(t_start, t_stop)
     ms = max_over_ranks(ms)
     launches = engine.launch_count() - launches0
     kernel_ms = engine.kernel_ms()
@@ -360,8 +386,9 @@ def gpu_arm(args, rank, local_rank, world):
                     total * 90 / 1e9),
                 "parallelism": "reads sharded per GPU; NCCL all-reduce of the count tables per step" if world > 1
                 else "single GPU",
+                "host_cpus_bound": None if cpus is None else len(cpus),
             },
-            "clocks": clocks.summary(),
+            "clocks": clock_summary,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {

@@ -110,6 +110,10 @@ void mdg_destroy(mdg_ctx *ctx);
 const char *mdg_last_error(const mdg_ctx *ctx);
 int mdg_abi_version(void);
 
+/* "domain:bus:device.function" of a CUDA device: lets the host side place its threads and pinned
+ * buffers on the NUMA node the GPU hangs off (engine.bind_host_to_device). */
+int mdg_device_pci_bus_id(int32_t device, char *buf, int32_t cap);
+
 /* Page-locked host memory for batches/results (cudaHostAlloc). */
 void *mdg_host_alloc(size_t bytes);
 void mdg_host_free(void *ptr);

@@ -56,6 +56,7 @@ SYMBOLS = {
     "mdg_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Config)]),
     "mdg_destroy": (None, [C.c_void_p]),
     "mdg_last_error": (C.c_char_p, [C.c_void_p]),
+    "mdg_device_pci_bus_id": (C.c_int, [C.c_int32, C.c_char_p, C.c_int32]),
     "mdg_host_alloc": (C.c_void_p, [C.c_size_t]),
     "mdg_host_free": (None, [C.c_void_p]),
     "mdg_set_reference": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),

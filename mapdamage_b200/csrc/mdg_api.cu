@@ -455,6 +455,16 @@ int mdg_abi_version(void) { return MDG_ABI_VERSION; }
 
 const char *mdg_last_error(const mdg_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
+int mdg_device_pci_bus_id(int32_t device, char *buf, int32_t cap)
+{
+    if (!buf || cap < 16) return MDG_ERR_ARGUMENT;
+    if (cudaDeviceGetPCIBusId(buf, cap, device) != cudaSuccess) {
+        cudaGetLastError();
+        return MDG_ERR_NO_DEVICE;
+    }
+    return MDG_OK;
+}
+
 void *mdg_host_alloc(size_t bytes)
 {
     void *p = nullptr;

@@ -39,6 +39,31 @@ def batch_struct(batch, compact=False):
     return s
 
 
+def bind_host_to_device(device):
+    """Pins the calling process to the CPUs of the NUMA node GPU ``device`` is attached to, so that pinned
+    batches (first touch) and the copy engine's reads stay on that node.  Returns the CPU set, or ``None``
+    when the topology cannot be read.  Call before allocating pinned memory; one process per GPU."""
+    import os
+
+    buf = C.create_string_buffer(64)
+    if _native.load().mdg_device_pci_bus_id(device, buf, len(buf)) < 0:
+        return None
+    path = "/sys/bus/pci/devices/%s/local_cpulist" % buf.value.decode().lower()
+    try:
+        text = open(path).read().strip()
+        cpus = set()
+        for part in text.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except (OSError, ValueError):
+        return None
+
+
 class PinnedArena:
     """numpy arrays carved out of page-locked host memory (``mdg_host_alloc``)."""
 
