@@ -74,6 +74,8 @@ typedef struct {
  *
  * Optional arrays -- a NULL pointer stands for the common case and saves its
  * bytes on the host->device link (the pass is PCIe-bound end to end):
+ *   tid       NULL: every read is on contig 0 (single-contig references)
+ *   l_seq     NULL: the bases the read's CIGAR consumes (sum of M, I, S, =, X)
  *   lib       NULL: every read is in library 0
  *   tlen      NULL: 0 (only read for proper-pair first mates, statistics.py:121-124)
  *   mtid/mpos NULL: -1 (only read by the rescale pairing rule, rescale.py:318-337)

@@ -89,6 +89,14 @@ class ReadBatch:
             n = self.n
             drop = set()
             if n:
+                if not self.tid.any():
+                    drop.add("tid")
+                consumes = np.isin(self.cigar & 0xF, (0, 1, 4, 7, 8))
+                from_cigar = np.add.reduceat(np.where(consumes, self.cigar >> 4, 0).astype(np.int64),
+                                             self.cigar_off[:-1].astype(np.int64)) if self.cigar.shape[0] else None
+                if from_cigar is not None and np.all(np.diff(self.cigar_off.astype(np.int64)) > 0) \
+                        and np.array_equal(from_cigar, self.l_seq):
+                    drop.add("l_seq")
                 if not self.lib.any():
                     drop.add("lib")
                 if not (self.flag & 1).any():

@@ -206,8 +206,8 @@ int check_batch(mdg_ctx *ctx, const mdg_batch *h)
         return fail(ctx, MDG_ERR_ARGUMENT, "batch sizes must be non-negative and n_bases even");
     if (h->n_reads >= (1ll << 31) || h->n_cigar >= (1ll << 32) || h->n_bases >= (1ll << 32))
         return fail(ctx, MDG_ERR_ARGUMENT, "batch too large: split it (offsets are 32-bit)");
-    if (h->n_reads && (!h->flag || !h->tid || !h->pos || !h->l_seq || (h->n_cigar && !h->cigar) || (h->n_bases && !h->seq4)))
-        return fail(ctx, MDG_ERR_ARGUMENT, "batch lacks a required array (flag, tid, pos, l_seq, cigar, seq4)");
+    if (h->n_reads && (!h->flag || !h->pos || (h->n_cigar && !h->cigar) || (h->n_bases && !h->seq4)))
+        return fail(ctx, MDG_ERR_ARGUMENT, "batch lacks a required array (flag, pos, cigar, seq4)");
     if (h->n_reads && !h->cigar_off && h->n_cigar != h->n_reads)
         return fail(ctx, MDG_ERR_ARGUMENT, "cigar_off may only be NULL when every read has exactly one CIGAR op");
     return MDG_OK;
@@ -232,11 +232,11 @@ int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t s
 #define MDG_FILL(field, byte, bytes) \
     MDG_CUDA(ctx, cudaMemsetAsync((void *)a.view.field, byte, (size_t)(bytes), stream))
     MDG_H2D(flag, n * 2);
-    MDG_H2D(tid, n * 4);
     MDG_H2D(pos, n * 4);
-    MDG_H2D(l_seq, n * 4);
     MDG_H2D(cigar, h->n_cigar * 4);
     MDG_H2D(seq4, h->n_bases / 2);
+    if (h->tid) MDG_H2D(tid, n * 4);
+    else MDG_FILL(tid, 0, n * 4);
     // optional arrays: what a NULL pointer stands for is made on the device instead of crossing PCIe
     if (h->lib) MDG_H2D(lib, n * 2);
     else MDG_FILL(lib, 0, n * 2);
@@ -250,8 +250,16 @@ int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t s
     }
     if (h->cigar_off) MDG_H2D(cigar_off, (n + 1) * 4);
     if (h->base_off) MDG_H2D(base_off, n * 4);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (h->l_seq) {
+        MDG_H2D(l_seq, n * 4);
+    } else {
+        mdg::lseq_from_cigar<<<blocks, 256, 0, stream>>>(a.view.cigar, h->cigar_off ? a.view.cigar_off : nullptr, n,
+                                                         (uint32_t *)a.view.l_seq);
+        MDG_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
     if (!h->cigar_off || !h->base_off) {
-        const unsigned blocks = (unsigned)((n + 255) / 256);
         mdg::layout_block_totals<<<blocks, 256, 0, stream>>>(a.view.l_seq, n, a.scan_tmp);
         mdg::synth_scan_totals<<<1, 1024, 0, stream>>>(a.scan_tmp, (int64_t)blocks);
         mdg::layout_fill<<<blocks, 256, 0, stream>>>(a.view.l_seq, n, a.scan_tmp, h->base_off ? nullptr : (uint32_t *)a.view.base_off,

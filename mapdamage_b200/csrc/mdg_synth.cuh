@@ -188,6 +188,22 @@ __global__ void __launch_bounds__(256) layout_fill(const uint32_t *__restrict__ 
     }
 }
 
+// l_seq of a batch passed without it: the bases its CIGAR consumes from the read (M, I, S, =, X).
+// cigar_off == null: one op per read.
+__global__ void __launch_bounds__(256) lseq_from_cigar(const uint32_t *__restrict__ cigar, const uint32_t *__restrict__ cigar_off,
+                                                       int64_t n, uint32_t *l_seq)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c0 = cigar_off ? cigar_off[i] : (uint32_t)i, c1 = cigar_off ? cigar_off[i + 1] : (uint32_t)i + 1;
+    uint32_t len = 0;
+    for (uint32_t k = c0; k < c1; ++k) {
+        const uint32_t w = cigar[k], op = w & 0xF;
+        if (op == OP_M || op == OP_I || op == OP_S || op == OP_EQ || op == OP_X) len += w >> 4;
+    }
+    l_seq[i] = len;
+}
+
 __device__ __forceinline__ void place_read(const SynthDev &p, const DevRef &ref, uint64_t h, int32_t rspan,
                                            int32_t *tid, int64_t *pos)
 {

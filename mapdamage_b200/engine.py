@@ -216,9 +216,9 @@ class DamageEngine:
         """Bytes ``count`` (or ``rescale``) copies to the device for ``batch`` (see ``copy_batch``)."""
         n = batch.n
         drop = batch.droppable() if compact else ()
-        total = n * (2 + 4 + 4 + 4) + batch.cigar.nbytes + batch.total_bases // 2  # flag, tid, pos, l_seq, cigar, seq4
-        total += sum(size for name, size in (("lib", 2 * n), ("tlen", 4 * n), ("base_off", 4 * n),
-                                             ("cigar_off", 4 * (n + 1))) if name not in drop)
+        total = n * (2 + 4) + batch.cigar.nbytes + batch.total_bases // 2  # flag, pos, cigar, seq4
+        total += sum(size for name, size in (("tid", 4 * n), ("l_seq", 4 * n), ("lib", 2 * n), ("tlen", 4 * n),
+                                             ("base_off", 4 * n), ("cigar_off", 4 * (n + 1))) if name not in drop)
         if rescale:
             total += sum(4 * n for name in ("mtid", "mpos") if name not in drop)
         if batch.qual is not None and (rescale or self.min_qual > 0):

@@ -234,7 +234,7 @@ def test_optional_arrays_default_on_device(name):
     """NULL lib / tlen / base_off / cigar_off (mdg_batch optional arrays) count like the explicit arrays."""
     reference = synth.make_reference([300_000, 150_000, 4_000], seed=5)
     batch = synth.simulate_reads(reference, 30_000, seed=21, **SYNTH[name])
-    assert "base_off" in batch.droppable() and "lib" in batch.droppable()
+    assert {"base_off", "lib", "l_seq"} <= batch.droppable()
     if name == "se100_noqual":
         assert {"cigar_off", "tlen"} <= batch.droppable()
     tables = []
