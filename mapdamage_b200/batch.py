@@ -243,6 +243,28 @@ class _Concat:
         )
 
 
+def concatenate(batches):
+    """One batch holding the records of ``batches`` in order (all with or all without qualities)."""
+    batches = [b for b in batches if b.n]
+    if not batches:
+        return empty_batch()
+    base_shift = np.cumsum([0] + [b.total_bases for b in batches])
+    cigar_shift = np.cumsum([0] + [b.cigar.shape[0] for b in batches])
+    if base_shift[-1] >= 1 << 32:
+        raise ValueError("batch exceeds 2^32 bases")
+    with_qual = all(b.qual is not None for b in batches)
+    cat = np.concatenate
+    return ReadBatch(
+        flag=cat([b.flag for b in batches]), tid=cat([b.tid for b in batches]), pos=cat([b.pos for b in batches]),
+        lib=cat([b.lib for b in batches]), l_seq=cat([b.l_seq for b in batches]),
+        base_off=cat([b.base_off.astype(np.int64) + s for b, s in zip(batches, base_shift)]),
+        cigar_off=cat([b.cigar_off[:-1].astype(np.int64) + s for b, s in zip(batches, cigar_shift)] + [cigar_shift[-1:]]),
+        cigar=cat([b.cigar for b in batches]), seq4=cat([b.seq4[:b.total_bases // 2] for b in batches]),
+        qual=cat([b.qual[:b.total_bases] for b in batches]) if with_qual else None,
+        tlen=cat([b.tlen for b in batches]), mtid=cat([b.mtid for b in batches]), mpos=cat([b.mpos for b in batches]),
+    )
+
+
 def empty_batch(with_qual=True):
     z = np.zeros(0)
     return ReadBatch(flag=z, tid=z, pos=z, lib=z, l_seq=z, base_off=z,

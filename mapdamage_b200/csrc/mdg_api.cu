@@ -299,14 +299,10 @@ SwarKernel swar_kernel(bool qual, int max_threads, int reads)
 #define MDG_VARIANT(T, R) \
     if (max_threads == T && reads == R) return qual ? mdg::count_swar_kernel<true, T, R> : mdg::count_swar_kernel<false, T, R>;
     MDG_VARIANT(512, 1)
-    MDG_VARIANT(512, 2)
     MDG_VARIANT(384, 2)
-    MDG_VARIANT(384, 3)
-    MDG_VARIANT(256, 3)
 #undef MDG_VARIANT
-    // two co-resident blocks per SM: one stages its tile while the other counts
+    // the default: two co-resident 256-thread blocks per SM, one stages its tile while the other counts
     if (max_threads == 256 && reads == 1) return qual ? mdg::count_swar_kernel<true, 256, 1, 2> : mdg::count_swar_kernel<false, 256, 1, 2>;
-    if (max_threads == 256 && reads == 2) return qual ? mdg::count_swar_kernel<true, 256, 2, 2> : mdg::count_swar_kernel<false, 256, 2, 2>;
     return nullptr;
 }
 
@@ -586,7 +582,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             g.threads = (g.work_threads + 31) / 32 * 32;
             const char *tile_env = getenv("MDG_SWAR_TILE");
             const int tile_max = tile_env ? atoi(tile_env) : 2048;
-            const int blocks_per_sm = ctx->swar_max_threads == 256 && ctx->swar_reads <= 2 ? 2 : 1;
+            const int blocks_per_sm = ctx->swar_max_threads == 256 ? 2 : 1;
             ctx->swar_blocks_per_sm = blocks_per_sm;
             for (int tile : {2048, 1024, 512}) {
                 if (tile > tile_max) continue;
@@ -599,6 +595,8 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             }
             const char *uenv = getenv("MDG_SWAR_UNIFORM");
             g.uniform = !(uenv && uenv[0] == '0');
+            const char *fenv = getenv("MDG_SWAR_FLUSH_TILES");
+            g.flush_tiles = fenv ? atoi(fenv) : 0;
             if (g.tile) {
                 for (bool q : {false, true})
                     MDG_CREATE_CUDA(cudaFuncSetAttribute(swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads),

@@ -47,6 +47,7 @@ struct SwarGeom {
     int32_t work_threads;  // 2 * words * slots
     int32_t tile;          // reads staged per iteration of the block
     int32_t uniform;       // 1: tiles whose gap-free reads all have the same length are counted in one window per read
+    int32_t flush_tiles;   // > 0: reduce the private counters every so many tiles (tests); 0: only when they could overflow
 };
 
 // One staged read (16 bytes), shared by both anchors.  Base indices are kept as (32-bit word, nibble)
@@ -267,7 +268,7 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
     };
     // worst case every read of a tile lands on one strand: T / (slots / 2) reads per thread per tile
     // (the uniform mode never has fewer slots than the two-anchor mode it replaces)
-    const int flush_period = max(1, 60000 / ((T + (g.slots >> 1) - 1) / (g.slots >> 1)));
+    const int flush_period = g.flush_tiles > 0 ? g.flush_tiles : max(1, 60000 / ((T + (g.slots >> 1) - 1) / (g.slots >> 1)));
     int tiles_since_flush = 0;
     bool dirty = false;  // counters hold counts of the current mode
 
@@ -565,7 +566,6 @@ count_swar_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, SwarGeom
             for (int u = 0; u < PREP; ++u) h[u].cig0 = h[u].live && h[u].c1 > h[u].c0 ? __ldg(b.cigar + h[u].c0) : 0;
 #pragma unroll
             for (int u = 0; u < PREP; ++u) {
-                const int q = q0 + u * nthreads + tid;
                 int kind, rstrand;
                 uint32_t columns;
                 SwarRecord rec{};

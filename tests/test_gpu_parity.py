@@ -258,3 +258,39 @@ def test_optional_arrays_default_on_device(name):
         with pytest.raises(_native.NativeError) as info:
             engine.sync()
         assert info.value.code == _native.ERR_DATA
+
+
+@pytest.mark.parametrize("env", [{}, {"MDG_SWAR_FLUSH_TILES": "3"}, {"MDG_SWAR_VARIANT": "512,1"}, {"MDG_SWAR_VARIANT": "384,2"},
+                                 {"MDG_SWAR_UNIFORM": "0"}])
+@pytest.mark.parametrize("min_qual", [0, 25])
+def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
+    """1.3 M reads laid out so that every block of the bit-sliced kernel alternates between equal-length tiles
+    (two different lengths) and mixed tiles: exercises the counter flush on mode changes, the periodic flush,
+    and the other compiled variants of the kernel."""
+    from mapdamage_b200.batch import concatenate
+
+    for key, value in env.items():
+        monkeypatch.setenv(key, value)
+    reference = synth.make_reference([400_000, 90_000], seed=5, other_rate=0.001)
+    with DamageEngine(min_qual=min_qual, max_reads=1024) as engine:
+        engine.set_reference(reference)
+        parts = []
+        for k, kw in enumerate((dict(length=(100, 100)), dict(length=(35, 140), mix=(6, 1, 1, 2), read_n_rate=0.01),
+                                dict(length=(83, 83)), dict(length=(100, 100), filtered_rate=0.2))):
+            dev = engine.synth_batch(330_000, seed=50 + k, **kw)
+            parts.append(engine.download(dev))
+            dev.free()
+    batch = concatenate(parts)
+    want = oracle.count(batch, reference, minqual=min_qual, lg_bins=8192, threads=8)
+    with DamageEngine(min_qual=min_qual, max_reads=batch.n, max_cigar_ops=batch.cigar.shape[0],
+                      max_bases=batch.total_bases) as engine:
+        engine.set_reference(reference)
+        engine.count(batch)
+        got = engine.tables()
+        dev = engine.upload(batch)
+        engine.count_resident(dev)
+        twice = engine.tables()
+        dev.free()
+    for name, a, b, c in zip(("misincorp", "dnacomp", "lghist"), got, want, twice):
+        assert np.array_equal(a, b), name
+        assert np.array_equal(2 * a, c), name
