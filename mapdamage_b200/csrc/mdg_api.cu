@@ -16,6 +16,7 @@
 #include "../../include/mapdamage_b200.h"
 #include "mdg_count.cuh"
 #include "mdg_swar.cuh"
+#include "mdg_stage.cuh"
 #include "mdg_rescale.cuh"
 #include "mdg_synth.cuh"
 
@@ -128,6 +129,11 @@ struct mdg_ctx {
     // bit-sliced kernel for gap-free reads; complex reads go through a per-stream work list
     bool swar_enabled = false, force_general = false;
     int swar_max_threads = 256, swar_reads = 1, swar_blocks_per_sm = 2;
+    // staged bit-sliced kernel (mdg_stage.cuh): the default for gap-free reads
+    bool staged_enabled = false;
+    mdg::StagedGeom staged{};
+    size_t staged_smem_plain = 0, staged_smem_qual = 0;
+    int staged_tile_plain = 0, staged_tile_qual = 0, staged_threads = 512, staged_blocks_per_sm = 1;
     mdg::SwarGeom swar{};
     size_t swar_smem = 0;
     std::vector<WorkList> worklists;
@@ -289,6 +295,8 @@ int next_kernel_events(mdg_ctx *ctx, cudaEvent_t *start, cudaEvent_t *stop)
     return MDG_OK;
 }
 
+typedef void (*SwarKernelStaged)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::StagedGeom, uint32_t *,
+                                 unsigned long long *, mdg::SwarSubset);
 typedef void (*SwarKernel)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::SwarGeom, uint32_t *,
                            unsigned long long *, mdg::SwarSubset);
 
@@ -303,6 +311,15 @@ SwarKernel swar_kernel(bool qual, int max_threads, int reads)
 #undef MDG_VARIANT
     // the default: two co-resident 256-thread blocks per SM, one stages its tile while the other counts
     if (max_threads == 256 && reads == 1) return qual ? mdg::count_swar_kernel<true, 256, 1, 2> : mdg::count_swar_kernel<false, 256, 1, 2>;
+    return nullptr;
+}
+
+// staged kernel variants: block size / co-resident blocks
+SwarKernelStaged staged_kernel(bool qual, int threads)
+{
+    if (threads == 256) return qual ? mdg::count_staged_kernel<true, 256, 2> : mdg::count_staged_kernel<false, 256, 2>;
+    if (threads == 768) return qual ? mdg::count_staged_kernel<true, 768, 1> : mdg::count_staged_kernel<false, 768, 1>;
+    if (threads == 512) return qual ? mdg::count_staged_kernel<true, 512, 1> : mdg::count_staged_kernel<false, 512, 1>;
     return nullptr;
 }
 
@@ -367,11 +384,23 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         const int64_t n_tiles = (b.n_reads + ctx->swar.tile - 1) / ctx->swar.tile;
         const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->swar_blocks_per_sm, n_tiles);
         const bool q = b.qual && p.min_qual > 0;
-        SwarKernel kernel = swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads);
         const int nl = ctx->cfg.n_libraries;
+        // one launch of the bit-sliced kernel over a library's reads (or all reads) into the tables `tl`
+        auto launch_bitsliced = [&](const mdg::CountTables &tl, const mdg::SwarSubset &subset) {
+            if (ctx->staged_enabled) {
+                mdg::StagedGeom sg = ctx->staged;
+                sg.tile = q ? ctx->staged_tile_qual : ctx->staged_tile_plain;
+                const int64_t tiles = (b.n_reads + sg.tile - 1) / sg.tile;
+                const int sgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->staged_blocks_per_sm, tiles);
+                staged_kernel(q, ctx->staged_threads)<<<sgrid, sg.threads, q ? ctx->staged_smem_qual : ctx->staged_smem_plain, stream>>>(
+                    b, ctx->ref, p, tl, sg, wl->reads, wl->count, subset);
+            } else {
+                swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads)<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(
+                    b, ctx->ref, p, tl, ctx->swar, wl->reads, wl->count, subset);
+            }
+        };
         if (nl == 1) {
-            kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, ctx->count_tables, ctx->swar, wl->reads,
-                                                                         wl->count, mdg::SwarSubset{nullptr, nullptr, 0});
+            launch_bitsliced(ctx->count_tables, mdg::SwarSubset{nullptr, nullptr, 0});
             ctx->launches += 1;
         } else {
             // group the reads by library, then one pass per library into that library's tables
@@ -383,9 +412,7 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             mdg::library_scatter_kernel<<<(unsigned)((b.n_reads + 1023) / 1024), 256, (size_t)nl * 8, stream>>>(b, nl, cursors,
                                                                                                                 wl->by_library);
             MDG_CUDA(ctx, cudaGetLastError());
-            for (int lib = 0; lib < nl; ++lib)
-                kernel<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(b, ctx->ref, p, lib_tables(ctx, lib), ctx->swar, wl->reads,
-                                                                             wl->count, mdg::SwarSubset{wl->by_library, offsets, lib});
+            for (int lib = 0; lib < nl; ++lib) launch_bitsliced(lib_tables(ctx, lib), mdg::SwarSubset{wl->by_library, offsets, lib});
             ctx->launches += 3 + nl;
         }
         MDG_CUDA(ctx, cudaGetLastError());
@@ -604,6 +631,38 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 ctx->swar_enabled = true;
             }
         }
+        // staged kernel geometry
+        {
+            mdg::StagedGeom &sg = ctx->staged;
+            sg.words = g.words;
+            sg.uniform = g.uniform;
+            sg.flush_tiles = g.flush_tiles;
+            const char *kenv = getenv("MDG_KERNEL");
+            const char *tenv = getenv("MDG_STAGE_THREADS");
+            ctx->staged_threads = tenv && staged_kernel(false, atoi(tenv)) ? atoi(tenv) : 512;
+            ctx->staged_blocks_per_sm = ctx->staged_threads == 256 ? 2 : 1;
+            const int wpr = 2 * sg.words;
+            sg.threads = ctx->staged_threads / 32 * 32;
+            const bool fits_block = wpr * 2 <= sg.threads && cfg->length + cfg->around <= 2048 && cfg->around <= 64;
+            if (ctx->swar_enabled && fits_block && !(kenv && !strcmp(kenv, "swar"))) {
+                const size_t budget = (ctx->smem_optin + 1024) / ctx->staged_blocks_per_sm - 1024;
+                for (int with_qual = 0; with_qual < 2; ++with_qual) {
+                    const size_t nw = with_qual ? 3 : 2;
+                    const size_t fixed = ((size_t)32 * sg.threads + (size_t)wpr * 2 * 96 + 2 * wpr + 4 * MDG_LG_SMEM_BINS + 4 * L + 8) * 4;
+                    const size_t per_read = (4 + (size_t)(wpr | 1) * nw + 1) * 4;
+                    int tile = 0;
+                    if (fixed + 64 * per_read <= budget) tile = (int)std::min<size_t>(2048, (budget - fixed) / per_read / 32 * 32);
+                    if (const char *tile_env2 = getenv("MDG_STAGE_TILE")) tile = std::min(tile, std::max(32, atoi(tile_env2)));
+                    const size_t bytes = fixed + (size_t)tile * per_read;
+                    (with_qual ? ctx->staged_tile_qual : ctx->staged_tile_plain) = tile;
+                    (with_qual ? ctx->staged_smem_qual : ctx->staged_smem_plain) = bytes;
+                    if (tile)
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(staged_kernel(with_qual != 0, ctx->staged_threads),
+                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                }
+                ctx->staged_enabled = ctx->staged_tile_plain >= 64 && ctx->staged_tile_qual >= 64;
+            }
+        }
         const char *env = getenv("MDG_FORCE_GENERAL");
         ctx->force_general = env && env[0] == '1';
     }
@@ -673,8 +732,8 @@ int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, cons
     cudaFree(ctx->ref_block);
     ctx->ref_block = nullptr;
     ctx->ref = mdg::DevRef{};
-    // 256 bytes of "not a base" on both sides: the kernels read whole words around an alignment
-    const size_t pad = 256;
+    // 4 KB of "not a base" on both sides: the kernels read whole words around an alignment (up to L + A bases away)
+    const size_t pad = 4096;
     size_t words_bytes = align_up((size_t)n_bytes + pad);
     size_t off_bytes = align_up((size_t)n_contigs * 8);
     size_t len_bytes = align_up((size_t)n_contigs * 4);
