@@ -49,7 +49,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     uint32_t *const s_cx = s_mask + 2 * wpr_max;                  // [T] complex reads of the tile
     uint32_t *const s_lg = s_cx + T;                              // [kind][strand][MDG_LG_SMEM_BINS]
     uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;         // [end][strand][L]
-    uint32_t *const s_ctl = s_clip + 4 * L;                       // n_fwd, n_rev, n_cx, min / max columns
+    uint32_t *const s_ctl_base = s_clip + 4 * L;                  // two sets of {n_fwd, n_rev, n_cx, min / max columns, -, -, -}
 
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < l2_words + sub_words; i += nthreads) s_l2[i] = 0;
@@ -483,9 +483,15 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         if (live0) prefetch_bases(boff0, coff0);
         if (live1) prefetch_bases(boff1, coff1);
     }
+    int tile_parity = 0;
+    if (tid < 5) s_ctl_base[tid] = tid == 3 ? 0xffffffffu : 0u;
+    __syncthreads();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (tid < 5) s_ctl[tid] = tid == 3 ? 0xffffffffu : 0u;  // n_fwd, n_rev, n_cx, min columns, max columns
-        __syncthreads();
+        // the tile counters alternate between two sets: the other set was reset while the previous tile was counted,
+        // behind that tile's barriers, so no barrier is needed before this tile's appends
+        uint32_t *const s_ctl = s_ctl_base + 8 * (tile_parity & 1);
+        uint32_t *const s_ctl_next = s_ctl_base + 8 * ((tile_parity & 1) ^ 1);
+        ++tile_parity;
 
         const int64_t tile_start = tile * T;
         for (int q0 = 0; q0 < T; q0 += nthreads * PREP) {
@@ -590,6 +596,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
         __syncthreads();
 
+        if (tid < 5) s_ctl_next[tid] = tid == 3 ? 0xffffffffu : 0u;  // n_fwd, n_rev, n_cx, min columns, max columns
         // ---- count phase: this thread's window word of every stride-th read of its strand ----
         if (active) {
             const int n_mine = strand ? n_rev : n_fwd;
