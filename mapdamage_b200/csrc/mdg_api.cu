@@ -307,7 +307,6 @@ SwarKernel swar_kernel(bool qual, int max_threads, int reads)
 #define MDG_VARIANT(T, R) \
     if (max_threads == T && reads == R) return qual ? mdg::count_swar_kernel<true, T, R> : mdg::count_swar_kernel<false, T, R>;
     MDG_VARIANT(512, 1)
-    MDG_VARIANT(384, 2)
 #undef MDG_VARIANT
     // the default: two co-resident 256-thread blocks per SM, one stages its tile while the other counts
     if (max_threads == 256 && reads == 1) return qual ? mdg::count_swar_kernel<true, 256, 1, 2> : mdg::count_swar_kernel<false, 256, 1, 2>;
@@ -318,7 +317,6 @@ SwarKernel swar_kernel(bool qual, int max_threads, int reads)
 SwarKernelStaged staged_kernel(bool qual, int threads)
 {
     if (threads == 256) return qual ? mdg::count_staged_kernel<true, 256, 2> : mdg::count_staged_kernel<false, 256, 2>;
-    if (threads == 768) return qual ? mdg::count_staged_kernel<true, 768, 1> : mdg::count_staged_kernel<false, 768, 1>;
     if (threads == 512) return qual ? mdg::count_staged_kernel<true, 512, 1> : mdg::count_staged_kernel<false, 512, 1>;
     return nullptr;
 }

@@ -260,13 +260,14 @@ def test_optional_arrays_default_on_device(name):
         assert info.value.code == _native.ERR_DATA
 
 
-@pytest.mark.parametrize("env", [{}, {"MDG_SWAR_FLUSH_TILES": "3"}, {"MDG_SWAR_VARIANT": "512,1"}, {"MDG_SWAR_VARIANT": "384,2"},
-                                 {"MDG_SWAR_UNIFORM": "0"}])
+@pytest.mark.parametrize("env", [{}, {"MDG_SWAR_FLUSH_TILES": "3"}, {"MDG_SWAR_UNIFORM": "0"}, {"MDG_STAGE_THREADS": "256"},
+                                 {"MDG_STAGE_TILE": "96"}, {"MDG_KERNEL": "swar"},
+                                 {"MDG_KERNEL": "swar", "MDG_SWAR_VARIANT": "512,1", "MDG_SWAR_FLUSH_TILES": "2"}])
 @pytest.mark.parametrize("min_qual", [0, 25])
 def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
     """1.3 M reads laid out so that every block of the bit-sliced kernel alternates between equal-length tiles
     (two different lengths) and mixed tiles: exercises the counter flush on mode changes, the periodic flush,
-    and the other compiled variants of the kernel."""
+    and the other compiled variants of the bit-sliced kernels (staged: the default; one-phase: MDG_KERNEL=swar)."""
     from mapdamage_b200.batch import concatenate
 
     for key, value in env.items():
