@@ -311,31 +311,33 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         }
     };
 
-    // ---- count phase: class masks of one staged word pair ----
-    auto count = [&](uint32_t x, uint32_t y, uint32_t xc) {
-        const uint32_t y1 = y >> 1, y2 = y >> 2, y3 = y >> 3;
-        const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
-        acc0[0] += y & K1;
-        acc0[1] += y1 & K1;
-        acc0[2] += y2 & K1;
-        acc0[3] += y3 & K1;
-        acc0[4] += xc & K1;
-        acc0[5] += (xc >> 1) & K1;
-        acc0[6] += (xc >> 2) & K1;
-        acc0[7] += (xc >> 3) & K1;
-        acc0[8] += y & x1 & K1;    // A>C
-        acc0[9] += y & x2 & K1;    // A>G
-        acc0[10] += y & x3 & K1;   // A>T
-        acc0[11] += y1 & x & K1;   // C>A
-        acc0[12] += y1 & x2 & K1;  // C>G
-        acc0[13] += y1 & x3 & K1;  // C>T
-        acc0[14] += y2 & x & K1;   // G>A
-        acc0[15] += y2 & x1 & K1;  // G>C
-        acc0[16] += y2 & x3 & K1;  // G>T
-        acc0[17] += y3 & x & K1;   // T>A
-        acc0[18] += y3 & x1 & K1;  // T>C
-        acc0[19] += y3 & x2 & K1;  // T>G
-        if (++n0 == 15) spill0();
+    // ---- count phase: class masks of the staged word pairs of two reads at a time: the two instruction streams
+    // interleave and their masks are summed before they touch the counters (one 3-input add per class) ----
+    auto count2 = [&](uint32_t xa, uint32_t ya, uint32_t xca, uint32_t xb, uint32_t yb, uint32_t xcb) {
+#define MDG_CLASS(c, ea, eb) acc0[c] += ((ea) & K1) + ((eb) & K1);
+        MDG_CLASS(0, ya, yb)
+        MDG_CLASS(1, ya >> 1, yb >> 1)
+        MDG_CLASS(2, ya >> 2, yb >> 2)
+        MDG_CLASS(3, ya >> 3, yb >> 3)
+        MDG_CLASS(4, xca, xcb)
+        MDG_CLASS(5, xca >> 1, xcb >> 1)
+        MDG_CLASS(6, xca >> 2, xcb >> 2)
+        MDG_CLASS(7, xca >> 3, xcb >> 3)
+        MDG_CLASS(8, ya & (xa >> 1), yb & (xb >> 1))                  // A>C
+        MDG_CLASS(9, ya & (xa >> 2), yb & (xb >> 2))                  // A>G
+        MDG_CLASS(10, ya & (xa >> 3), yb & (xb >> 3))                 // A>T
+        MDG_CLASS(11, (ya >> 1) & xa, (yb >> 1) & xb)                 // C>A
+        MDG_CLASS(12, (ya >> 1) & (xa >> 2), (yb >> 1) & (xb >> 2))   // C>G
+        MDG_CLASS(13, (ya >> 1) & (xa >> 3), (yb >> 1) & (xb >> 3))   // C>T
+        MDG_CLASS(14, (ya >> 2) & xa, (yb >> 2) & xb)                 // G>A
+        MDG_CLASS(15, (ya >> 2) & (xa >> 1), (yb >> 2) & (xb >> 1))   // G>C
+        MDG_CLASS(16, (ya >> 2) & (xa >> 3), (yb >> 2) & (xb >> 3))   // G>T
+        MDG_CLASS(17, (ya >> 3) & xa, (yb >> 3) & xb)                 // T>A
+        MDG_CLASS(18, (ya >> 3) & (xa >> 1), (yb >> 3) & (xb >> 1))   // T>C
+        MDG_CLASS(19, (ya >> 3) & (xa >> 2), (yb >> 3) & (xb >> 2))   // T>G
+#undef MDG_CLASS
+        n0 += 2;
+        if (n0 >= 14) spill0();  // a 4-bit counter holds 15
     };
 
     // ---- staging of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
@@ -603,11 +605,16 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             const int stride = slots_of(mode) >> 1;
             const int row_step = (strand ? -stride : stride) * row_words;
             const uint32_t *at = s_stage + (size_t)(strand ? T - 1 - (slot >> 1) : (slot >> 1)) * row_words + ws;
-            for (int i = slot >> 1; i < n_mine; i += stride) {
-                const uint32_t x = at[0], y = at[plane];
-                const uint32_t xc = kQual ? at[2 * plane] : x;
-                at += row_step;
-                if (x | y | xc) count(x, y, xc);
+            for (int i = slot >> 1; i < n_mine; i += 2 * stride) {
+                const bool second = i + stride < n_mine;
+                const uint32_t xa = at[0], ya = at[plane];
+                const uint32_t xca = kQual ? at[2 * plane] : xa;
+                const uint32_t *at2 = second ? at + row_step : at;
+                uint32_t xb = at2[0], yb = at2[plane];
+                uint32_t xcb = kQual ? at2[2 * plane] : xb;
+                if (!second) xb = yb = xcb = 0;
+                at += 2 * row_step;
+                if (xa | ya | xca | xb | yb | xcb) count2(xa, ya, xca, xb, yb, xcb);
             }
         }
         __syncthreads();
