@@ -134,6 +134,12 @@ struct mdg_ctx {
     mdg::StagedGeom staged{};
     size_t staged_smem_plain = 0, staged_smem_qual = 0;
     int staged_tile_plain = 0, staged_tile_qual = 0, staged_threads = 512, staged_blocks_per_sm = 1;
+    // reads with one indel: staged too (three planes, smaller tiles) or left to the general kernel.  Chosen per
+    // launch from what the previous launches met (MDG_STAGE_INDELS=0/1 pins it): both give the same tables.
+    bool staged_indels = false, staged_indels_auto = true;
+    unsigned long long *indel_seen_dev = nullptr;  // reads with one indel met by the parse phase so far
+    unsigned long long *indel_seen_host = nullptr; // pinned copy, refreshed after every launch
+    int64_t reads_launched = 0;
     mdg::SwarGeom swar{};
     size_t swar_smem = 0;
     std::vector<WorkList> worklists;
@@ -313,11 +319,17 @@ SwarKernel swar_kernel(bool qual, int max_threads, int reads)
     return nullptr;
 }
 
-// staged kernel variants: block size / co-resident blocks
-SwarKernelStaged staged_kernel(bool qual, int threads)
+// staged kernel variants: quality mask, indel reads staged too (third plane), block size / co-resident blocks
+SwarKernelStaged staged_kernel(bool qual, bool indel, int threads)
 {
-    if (threads == 256) return qual ? mdg::count_staged_kernel<true, 256, 2> : mdg::count_staged_kernel<false, 256, 2>;
-    if (threads == 512) return qual ? mdg::count_staged_kernel<true, 512, 1> : mdg::count_staged_kernel<false, 512, 1>;
+    if (threads == 256) {
+        if (qual) return mdg::count_staged_kernel<true, true, 256, 2>;
+        return indel ? mdg::count_staged_kernel<false, true, 256, 2> : mdg::count_staged_kernel<false, false, 256, 2>;
+    }
+    if (threads == 512) {
+        if (qual) return mdg::count_staged_kernel<true, true, 512, 1>;
+        return indel ? mdg::count_staged_kernel<false, true, 512, 1> : mdg::count_staged_kernel<false, false, 512, 1>;
+    }
     return nullptr;
 }
 
@@ -383,14 +395,22 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->swar_blocks_per_sm, n_tiles);
         const bool q = b.qual && p.min_qual > 0;
         const int nl = ctx->cfg.n_libraries;
+        if (ctx->staged_enabled && ctx->staged_indels_auto && !ctx->staged_indels && ctx->indel_seen_host) {
+            // what earlier launches reported (the copy may lag a launch or two; it only steers speed)
+            const unsigned long long seen = *(volatile unsigned long long *)ctx->indel_seen_host;
+            if (seen * 50 > (unsigned long long)ctx->reads_launched && seen > 1000) ctx->staged_indels = true;
+        }
         // one launch of the bit-sliced kernel over a library's reads (or all reads) into the tables `tl`
         auto launch_bitsliced = [&](const mdg::CountTables &tl, const mdg::SwarSubset &subset) {
             if (ctx->staged_enabled) {
+                // three planes (quality mask or indel reads staged) leave room for fewer reads per tile
+                const bool three = q || ctx->staged_indels;
                 mdg::StagedGeom sg = ctx->staged;
-                sg.tile = q ? ctx->staged_tile_qual : ctx->staged_tile_plain;
+                sg.indel_seen = ctx->indel_seen_dev;
+                sg.tile = three ? ctx->staged_tile_qual : ctx->staged_tile_plain;
                 const int64_t tiles = (b.n_reads + sg.tile - 1) / sg.tile;
                 const int sgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->staged_blocks_per_sm, tiles);
-                staged_kernel(q, ctx->staged_threads)<<<sgrid, sg.threads, q ? ctx->staged_smem_qual : ctx->staged_smem_plain, stream>>>(
+                staged_kernel(q, ctx->staged_indels, ctx->staged_threads)<<<sgrid, sg.threads, three ? ctx->staged_smem_qual : ctx->staged_smem_plain, stream>>>(
                     b, ctx->ref, p, tl, sg, wl->reads, wl->count, subset);
             } else {
                 swar_kernel(q, ctx->swar_max_threads, ctx->swar_reads)<<<grid, ctx->swar.threads, ctx->swar_smem, stream>>>(
@@ -414,6 +434,9 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             ctx->launches += 3 + nl;
         }
         MDG_CUDA(ctx, cudaGetLastError());
+        ctx->reads_launched += b.n_reads;
+        if (ctx->staged_enabled && ctx->staged_indels_auto && !ctx->staged_indels && ctx->indel_seen_host)
+            MDG_CUDA(ctx, cudaMemcpyAsync(ctx->indel_seen_host, ctx->indel_seen_dev, 8, cudaMemcpyDeviceToHost, stream));
         // reads with indels / skips: the general kernel over the work list(s) (returns at once when empty)
         const int ggrid = (int)std::min<int64_t>(ctx->general_grid, (b.n_reads + 7) / 8);
         if (nl == 1 || !ctx->shared_slab) {
@@ -637,7 +660,10 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             sg.flush_tiles = g.flush_tiles;
             const char *kenv = getenv("MDG_KERNEL");
             const char *tenv = getenv("MDG_STAGE_THREADS");
-            ctx->staged_threads = tenv && staged_kernel(false, atoi(tenv)) ? atoi(tenv) : 512;
+            ctx->staged_threads = tenv && staged_kernel(false, false, atoi(tenv)) ? atoi(tenv) : 512;
+            const char *ienv = getenv("MDG_STAGE_INDELS");
+            ctx->staged_indels = ienv ? ienv[0] == '1' : false;
+            ctx->staged_indels_auto = !ienv;
             ctx->staged_blocks_per_sm = ctx->staged_threads == 256 ? 2 : 1;
             const int wpr = 2 * sg.words;
             sg.threads = ctx->staged_threads / 32 * 32;
@@ -647,18 +673,29 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 for (int with_qual = 0; with_qual < 2; ++with_qual) {
                     const size_t nw = with_qual ? 3 : 2;
                     const size_t fixed = ((size_t)32 * sg.threads + (size_t)wpr * 2 * 96 + 2 * wpr + 4 * MDG_LG_SMEM_BINS + 4 * L + 16) * 4;
-                    const size_t per_read = (4 + (size_t)(wpr | 1) * nw + 1) * 4;
+                    const size_t per_read = (4 + (size_t)(wpr | 1) * nw + 1 + (with_qual ? 1 : 0)) * 4;
                     int tile = 0;
                     if (fixed + 64 * per_read <= budget) tile = (int)std::min<size_t>(2048, (budget - fixed) / per_read / 32 * 32);
                     if (const char *tile_env2 = getenv("MDG_STAGE_TILE")) tile = std::min(tile, std::max(32, atoi(tile_env2)));
                     const size_t bytes = fixed + (size_t)tile * per_read;
                     (with_qual ? ctx->staged_tile_qual : ctx->staged_tile_plain) = tile;
                     (with_qual ? ctx->staged_smem_qual : ctx->staged_smem_plain) = bytes;
-                    if (tile)
-                        MDG_CREATE_CUDA(cudaFuncSetAttribute(staged_kernel(with_qual != 0, ctx->staged_threads),
+                    if (tile) {
+                        // with_qual sizes the three-plane layout: the quality-mask kernel and the indel-staging one
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(staged_kernel(with_qual != 0, with_qual != 0, ctx->staged_threads),
                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                        if (with_qual)
+                            MDG_CREATE_CUDA(cudaFuncSetAttribute(staged_kernel(false, true, ctx->staged_threads),
+                                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                    }
                 }
                 ctx->staged_enabled = ctx->staged_tile_plain >= 64 && ctx->staged_tile_qual >= 64;
+                if (ctx->staged_enabled) {
+                    MDG_CREATE_CUDA(cudaMalloc(&ctx->indel_seen_dev, 8));
+                    MDG_CREATE_CUDA(cudaMemset(ctx->indel_seen_dev, 0, 8));
+                    MDG_CREATE_CUDA(cudaHostAlloc((void **)&ctx->indel_seen_host, 8, cudaHostAllocDefault));
+                    *ctx->indel_seen_host = 0;
+                }
             }
         }
         const char *env = getenv("MDG_FORCE_GENERAL");
@@ -695,6 +732,8 @@ void mdg_destroy(mdg_ctx *ctx)
         cudaFree(slot.mr_out);
         cudaFree(slot.status_out);
     }
+    cudaFree(ctx->indel_seen_dev);
+    if (ctx->indel_seen_host) cudaFreeHost(ctx->indel_seen_host);
     for (auto &w : ctx->worklists) {
         cudaFree(w.reads);
         cudaFree(w.count);

@@ -24,16 +24,22 @@ struct StagedGeom {
     int32_t tile;         // reads staged per iteration of the block
     int32_t uniform;      // 1: one window per read for tiles of equal-length reads
     int32_t flush_tiles;  // > 0: reduce the counters every so many tiles (tests)
+    unsigned long long *indel_seen;  // kIndel == false: counts the one-indel reads handed to the general kernel
 };
 
 constexpr int STAGE_CHUNK = 4;  // consecutive words one thread stages at a time
 
-template <bool kQual, int kMaxThreads, int kBlocksPerSm>
+// kIndel: reads with exactly one insertion or deletion between two match blocks are staged too (a third plane holds
+// the read as the composition tables see it); without it they go to the general kernel's work list.
+template <bool kQual, bool kIndel, int kMaxThreads, int kBlocksPerSm>
 __global__ void __launch_bounds__(kMaxThreads, kBlocksPerSm)
 count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, StagedGeom g, uint32_t *__restrict__ worklist,
                     unsigned long long *__restrict__ work_count, SwarSubset sub)
 {
-    constexpr int NW = kQual ? 3 : 2;  // words staged per (read, window word): read, reference[, read before the quality mask]
+    // words staged per (read, window word): read and reference as the misincorporation tables see them[, the read as the
+    // composition tables see it: before the quality mask, and contiguous across a deletion]
+    constexpr bool kThree = kQual || kIndel;
+    constexpr int NW = kThree ? 3 : 2;
     extern __shared__ uint32_t smem[];
     const int nthreads = g.threads, T = g.tile, L = p.L, A = p.A, W = g.words;
     const int wpr_max = 2 * W;  // window words per read in the two-anchor mode (the uniform mode uses fewer)
@@ -46,7 +52,8 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     const int plane = T * row_words;
     uint32_t *const s_stage = (uint32_t *)(s_rec + T);            // [NW planes: read, reference(, unmasked read)][T][row_words]
     uint32_t *const s_mask = s_stage + (size_t)NW * plane;        // [wpr_max][2]: aligned / flank masks of a typical read
-    uint32_t *const s_cx = s_mask + 2 * wpr_max;                  // [T] complex reads of the tile
+    uint32_t *const s_gap = s_mask + 2 * wpr_max;                 // [T] (kIndel) first block | indel length << 15 | deletion << 19, or 0
+    uint32_t *const s_cx = s_gap + (kIndel ? T : 0);              // [T] complex reads of the tile
     uint32_t *const s_lg = s_cx + T;                              // [kind][strand][MDG_LG_SMEM_BINS]
     uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;         // [end][strand][L]
     uint32_t *const s_ctl_base = s_clip + 4 * L;                  // two sets of {n_fwd, n_rev, n_cx, min / max columns, -, -, -}
@@ -236,6 +243,102 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     int tiles_since_flush = 0;
     bool dirty = false;  // counters hold counts of the current mode
 
+    // ---- stage phase, reads with one indel (kIndel): window words [k0, k1) of one anchor ----
+    // Seen from an anchor, the alignment is a near block of n1 columns, the indel's g gap columns, and the far block.
+    // Read and reference run contiguously from the anchor through the near block; across the gap the side that
+    // has the gap falls g bases behind: after an insertion the reference, after a deletion the read.  Misincorporation
+    // positions are columns (statistics.py:26); composition positions are read bases (statistics.py:76-83), so the
+    // third plane holds the read contiguously.  The gap columns themselves are rare: their classes (ref>- / ->read)
+    // go straight to the tables with atomics.
+    auto eight_at = [&](const uint32_t *words32, int word0, int nibble_index, bool bam_order) {
+        // eight nibbles starting `nibble_index` nibbles after word word0 (may be negative)
+        const uint32_t *at = words32 + (word0 + (nibble_index >> 3));
+        uint32_t lo = __ldg(at), hi = __ldg(at + 1);
+        if (bam_order) { lo = natural_order(lo); hi = natural_order(hi); }
+        return __funnelshift_r(lo, hi, (nibble_index & 7) << 2);
+    };
+    auto low_quality = [&](int qword0, int nibble_index) {  // nibbles whose base quality is below --min-basequal
+        const int tq = nibble_index;
+        const uint32_t *q32 = (const uint32_t *)b.qual + 2 * (int64_t)(qword0 + (tq >> 3)) + ((tq >> 2) & 1);
+        const uint32_t qa = __ldg(q32), qm = __ldg(q32 + 1), qz = __ldg(q32 + 2);
+        const int sq = (tq & 3) << 3;
+        const uint32_t lo = __funnelshift_r(qa, qm, sq), hi = __funnelshift_r(qm, qz, sq);
+        const uint32_t mq = (uint32_t)p.min_qual * 0x01010101u;
+        uint32_t zl = (~((lo | 0x80808080u) - mq) & 0x80808080u) >> 7;
+        uint32_t zh = (~((hi | 0x80808080u) - mq) & 0x80808080u) >> 7;
+        zl |= zl >> 4;
+        zh |= zh >> 4;
+        return (((zl & 0x11u) | ((zl >> 8) & 0x1100u)) | (((zh & 0x11u) | ((zh >> 8) & 0x1100u)) << 16)) * 15u;
+    };
+    auto stage_indel_words = [&](const SwarRecord &rec, uint32_t gi, uint32_t *row, int anchor, int k0, int k1, int rstrand) {
+        const int cols = (int)(rec.cols & 0x7FFF);
+        const int gap = (int)((gi >> 15) & 15), first = (int)(gi & 0x7FFF);
+        const bool deletion = (gi >> 19) & 1;
+        const int n_query = cols - (deletion ? gap : 0), ref_span = cols - (deletion ? 0 : gap);
+        const int n1 = anchor ? cols - first - gap : first;  // near block as this anchor sees it
+        const int lf = (int)((rec.cols >> 16) & 0xFF), rf = (int)(rec.cols >> 24);
+        const int v_cols = min(L, cols), v_query = min(L, n_query);
+        const int qnib = (int)(rec.misc >> 20), rnib = (int)((rec.misc >> 16) & 7);
+        for (int k = k0; k < k1; ++k) {
+            const int pbase = 8 * k - A;
+            // memory offsets (bases from the first aligned base / reference base) of nibble 0, contiguous from the anchor
+            const int q_off = anchor ? n_query - 8 - pbase : pbase, r_off = anchor ? ref_span - 8 - pbase : pbase;
+            const int behind = anchor ? gap : -gap;  // where the lagging side sits, in memory order
+            uint32_t aligned, flank, comp, unused;
+            window_masks(anchor, k, v_cols, lf, rf, aligned, flank);
+            window_masks(anchor, k, v_query, 0, 0, comp, unused);
+            // near / gap / far columns of this word
+            uint32_t near, far;
+            if (anchor == 0) {
+                near = low_nibbles(4 * (n1 - pbase));            // positions < n1 (flank positions included)
+                far = ~low_nibbles(4 * (n1 + gap - pbase));      // positions >= n1 + gap
+            } else {
+                near = ~low_nibbles(4 * (pbase + 8 - n1));
+                far = low_nibbles(4 * (pbase + 8 - n1 - gap));
+            }
+            const uint32_t gap_cols = ~(near | far) & aligned;
+            const uint32_t xq = eight_at(seq32, (int)rec.qi, qnib + q_off, true);
+            const uint32_t yr = eight_at(ref32, (int)rec.ri, rnib + r_off, false);
+            uint32_t x_col, y_col, low = 0;
+            if (deletion) {
+                const uint32_t xs = eight_at(seq32, (int)rec.qi, qnib + q_off + behind, true);
+                x_col = (xq & near) | (xs & far);
+                y_col = yr;
+                if (kQual && (rec.cols & 0x8000u))
+                    low = (low_quality((int)rec.qi, qnib + q_off) & near) | (low_quality((int)rec.qi, qnib + q_off + behind) & far);
+            } else {
+                const uint32_t ys = eight_at(ref32, (int)rec.ri, rnib + r_off + behind, false);
+                x_col = xq;
+                y_col = (yr & near) | (ys & far);
+                if (kQual && (rec.cols & 0x8000u)) low = low_quality((int)rec.qi, qnib + q_off);
+            }
+            // composition: the read base at each query position, whatever its quality (statistics.py:75-83)
+            const uint32_t xc = xq & (one_hot_nibbles(xq) * 15u) & comp;
+            // misincorporation: columns with an A/C/G/T read base of sufficient quality; a deletion column has no
+            // read base but still counts its reference base (statistics.py:27-30)
+            const uint32_t valid = (one_hot_nibbles(x_col) * 15u) & aligned & ~low;
+            x_col &= valid;
+            const uint32_t del_cols = deletion ? gap_cols : 0u;
+            y_col &= valid | flank | del_cols;
+            uint32_t *at = row + (mode ? 0 : anchor * W) + k;
+            at[0] = x_col;
+            at[plane] = y_col;
+            at[2 * plane] = xc;
+            // the gap columns: ->read (insertion, needs a valid read base) or ref>- (deletion, needs a reference base)
+            uint32_t events = (deletion ? y_col : x_col) & gap_cols;
+            while (events) {
+                const int nib = (__ffs(events) - 1) >> 2;
+                uint32_t code = 31 - __clz((events >> (4 * nib)) & 15u);  // one-hot nibble -> base 0..3
+                events &= ~(15u << (4 * nib));
+                const int pos = anchor ? pbase + 7 - nib : pbase + nib;
+                if (rstrand) code = 3 - code;
+                const int cls = deletion ? 4 + 5 * (int)code + 4 : 4 + 5 * 4 + (int)code;
+                const int es = (anchor ^ rstrand) * 2 + rstrand;
+                atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + cls) * L + pos, 1ull);
+            }
+        }
+    };
+
     // ---- stage phase: the masked word pairs of window words [k0, k1) of one anchor of one read ----
     auto stage_words = [&](const SwarRecord &rec, uint32_t *row, int anchor, int k0, int k1) {
         const int cols = (int)(rec.cols & 0x7FFF);
@@ -281,8 +384,8 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             const uint32_t valid = (one_hot_nibbles(x) * 15u) & aligned;
             x &= valid;
             y &= valid | flank;
+            if (kThree) at[2 * plane] = x;  // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
             if (kQual) {
-                at[2 * plane] = x;  // DNAComposition.update_read ignores the quality mask (statistics.py:75-83)
                 if (rec.cols & 0x8000u) {
                     // align_with_qual, align.py:67-71: bases below --min-basequal become N on both sides.  The eight
                     // qualities of memory word j start at byte 8 (word) + shift / 4; three aligned words cover them.
@@ -340,16 +443,22 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         if (n0 >= 14) spill0();  // a 4-bit counter holds 15
     };
 
+    __shared__ uint32_t indel_here;  // one-indel reads this block left to the general kernel
+    if (tid == 0) indel_here = 0;
     // ---- staging of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
     struct Header {
         uint32_t index, flag, lib, l_seq, boff, c0, c1, cig0;
         int32_t tid_ref, pos;
         bool live;
     };
-    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, uint32_t &columns, SwarRecord &rec) {
+    auto stage_read = [&](const Header &h, int64_t r, int &kind, int &rstrand, uint32_t &columns, uint32_t &gap_info,
+                          SwarRecord &rec) {
         kind = 0;
         rstrand = 0;
         columns = 0;
+        gap_info = 0;
+        bool one_indel = false;
+        (void)one_indel;
         if (!h.live || (h.flag & FILTERED_FLAGS)) return;
         if (h.lib >= (uint32_t)p.n_lib) {
             atomicCAS(t.error_flag, 0, DATA_ERR_LIB);
@@ -362,6 +471,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         }
         rstrand = (h.flag >> 4) & 1;
         uint32_t lead = 0, trail = 0, cols = 0;
+        uint32_t gap_at = 0, gap_len = 0, gap_del = 0;  // one insertion / deletion between two match blocks (kIndel)
         int state = 0, n_lead = 0, n_trail = 0;
         bool simple = h.c1 > h.c0;
         for (uint32_t k = h.c0; k < h.c1 && simple; ++k) {
@@ -376,25 +486,41 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
                 if (match) cols += len;
                 else if (op == OP_S) { trail += len; ++n_trail; state = 2; }
                 else if (op == OP_H) state = 3;
-                else simple = false;
+                else if ((op == OP_I || op == OP_D) && !gap_len && len >= 1 && len <= 7 && cols >= 1) {
+                    gap_at = cols; gap_len = len; gap_del = op == OP_D;
+                    cols += len;
+                    state = 4;
+                } else simple = false;
             } else if (state == 2) {
                 if (op == OP_S) { trail += len; ++n_trail; }
                 else if (op == OP_H) state = 3;
+                else simple = false;
+            } else if (state == 4) {  // the match block after the indel
+                if (match && len >= 1) { cols += len; state = 1; }
                 else simple = false;
             } else {
                 simple = op == OP_H;
             }
         }
+        simple = simple && state != 4;
+        if (!kIndel && simple && gap_len) {
+            // this variant leaves one-indel reads to the general kernel; tell the host how common they are
+            simple = false;
+            one_indel = true;
+        }
+        const uint32_t n_query = cols - (gap_del ? gap_len : 0), ref_span = cols - (gap_len && !gap_del ? gap_len : 0);
         const int64_t pos = h.pos;
         const int64_t contig_len = ref.contig_len[h.tid_ref];
         const uint64_t ref0 = ref.contig_off[h.tid_ref] + (uint64_t)(pos > 0 ? pos : 0);
         simple = simple && state >= 1 && cols > 0 && cols < 32768 && n_lead <= 1 && n_trail <= 1 &&
-                 (uint64_t)lead + cols + trail == h.l_seq && pos >= 0 && pos + (int64_t)cols <= contig_len &&
+                 (uint64_t)lead + n_query + trail == h.l_seq && pos >= 0 && pos + (int64_t)ref_span <= contig_len &&
                  ref0 < (1ull << 33);
         kind = simple ? 1 : 2;
+        if (!kIndel && one_indel) atomicAdd(&indel_here, 1u);
         if (!simple) return;
-        columns = cols;
-        const int64_t aend = pos + cols;
+        columns = gap_len ? cols | 0x8000u : cols;  // a read with an indel never makes a tile "equal length"
+        gap_info = gap_len ? gap_at | gap_len << 15 | gap_del << 19 : 0;
+        const int64_t aend = pos + ref_span;
         const uint32_t lf = (uint32_t)min((int64_t)A, pos);
         const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
         uint32_t has_qual = 0;
@@ -414,7 +540,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             }
         } else {
             lkind = 1;
-            length = cols;
+            length = ref_span;
         }
         if (length >= 0) {
             if (length < MDG_LG_SMEM_BINS && length < p.lg_bins) {
@@ -520,9 +646,9 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
 #pragma unroll
             for (int u = 0; u < PREP; ++u) {
                 int kind, rstrand;
-                uint32_t columns;
+                uint32_t columns, gap_info;
                 SwarRecord rec{};
-                stage_read(h[u], h[u].index, kind, rstrand, columns, rec);
+                stage_read(h[u], h[u].index, kind, rstrand, columns, gap_info, rec);
                 if (g.uniform) {
                     const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
                     const uint32_t hi = __reduce_max_sync(0xffffffffu, kind == 1 ? columns : 0u);
@@ -544,7 +670,11 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
                         if (mine) {
                             const uint32_t at = base + __popc(m & lt);
                             if (which == 2) s_cx[at] = h[u].index;
-                            else s_rec[which == 0 ? at : T - 1 - at] = rec;
+                            else {
+                                const uint32_t row = which == 0 ? at : T - 1 - at;
+                                s_rec[row] = rec;
+                                if (kIndel) s_gap[row] = gap_info;
+                            }
                         }
                     }
                 }
@@ -592,7 +722,10 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         if (st_first >= 0) {
             for (int li = st_first; li < n_fwd + n_rev; li += st_step) {
                 const int row = li < n_fwd ? li : T - 1 - (li - n_fwd);
-                stage_words(s_rec[row], s_stage + (size_t)row * row_words, st_anchor, st_k0, st_k1);
+                if (kIndel && s_gap[row])
+                    stage_indel_words(s_rec[row], s_gap[row], s_stage + (size_t)row * row_words, st_anchor, st_k0, st_k1, li >= n_fwd);
+                else
+                    stage_words(s_rec[row], s_stage + (size_t)row * row_words, st_anchor, st_k0, st_k1);
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
@@ -608,10 +741,10 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             for (int i = slot >> 1; i < n_mine; i += 2 * stride) {
                 const bool second = i + stride < n_mine;
                 const uint32_t xa = at[0], ya = at[plane];
-                const uint32_t xca = kQual ? at[2 * plane] : xa;
+                const uint32_t xca = kThree ? at[2 * plane] : xa;
                 const uint32_t *at2 = second ? at + row_step : at;
                 uint32_t xb = at2[0], yb = at2[plane];
-                uint32_t xcb = kQual ? at2[2 * plane] : xb;
+                uint32_t xcb = kThree ? at2[2 * plane] : xb;
                 if (!second) xb = yb = xcb = 0;
                 at += 2 * row_step;
                 if (xa | ya | xca | xb | yb | xcb) count2(xa, ya, xca, xb, yb, xcb);
@@ -626,6 +759,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     }
 
     flush_block();
+    if (!kIndel && tid == 0 && indel_here && g.indel_seen) atomicAdd(g.indel_seen, (unsigned long long)indel_here);
     for (int i = tid; i < 4 * MDG_LG_SMEM_BINS; i += nthreads) {
         const uint32_t v = s_lg[i];
         if (v) atomicAdd(t.lghist + (size_t)(i / MDG_LG_SMEM_BINS) * p.lg_bins + i % MDG_LG_SMEM_BINS, (unsigned long long)v);

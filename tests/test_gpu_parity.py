@@ -261,7 +261,7 @@ def test_optional_arrays_default_on_device(name):
 
 
 @pytest.mark.parametrize("env", [{}, {"MDG_SWAR_FLUSH_TILES": "3"}, {"MDG_SWAR_UNIFORM": "0"}, {"MDG_STAGE_THREADS": "256"},
-                                 {"MDG_STAGE_TILE": "96"}, {"MDG_KERNEL": "swar"},
+                                 {"MDG_STAGE_TILE": "96"}, {"MDG_STAGE_INDELS": "1"}, {"MDG_STAGE_INDELS": "0"}, {"MDG_KERNEL": "swar"},
                                  {"MDG_KERNEL": "swar", "MDG_SWAR_VARIANT": "512,1", "MDG_SWAR_FLUSH_TILES": "2"}])
 @pytest.mark.parametrize("min_qual", [0, 25])
 def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
@@ -295,3 +295,32 @@ def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
     for name, a, b, c in zip(("misincorp", "dnacomp", "lghist"), got, want, twice):
         assert np.array_equal(a, b), name
         assert np.array_equal(2 * a, c), name
+
+
+@pytest.mark.parametrize("name", ["pe_mixed", "short", "long"])
+@pytest.mark.parametrize("min_qual,n_lib", [(0, 1), (20, 1), (0, 2), (13, 3)])
+def test_indel_reads_in_the_staged_kernel(name, min_qual, n_lib, monkeypatch):
+    """MDG_STAGE_INDELS=1: reads with one insertion / deletion are counted by the bit-sliced kernel itself (near block,
+    gap columns, lagging far block) instead of the general kernel; the tables do not change."""
+    monkeypatch.setenv("MDG_STAGE_INDELS", "1")
+    reference = synth.make_reference([300_000, 150_000, 4_000], seed=5, other_rate=0.002)
+    kw = dict(SYNTH[name])
+    kw["mix"] = (2, 3, 3, 2)  # mostly indel reads
+    batch = synth.simulate_reads(reference, 50_000, seed=31, n_libs=n_lib, **kw)
+    want = oracle.count(batch, reference, minqual=min_qual, n_lib=n_lib, lg_bins=8192, threads=4)
+    got = run_engine(batch, reference, n_lib=n_lib, min_qual=min_qual, chunks=2)
+    for key, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
+        assert np.array_equal(a, b), key
+    assert want[0][:, :, :, 4 + 5 * 4:4 + 5 * 4 + 4].sum() > 1000  # insertion classes are populated
+
+
+@pytest.mark.parametrize("case_dir,params", [c for c in golden_cases("counting")
+                                              if not c.values[1]["exception"]])
+def test_counting_golden_with_indels_staged(case_dir, params, tmp_path, monkeypatch):
+    monkeypatch.setenv("MDG_STAGE_INDELS", "1")
+    batch, reference, libraries, _ = load_counting_case(case_dir, params, tmp_path)
+    L, A = params["length"], params["around"]
+    mis, comp, lg, overflow = run_engine(batch, reference, n_lib=len(libraries), length=L, around=A,
+                                         min_qual=params["minqual"], chunks=2)
+    render_tables(tmp_path / "out", libraries, L, A, mis, comp, lg)
+    assert_tables_equal(tmp_path / "out", case_dir)
