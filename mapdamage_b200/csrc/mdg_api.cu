@@ -673,7 +673,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 for (int with_qual = 0; with_qual < 2; ++with_qual) {
                     const size_t nw = with_qual ? 3 : 2;
                     const size_t fixed = ((size_t)32 * sg.threads + (size_t)wpr * 2 * 96 + 2 * wpr + 4 * MDG_LG_SMEM_BINS + 4 * L + 16) * 4;
-                    const size_t per_read = (4 + (size_t)(wpr | 1) * nw + 1 + (with_qual ? 1 : 0)) * 4;
+                    const size_t per_read = (4 + (size_t)(wpr | 1) * nw + 1 + (with_qual ? 2 : 0)) * 4;
                     int tile = 0;
                     if (fixed + 64 * per_read <= budget) tile = (int)std::min<size_t>(2048, (budget - fixed) / per_read / 32 * 32);
                     if (const char *tile_env2 = getenv("MDG_STAGE_TILE")) tile = std::min(tile, std::max(32, atoi(tile_env2)));

@@ -53,7 +53,8 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     uint32_t *const s_stage = (uint32_t *)(s_rec + T);            // [NW planes: read, reference(, unmasked read)][T][row_words]
     uint32_t *const s_mask = s_stage + (size_t)NW * plane;        // [wpr_max][2]: aligned / flank masks of a typical read
     uint32_t *const s_gap = s_mask + 2 * wpr_max;                 // [T] (kIndel) first block | indel length << 15 | deletion << 19, or 0
-    uint32_t *const s_cx = s_gap + (kIndel ? T : 0);              // [T] complex reads of the tile
+    uint16_t *const s_gap_rows = (uint16_t *)(s_gap + (kIndel ? T : 0));  // [T] (kIndel) rows holding a read with an indel
+    uint32_t *const s_cx = s_gap + (kIndel ? T + (T + 1) / 2 : 0);  // [T] complex reads of the tile
     uint32_t *const s_lg = s_cx + T;                              // [kind][strand][MDG_LG_SMEM_BINS]
     uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;         // [end][strand][L]
     uint32_t *const s_ctl_base = s_clip + 4 * L;                  // two sets of {n_fwd, n_rev, n_cx, min / max columns, -, -, -}
@@ -612,7 +613,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         if (live1) prefetch_bases(boff1, coff1);
     }
     int tile_parity = 0;
-    if (tid < 5) s_ctl_base[tid] = tid == 3 ? 0xffffffffu : 0u;
+    if (tid < 6) s_ctl_base[tid] = tid == 3 ? 0xffffffffu : 0u;
     __syncthreads();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // the tile counters alternate between two sets: the other set was reset while the previous tile was counted,
@@ -673,7 +674,10 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
                             else {
                                 const uint32_t row = which == 0 ? at : T - 1 - at;
                                 s_rec[row] = rec;
-                                if (kIndel) s_gap[row] = gap_info;
+                                if (kIndel) {
+                                    s_gap[row] = gap_info;
+                                    if (gap_info) s_gap_rows[atomicAdd(s_ctl + 5, 1u)] = (uint16_t)row;
+                                }
                             }
                         }
                     }
@@ -722,16 +726,22 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         if (st_first >= 0) {
             for (int li = st_first; li < n_fwd + n_rev; li += st_step) {
                 const int row = li < n_fwd ? li : T - 1 - (li - n_fwd);
-                if (kIndel && s_gap[row])
-                    stage_indel_words(s_rec[row], s_gap[row], s_stage + (size_t)row * row_words, st_anchor, st_k0, st_k1, li >= n_fwd);
-                else
-                    stage_words(s_rec[row], s_stage + (size_t)row * row_words, st_anchor, st_k0, st_k1);
+                if (kIndel && s_gap[row]) continue;  // second pass below: whole warps of indel reads
+                stage_words(s_rec[row], s_stage + (size_t)row * row_words, st_anchor, st_k0, st_k1);
+            }
+            if (kIndel) {
+                const int n_gap = (int)s_ctl[5];
+                for (int gi = st_first; gi < n_gap; gi += st_step) {
+                    const int row = s_gap_rows[gi];
+                    stage_indel_words(s_rec[row], s_gap[row], s_stage + (size_t)row * row_words, st_anchor, st_k0, st_k1,
+                                      row >= T - n_rev);
+                }
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
         __syncthreads();
 
-        if (tid < 5) s_ctl_next[tid] = tid == 3 ? 0xffffffffu : 0u;  // n_fwd, n_rev, n_cx, min columns, max columns
+        if (tid < 6) s_ctl_next[tid] = tid == 3 ? 0xffffffffu : 0u;  // n_fwd, n_rev, n_cx, min / max columns, indel rows
         // ---- count phase: this thread's window word of every stride-th read of its strand ----
         if (active) {
             const int n_mine = strand ? n_rev : n_fwd;
