@@ -292,6 +292,19 @@ int64_t mdg_bam_read_batch(mdg_bam_reader *reader, const mdg_batch *out, int64_t
 /* Records walked so far, dropped ones included. */
 int64_t mdg_bam_records_seen(const mdg_bam_reader *reader);
 
+/*
+ * Down-sampling of the kept reads (reader.py:134-164).  `mt_state` is the state of CPython's random.Random(seed):
+ * 624 MT19937 words followed by the position (getstate()[1]); it is advanced in place, so consecutive calls continue
+ * the reference's single stream of draws.
+ *   fraction:  keep[i] = (random() < fraction) for the next n kept reads, one draw per read (reader.py:139-142).
+ *   reservoir: reads first_index .. first_index + n of the stream; read `index` lands in slot `index` while
+ *              index < n_slots, else in slot randint(0, index) when that is < n_slots (reader.py:151-158).
+ *              slots[n_slots] holds the index of the read currently in each slot; the caller fills it with -1 first
+ *              and selects the reads left in it after the last call.
+ */
+int mdg_sample_fraction(uint32_t *mt_state, double fraction, int64_t n, uint8_t *keep);
+int mdg_sample_reservoir(uint32_t *mt_state, int64_t first_index, int64_t n, int64_t n_slots, int64_t *slots);
+
 /* BAM writer: header as given, BGZF blocks deflated at `level` (0-9, < 0 = 1) on n_threads threads. */
 int mdg_bam_create(const char *path, const char *header_text, const char *const *ref_names, const uint32_t *ref_lengths,
                    int32_t n_refs, int32_t n_threads, int32_t level, mdg_bam_writer **out);

@@ -4,6 +4,7 @@ There is no Python or CPU implementation behind this module: if the CUDA
 library is missing or cannot be loaded, importing the engine fails loudly.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 LIBRARY = Path(__file__).resolve().parent / "libmapdamage_b200.so"
@@ -88,6 +89,8 @@ SYMBOLS = {
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]),
     "mdg_bam_records_seen": (C.c_int64, [C.c_void_p]),
+    "mdg_sample_fraction": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, C.c_void_p]),
+    "mdg_sample_reservoir": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "mdg_bam_create": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_int32, C.POINTER(C.c_void_p)]),
     "mdg_bam_writer_error": (C.c_char_p, [C.c_void_p]),
@@ -117,7 +120,7 @@ def load():
             raise ImportError(
                 "%s is missing: build it with `python -m mapdamage_b200.build` "
                 "(mapdamage_b200 has no CPU implementation)" % LIBRARY)
-        lib = C.CDLL(str(LIBRARY))
+        lib = C.CDLL(os.environ.get("MDG_LIBRARY") or str(LIBRARY))  # MDG_LIBRARY: an alternative build (A/B runs)
         for name, (restype, argtypes) in SYMBOLS.items():
             fn = getattr(lib, name)
             fn.restype = restype

@@ -16,8 +16,11 @@ image) or SAM text (per-record Python, for small files and tests).
 import logging
 from pathlib import Path
 
+import numpy as np
+
+from . import downsample as _downsample
 from . import statistics
-from .batch import BatchBuilder
+from .batch import FILTERED_FLAGS, BatchBuilder
 from .engine import DamageEngine
 from .refgenome import Reference
 from .samtext import iter_sam
@@ -26,7 +29,8 @@ TABLE_FILES = ("misincorporation.txt", "dnacomp.txt", "lgdistribution.txt")
 
 
 def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_libraries=False,
-                     folder=None, batch_reads=1 << 20, device=0, lg_bins=1 << 16, engine=None):
+                     folder=None, batch_reads=1 << 20, device=0, lg_bins=1 << 16, engine=None,
+                     downsample=None, downsample_seed=None):
     """Counting pass over one alignment file.
 
     ``ref`` is a FASTA path or a :class:`Reference`.  Returns
@@ -35,13 +39,24 @@ def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_
     when ``folder`` is given, writes the three tables into it the way
     ``main.py:229-231`` does.  Raises :class:`~mapdamage_b200.batch.BAMError`
     where the reference does (read without a known read group, ``reader.py:63-81``).
+
+    ``downsample`` / ``downsample_seed`` are the reference's ``-n`` / ``--downsample-seed`` (``reader.py:84-96``):
+    a fraction below 1 or a number of reads, drawn with the reference's own sequence of random numbers
+    (:mod:`~mapdamage_b200.downsample`).
     """
     log = logging.getLogger(__name__)
     filename = Path(filename)
+    sampler = _downsample.sampler_for(downsample, downsample_seed)
     if filename.suffix.lower() == ".bam":
         return _count_bam(filename, ref, length, around, min_basequal, merge_libraries, folder, batch_reads, device,
-                          lg_bins, engine)
+                          lg_bins, engine, sampler)
+    if isinstance(sampler, _downsample.ReservoirSampler):
+        # the reservoir is known once the whole stream has been walked: first pass over the flags only
+        sampler.feed(sum(1 for record in iter_sam(filename)[1] if not record.flag & FILTERED_FLAGS))
+        sampler = _downsample.Selection(sampler.selected())
     header, records = iter_sam(filename)
+    if sampler is not None:
+        records = _drawn(records, sampler)
     reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
     reference = reference.reordered(header.references)
     builder = BatchBuilder(readgroups=None if merge_libraries else header.libraries(),
@@ -70,11 +85,35 @@ def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_
     return _finish(libraries, length, around, mis, comp, lg, overflow, folder)
 
 
-def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, folder, batch_reads, device, lg_bins, engine):
+def _drawn(records, sampler, chunk=4096):
+    """Records the flag filter drops pass through (the builder counts and drops them); of the others, those drawn."""
+    keep, k = sampler.mask(chunk), 0
+    for record in records:
+        if record.flag & FILTERED_FLAGS:
+            yield record
+            continue
+        if k == chunk:
+            keep, k = sampler.mask(chunk), 0
+        if keep[k]:
+            yield record
+        k += 1
+
+
+def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, folder, batch_reads, device, lg_bins, engine,
+               sampler=None):
     """BAM input: batches come straight out of the native decoder (``bamio.BamReader``) into pinned buffers."""
     from .bamio import BamReader
 
     log = logging.getLogger(__name__)
+    if isinstance(sampler, _downsample.ReservoirSampler):
+        with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True) as reader:
+            buffers = reader.buffers(batch_reads, with_qual=False)
+            while True:
+                batch = reader.read_batch(buffers=buffers)
+                if batch is None:
+                    break
+                sampler.feed(batch.n)
+        sampler = _downsample.Selection(sampler.selected())
     with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True) as reader:
         reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
         reference = reference.reordered(reader.header.references)
@@ -94,6 +133,9 @@ def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, fol
                 batch = reader.read_batch(buffers=sets[turn % 3])
                 if batch is None:
                     break
+                if sampler is not None:
+                    # every read of the batch passed the flag filter; those not drawn get a filtered flag
+                    _downsample.apply_mask(batch, np.ones(batch.n, dtype=np.bool_), sampler.mask(batch.n))
                 engine.count(batch, compact=False)
                 n_kept += batch.n
                 turn += 1

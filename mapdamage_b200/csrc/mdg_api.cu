@@ -884,6 +884,19 @@ int mdg_sync(mdg_ctx *ctx)
     for (auto &slot : ctx->slots)
         if (slot.stream) MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
     MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+#ifdef MDG_PHASE_CLOCKS
+    {
+        unsigned int pc[16];
+        if (cudaMemcpyFromSymbol(pc, mdg::mdg_phase_dump, sizeof(pc)) == cudaSuccess) {
+            static const char *names[8] = {"parse", "sync", "mode", "stage", "sync", "count", "sync", "rest"};
+            for (int w = 0; w < 2; ++w) {
+                fprintf(stderr, "phase clocks %s warp:", w ? "last " : "first");
+                for (int i = 0; i < 8; ++i) fprintf(stderr, " %s %u", names[i], pc[8 * w + i]);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
+#endif
     return check_device_errors(ctx);
 }
 

@@ -31,6 +31,10 @@ constexpr int STAGE_CHUNK = 4;  // consecutive words one thread stages at a time
 
 // kIndel: reads with exactly one insertion or deletion between two match blocks are staged too (a third plane holds
 // the read as the composition tables see it); without it they go to the general kernel's work list.
+#ifdef MDG_PHASE_CLOCKS
+__device__ unsigned int mdg_phase_dump[16];
+#endif
+
 template <bool kQual, bool kIndel, int kMaxThreads, int kBlocksPerSm>
 __global__ void __launch_bounds__(kMaxThreads, kBlocksPerSm)
 count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, StagedGeom g, uint32_t *__restrict__ worklist,
@@ -615,6 +619,28 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     int tile_parity = 0;
     if (tid < 6) s_ctl_base[tid] = tid == 3 ? 0xffffffffu : 0u;
     __syncthreads();
+#ifdef MDG_PHASE_CLOCKS
+    // per-phase cycle counts as the first and the last warp see them (shared memory: no registers held);
+    // block 3's land in mdg_phase_dump, which mdg_sync prints
+    __shared__ unsigned int s_pc[2][9];
+    if (tid < 18) (&s_pc[0][0])[tid] = 0;
+    __syncthreads();
+    const int warp = tid >> 5;
+    const bool pc_warp = warp == 0 || warp == (nthreads >> 5) - 1;
+    if (pc_warp && lane == 0) s_pc[warp != 0][8] = (unsigned int)clock();
+    __syncwarp();
+#define MDG_PHASE(i)                                              \
+    if (pc_warp) {                                                \
+        const unsigned int pt1 = (unsigned int)clock();           \
+        if (lane == 0) {                                          \
+            s_pc[warp != 0][i] += pt1 - s_pc[warp != 0][8];       \
+            s_pc[warp != 0][8] = pt1;                             \
+        }                                                         \
+        __syncwarp();                                             \
+    }
+#else
+#define MDG_PHASE(i)
+#endif
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // the tile counters alternate between two sets: the other set was reset while the previous tile was counted,
         // behind that tile's barriers, so no barrier is needed before this tile's appends
@@ -684,9 +710,9 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
                 }
             }
         }
+        MDG_PHASE(0)
         __syncthreads();
-
-        __syncthreads();
+        MDG_PHASE(1)
 
         // ---- complex reads go to the general kernel's work list ----
         if (tid < 32 && s_ctl[2]) {
@@ -722,6 +748,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         const bool ahead_live = !subset && prefetch_headers(tile + 2 * (int64_t)gridDim.x, ahead_boff, ahead_coff);
 
         // ---- stage phase ----
+        MDG_PHASE(2)
         const int n_fwd = (int)s_ctl[0], n_rev = (int)s_ctl[1];
         if (st_first >= 0) {
             for (int li = st_first; li < n_fwd + n_rev; li += st_step) {
@@ -739,7 +766,9 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
+        MDG_PHASE(3)
         __syncthreads();
+        MDG_PHASE(4)
 
         if (tid < 6) s_ctl_next[tid] = tid == 3 ? 0xffffffffu : 0u;  // n_fwd, n_rev, n_cx, min / max columns, indel rows
         // ---- count phase: this thread's window word of every stride-th read of its strand ----
@@ -760,13 +789,20 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
                 if (xa | ya | xca | xb | yb | xcb) count2(xa, ya, xca, xb, yb, xcb);
             }
         }
+        MDG_PHASE(5)
         __syncthreads();
+        MDG_PHASE(6)
         if (++tiles_since_flush == flush_period) {
             flush_block();
             tiles_since_flush = 0;
             dirty = false;
         }
+        MDG_PHASE(7)
     }
+#ifdef MDG_PHASE_CLOCKS
+    __syncthreads();
+    if (blockIdx.x == 3 && tid < 16) mdg_phase_dump[tid] = s_pc[tid >> 3][tid & 7];
+#endif
 
     flush_block();
     if (!kIndel && tid == 0 && indel_here && g.indel_seen) atomicAdd(g.indel_seen, (unsigned long long)indel_here);

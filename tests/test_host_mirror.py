@@ -115,6 +115,21 @@ def test_count_alignments_from_bam(case_dir, params, tmp_path):
     assert_tables_equal(tmp_path / "out", case_dir)
 
 
+@pytest.mark.parametrize("as_bam", [False, True], ids=["sam", "bam"])
+@pytest.mark.parametrize("case_dir,params", golden_cases("counting_downsample"))
+def test_count_alignments_downsampled(case_dir, params, as_bam, tmp_path):
+    """``-n X --downsample-seed S`` (reader.py:84-96): the reads the reference drew, the tables it wrote."""
+    sam, fasta = materialise_inputs(case_dir.parent / params["source"], params, tmp_path)
+    if as_bam:
+        _as_bam(sam, tmp_path / "input.bam", block_bytes=4096)
+        sam = tmp_path / "input.bam"
+    counting.count_alignments(sam, fasta, length=params["length"], around=params["around"],
+                              min_basequal=params["minqual"], merge_libraries=params["merge_libraries"],
+                              folder=tmp_path / "out", batch_reads=256,
+                              downsample=params["downsample"], downsample_seed=params["downsample_seed"])
+    assert_tables_equal(tmp_path / "out", case_dir)
+
+
 @pytest.mark.parametrize("case_dir,params", [c for c in golden_cases("rescale")])
 def test_rescale_qual_bam_to_bam(case_dir, params, tmp_path, caplog):
     import bam_py

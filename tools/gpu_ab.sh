@@ -9,7 +9,7 @@ fi
 shift
 for variant in "$@"; do
   echo "== bench $variant"
-  name=$(echo $variant | tr '= ,' '___')
+  name=$(echo $variant | tr '= ,/.' '_____')
   env $variant timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --cpu-sample 100000 > "$OUT/bench_$name.json" 2> "$OUT/err.log"
   tail -2 "$OUT/err.log"
   python - "$OUT/bench_$name.json" <<'PY'
