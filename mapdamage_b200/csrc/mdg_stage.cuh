@@ -607,6 +607,43 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     };
 
 
+    // the same for a tile of a library's index list: the reads are scattered, so each thread pulls the records of
+    // (up to two of) the tile's reads itself and later the lines their bases start in
+    auto prefetch_listed_headers = [&](int64_t tile_index, uint32_t (&boff)[2], uint32_t (&coff)[2]) {
+        uint32_t live = 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int q = tid + u * nthreads;
+            const int64_t at = tile_index * T + q;
+            if (q < T && at < n_todo) {
+                const uint32_t r = subset[at];
+                boff[u] = b.base_off[r];
+                coff[u] = b.cigar_off[r];
+                prefetch_l2(b.flag + r);
+                prefetch_l2(b.tid + r);
+                prefetch_l2(b.pos + r);
+                prefetch_l2(b.l_seq + r);
+                prefetch_l2(b.tlen + r);
+                live |= 1u << u;
+            }
+        }
+        return live;
+    };
+    auto prefetch_listed_bases = [&](uint32_t live, const uint32_t (&boff)[2], const uint32_t (&coff)[2]) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!(live >> u & 1)) continue;
+            const char *seq_at = (const char *)b.seq4 + (boff[u] >> 1);
+            prefetch_l2(seq_at);
+            prefetch_l2(seq_at + 127);
+            prefetch_l2(b.cigar + coff[u]);
+            if (kQual) {
+                prefetch_l2((const char *)b.qual + boff[u]);
+                prefetch_l2((const char *)b.qual + boff[u] + 127);
+            }
+        }
+    };
+
     constexpr int PREP = 2;  // reads parsed per thread with their loads in flight together
     const int64_t n_tiles = (n_todo + T - 1) / T;
     if (!subset) {  // the block's first two tiles have nobody to prefetch them
@@ -615,6 +652,10 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         const bool live1 = prefetch_headers(blockIdx.x + (int64_t)gridDim.x, boff1, coff1);
         if (live0) prefetch_bases(boff0, coff0);
         if (live1) prefetch_bases(boff1, coff1);
+    } else {
+        uint32_t boff1[2] = {0, 0}, coff1[2] = {0, 0};
+        const uint32_t live1 = prefetch_listed_headers(blockIdx.x + (int64_t)gridDim.x, boff1, coff1);
+        prefetch_listed_bases(live1, boff1, coff1);
     }
     int tile_parity = 0;
     if (tid < 6) s_ctl_base[tid] = tid == 3 ? 0xffffffffu : 0u;
@@ -746,6 +787,8 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         // ---- pull the tile after next towards L2 ----
         uint32_t ahead_boff = 0, ahead_coff = 0;
         const bool ahead_live = !subset && prefetch_headers(tile + 2 * (int64_t)gridDim.x, ahead_boff, ahead_coff);
+        uint32_t listed_boff[2] = {0, 0}, listed_coff[2] = {0, 0};
+        const uint32_t listed_live = subset ? prefetch_listed_headers(tile + 2 * (int64_t)gridDim.x, listed_boff, listed_coff) : 0u;
 
         // ---- stage phase ----
         MDG_PHASE(2)
@@ -766,6 +809,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
+        if (listed_live) prefetch_listed_bases(listed_live, listed_boff, listed_coff);
         MDG_PHASE(3)
         __syncthreads();
         MDG_PHASE(4)
