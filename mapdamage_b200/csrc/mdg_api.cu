@@ -75,7 +75,6 @@ struct Slot {
     cudaStream_t stream = nullptr;
     DeviceArrays arrays;
     // rescale outputs
-    uint8_t *qual_out = nullptr;
     float *mr_out = nullptr;
     uint8_t *status_out = nullptr;
 };
@@ -709,7 +708,6 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             MDG_CREATE_CUDA(cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking));
             int64_t bases = (cfg->max_bases + 1) & ~1ll;
             if (alloc_arrays(ctx, slot.arrays, cfg->max_reads, cfg->max_cigar_ops, bases, true)) return bail(MDG_ERR_CUDA);
-            MDG_CREATE_CUDA(cudaMalloc(&slot.qual_out, bases + 8));
             MDG_CREATE_CUDA(cudaMalloc(&slot.mr_out, cfg->max_reads * 4 + 8));
             MDG_CREATE_CUDA(cudaMalloc(&slot.status_out, cfg->max_reads + 8));
         }
@@ -728,7 +726,6 @@ void mdg_destroy(mdg_ctx *ctx)
     for (auto &slot : ctx->slots) {
         if (slot.stream) cudaStreamDestroy(slot.stream);
         cudaFree(slot.arrays.block);
-        cudaFree(slot.qual_out);
         cudaFree(slot.mr_out);
         cudaFree(slot.status_out);
     }
@@ -984,18 +981,37 @@ int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, f
     const int64_t n = host->n_reads;
     if (n == 0) return MDG_OK;
     const size_t n_sub = (size_t)2 * ctx->model.n_slots * 94;
-    mdg::RescaleOut out{slot.qual_out, slot.mr_out, slot.status_out, ctx->rescale_stats, ctx->count_tables.error_flag,
+    // qualities are rewritten in place in the slot's copy of the batch and read back from there
+    uint8_t *const dev_qual = const_cast<uint8_t *>(slot.arrays.view.qual);
+    mdg::RescaleOut out{dev_qual, slot.mr_out, slot.status_out, ctx->rescale_stats, ctx->count_tables.error_flag,
                         ctx->rescale_hist, ctx->rescale_hist + n_sub, ctx->rescale_hist + n_sub + 2 * 94};
-    int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 7) / 8);
+    WorkList *wl = nullptr;
+    rc = worklist_for(ctx, slot.stream, n, &wl);
+    if (rc) return rc;
+    MDG_CUDA(ctx, cudaMemsetAsync(wl->count, 0, 8, slot.stream));
     cudaEvent_t e0, e1;
     rc = next_kernel_events(ctx, &e0, &e1);
     if (rc) return rc;
     MDG_CUDA(ctx, cudaEventRecord(e0, slot.stream));
-    mdg::rescale_kernel<<<grid, 256, 0, slot.stream>>>(slot.arrays.view, ctx->ref, ctx->model, out);
-    ctx->launches += 1;
+    const bool general_only = getenv("MDG_RESCALE_GENERAL") != nullptr;  // A/B and tests: every record by the warp kernel
+    const int warp_grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 7) / 8);
+    if (!general_only) {
+        // block histograms in shared memory when the model's table fits (it does for any sensible --rescale-length)
+        const size_t hist_words = n_sub + 2 * 94;
+        const bool shared_hist = hist_words * 4 <= 48 * 1024;
+        const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 255) / 256);
+        mdg::rescale_gapfree_kernel<<<grid, 256, shared_hist ? hist_words * 4 : 0, slot.stream>>>(
+            slot.arrays.view, ctx->ref, ctx->model, out, wl->reads, wl->count, shared_hist ? (int)hist_words : 0);
+        MDG_CUDA(ctx, cudaGetLastError());
+        mdg::rescale_kernel<<<warp_grid, 256, 0, slot.stream>>>(slot.arrays.view, ctx->ref, ctx->model, out, wl->reads, wl->count);
+        ctx->launches += 2;
+    } else {
+        mdg::rescale_kernel<<<warp_grid, 256, 0, slot.stream>>>(slot.arrays.view, ctx->ref, ctx->model, out, nullptr, nullptr);
+        ctx->launches += 1;
+    }
     MDG_CUDA(ctx, cudaGetLastError());
     MDG_CUDA(ctx, cudaEventRecord(e1, slot.stream));
-    MDG_CUDA(ctx, cudaMemcpyAsync(qual_out, slot.qual_out, (size_t)host->n_bases, cudaMemcpyDeviceToHost, slot.stream));
+    MDG_CUDA(ctx, cudaMemcpyAsync(qual_out, dev_qual, (size_t)host->n_bases, cudaMemcpyDeviceToHost, slot.stream));
     MDG_CUDA(ctx, cudaMemcpyAsync(mr_out, slot.mr_out, (size_t)n * 4, cudaMemcpyDeviceToHost, slot.stream));
     MDG_CUDA(ctx, cudaMemcpyAsync(status_out, slot.status_out, (size_t)n, cudaMemcpyDeviceToHost, slot.stream));
     return MDG_OK;

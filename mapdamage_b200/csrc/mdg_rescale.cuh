@@ -1,4 +1,7 @@
-// Rescale pass: one warp per record, every record of the batch.
+// Rescale pass over every record of the batch: gap-free reads one per thread with word-wide compares
+// (rescale_gapfree_kernel), everything else one warp per record (rescale_kernel, fed by a work list).
+// The qualities are rewritten in place in the batch's device copy: a record nobody touches is passed through as is
+// (rescale.py:344).
 //
 // Replaces rescale._rescale_qual_core and _rescale_qual_read
 // (rescale.py:195-365).  The new Phred score of a C->T / G->A base is a pure
@@ -10,6 +13,7 @@
 // the summation order and the decimal rounding are reproduced exactly.
 #pragma once
 #include "mdg_device.cuh"
+#include "mdg_swar.cuh"
 
 namespace mdg {
 
@@ -61,8 +65,6 @@ __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const Rescale
     const uint32_t flag = b.flag[r];
     const uint32_t l_seq = b.l_seq[r];
     const uint64_t boff = b.base_off[r];
-    // every record is written back, changed or not (rescale.py:344)
-    for (uint32_t i = lane; i < l_seq; i += 32) out.qual[boff + i] = b.qual[boff + i];
     if (lane == 0) {
         out.status[r] = 0;
         out.mr[r] = __int_as_float(0x7fc00000);
@@ -109,7 +111,7 @@ __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const Rescale
     const uint64_t contig_off = ref.contig_off[tid];
     const int64_t contig_len = ref.contig_len[tid];
     const uint64_t qbase = boff + ct.clip_lead;
-    __syncwarp();  // pass-through copy above is ordered before the rewrites below
+    __syncwarp();  // every lane has looked at the first quality before any is rewritten
 
     double mr = 0.0;
     // walk the alignment 5'->3': step i is column i (forward) or C-1-i (reverse)
@@ -199,16 +201,196 @@ __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const Rescale
     }
 }
 
-__global__ void __launch_bounds__(256) rescale_kernel(DevBatch b, DevRef ref, RescaleModel m, RescaleOut out)
+// `list` / `count`: the records rescale_gapfree_kernel left over, or null: every record of the batch.
+__global__ void __launch_bounds__(256) rescale_kernel(DevBatch b, DevRef ref, RescaleModel m, RescaleOut out,
+                                                      const uint32_t *__restrict__ list,
+                                                      const unsigned long long *__restrict__ count)
 {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * warps_per_block;
+    const int64_t n = list ? (int64_t)*count : b.n_reads;
     uint32_t ref_seen[4] = {0, 0, 0, 0};  // identical in every lane (ballot counts)
-    for (int64_t r = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < b.n_reads; r += stride)
-        rescale_read(b, ref, m, out, r, lane, ref_seen);
+    for (int64_t i = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += stride)
+        rescale_read(b, ref, m, out, list ? (int64_t)list[i] : i, lane, ref_seen);
     const uint32_t mine = lane == 0 ? ref_seen[0] : lane == 1 ? ref_seen[1] : lane == 2 ? ref_seen[2] : ref_seen[3];
     if (lane < 4 && mine) atomicAdd(out.ref_count + lane, (unsigned long long)mine);
+}
+
+// One thread per record.  A gap-free read ([S] M/=/X.. [S], inside its contig) needs no column arithmetic: column =
+// read base = reference offset, so eight columns are one word of the BAM sequence against one word of the one-hot
+// genome, and the four transition classes of _record_subs / _rescale_qual_read (rescale.py:106-139,229-247) are bit
+// masks of those words.  Only the set bits -- a few per read -- cost a quality load, a table lookup and a store;
+// they are visited in 5'->3' order, so the fp64 MR sum keeps the reference's order of additions (rescale.py:244).
+// Anything else is appended to `worklist` for rescale_kernel.
+// Histograms live in shared memory (32-bit, flushed once per block) when `hist_words` > 0.
+__global__ void __launch_bounds__(256) rescale_gapfree_kernel(DevBatch b, DevRef ref, RescaleModel m, RescaleOut out,
+                                                              uint32_t *__restrict__ worklist,
+                                                              unsigned long long *__restrict__ work_count, int hist_words)
+{
+    extern __shared__ uint32_t s_hist[];  // [2][n_slots][94] rescaled | [2][94] reverse transitions
+    const int n_sub = 2 * m.n_slots * 94;
+    for (int i = threadIdx.x; i < hist_words; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const bool shared_hist = hist_words > 0;
+    const int lane = threadIdx.x & 31;
+    const uint32_t *const seq32 = (const uint32_t *)b.seq4;
+    uint32_t n_pairs = 0, n_improper = 0, n_noqual = 0, n_rescaled = 0;
+    uint32_t ref_seen[4] = {0, 0, 0, 0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (b.n_reads + stride - 1) / stride;
+    for (int64_t round = 0; round < rounds; ++round) {
+        const int64_t r = round * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool complex = false;
+        if (r < b.n_reads) do {
+            const uint32_t flag = b.flag[r];
+            const uint32_t l_seq = b.l_seq[r];
+            const uint64_t boff = b.base_off[r];
+            out.status[r] = 0;
+            out.mr[r] = __int_as_float(0x7fc00000);
+            if (flag & 0x4) break;  // rescale.py:301
+            if (!(l_seq > 0 && b.qual[boff] != 0xFF)) {  // rescale.py:303-304
+                ++n_noqual;
+                break;
+            }
+            const int strand = (flag >> 4) & 1;
+            const int tid = b.tid[r];
+            const int64_t pos = b.pos[r];
+            bool both_ends = true;
+            if (flag & 0x1) {  // rescale.py:305-340: only inward-facing mates on one contig
+                const bool mate_rev = (flag & 0x20) != 0;
+                const int64_t mpos = b.mpos[r];
+                const bool same = tid == b.mtid[r];
+                if (!((!strand && mate_rev && mpos > pos && same) || (strand && !mate_rev && mpos < pos && same))) {
+                    ++n_pairs;
+                    ++n_improper;
+                    break;
+                }
+                both_ends = false;  // direction="forward"
+            }
+            // [S] M/=/X.. [S] and nothing else
+            const uint32_t c0 = b.cigar_off[r], c1 = b.cigar_off[r + 1];
+            uint32_t lead = 0, trail = 0, C = 0;
+            int state = 0;
+            bool simple = c1 > c0 && tid >= 0 && tid < ref.n_contigs;
+            for (uint32_t k = c0; k < c1 && simple; ++k) {
+                const uint32_t w = __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
+                const bool match = op == OP_M || op == OP_EQ || op == OP_X;
+                if (match && state <= 1) { C += len; state = 1; }
+                else if (op == OP_S && state == 0 && k == c0) lead = len;
+                else if (op == OP_S && state == 1 && k + 1 == c1) { trail = len; state = 2; }
+                else simple = false;
+            }
+            simple = simple && state >= 1 && C > 0 && (uint64_t)lead + C + trail == l_seq && pos >= 0;
+            if (simple) simple = pos + (int64_t)C <= (int64_t)ref.contig_len[tid];
+            if (!simple) {
+                complex = true;  // rescale_kernel starts over with this record, its statistics included
+                break;
+            }
+            n_pairs += flag & 0x1;
+            const uint64_t q0 = boff + lead, ref0 = ref.contig_off[tid] + (uint64_t)pos;
+            const uint32_t *const qw = seq32 + (q0 >> 3), *const rw = ref.words + (ref0 >> 3);
+            const int sq = (int)(q0 & 7) << 2, sr = (int)(ref0 & 7) << 2;
+            const int n_words = (int)((C + 7) >> 3);
+            const uint32_t n = C;
+            double mr = 0.0;
+            // words in 5'->3' order: ascending on the forward strand, descending on the reverse strand; the word pair
+            // loaded for one window word is half of the next one's
+            const int step = strand ? -1 : 1;
+            int w = strand ? n_words - 1 : 0;
+            uint32_t q_keep = natural_order(__ldg(qw + w + strand)), r_keep = __ldg(rw + w + strand);
+            for (int it = 0; it < n_words; ++it, w += step) {
+                uint32_t q_lo, q_hi, r_lo, r_hi;
+                if (strand) {
+                    q_hi = q_keep; r_hi = r_keep;
+                    q_lo = natural_order(__ldg(qw + w)); r_lo = __ldg(rw + w);
+                    q_keep = q_lo; r_keep = r_lo;
+                } else {
+                    q_lo = q_keep; r_lo = r_keep;
+                    q_hi = natural_order(__ldg(qw + w + 1)); r_hi = __ldg(rw + w + 1);
+                    q_keep = q_hi; r_keep = r_hi;
+                }
+                const uint32_t live = low_nibbles(4 * ((int)C - 8 * w));
+                uint32_t x = __funnelshift_r(q_lo, q_hi, sq) & live;
+                const uint32_t y = __funnelshift_r(r_lo, r_hi, sr) & live;
+                x &= one_hot_nibbles(x) * 15u;  // anything but A/C/G/T pairs with nothing (CODE_OTHER)
+                // _record_subs counts the reference base of every walked column (rescale.py:119-122)
+                // -- of the read's strand: a reverse read sees the complement
+                const uint32_t na = __popc(y & K1), nc = __popc(y & (K1 << 1)), ng = __popc(y & (K1 << 2)),
+                               nt = __popc(y & (K1 << 3));
+                ref_seen[0] += strand ? nt : na;
+                ref_seen[1] += strand ? ng : nc;
+                ref_seen[2] += strand ? nc : ng;
+                ref_seen[3] += strand ? na : nt;
+                const uint32_t xa = x & K1, xc = (x >> 1) & K1, xg = (x >> 2) & K1, xt = (x >> 3) & K1;
+                const uint32_t ya = y & K1, yc = (y >> 1) & K1, yg = (y >> 2) & K1, yt = (y >> 3) & K1;
+                // on the read's own strand: type 0 = T on reference C, type 1 = A on reference G (rescaled);
+                // C on reference T and G on reference A are only counted.  Reverse reads see complements.
+                uint32_t type0 = xt & yc, type1 = xa & yg, back0 = xc & yt, back1 = xg & ya;
+                if (strand) {
+                    uint32_t t = type0; type0 = type1; type1 = t;
+                    t = back0; back0 = back1; back1 = t;
+                }
+                uint32_t todo = type0 | type1 | back0 | back1;
+                while (todo) {
+                    const int bit = strand ? 31 - __clz(todo) : __ffs(todo) - 1;  // bit 4 k of nibble k
+                    todo &= ~(1u << bit);
+                    const uint32_t j = 8u * (uint32_t)w + ((uint32_t)bit >> 2);
+                    const uint32_t q = b.qual[q0 + j];
+                    const uint32_t sel = 1u << bit;
+                    if ((type0 | type1) & sel) {
+                        const int type = (type1 & sel) ? 1 : 0;
+                        // _corr_this_base, rescale.py:49-79
+                        const int64_t p5 = (int64_t)(strand ? n - 1 - j : j) + 1;
+                        const int64_t back = p5 - (int64_t)n - 1;
+                        int64_t pp = p5;
+                        if (both_ends && p5 >= -back) pp = back;
+                        int slot = 0;
+                        if (pp > 0 && pp <= m.len5p) slot = (int)pp;
+                        else if (pp < 0 && -pp <= m.len3p) slot = m.len5p + (int)(-pp);
+                        if (q > 93) {
+                            atomicCAS(out.error_flag, 0, DATA_ERR_QUAL);
+                        } else {
+                            const int cell = (type * m.n_slots + slot) * 94 + (int)q;
+                            out.qual[q0 + j] = m.lut[cell];
+                            if (slot) mr += m.inc[type * m.n_slots + slot];  // slot 0 adds exactly 0.0
+                            if (shared_hist) atomicAdd(s_hist + cell, 1u);
+                            else atomicAdd(out.hist_sub + cell, 1ull);
+                        }
+                    } else if (q <= 93) {
+                        const int cell = ((back1 & sel) ? 94 : 0) + (int)q;
+                        if (shared_hist) atomicAdd(s_hist + n_sub + cell, 1u);
+                        else atomicAdd(out.hist_rev + cell, 1ull);
+                    }
+                }
+            }
+            out.status[r] = 1;
+            out.mr[r] = round_5_decimals(mr);
+            ++n_rescaled;
+        } while (false);
+        // warp-aggregated append of the records left to rescale_kernel
+        const uint32_t cx = __ballot_sync(0xffffffffu, complex);
+        if (cx) {
+            unsigned long long base = 0;
+            if (lane == __ffs(cx) - 1) base = atomicAdd(work_count, (unsigned long long)__popc(cx));
+            base = __shfl_sync(0xffffffffu, base, __ffs(cx) - 1);
+            if (complex) worklist[base + __popc(cx & ((1u << lane) - 1u))] = (uint32_t)r;
+        }
+    }
+    auto warp_sum = [](uint32_t v) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        return v;
+    };
+    const uint32_t totals[8] = {warp_sum(n_pairs), warp_sum(n_improper), warp_sum(n_noqual), warp_sum(n_rescaled),
+                                warp_sum(ref_seen[0]), warp_sum(ref_seen[1]), warp_sum(ref_seen[2]), warp_sum(ref_seen[3])};
+    if (lane < 4 && totals[lane]) atomicAdd(out.stats + lane, (unsigned long long)totals[lane]);
+    if (lane >= 4 && lane < 8 && totals[lane]) atomicAdd(out.ref_count + (lane - 4), (unsigned long long)totals[lane]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < hist_words; i += blockDim.x) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(i < n_sub ? out.hist_sub + i : out.hist_rev + (i - n_sub), (unsigned long long)v);
+    }
 }
 
 }  // namespace mdg

@@ -57,7 +57,10 @@ def main():
         qual, mr, status = engine.rescale(sample)
         engine.sync()
         assert rc == 0 and np.array_equal(status, want_status) and np.array_equal(mr[status == 1], want_mr[status == 1])
-        assert np.array_equal(qual[:sample.total_bases], want_qual[:sample.total_bases])
+        # quality bytes of real bases only: the pad slot behind an odd-length read is unspecified
+        starts, lens = sample.base_off.astype(np.int64), sample.l_seq.astype(np.int64)
+        idx = np.repeat(starts, lens) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens) - lens, lens))
+        assert np.array_equal(qual[idx], want_qual[idx])
 
         def one_pass():
             for i, b in enumerate(host):
