@@ -293,6 +293,14 @@ int64_t mdg_bam_read_batch(mdg_bam_reader *reader, const mdg_batch *out, int64_t
 int64_t mdg_bam_records_seen(const mdg_bam_reader *reader);
 
 /*
+ * Raw DEFLATE (RFC 1951) stream -> out; returns the number of bytes written, or a negative code when the stream is
+ * damaged, does not fit out_cap, or uses a form this decoder leaves to zlib.  What mdg_bam_read_batch inflates BGZF
+ * blocks with (htslib / zlib under pysam.AlignmentFile in the reference, reader.py:38); every block's CRC32 is
+ * checked by the caller, and a block rejected here is given to zlib.
+ */
+int64_t mdg_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_cap);
+
+/*
  * Down-sampling of the kept reads (reader.py:134-164).  `mt_state` is the state of CPython's random.Random(seed):
  * 624 MT19937 words followed by the position (getstate()[1]); it is advanced in place, so consecutive calls continue
  * the reference's single stream of draws.

@@ -43,7 +43,7 @@ def build_library(force=False, verbose=False):
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += os.environ.get("MDG_NVCC_FLAGS", "").split()  # e.g. -DMDG_PHASE_CLOCKS: per-phase cycle counts, printed
-    cmd += ["-o", str(LIBRARY), str(CSRC / "mdg_api.cu"), str(CSRC / "mdg_bamio.cpp"), str(CSRC / "mdg_sampler.cpp"), "-lcudart", "-ldl", "-lz", "-lpthread"]
+    cmd += ["-o", str(LIBRARY), str(CSRC / "mdg_api.cu"), str(CSRC / "mdg_bamio.cpp"), str(CSRC / "mdg_sampler.cpp"), str(CSRC / "mdg_inflate.cpp"), "-lcudart", "-ldl", "-lz", "-lpthread"]
     env = dict(os.environ)
     result = subprocess.run(cmd, env=env, capture_output=True, text=True)
     if result.returncode != 0:

@@ -96,6 +96,7 @@ struct Chunk {
 struct mdg_bam_reader {
     FILE *fp = nullptr;
     int n_threads = 1;
+    bool native_inflate = true;  // MDG_BAM_ZLIB=1: zlib only (A/B runs, tests)
     std::string error;
     std::string header_text;
     std::vector<std::string> ref_names;
@@ -230,6 +231,12 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
     parallel_for((int64_t)c.blocks.size(), r->n_threads, [&](int64_t i) {
         const Block &b = c.blocks[(size_t)i];
         if (!b.isize) return;
+        const uint32_t want_crc = le32(c.compressed.p + b.in_off + b.in_len);
+        // the native decoder first (mdg_inflate.cpp); zlib for anything it turns down or gets wrong
+        if (r->native_inflate &&
+            mdg_inflate_raw(c.compressed.p + b.in_off, (int64_t)b.in_len, c.inflated.p + b.out_off, (int64_t)b.isize) == (int64_t)b.isize &&
+            (uint32_t)crc32(crc32(0L, Z_NULL, 0), c.inflated.p + b.out_off, b.isize) == want_crc)
+            return;
         z_stream z;
         memset(&z, 0, sizeof z);
         if (inflateInit2(&z, -15) != Z_OK) {
@@ -242,7 +249,7 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         z.avail_out = b.isize;
         const int rc = inflate(&z, Z_FINISH);
         if (rc != Z_STREAM_END || z.avail_out != 0) bad = 1;
-        else if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), c.inflated.p + b.out_off, b.isize) != le32(c.compressed.p + b.in_off + b.in_len))
+        else if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), c.inflated.p + b.out_off, b.isize) != want_crc)
             bad = 2;
         inflateEnd(&z);
     });
@@ -448,6 +455,10 @@ int mdg_bam_open(const char *path, int32_t n_threads, mdg_bam_reader **out)
     mdg_bam_reader *r = new (std::nothrow) mdg_bam_reader();
     if (!r) return rfail(nullptr, MDG_ERR_ARGUMENT, "out of host memory");
     r->n_threads = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    {
+        const char *env = getenv("MDG_BAM_ZLIB");
+        r->native_inflate = !(env && env[0] == '1');
+    }
     r->fp = fopen(path, "rb");
     if (!r->fp) {
         rfail(nullptr, MDG_ERR_ARGUMENT, "cannot open %s", path);
