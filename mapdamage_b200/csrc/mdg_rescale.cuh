@@ -217,13 +217,16 @@ __global__ void __launch_bounds__(256) rescale_kernel(DevBatch b, DevRef ref, Re
     if (lane < 4 && mine) atomicAdd(out.ref_count + lane, (unsigned long long)mine);
 }
 
-// One thread per record.  A gap-free read ([S] M/=/X.. [S], inside its contig) needs no column arithmetic: column =
-// read base = reference offset, so eight columns are one word of the BAM sequence against one word of the one-hot
-// genome, and the four transition classes of _record_subs / _rescale_qual_read (rescale.py:106-139,229-247) are bit
-// masks of those words.  Only the set bits -- a few per read -- cost a quality load, a table lookup and a store;
-// they are visited in 5'->3' order, so the fp64 MR sum keeps the reference's order of additions (rescale.py:244).
-// Anything else is appended to `worklist` for rescale_kernel.
-// Histograms live in shared memory (32-bit, flushed once per block) when `hist_words` > 0.
+// One thread per record, for CIGARs made of match blocks, insertions and deletions with soft clips at the very ends
+// (anything a short-read aligner emits for DNA).  Inside a match block column = read base = reference offset, so
+// eight columns are one word of the BAM sequence against one word of the one-hot genome, and the four transition
+// classes of _record_subs / _rescale_qual_read (rescale.py:106-139,229-247) are bit masks of those words.  Only the
+// set bits -- a few per read -- cost a quality load, a table lookup and a store.  Blocks, words and bits are visited
+// in 5'->3' order of the read, so the fp64 MR sum keeps the reference's order of additions (rescale.py:244).  An
+// insertion has no reference base and changes nothing; a deletion only adds its reference bases to the base counts,
+// and only while read bases remain behind it (rescale.py:249-261).  Skips (N), pads, hard clips, reads over a contig
+// end and malformed records are appended to `worklist` for rescale_kernel, which spells the reference's semantics
+// out column by column.  Histograms live in shared memory (32-bit, flushed once per block) when `hist_words` > 0.
 __global__ void __launch_bounds__(256) rescale_gapfree_kernel(DevBatch b, DevRef ref, RescaleModel m, RescaleOut out,
                                                               uint32_t *__restrict__ worklist,
                                                               unsigned long long *__restrict__ work_count, int hist_words)
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(256) rescale_gapfree_kernel(DevBatch b, DevRef
     const bool shared_hist = hist_words > 0;
     const int lane = threadIdx.x & 31;
     const uint32_t *const seq32 = (const uint32_t *)b.seq4;
-    uint32_t n_pairs = 0, n_improper = 0, n_noqual = 0, n_rescaled = 0;
+    uint32_t n_pairs = 0, n_improper = 0, n_noqual = 0, n_rescaled = 0, n_too_long = 0;
     uint32_t ref_seen[4] = {0, 0, 0, 0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t rounds = (b.n_reads + stride - 1) / stride;
@@ -268,102 +271,138 @@ __global__ void __launch_bounds__(256) rescale_gapfree_kernel(DevBatch b, DevRef
                 }
                 both_ends = false;  // direction="forward"
             }
-            // [S] M/=/X.. [S] and nothing else
+            // [S] then M/=/X/I/D in any order, then [S]
             const uint32_t c0 = b.cigar_off[r], c1 = b.cigar_off[r + 1];
-            uint32_t lead = 0, trail = 0, C = 0;
-            int state = 0;
+            uint32_t lead = 0, trail = 0, n = 0, span = 0, matched = 0;
             bool simple = c1 > c0 && tid >= 0 && tid < ref.n_contigs;
+            const uint32_t first_word = simple ? __ldg(b.cigar + c0) : 0;
             for (uint32_t k = c0; k < c1 && simple; ++k) {
-                const uint32_t w = __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
-                const bool match = op == OP_M || op == OP_EQ || op == OP_X;
-                if (match && state <= 1) { C += len; state = 1; }
-                else if (op == OP_S && state == 0 && k == c0) lead = len;
-                else if (op == OP_S && state == 1 && k + 1 == c1) { trail = len; state = 2; }
+                const uint32_t w = k == c0 ? first_word : __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
+                if (op == OP_M || op == OP_EQ || op == OP_X) { n += len; span += len; matched += len; }
+                else if (op == OP_I) n += len;
+                else if (op == OP_D) span += len;
+                else if (op == OP_S && k == c0 && c1 - c0 > 1) lead = len;
+                else if (op == OP_S && k + 1 == c1 && k > c0) trail = len;
                 else simple = false;
             }
-            simple = simple && state >= 1 && C > 0 && (uint64_t)lead + C + trail == l_seq && pos >= 0;
-            if (simple) simple = pos + (int64_t)C <= (int64_t)ref.contig_len[tid];
+            simple = simple && matched > 0 && (uint64_t)lead + n + trail == l_seq && pos >= 0;
+            if (simple) simple = pos + (int64_t)span <= (int64_t)ref.contig_len[tid];
             if (!simple) {
                 complex = true;  // rescale_kernel starts over with this record, its statistics included
                 break;
             }
             n_pairs += flag & 0x1;
             const uint64_t q0 = boff + lead, ref0 = ref.contig_off[tid] + (uint64_t)pos;
-            const uint32_t *const qw = seq32 + (q0 >> 3), *const rw = ref.words + (ref0 >> 3);
-            const int sq = (int)(q0 & 7) << 2, sr = (int)(ref0 & 7) << 2;
-            const int n_words = (int)((C + 7) >> 3);
-            const uint32_t n = C;
             double mr = 0.0;
-            // words in 5'->3' order: ascending on the forward strand, descending on the reverse strand; the word pair
-            // loaded for one window word is half of the next one's
-            const int step = strand ? -1 : 1;
-            int w = strand ? n_words - 1 : 0;
-            uint32_t q_keep = natural_order(__ldg(qw + w + strand)), r_keep = __ldg(rw + w + strand);
-            for (int it = 0; it < n_words; ++it, w += step) {
-                uint32_t q_lo, q_hi, r_lo, r_hi;
-                if (strand) {
-                    q_hi = q_keep; r_hi = r_keep;
-                    q_lo = natural_order(__ldg(qw + w)); r_lo = __ldg(rw + w);
-                    q_keep = q_lo; r_keep = r_lo;
-                } else {
-                    q_lo = q_keep; r_lo = r_keep;
-                    q_hi = natural_order(__ldg(qw + w + 1)); r_hi = __ldg(rw + w + 1);
-                    q_keep = q_hi; r_keep = r_hi;
-                }
-                const uint32_t live = low_nibbles(4 * ((int)C - 8 * w));
-                uint32_t x = __funnelshift_r(q_lo, q_hi, sq) & live;
-                const uint32_t y = __funnelshift_r(r_lo, r_hi, sr) & live;
-                x &= one_hot_nibbles(x) * 15u;  // anything but A/C/G/T pairs with nothing (CODE_OTHER)
-                // _record_subs counts the reference base of every walked column (rescale.py:119-122)
-                // -- of the read's strand: a reverse read sees the complement
+
+            // reference bases of `len` columns from reference offset r_at, as the read's strand sees them
+            auto count_reference = [&](uint32_t y) {
                 const uint32_t na = __popc(y & K1), nc = __popc(y & (K1 << 1)), ng = __popc(y & (K1 << 2)),
                                nt = __popc(y & (K1 << 3));
                 ref_seen[0] += strand ? nt : na;
                 ref_seen[1] += strand ? ng : nc;
                 ref_seen[2] += strand ? nc : ng;
                 ref_seen[3] += strand ? na : nt;
-                const uint32_t xa = x & K1, xc = (x >> 1) & K1, xg = (x >> 2) & K1, xt = (x >> 3) & K1;
-                const uint32_t ya = y & K1, yc = (y >> 1) & K1, yg = (y >> 2) & K1, yt = (y >> 3) & K1;
-                // on the read's own strand: type 0 = T on reference C, type 1 = A on reference G (rescaled);
-                // C on reference T and G on reference A are only counted.  Reverse reads see complements.
-                uint32_t type0 = xt & yc, type1 = xa & yg, back0 = xc & yt, back1 = xg & ya;
-                if (strand) {
-                    uint32_t t = type0; type0 = type1; type1 = t;
-                    t = back0; back0 = back1; back1 = t;
-                }
-                uint32_t todo = type0 | type1 | back0 | back1;
-                while (todo) {
-                    const int bit = strand ? 31 - __clz(todo) : __ffs(todo) - 1;  // bit 4 k of nibble k
-                    todo &= ~(1u << bit);
-                    const uint32_t j = 8u * (uint32_t)w + ((uint32_t)bit >> 2);
-                    const uint32_t q = b.qual[q0 + j];
-                    const uint32_t sel = 1u << bit;
-                    if ((type0 | type1) & sel) {
-                        const int type = (type1 & sel) ? 1 : 0;
-                        // _corr_this_base, rescale.py:49-79
-                        const int64_t p5 = (int64_t)(strand ? n - 1 - j : j) + 1;
-                        const int64_t back = p5 - (int64_t)n - 1;
-                        int64_t pp = p5;
-                        if (both_ends && p5 >= -back) pp = back;
-                        int slot = 0;
-                        if (pp > 0 && pp <= m.len5p) slot = (int)pp;
-                        else if (pp < 0 && -pp <= m.len3p) slot = m.len5p + (int)(-pp);
-                        if (q > 93) {
-                            atomicCAS(out.error_flag, 0, DATA_ERR_QUAL);
-                        } else {
-                            const int cell = (type * m.n_slots + slot) * 94 + (int)q;
-                            out.qual[q0 + j] = m.lut[cell];
-                            if (slot) mr += m.inc[type * m.n_slots + slot];  // slot 0 adds exactly 0.0
-                            if (shared_hist) atomicAdd(s_hist + cell, 1u);
-                            else atomicAdd(out.hist_sub + cell, 1ull);
+            };
+            // one match block: read bases j0 .. j0 + len (0 = first aligned base) on reference offsets r_at ..
+            auto match_block = [&](uint32_t j0, uint32_t r_at, uint32_t len) {
+                const uint64_t qa = q0 + j0, ra = ref0 + r_at;
+                const uint32_t *const qw = seq32 + (qa >> 3), *const rw = ref.words + (ra >> 3);
+                const int sq = (int)(qa & 7) << 2, sr = (int)(ra & 7) << 2;
+                const int n_words = (int)((len + 7) >> 3);
+                // words in 5'->3' order: ascending on the forward strand, descending on the reverse strand; the word
+                // pair loaded for one window word is half of the next one's
+                const int step = strand ? -1 : 1;
+                int w = strand ? n_words - 1 : 0;
+                uint32_t q_keep = natural_order(__ldg(qw + w + strand)), r_keep = __ldg(rw + w + strand);
+                for (int it = 0; it < n_words; ++it, w += step) {
+                    uint32_t q_lo, q_hi, r_lo, r_hi;
+                    if (strand) {
+                        q_hi = q_keep; r_hi = r_keep;
+                        q_lo = natural_order(__ldg(qw + w)); r_lo = __ldg(rw + w);
+                        q_keep = q_lo; r_keep = r_lo;
+                    } else {
+                        q_lo = q_keep; r_lo = r_keep;
+                        q_hi = natural_order(__ldg(qw + w + 1)); r_hi = __ldg(rw + w + 1);
+                        q_keep = q_hi; r_keep = r_hi;
+                    }
+                    const uint32_t live = low_nibbles(4 * ((int)len - 8 * w));
+                    uint32_t x = __funnelshift_r(q_lo, q_hi, sq) & live;
+                    const uint32_t y = __funnelshift_r(r_lo, r_hi, sr) & live;
+                    x &= one_hot_nibbles(x) * 15u;  // anything but A/C/G/T pairs with nothing (CODE_OTHER)
+                    count_reference(y);  // _record_subs counts the reference base of every walked column
+                    const uint32_t xa = x & K1, xc = (x >> 1) & K1, xg = (x >> 2) & K1, xt = (x >> 3) & K1;
+                    const uint32_t ya = y & K1, yc = (y >> 1) & K1, yg = (y >> 2) & K1, yt = (y >> 3) & K1;
+                    // on the read's own strand: type 0 = T on reference C, type 1 = A on reference G (rescaled);
+                    // C on reference T and G on reference A are only counted.  Reverse reads see complements.
+                    uint32_t type0 = xt & yc, type1 = xa & yg, back0 = xc & yt, back1 = xg & ya;
+                    if (strand) {
+                        uint32_t t = type0; type0 = type1; type1 = t;
+                        t = back0; back0 = back1; back1 = t;
+                    }
+                    uint32_t todo = type0 | type1 | back0 | back1;
+                    while (todo) {
+                        const int bit = strand ? 31 - __clz(todo) : __ffs(todo) - 1;  // bit 4 k of nibble k
+                        todo &= ~(1u << bit);
+                        const uint32_t j = j0 + 8u * (uint32_t)w + ((uint32_t)bit >> 2);
+                        const uint32_t q = b.qual[q0 + j];
+                        const uint32_t sel = 1u << bit;
+                        if ((type0 | type1) & sel) {
+                            const int type = (type1 & sel) ? 1 : 0;
+                            // _corr_this_base, rescale.py:49-79
+                            const int64_t p5 = (int64_t)(strand ? n - 1 - j : j) + 1;
+                            const int64_t back = p5 - (int64_t)n - 1;
+                            int64_t pp = p5;
+                            if (both_ends && p5 >= -back) pp = back;
+                            int slot = 0;
+                            if (pp > 0 && pp <= m.len5p) slot = (int)pp;
+                            else if (pp < 0 && -pp <= m.len3p) slot = m.len5p + (int)(-pp);
+                            if (q > 93) {
+                                atomicCAS(out.error_flag, 0, DATA_ERR_QUAL);
+                            } else {
+                                const int cell = (type * m.n_slots + slot) * 94 + (int)q;
+                                out.qual[q0 + j] = m.lut[cell];
+                                if (slot) mr += m.inc[type * m.n_slots + slot];  // slot 0 adds exactly 0.0
+                                if (shared_hist) atomicAdd(s_hist + cell, 1u);
+                                else atomicAdd(out.hist_sub + cell, 1ull);
+                            }
+                        } else if (q <= 93) {
+                            const int cell = ((back1 & sel) ? 94 : 0) + (int)q;
+                            if (shared_hist) atomicAdd(s_hist + n_sub + cell, 1u);
+                            else atomicAdd(out.hist_rev + cell, 1ull);
                         }
-                    } else if (q <= 93) {
-                        const int cell = ((back1 & sel) ? 94 : 0) + (int)q;
-                        if (shared_hist) atomicAdd(s_hist + n_sub + cell, 1u);
-                        else atomicAdd(out.hist_rev + cell, 1ull);
                     }
                 }
+            };
+            auto deletion = [&](uint32_t r_at, uint32_t len) {
+                const uint64_t ra = ref0 + r_at;
+                const uint32_t *const rw = ref.words + (ra >> 3);
+                const int sr = (int)(ra & 7) << 2;
+                for (uint32_t w = 0; 8 * w < len; ++w)
+                    count_reference(__funnelshift_r(__ldg(rw + w), __ldg(rw + w + 1), sr) & low_nibbles(4 * (int)(len - 8 * w)));
+            };
+
+            // the operations in 5'->3' order of the read; one loop for both strands keeps a warp's lanes together
+            uint32_t j = strand ? n : 0, at = strand ? span : 0;  // read bases / reference bases left of the walk
+            uint32_t last_op = OP_M;
+            for (uint32_t i = 0; i < c1 - c0; ++i) {
+                const uint32_t k = strand ? c1 - 1 - i : c0 + i;
+                const uint32_t w = k == c0 ? first_word : __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
+                if (op == OP_S) continue;
+                last_op = op;
+                if (op == OP_I) {
+                    j = strand ? j - len : j + len;
+                } else if (op == OP_D) {
+                    if (strand) at -= len;
+                    if (strand ? j > 0 : j < n) deletion(at, len);
+                    if (!strand) at += len;
+                } else {
+                    if (strand) { j -= len; at -= len; }
+                    match_block(j, at, len);
+                    if (!strand) { j += len; at += len; }
+                }
             }
+            if (last_op == OP_D) ++n_too_long;  // the walk ends on gap columns (rescale.py:255-261)
             out.status[r] = 1;
             out.mr[r] = round_5_decimals(mr);
             ++n_rescaled;
@@ -382,10 +421,11 @@ __global__ void __launch_bounds__(256) rescale_gapfree_kernel(DevBatch b, DevRef
         for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         return v;
     };
-    const uint32_t totals[8] = {warp_sum(n_pairs), warp_sum(n_improper), warp_sum(n_noqual), warp_sum(n_rescaled),
-                                warp_sum(ref_seen[0]), warp_sum(ref_seen[1]), warp_sum(ref_seen[2]), warp_sum(ref_seen[3])};
-    if (lane < 4 && totals[lane]) atomicAdd(out.stats + lane, (unsigned long long)totals[lane]);
-    if (lane >= 4 && lane < 8 && totals[lane]) atomicAdd(out.ref_count + (lane - 4), (unsigned long long)totals[lane]);
+    const uint32_t totals[9] = {warp_sum(n_pairs), warp_sum(n_improper), warp_sum(n_noqual), warp_sum(n_rescaled),
+                                warp_sum(n_too_long), warp_sum(ref_seen[0]), warp_sum(ref_seen[1]), warp_sum(ref_seen[2]),
+                                warp_sum(ref_seen[3])};
+    if (lane < 5 && totals[lane]) atomicAdd(out.stats + lane, (unsigned long long)totals[lane]);
+    if (lane >= 5 && lane < 9 && totals[lane]) atomicAdd(out.ref_count + (lane - 5), (unsigned long long)totals[lane]);
     __syncthreads();
     for (int i = threadIdx.x; i < hist_words; i += blockDim.x) {
         const uint32_t v = s_hist[i];

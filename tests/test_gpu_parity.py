@@ -7,7 +7,7 @@ import oracle
 from conftest import golden_cases
 from helpers import (assert_tables_equal, expected_rescale, load_counting_case,
                      load_rescale_case, render_tables)
-from mapdamage_b200 import _native, synth
+from mapdamage_b200 import _native, rescale, synth
 from mapdamage_b200.engine import DamageEngine
 from mapdamage_b200.rescale_model import RescaleModel, get_corr_prob
 
@@ -189,6 +189,37 @@ def test_rescale_vs_oracle(name, l5, l3):
     assert (qual[mask] != batch.qual[:qual.shape[0]][mask]).sum() > 100
     assert stats["rescaled"] == int(want_status.sum()) == subs.n_rescaled
     assert stats["pairs"] == subs.n_pairs and stats["improper_pairs"] == subs.n_improper
+
+
+def test_rescale_long_model_uses_global_histograms():
+    """A correction model too long for the block's shared-memory histograms (rescale lengths 45 + 40): same numbers."""
+    l5, l3 = 45, 40
+    reference = synth.make_reference([200_000], seed=15)
+    batch = synth.simulate_reads(reference, 20_000, seed=17, **SYNTH["pe_mixed"])
+    corr = {("C", "T", p): 0.8 * 0.9 ** (p - 1) for p in range(1, l5 + 1)}
+    corr.update({("G", "A", -p): 0.7 * 0.9 ** (p - 1) for p in range(1, l3 + 1)})
+    corr.update({("G", "A", p): 0.01 for p in range(1, l5 + 1)})
+    corr.update({("C", "T", -p): 0.02 for p in range(1, l3 + 1)})
+    model = RescaleModel(corr, l5, l3)
+    want_qual, want_mr, want_status, subs, rc = oracle.rescale(batch, reference, corr)
+    assert rc == 0
+    with DamageEngine(max_reads=batch.n, max_cigar_ops=batch.cigar.shape[0], max_bases=batch.total_bases) as engine:
+        engine.set_reference(reference)
+        engine.set_rescale_model(model)
+        qual, mr, status = engine.rescale(batch)
+        engine.sync()
+        summary = rescale.SubstitutionSummary(model, *engine.rescale_hist(model.n_slots))
+    assert np.array_equal(status, want_status)
+    assert np.array_equal(mr[status == 1], want_mr[want_status == 1])
+    starts, lens = batch.base_off.astype(np.int64), batch.l_seq.astype(np.int64)
+    idx = np.repeat(starts, lens) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens) - lens, lens))
+    assert np.array_equal(qual[idx], want_qual[idx])
+    want = np.array(subs.hist, dtype=np.int64)  # [CT, TC, GA, AG][before, after][130]
+    for t, key in enumerate(("CT", "TC", "GA", "AG")):
+        assert np.array_equal(summary.data[key + "-before"], want[t, 0]), key
+        assert np.array_equal(summary.data[key + "-after"], want[t, 1]), key
+    assert [summary.data[b] for b in "ACGT"] == list(subs.ref_count)
+    assert want[0, 0].sum() > 100
 
 
 DEVICE_SYNTH = {
