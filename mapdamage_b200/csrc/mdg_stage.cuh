@@ -150,8 +150,10 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         }
         n1 = 0;
     };
-    auto spill0 = [&]() {  // 4-bit counters: base classes -> 8-bit registers; substitution classes (mostly zero)
-                           // -> the block's shared table, one atomic per non-zero counter
+    // 4-bit counters: base classes -> 8-bit registers; substitution classes (mostly zero) -> the block's shared
+    // table, one atomic per non-zero counter.  A substitution class whose counters are all 0 or 1 is left where it
+    // is unless `all`: 14 more reads cannot overflow it, and most classes never get further between two spills.
+    auto spill0 = [&](bool all) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             acc1[2 * c] += acc0[c] & 0x0F0F0F0Fu;
@@ -162,6 +164,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
 #pragma unroll
         for (int c = 8; c < SWAR_CLASSES; ++c) {
             uint32_t v = acc0[c];
+            if (!(all ? v : v & 0xEEEEEEEEu)) continue;
             while (v) {
                 const int nib = (__ffs(v) - 1) >> 2;
                 atomicAdd(mine + (c - 8) * 8 + nib, (v >> (4 * nib)) & 15u);
@@ -198,7 +201,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     // reduces the block's counters into the 64-bit tables (end of the kernel, on mode changes, and before a
     // thread's 16-bit counters could overflow)
     auto flush_block = [&]() {
-        if (n0) spill0();
+        spill0(true);
         if (n1) spill1();
         __syncthreads();
         const int wpr = words_of(mode), mode_slots = slots_of(mode);
@@ -445,7 +448,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         MDG_CLASS(19, (ya >> 3) & (xa >> 2), (yb >> 3) & (xb >> 2))   // T>G
 #undef MDG_CLASS
         n0 += 2;
-        if (n0 >= 14) spill0();  // a 4-bit counter holds 15
+        if (n0 >= 14) spill0(false);  // a 4-bit counter holds 15
     };
 
     __shared__ uint32_t indel_here;  // one-indel reads this block left to the general kernel
