@@ -14,6 +14,7 @@
 // Substitution classes (rare events) are spilled from the 4-bit counters straight into a shared table with
 // atomics, which leaves 32 words of private 16-bit counters per thread for the base classes.
 #pragma once
+#include <type_traits>
 #include "mdg_swar.cuh"
 
 namespace mdg {
@@ -27,7 +28,7 @@ struct StagedGeom {
     unsigned long long *indel_seen;  // kIndel == false: counts the one-indel reads handed to the general kernel
 };
 
-constexpr int STAGE_CHUNK = 4;  // consecutive words one thread stages at a time
+constexpr int STAGE_CHUNK = 5;  // consecutive words one thread stages at a time, at most (see set_mode)
 
 // kIndel: reads with exactly one insertion or deletion between two match blocks are staged too (a third plane holds
 // the read as the composition tables see it); without it they go to the general kernel's work list.
@@ -113,13 +114,16 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         strand = slot & 1;
         {
             const int n_anchors = columns ? 1 : 2, per_anchor = columns ? wpr : W;
-            const int chunks = (per_anchor + STAGE_CHUNK - 1) / STAGE_CHUNK, per_read = n_anchors * chunks;
+            // measured: the ten words of an anchor window go best as 5 + 5, the one window of an equal-length tile
+            // in fours
+            const int chunk = columns ? STAGE_CHUNK - 1 : STAGE_CHUNK;
+            const int chunks = (per_anchor + chunk - 1) / chunk, per_read = n_anchors * chunks;
             st_step = nthreads / per_read;
             const int c = tid % per_read;
             st_first = tid / per_read < st_step ? tid / per_read : -1;
             st_anchor = c / chunks;
-            st_k0 = (c - st_anchor * chunks) * STAGE_CHUNK;
-            st_k1 = min(st_k0 + STAGE_CHUNK, per_anchor);
+            st_k0 = (c - st_anchor * chunks) * chunk;
+            st_k1 = min(st_k0 + chunk, per_anchor);
         }
         // masks of the typical read (all flank bases on the contig, at least L columns), by window word
         for (int w = tid; w < wpr; w += nthreads) {
@@ -348,7 +352,8 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     };
 
     // ---- stage phase: the masked word pairs of window words [k0, k1) of one anchor of one read ----
-    auto stage_words = [&](const SwarRecord &rec, uint32_t *row, int anchor, int k0, int k1) {
+    auto stage_words = [&](auto chunk_tag, const SwarRecord &rec, uint32_t *row, int anchor, int k0, int k1) {
+        constexpr int kChunk = decltype(chunk_tag)::value;  // words per call, at most: fixes the unrolling
         const int cols = (int)(rec.cols & 0x7FFF);
         const int v = (int)(rec.misc & 0xFFFF);
         const int lf = (int)((rec.cols >> 16) & 0xFF), rf = (int)(rec.cols >> 24);
@@ -361,14 +366,14 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         const int sx = (tq & 7) << 2, sy = (tr & 7) << 2;
         const uint32_t *qp = seq32 + ((int)rec.qi + (tq >> 3));
         const uint32_t *rp = ref32 + ((int)rec.ri + (tr >> 3));
-        uint32_t wq[STAGE_CHUNK + 1], wr[STAGE_CHUNK + 1];
+        uint32_t wq[kChunk + 1], wr[kChunk + 1];
 #pragma unroll
-        for (int j = 0; j <= STAGE_CHUNK; ++j) {
+        for (int j = 0; j <= kChunk; ++j) {
             wq[j] = j <= n ? __ldg(qp + j) : 0;
             wr[j] = j <= n ? __ldg(rp + j) : 0;
         }
 #pragma unroll
-        for (int j = 0; j <= STAGE_CHUNK; ++j) wq[j] = natural_order(wq[j]);
+        for (int j = 0; j <= kChunk; ++j) wq[j] = natural_order(wq[j]);
         // memory word j holds window word k0 + j (left anchor) or k1 - 1 - j (right anchor): walk the stage row and
         // the mask table by +-1 from there
         const int wfirst = (mode ? 0 : anchor * W) + (anchor ? k1 - 1 : k0), dir = anchor ? -1 : 1;
@@ -376,7 +381,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         const uint32_t *mask_at = s_mask + 2 * wfirst;
         int k = anchor ? k1 - 1 : k0;
 #pragma unroll
-        for (int j = 0; j < STAGE_CHUNK; ++j) {
+        for (int j = 0; j < kChunk; ++j) {
             if (j >= n) break;
             uint32_t aligned, flank;
             if (typical) {
@@ -800,7 +805,12 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             for (int li = st_first; li < n_fwd + n_rev; li += st_step) {
                 const int row = li < n_fwd ? li : T - 1 - (li - n_fwd);
                 if (kIndel && s_gap[row]) continue;  // second pass below: whole warps of indel reads
-                stage_words(s_rec[row], s_stage + (size_t)row * row_words, st_anchor, st_k0, st_k1);
+                if (mode)
+                    stage_words(std::integral_constant<int, STAGE_CHUNK - 1>{}, s_rec[row], s_stage + (size_t)row * row_words,
+                                st_anchor, st_k0, st_k1);
+                else
+                    stage_words(std::integral_constant<int, STAGE_CHUNK>{}, s_rec[row], s_stage + (size_t)row * row_words,
+                                st_anchor, st_k0, st_k1);
             }
             if (kIndel) {
                 const int n_gap = (int)s_ctl[5];
