@@ -28,7 +28,15 @@ struct StagedGeom {
     unsigned long long *indel_seen;  // kIndel == false: counts the one-indel reads handed to the general kernel
 };
 
-constexpr int STAGE_CHUNK = 5;  // consecutive words one thread stages at a time, at most (see set_mode)
+#ifndef MDG_CHUNK_ANCHOR
+#define MDG_CHUNK_ANCHOR 5
+#endif
+#ifndef MDG_CHUNK_UNIFORM
+#define MDG_CHUNK_UNIFORM 4
+#endif
+// consecutive window words one thread stages at a time: measured, the ten words of an anchor window go best as 5 + 5,
+// the one window of an equal-length tile in fours
+constexpr int STAGE_CHUNK = MDG_CHUNK_ANCHOR, STAGE_CHUNK_UNIFORM = MDG_CHUNK_UNIFORM;
 
 // kIndel: reads with exactly one insertion or deletion between two match blocks are staged too (a third plane holds
 // the read as the composition tables see it); without it they go to the general kernel's work list.
@@ -114,9 +122,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
         strand = slot & 1;
         {
             const int n_anchors = columns ? 1 : 2, per_anchor = columns ? wpr : W;
-            // measured: the ten words of an anchor window go best as 5 + 5, the one window of an equal-length tile
-            // in fours
-            const int chunk = columns ? STAGE_CHUNK - 1 : STAGE_CHUNK;
+            const int chunk = columns ? STAGE_CHUNK_UNIFORM : STAGE_CHUNK;
             const int chunks = (per_anchor + chunk - 1) / chunk, per_read = n_anchors * chunks;
             st_step = nthreads / per_read;
             const int c = tid % per_read;
@@ -806,7 +812,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
                 const int row = li < n_fwd ? li : T - 1 - (li - n_fwd);
                 if (kIndel && s_gap[row]) continue;  // second pass below: whole warps of indel reads
                 if (mode)
-                    stage_words(std::integral_constant<int, STAGE_CHUNK - 1>{}, s_rec[row], s_stage + (size_t)row * row_words,
+                    stage_words(std::integral_constant<int, STAGE_CHUNK_UNIFORM>{}, s_rec[row], s_stage + (size_t)row * row_words,
                                 st_anchor, st_k0, st_k1);
                 else
                     stage_words(std::integral_constant<int, STAGE_CHUNK>{}, s_rec[row], s_stage + (size_t)row * row_words,
