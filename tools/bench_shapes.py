@@ -11,6 +11,7 @@ from mapdamage_b200.engine import DamageEngine  # noqa: E402
 SHAPES = {
     "se100": dict(length=(100, 100)),
     "se50-150": dict(length=(50, 150)),
+    "se30-90": dict(length=(30, 90)),
     "se50-150+clips": dict(length=(50, 150), mix=(9, 0, 0, 1)),
     "se50-150+indels": dict(length=(50, 150), mix=(8, 1, 1, 0)),
     "pe50-150": dict(length=(50, 150), paired=True),
