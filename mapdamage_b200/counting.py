@@ -45,9 +45,13 @@ def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_
     (:mod:`~mapdamage_b200.downsample`).
     """
     log = logging.getLogger(__name__)
-    filename = Path(filename)
+    filename, is_bam, is_stream = input_kind(filename)
     sampler = _downsample.sampler_for(downsample, downsample_seed)
-    if filename.suffix.lower() == ".bam":
+    if is_stream and isinstance(sampler, _downsample.ReservoirSampler):
+        # the reservoir is drawn in a first pass over the flags; the reference holds the sampled records in memory
+        # instead (reader.py:144-164), which a pipe allows and this does not
+        raise ValueError("down-sampling to a fixed number of reads needs a file, not a pipe")
+    if is_bam:
         return _count_bam(filename, ref, length, around, min_basequal, merge_libraries, folder, batch_reads, device,
                           lg_bins, engine, sampler)
     if isinstance(sampler, _downsample.ReservoirSampler):
@@ -83,6 +87,20 @@ def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_
             engine.close()
     log.debug("Counted %d of %d alignments", n_kept, builder.n_seen)
     return _finish(libraries, length, around, mis, comp, lg, overflow, folder)
+
+
+def input_kind(filename):
+    """``(path, is_bam, is_stream)``.  The reference hands any path, ``-`` or pipe to ``pysam.AlignmentFile``
+    (``reader.py:34-38``), which looks at the content; so does this for files (BGZF magic), while a pipe is taken for
+    BAM unless it is named ``*.sam``."""
+    if str(filename) == "-":
+        return Path("/dev/stdin"), True, True
+    path = Path(filename)
+    if path.is_fifo() or path.is_char_device():
+        return path, path.suffix.lower() != ".sam", True
+    with open(path, "rb") as handle:
+        magic = handle.read(2)
+    return path, magic == b"\x1f\x8b", False
 
 
 def _drawn(records, sampler, chunk=4096):

@@ -114,8 +114,10 @@ def _rescale_qual_core(ref, options, engine=None, batch_reads=1 << 18):
                               rescale_length_5p=options.rescale_length_5p,
                               rescale_length_3p=options.rescale_length_3p)
     model = RescaleModel(corr_prob, options.rescale_length_5p, options.rescale_length_3p)
-    filename = Path(options.filename)
-    if filename.suffix.lower() == ".bam":
+    from .counting import input_kind
+
+    filename, is_bam, _ = input_kind(options.filename)  # by content, like pysam (rescale.py:298)
+    if is_bam:
         return _rescale_bam(ref, options, model, engine, batch_reads, log)
     header, records = iter_sam(filename)
     reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
@@ -156,7 +158,9 @@ def _rescale_bam(ref, options, model, engine, batch_reads, log):
     """BAM in, BAM out: batches from the native decoder, records re-emitted by the native encoder."""
     from .bamio import BamReader, BamWriter
 
-    with BamReader(options.filename, merge_libraries=True, apply_filter=False) as reader:
+    from .counting import input_kind
+
+    with BamReader(input_kind(options.filename)[0], merge_libraries=True, apply_filter=False) as reader:
         reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
         reference = reference.reordered(reader.header.references)
         own_engine = engine is None

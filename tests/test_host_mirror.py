@@ -115,6 +115,38 @@ def test_count_alignments_from_bam(case_dir, params, tmp_path):
     assert_tables_equal(tmp_path / "out", case_dir)
 
 
+def test_input_format_is_read_from_the_content(tmp_path, golden_dir):
+    """Like pysam under the reference (reader.py:38), not from the file name; a pipe is taken for BAM."""
+    import json
+    import os
+    import threading
+
+    case = golden_dir / "fuzz_0_l70_a10_q0"
+    params = json.loads((case / "params.json").read_text())
+    _as_bam(case / "input.sam", tmp_path / "alignments.dat", block_bytes=4096)
+    (tmp_path / "alignments.txt").write_bytes((case / "input.sam").read_bytes())
+    assert counting.input_kind(tmp_path / "alignments.dat")[1:] == (True, False)
+    assert counting.input_kind(tmp_path / "alignments.txt")[1:] == (False, False)
+    kwargs = dict(length=params["length"], around=params["around"], min_basequal=params["minqual"],
+                  merge_libraries=params["merge_libraries"], batch_reads=512)
+    for name in ("alignments.dat", "alignments.txt"):
+        counting.count_alignments(tmp_path / name, case / "ref.fa", folder=tmp_path / ("out_" + name), **kwargs)
+        assert_tables_equal(tmp_path / ("out_" + name), case)
+    # through a named pipe
+    fifo = tmp_path / "pipe"
+    os.mkfifo(fifo)
+    writer = threading.Thread(target=lambda: fifo.write_bytes((tmp_path / "alignments.dat").read_bytes()))
+    writer.start()
+    try:
+        assert counting.input_kind(fifo)[1:] == (True, True)
+        counting.count_alignments(fifo, case / "ref.fa", folder=tmp_path / "out_pipe", **kwargs)
+    finally:
+        writer.join()
+    assert_tables_equal(tmp_path / "out_pipe", case)
+    with pytest.raises(ValueError):
+        counting.count_alignments(fifo, case / "ref.fa", downsample=10, **kwargs)
+
+
 @pytest.mark.parametrize("as_bam", [False, True], ids=["sam", "bam"])
 @pytest.mark.parametrize("case_dir,params", golden_cases("counting_downsample"))
 def test_count_alignments_downsampled(case_dir, params, as_bam, tmp_path):
