@@ -34,6 +34,18 @@ from pathlib import Path
 
 import numpy as np
 
+# stdout carries one JSON line and nothing else: whatever libraries write to file descriptor 1 (NCCL prints its
+# version banner there when NCCL_DEBUG is VERSION or WARN, as it is on the GPU boxes) is sent to stderr, and the result
+# line goes to a private copy of the original stdout
+RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    RESULT_OUT.write(json.dumps(line) + "\n")
+    RESULT_OUT.flush()
+
+
 ROOT = Path(__file__).resolve().parent
 for _p in (ROOT, ROOT / "oracle"):
     if str(_p) not in sys.path:
@@ -179,7 +191,7 @@ def reference_arm(args, rank, world):
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     what = "%d reads per step of the same synthetic workload (host-generated, seed %d)" % (sample, args.seed + 1)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64",
@@ -192,7 +204,7 @@ def reference_arm(args, rank, world):
                                  "on one core (SURVEY.md section 6)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ---------------------------------------------------------------------------
@@ -402,7 +414,7 @@ def gpu_arm(args, rank, local_rank, world):
             "cpu_baseline": cpu,
             "check": check,
         }
-        print(json.dumps(line))
+        emit(line)
     engine.close()
     if dist is not None:
         dist.destroy_process_group()
