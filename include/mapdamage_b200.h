@@ -7,6 +7,9 @@
  * reference's mapdamage/ package).  INTEGRATION.md shows the ctypes binding a
  * maintainer adds on the reference side.
  *
+ * Life-cycle, memory, multi-GPU, synthetic-input and measurement entry points have no counterpart in the
+ * reference (a single-process Python program); they say so by citing nothing.
+ *
  * Conventions: plain pointers and sizes only; every function returns 0 on
  * success or a negative mdg_status; no function throws, exits or falls back
  * to the CPU.  The message for the last failure on a context is returned by
@@ -157,6 +160,7 @@ int mdg_count_resident(mdg_ctx *ctx, const mdg_dev_batch *batch);
 
 /* Waits for all queued work; surfaces asynchronous CUDA errors. */
 int mdg_sync(mdg_ctx *ctx);
+/* Zeroes the tables: fresh accumulators, as main.py:147-155 builds them per run. */
 int mdg_reset_tables(mdg_ctx *ctx);
 
 /*
@@ -173,8 +177,8 @@ int mdg_reset_tables(mdg_ctx *ctx);
  * Any pointer may be NULL to skip that table.
  */
 int mdg_fetch_tables(mdg_ctx *ctx, uint64_t *misincorp, uint64_t *dnacomp, uint64_t *lghist);
-/* Fragment lengths >= lg_bins: rows of {lib, kind, strand, length}; returns the
- * row count (or < 0); at most max_rows rows are written. */
+/* Fragment lengths >= lg_bins (FragmentLengths keeps a dict of any length, statistics.py:117-126):
+ * rows of {lib, kind, strand, length}; returns the row count (or < 0); at most max_rows rows are written. */
 int64_t mdg_fetch_lg_overflow(mdg_ctx *ctx, int32_t *rows, int64_t max_rows);
 
 /* ---- rescale pass: replaces rescale._rescale_qual_core (rescale.py:285-365) */
@@ -197,6 +201,7 @@ int mdg_set_rescale_model(mdg_ctx *ctx, const uint8_t *lut, const double *inc, i
  */
 int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, float *mr_out,
                        uint8_t *status_out);
+/* The counters behind the log lines of rescale.py:303-304,335-343,255-261 (see mdg_rescale_submit). */
 int mdg_fetch_rescale_stats(mdg_ctx *ctx, uint64_t *stats8);
 /*
  * Integer part of the substitution bookkeeping of rescale._record_subs
@@ -313,7 +318,8 @@ int64_t mdg_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t
 int mdg_sample_fraction(uint32_t *mt_state, double fraction, int64_t n, uint8_t *keep);
 int mdg_sample_reservoir(uint32_t *mt_state, int64_t first_index, int64_t n, int64_t n_slots, int64_t *slots);
 
-/* BAM writer: header as given, BGZF blocks deflated at `level` (0-9, < 0 = 1) on n_threads threads. */
+/* BAM writer (pysam.AlignmentFile(path, "wb", template=...) at rescale.py:298-299): header as given, BGZF blocks
+ * deflated at `level` (0-9, < 0 = 1) on n_threads threads. */
 int mdg_bam_create(const char *path, const char *header_text, const char *const *ref_names, const uint32_t *ref_lengths,
                    int32_t n_refs, int32_t n_threads, int32_t level, mdg_bam_writer **out);
 const char *mdg_bam_writer_error(const mdg_bam_writer *writer);
