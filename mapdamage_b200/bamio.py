@@ -23,10 +23,12 @@ class BamReader:
     ``libraries`` is the sorted ``(sample, library)`` list indexing the count slabs.
     """
 
-    def __init__(self, path, threads=0, merge_libraries=False, apply_filter=True):
+    def __init__(self, path, threads=0, merge_libraries=False, apply_filter=True, device=None):
+        """``device``: inflate the BGZF blocks on that GPU (``mdg_bam_use_device``) instead of on host threads."""
         self._lib = _native.load()
         self._reader = C.c_void_p()
-        code = self._lib.mdg_bam_open(str(path).encode(), threads, C.byref(self._reader))
+        code = self._lib.mdg_bam_open_on(str(path).encode(), threads, -1 if device is None else int(device),
+                                         C.byref(self._reader))
         if code < 0:
             raise BAMError((self._lib.mdg_bam_error(None) or b"").decode())
         text = C.create_string_buffer(int(self._lib.mdg_bam_header_text(self._reader, None, 0)) + 1)
@@ -73,6 +75,11 @@ class BamReader:
     def __exit__(self, *exc):
         self.close()
         return False
+
+    @property
+    def device_blocks(self):
+        """BGZF blocks inflated on the GPU so far."""
+        return int(self._lib.mdg_bam_device_blocks(self._reader))
 
     @property
     def records_seen(self):

@@ -14,6 +14,7 @@ Input is BAM (decoded natively on host threads, ``bamio.BamReader``: pysam/htsli
 image) or SAM text (per-record Python, for small files and tests).
 """
 import logging
+import os
 from pathlib import Path
 
 import numpy as np
@@ -132,7 +133,10 @@ def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, fol
                     break
                 sampler.feed(batch.n)
         sampler = _downsample.Selection(sampler.selected())
-    with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True) as reader:
+    # MDG_BAM_GPU=1: BGZF blocks are inflated on the GPU the kernels run on instead of on the host threads (measured
+    # slower than sixteen host threads for files of a few GB: see DESIGN.md, section 4.2)
+    inflate_on = device if os.environ.get("MDG_BAM_GPU") == "1" else None
+    with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True, device=inflate_on) as reader:
         reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
         reference = reference.reordered(reader.header.references)
         libraries = reader.libraries

@@ -19,6 +19,7 @@
 #include "mdg_stage.cuh"
 #include "mdg_rescale.cuh"
 #include "mdg_synth.cuh"
+#include "mdg_inflate_dev.cuh"
 
 namespace {
 

@@ -21,6 +21,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda_runtime.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include "../../include/mapdamage_b200.h"
@@ -63,7 +65,15 @@ struct Block {
 struct Bytes {
     uint8_t *p = nullptr;
     size_t len = 0, cap = 0;
-    ~Bytes() { free(p); }
+    bool pinned = false;  // page-locked (cudaHostAlloc): what the GPU inflater copies from and to at full speed
+    ~Bytes() { release(); }
+    void release()
+    {
+        if (pinned) cudaFreeHost(p);
+        else free(p);
+        p = nullptr;
+        cap = 0;
+    }
     uint8_t *data() { return p; }
     const uint8_t *data() const { return p; }
     size_t size() const { return len; }
@@ -71,11 +81,26 @@ struct Bytes {
     {
         if (want <= cap) return true;
         size_t grown = std::max(want, cap + cap / 2 + (1 << 20));
-        uint8_t *q = (uint8_t *)realloc(p, grown);
-        if (!q) return false;
+        uint8_t *q = nullptr;
+        if (pinned) {
+            if (cudaHostAlloc((void **)&q, grown, cudaHostAllocDefault) != cudaSuccess) return false;
+            if (len) memcpy(q, p, len);
+            cudaFreeHost(p);
+        } else {
+            q = (uint8_t *)realloc(p, grown);
+            if (!q) return false;
+        }
         p = q;
         cap = grown;
         return true;
+    }
+    // switches the allocator; contents are dropped
+    void set_pinned(bool on)
+    {
+        if (on == pinned) return;
+        release();
+        len = 0;
+        pinned = on;
     }
     void drop_front(size_t n)
     {
@@ -97,6 +122,11 @@ struct mdg_bam_reader {
     FILE *fp = nullptr;
     int n_threads = 1;
     bool native_inflate = true;  // MDG_BAM_ZLIB=1: zlib only (A/B runs, tests)
+    // inflate on the GPU (mdg_bam_use_device): the producer thread makes the inflater the first time it sees the wish
+    std::atomic<int> want_device{-1};
+    mdg_inflater *inflater = nullptr;
+    bool inflater_failed = false;
+    std::atomic<int64_t> blocks_on_device{0}, blocks_on_host{0};
     std::string error;
     std::string header_text;
     std::vector<std::string> ref_names;
@@ -146,6 +176,7 @@ int rfail(mdg_bam_reader *r, int code, const char *fmt, ...)
 }
 
 constexpr size_t SLAB_BYTES = 32u << 20;
+constexpr size_t SLAB_BYTES_DEVICE = 256u << 20;  // the GPU inflates a slab in one launch: the more blocks the better
 
 // Producer side: reads one slab of the file, cuts it into BGZF blocks and inflates them in parallel.
 void fill_chunk(mdg_bam_reader *r, Chunk &c)
@@ -154,16 +185,35 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
     c.error = 0;
     c.last = false;
     c.compressed.len = 0;
-    if (!c.compressed.reserve(r->carry.len + SLAB_BYTES)) {
+    // the GPU inflater, when asked for: made here, on the thread that uses it
+    const int device = r->want_device.load();
+    if (device >= 0 && !r->inflater && !r->inflater_failed) {
+        if (mdg_inflater_create(device, &r->inflater) != MDG_OK) {
+            r->inflater = nullptr;
+            r->inflater_failed = true;  // no device: the host decoders do all of it
+        }
+    }
+    const bool on_device = r->inflater != nullptr;
+    size_t SLAB = on_device ? SLAB_BYTES_DEVICE : SLAB_BYTES;
+    if (on_device) {
+        // no more than what is left of a regular file: the slab is page-locked memory
+        struct stat st;
+        const long at = ftell(r->fp);
+        if (fstat(fileno(r->fp), &st) == 0 && S_ISREG(st.st_mode) && at >= 0 && (size_t)st.st_size >= (size_t)at)
+            SLAB = std::min(SLAB, (size_t)st.st_size - (size_t)at + 1);
+    }
+    c.compressed.set_pinned(on_device);
+    c.inflated.set_pinned(on_device);
+    if (!c.compressed.reserve(r->carry.len + SLAB)) {
         c.error = MDG_ERR_ARGUMENT;
         c.message = "out of host memory";
         return;
     }
     memcpy(c.compressed.p, r->carry.p, r->carry.len);
-    const size_t got = fread(c.compressed.p + r->carry.len, 1, SLAB_BYTES, r->fp);
+    const size_t got = fread(c.compressed.p + r->carry.len, 1, SLAB, r->fp);
     c.compressed.len = r->carry.len + got;
     r->carry.len = 0;
-    const bool file_done = got < SLAB_BYTES;
+    const bool file_done = got < SLAB;
     size_t at = 0, out_off = 0;
     const uint8_t *in = c.compressed.p;
     while (true) {
@@ -227,11 +277,36 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         return;
     }
     c.inflated.len = out_off;
+    // on the GPU, all blocks of the slab in one launch; what it could not do (status != 0) or got wrong (CRC) is
+    // done again below by the host decoders
+    std::vector<int32_t> device_status;
+    if (on_device && c.blocks.size() >= 64) {
+        const size_t nb = c.blocks.size();
+        std::vector<uint64_t> in_off(nb), out_offs(nb);
+        std::vector<uint32_t> in_len(nb), isize(nb);
+        for (size_t i = 0; i < nb; ++i) {
+            in_off[i] = c.blocks[i].in_off;
+            in_len[i] = (uint32_t)c.blocks[i].in_len;
+            out_offs[i] = c.blocks[i].out_off;
+            isize[i] = c.blocks[i].isize;
+        }
+        device_status.assign(nb, 1);
+        if (mdg_inflate_blocks(r->inflater, c.compressed.p, (int64_t)c.compressed.len, in_off.data(), in_len.data(),
+                               c.inflated.p, (int64_t)out_off, out_offs.data(), isize.data(), (int32_t)nb,
+                               device_status.data()) != MDG_OK)
+            device_status.assign(nb, 1);
+    }
     std::atomic<int> bad{0};
+    std::atomic<int64_t> by_device{0};
     parallel_for((int64_t)c.blocks.size(), r->n_threads, [&](int64_t i) {
         const Block &b = c.blocks[(size_t)i];
         if (!b.isize) return;
         const uint32_t want_crc = le32(c.compressed.p + b.in_off + b.in_len);
+        if (!device_status.empty() && device_status[(size_t)i] == 0 &&
+            (uint32_t)crc32(crc32(0L, Z_NULL, 0), c.inflated.p + b.out_off, b.isize) == want_crc) {
+            ++by_device;
+            return;
+        }
         // the native decoder first (mdg_inflate.cpp); zlib for anything it turns down or gets wrong
         if (r->native_inflate &&
             mdg_inflate_raw(c.compressed.p + b.in_off, (int64_t)b.in_len, c.inflated.p + b.out_off, (int64_t)b.isize) == (int64_t)b.isize &&
@@ -253,6 +328,8 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
             bad = 2;
         inflateEnd(&z);
     });
+    r->blocks_on_device += by_device.load();
+    r->blocks_on_host += (int64_t)c.blocks.size() - by_device.load();
     if (bad) {
         c.error = MDG_ERR_DATA;
         c.message = bad == 2 ? "BGZF block fails its CRC32" : "BGZF block does not inflate";
@@ -450,6 +527,11 @@ extern "C" {
 
 int mdg_bam_open(const char *path, int32_t n_threads, mdg_bam_reader **out)
 {
+    return mdg_bam_open_on(path, n_threads, -1, out);
+}
+
+int mdg_bam_open_on(const char *path, int32_t n_threads, int32_t device, mdg_bam_reader **out)
+{
     if (!path || !out) return rfail(nullptr, MDG_ERR_ARGUMENT, "mdg_bam_open: NULL argument");
     *out = nullptr;
     mdg_bam_reader *r = new (std::nothrow) mdg_bam_reader();
@@ -466,6 +548,7 @@ int mdg_bam_open(const char *path, int32_t n_threads, mdg_bam_reader **out)
         return MDG_ERR_ARGUMENT;
     }
     setvbuf(r->fp, nullptr, _IONBF, 0);  // slabs are read whole
+    r->want_device.store(device < 0 ? -1 : device);
     r->producer = std::thread(producer_loop, r);
     int rc = read_header(r);
     if (rc) {
@@ -484,8 +567,18 @@ void mdg_bam_close(mdg_bam_reader *r)
     if (!r) return;
     stop_producer(r);
     if (r->fp) fclose(r->fp);
+    mdg_inflater_free(r->inflater);
     delete r;
 }
+
+int mdg_bam_use_device(mdg_bam_reader *r, int32_t device)
+{
+    if (!r) return MDG_ERR_ARGUMENT;
+    r->want_device.store(device < 0 ? -1 : device);
+    return MDG_OK;
+}
+
+int64_t mdg_bam_device_blocks(const mdg_bam_reader *r) { return r ? r->blocks_on_device.load() : 0; }
 
 const char *mdg_bam_error(const mdg_bam_reader *r) { return r ? r->error.c_str() : g_open_error.c_str(); }
 

@@ -48,28 +48,41 @@ def main():
     t_write = time.perf_counter() - t0
     size = bam.stat().st_size
 
-    t0 = time.perf_counter()
-    with BamReader(bam, threads=args.threads, merge_libraries=True) as reader:
-        buffers = reader.buffers(1 << 20, with_qual=False)
-        n = 0
-        while True:
-            batch = reader.read_batch(buffers=buffers)
-            if batch is None:
-                break
-            n += batch.n
-    t_decode = time.perf_counter() - t0
-    assert n == args.reads
+    def decode(device):
+        t0 = time.perf_counter()
+        with BamReader(bam, threads=args.threads, merge_libraries=True, device=device) as reader:
+            buffers = reader.buffers(1 << 20, with_qual=False)
+            n = 0
+            while True:
+                batch = reader.read_batch(buffers=buffers)
+                if batch is None:
+                    break
+                n += batch.n
+            blocks = reader.device_blocks
+        assert n == args.reads
+        return time.perf_counter() - t0, blocks
+
+    t_decode, _ = decode(None)
+    decode(0)  # warm-up: CUDA context, pinned slabs
+    t_decode_gpu, gpu_blocks = decode(0)
 
     counting.count_alignments(bam, fasta, merge_libraries=True, batch_reads=1 << 18)  # warm-up: CUDA context, page cache
     t0 = time.perf_counter()
     misincorp, _, lg = counting.count_alignments(bam, fasta, merge_libraries=True, batch_reads=1 << 20)
     t_count = time.perf_counter() - t0
     assert sum(sum(t.values()) for t in lg.data[("*", "*")].values()) == args.reads
+    os.environ["MDG_BAM_GPU"] = "1"
+    t0 = time.perf_counter()
+    counting.count_alignments(bam, fasta, merge_libraries=True, batch_reads=1 << 20)
+    t_count_gpu = time.perf_counter() - t0
+    del os.environ["MDG_BAM_GPU"]
     print(json.dumps({
         "metric": "reads/sec (BAM file -> count tables, end to end)", "reads": args.reads, "bam_bytes": size,
         "bytes_per_read_compressed": size / args.reads, "host_threads": args.threads or os.cpu_count(),
         "encode_reads_per_s": args.reads / t_write, "decode_only_reads_per_s": args.reads / t_decode,
+        "decode_only_gpu_inflate_reads_per_s": args.reads / t_decode_gpu, "blocks_inflated_on_gpu": gpu_blocks,
         "end_to_end_reads_per_s": args.reads / t_count, "end_to_end_s": t_count,
+        "end_to_end_gpu_inflate_reads_per_s": args.reads / t_count_gpu,
     }))
     for p in (bam, fasta):
         p.unlink()
