@@ -10,6 +10,7 @@
 // Format: SAM/BAM specification v1.6, sections 4.1 (BGZF) and 4.2 (BAM).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -175,6 +176,11 @@ int rfail(mdg_bam_reader *r, int code, const char *fmt, ...)
     return code;
 }
 
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 constexpr size_t SLAB_BYTES = 32u << 20;
 constexpr size_t SLAB_BYTES_DEVICE = 256u << 20;  // the GPU inflates a slab in one launch: the more blocks the better
 
@@ -202,15 +208,26 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         if (fstat(fileno(r->fp), &st) == 0 && S_ISREG(st.st_mode) && at >= 0 && (size_t)st.st_size >= (size_t)at)
             SLAB = std::min(SLAB, (size_t)st.st_size - (size_t)at + 1);
     }
+    static const bool timing = getenv("MDG_BAM_TIMING") != nullptr;  // per-slab stage times on stderr
+    const double t0 = now_s();
     c.compressed.set_pinned(on_device);
     c.inflated.set_pinned(on_device);
+    // page-locked slabs are sized once: room for the carried-over block, and for the inflated side the most DEFLATE
+    // can expand plus slack, so that no later slab makes them grow (growing means locking the pages again)
+    if (on_device && !(c.inflated.reserve(5 * SLAB / 2 + (1u << 20)) && c.compressed.reserve(SLAB + (2u << 20)))) {
+        c.error = MDG_ERR_ARGUMENT;
+        c.message = "out of host memory";
+        return;
+    }
     if (!c.compressed.reserve(r->carry.len + SLAB)) {
         c.error = MDG_ERR_ARGUMENT;
         c.message = "out of host memory";
         return;
     }
     memcpy(c.compressed.p, r->carry.p, r->carry.len);
+    const double t1 = now_s();
     const size_t got = fread(c.compressed.p + r->carry.len, 1, SLAB, r->fp);
+    const double t2 = now_s();
     c.compressed.len = r->carry.len + got;
     r->carry.len = 0;
     const bool file_done = got < SLAB;
@@ -277,6 +294,7 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         return;
     }
     c.inflated.len = out_off;
+    const double t3 = now_s();
     // on the GPU, all blocks of the slab in one launch; what it could not do (status != 0) or got wrong (CRC) is
     // done again below by the host decoders
     std::vector<int32_t> device_status;
@@ -296,6 +314,7 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
                                device_status.data()) != MDG_OK)
             device_status.assign(nb, 1);
     }
+    const double t4 = now_s();
     std::atomic<int> bad{0};
     std::atomic<int64_t> by_device{0};
     parallel_for((int64_t)c.blocks.size(), r->n_threads, [&](int64_t i) {
@@ -328,6 +347,9 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
             bad = 2;
         inflateEnd(&z);
     });
+    if (timing)
+        fprintf(stderr, "slab: %zu blocks, reserve %.3f s, read %.3f s, scan + reserve %.3f s, device inflate %.3f s, host crc / inflate %.3f s\n",
+                c.blocks.size(), t1 - t0, t2 - t1, t3 - t2, t4 - t3, now_s() - t4);
     r->blocks_on_device += by_device.load();
     r->blocks_on_host += (int64_t)c.blocks.size() - by_device.load();
     if (bad) {

@@ -18,7 +18,13 @@
 namespace mdg_inflate {
 
 
+// first-level table sizes: on the device a thread's tables have to stay in L1 next to those of its 31 neighbours
+// (the layout of InflateScratch differs between the two builds; only device code ever touches a device scratch)
+#ifdef __CUDA_ARCH__
+constexpr int LITLEN_BITS = 9, OFFSET_BITS = 7, PRECODE_BITS = 7;
+#else
 constexpr int LITLEN_BITS = 11, OFFSET_BITS = 8, PRECODE_BITS = 7;
+#endif
 constexpr int LITLEN_CAP = 2048 + 1024, OFFSET_CAP = 256 + 512, PRECODE_CAP = 128;
 
 // table entry: bits 0-4 code length | bits 5-7 kind | bits 8-12 extra bits (or second-level index bits) | 16-31 value
@@ -50,9 +56,13 @@ MDG_HD inline uint32_t symbol_entry(Alphabet alphabet, uint32_t sym, uint32_t le
 
 MDG_HD inline uint32_t reverse_bits(uint32_t code, int len)
 {
+#ifdef __CUDA_ARCH__
+    return __brev(code) >> (32 - len);
+#else
     uint32_t r = 0;
     for (int i = 0; i < len; ++i) r |= ((code >> i) & 1u) << (len - 1 - i);
     return r;
+#endif
 }
 
 // Canonical Huffman decode table from code lengths (RFC 1951 3.2.2).  false: over-subscribed, or incomplete in a way

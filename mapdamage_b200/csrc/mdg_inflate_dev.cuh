@@ -27,7 +27,11 @@ __device__ inline int64_t inflate_lockstep(const uint8_t *in, int64_t in_len, ui
     uint32_t pending = 0;
     const uint8_t *src = nullptr;
     while (__any_sync(0xffffffffu, !done)) {
-        if (done) continue;
+        // block headers are read by all lanes at once: building the decode tables is thousands of instructions, which
+        // 32 lanes arriving one by one would take turns at.  Streams of one file change tables after about as many
+        // symbols, so a lane seldom waits long for the others.
+        const bool headers_now = __all_sync(0xffffffffu, done || need_header);
+        if (done || (need_header && !headers_now)) continue;
         if (need_header) {
             br.refill();
             final_block = br.take(1) != 0;
