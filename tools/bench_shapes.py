@@ -18,14 +18,18 @@ SHAPES = {
     "c3 1 lib": dict(length=(50, 150), mix=(7, 1, 1, 1), paired=True),
     "c3 2 libs": dict(length=(50, 150), mix=(7, 1, 1, 1), paired=True, n_libs=2),
     "se100 2 libs": dict(length=(100, 100), n_libs=2),
+    "se100 -Q 20": dict(length=(100, 100), min_qual=20),
+    "se50-150 -Q 20": dict(length=(50, 150), min_qual=20),
 }
 
 reference = synth.make_reference([1_000_000], seed=5)
 n = 4_000_000
 for name, kw in SHAPES.items():
-    with DamageEngine(n_libraries=kw.get("n_libs", 1), max_reads=1024) as engine:
+    kw = dict(kw)
+    min_qual = kw.pop("min_qual", 0)
+    with DamageEngine(n_libraries=kw.get("n_libs", 1), max_reads=1024, min_qual=min_qual) as engine:
         engine.set_reference(reference)
-        dev = engine.synth_batch(n, seed=7, with_qual=False, **kw)
+        dev = engine.synth_batch(n, seed=7, with_qual=min_qual > 0, **kw)
         for _ in range(3):
             engine.count_resident(dev)
         engine.sync()
