@@ -369,11 +369,14 @@ def gpu_arm(args, rank, local_rank, world):
         import oracle
 
         sample = host0.slice(0, min(args.cpu_sample, host0.n))
+        passes = 3 if sample.n >= 1_000_000 else 1  # about 10 s of CPU work at the default sample
         t0 = time.perf_counter()
-        oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, n_lib=n_lib, threads=1)
+        for _ in range(passes):
+            oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, n_lib=n_lib, threads=1)
         dt = time.perf_counter() - t0
-        cpu = {"value": sample.n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "first %d reads of batch 0 of this workload, one thread, %.1f s" % (sample.n, dt)}
+        cpu = {"value": passes * sample.n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "first %d reads of batch 0 of this workload, %d passes, one thread, %.1f s"
+                         % (sample.n, passes, dt)}
 
     if rank == 0:
         peak, peak_source = measured_peak()
