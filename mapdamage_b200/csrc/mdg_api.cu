@@ -884,12 +884,13 @@ int mdg_sync(mdg_ctx *ctx)
     MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
 #ifdef MDG_PHASE_CLOCKS
     {
-        unsigned int pc[16];
+        unsigned int pc[24];
         if (cudaMemcpyFromSymbol(pc, mdg::mdg_phase_dump, sizeof(pc)) == cudaSuccess) {
-            static const char *names[8] = {"parse", "sync", "mode", "stage", "sync", "count", "sync", "rest"};
+            static const char *names[12] = {"parse", "sync", "prefetch", "stage", "sync", "count", "sync", "rest",
+                                            "worklist", "mode", "-", "-"};
             for (int w = 0; w < 2; ++w) {
                 fprintf(stderr, "phase clocks %s warp:", w ? "last " : "first");
-                for (int i = 0; i < 8; ++i) fprintf(stderr, " %s %u", names[i], pc[8 * w + i]);
+                for (int i = 0; i < 10; ++i) fprintf(stderr, " %s %u", names[i], pc[12 * w + i]);
                 fprintf(stderr, "\n");
             }
         }

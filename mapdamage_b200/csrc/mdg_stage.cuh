@@ -41,7 +41,7 @@ constexpr int STAGE_CHUNK = MDG_CHUNK_ANCHOR, STAGE_CHUNK_UNIFORM = MDG_CHUNK_UN
 // kIndel: reads with exactly one insertion or deletion between two match blocks are staged too (a third plane holds
 // the read as the composition tables see it); without it they go to the general kernel's work list.
 #ifdef MDG_PHASE_CLOCKS
-__device__ unsigned int mdg_phase_dump[16];
+__device__ unsigned int mdg_phase_dump[24];
 #endif
 
 template <bool kQual, bool kIndel, int kMaxThreads, int kBlocksPerSm>
@@ -677,19 +677,19 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
 #ifdef MDG_PHASE_CLOCKS
     // per-phase cycle counts as the first and the last warp see them (shared memory: no registers held);
     // block 3's land in mdg_phase_dump, which mdg_sync prints
-    __shared__ unsigned int s_pc[2][9];
-    if (tid < 18) (&s_pc[0][0])[tid] = 0;
+    __shared__ unsigned int s_pc[2][13];
+    if (tid < 26) (&s_pc[0][0])[tid] = 0;
     __syncthreads();
     const int warp = tid >> 5;
     const bool pc_warp = warp == 0 || warp == (nthreads >> 5) - 1;
-    if (pc_warp && lane == 0) s_pc[warp != 0][8] = (unsigned int)clock();
+    if (pc_warp && lane == 0) s_pc[warp != 0][12] = (unsigned int)clock();
     __syncwarp();
 #define MDG_PHASE(i)                                              \
     if (pc_warp) {                                                \
         const unsigned int pt1 = (unsigned int)clock();           \
         if (lane == 0) {                                          \
-            s_pc[warp != 0][i] += pt1 - s_pc[warp != 0][8];       \
-            s_pc[warp != 0][8] = pt1;                             \
+            s_pc[warp != 0][i] += pt1 - s_pc[warp != 0][12];      \
+            s_pc[warp != 0][12] = pt1;                            \
         }                                                         \
         __syncwarp();                                             \
     }
@@ -780,6 +780,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             for (uint32_t i = lane; i < n_cx; i += 32) wl[base + i] = s_cx[i];
         }
 
+        MDG_PHASE(8)
         // ---- one window per read when every gap-free read of the tile has the same length ----
         {
             int want = 0;
@@ -798,6 +799,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
             dirty = dirty || s_ctl[0] + s_ctl[1] > 0;
         }
 
+        MDG_PHASE(9)
         // ---- pull the tile after next towards L2 ----
         uint32_t ahead_boff = 0, ahead_coff = 0;
         const bool ahead_live = !subset && prefetch_headers(tile + 2 * (int64_t)gridDim.x, ahead_boff, ahead_coff);
@@ -864,7 +866,7 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     }
 #ifdef MDG_PHASE_CLOCKS
     __syncthreads();
-    if (blockIdx.x == 3 && tid < 16) mdg_phase_dump[tid] = s_pc[tid >> 3][tid & 7];
+    if (blockIdx.x == 3 && tid < 24) mdg_phase_dump[tid] = s_pc[tid / 12][tid % 12];
 #endif
 
     flush_block();
