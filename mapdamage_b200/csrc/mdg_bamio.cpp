@@ -150,6 +150,14 @@ struct mdg_bam_reader {
     int produce_at = 0, consume_at = 0;
     bool stop = false, producer_done = false;
     Bytes carry;  // bytes of a BGZF block cut by the end of a slab
+    // host decoders: the next slab is read (a copy out of the page cache, a quarter of a slab's turnaround) by a
+    // helper thread while this one is inflated; it lands behind HEADROOM bytes so that the carried-over block can be
+    // put in front of it without moving the slab
+    Bytes ahead;
+    size_t ahead_got = 0;
+    bool ahead_valid = false;
+    std::thread ahead_thread;
+    size_t slab_bytes = 0;  // MDG_BAM_SLAB: slab size of the host decoders (tests: many slabs from small files)
 };
 
 struct mdg_bam_writer {
@@ -182,6 +190,7 @@ static double now_s()
 }
 
 constexpr size_t SLAB_BYTES = 32u << 20;
+constexpr size_t AHEAD_HEADROOM = 1u << 16;  // a carried-over piece of a BGZF block is shorter than a block: 64 KB
 constexpr size_t SLAB_BYTES_DEVICE = 256u << 20;  // the GPU inflates a slab in one launch: the more blocks the better
 
 // Producer side: reads one slab of the file, cuts it into BGZF blocks and inflates them in parallel.
@@ -199,8 +208,10 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
             r->inflater_failed = true;  // no device: the host decoders do all of it
         }
     }
-    const bool on_device = r->inflater != nullptr;
-    size_t SLAB = on_device ? SLAB_BYTES_DEVICE : SLAB_BYTES;
+    if (r->ahead_thread.joinable()) r->ahead_thread.join();
+    const bool use_ahead = r->ahead_valid;
+    const bool on_device = r->inflater != nullptr && !use_ahead;
+    size_t SLAB = on_device ? SLAB_BYTES_DEVICE : r->slab_bytes;
     if (on_device) {
         // no more than what is left of a regular file: the slab is page-locked memory
         struct stat st;
@@ -224,14 +235,26 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         c.message = "out of host memory";
         return;
     }
-    memcpy(c.compressed.p, r->carry.p, r->carry.len);
+    size_t base = 0, got;
     const double t1 = now_s();
-    const size_t got = fread(c.compressed.p + r->carry.len, 1, SLAB, r->fp);
+    if (use_ahead) {
+        // read while the previous slab was inflated: take that buffer, the carried-over block goes in front of it
+        std::swap(c.compressed.p, r->ahead.p);
+        std::swap(c.compressed.cap, r->ahead.cap);
+        base = AHEAD_HEADROOM - r->carry.len;
+        memcpy(c.compressed.p + base, r->carry.p, r->carry.len);
+        got = r->ahead_got;
+        r->ahead_valid = false;
+        c.compressed.len = AHEAD_HEADROOM + got;
+    } else {
+        memcpy(c.compressed.p, r->carry.p, r->carry.len);
+        got = fread(c.compressed.p + r->carry.len, 1, SLAB, r->fp);
+        c.compressed.len = r->carry.len + got;
+    }
     const double t2 = now_s();
-    c.compressed.len = r->carry.len + got;
     r->carry.len = 0;
     const bool file_done = got < SLAB;
-    size_t at = 0, out_off = 0;
+    size_t at = base, out_off = 0;
     const uint8_t *in = c.compressed.p;
     while (true) {
         const size_t left = c.compressed.len - at;
@@ -294,6 +317,10 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         return;
     }
     c.inflated.len = out_off;
+    if (!file_done && !on_device && r->inflater == nullptr && r->ahead.reserve(AHEAD_HEADROOM + SLAB)) {
+        r->ahead_valid = true;
+        r->ahead_thread = std::thread([r, SLAB] { r->ahead_got = fread(r->ahead.p + AHEAD_HEADROOM, 1, SLAB, r->fp); });
+    }
     const double t3 = now_s();
     // on the GPU, all blocks of the slab in one launch; what it could not do (status != 0) or got wrong (CRC) is
     // done again below by the host decoders
@@ -445,6 +472,7 @@ void stop_producer(mdg_bam_reader *r)
     }
     r->cond.notify_all();
     if (r->producer.joinable()) r->producer.join();
+    if (r->ahead_thread.joinable()) r->ahead_thread.join();
 }
 
 int read_header(mdg_bam_reader *r)
@@ -571,6 +599,11 @@ int mdg_bam_open_on(const char *path, int32_t n_threads, int32_t device, mdg_bam
     }
     setvbuf(r->fp, nullptr, _IONBF, 0);  // slabs are read whole
     r->want_device.store(device < 0 ? -1 : device);
+    {
+        const char *env = getenv("MDG_BAM_SLAB");
+        const long long want = env ? atoll(env) : 0;
+        r->slab_bytes = want >= (1 << 16) ? (size_t)want : SLAB_BYTES;
+    }
     r->producer = std::thread(producer_loop, r);
     int rc = read_header(r);
     if (rc) {

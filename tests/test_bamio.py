@@ -151,3 +151,29 @@ def test_soa_encoder(tmp_path):
         assert reader.libraries == [("s", "libA"), ("s", "libB")]
         got = reader.read_batch(max_reads=6000)
     assert_same_batch(got, batch)
+
+
+@pytest.mark.parametrize("slab", ["65536", "70001", "250000"])
+def test_many_slabs_and_read_ahead(tmp_path, monkeypatch, slab):
+    """Slabs a little larger than a block: every slab ends inside a block (carried over) and, from the second on,
+    is read ahead by the helper thread while the previous one is inflated."""
+    import numpy as np
+
+    from conftest import GOLDEN
+
+    header, records = read_sam(GOLDEN / "fuzz_0_l70_a10_q0" / "input.sam")
+    bam_py.write_bam(tmp_path / "in.bam", header, records * 4, block_bytes=60_000)
+    with BamReader(tmp_path / "in.bam", merge_libraries=True) as reader:
+        want = reader.read_batch()
+    monkeypatch.setenv("MDG_BAM_SLAB", slab)
+    with BamReader(tmp_path / "in.bam", merge_libraries=True, threads=3) as reader:
+        parts = []
+        while True:
+            batch = reader.read_batch(max_reads=500)
+            if batch is None:
+                break
+            parts.append(batch)
+    assert sum(p.n for p in parts) == want.n
+    for name in ("flag", "pos", "l_seq"):
+        assert np.array_equal(np.concatenate([getattr(p, name) for p in parts]), getattr(want, name)), name
+    assert np.array_equal(np.concatenate([p.cigar for p in parts]), want.cigar)
