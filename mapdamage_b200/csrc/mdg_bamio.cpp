@@ -150,9 +150,9 @@ struct mdg_bam_reader {
     int produce_at = 0, consume_at = 0;
     bool stop = false, producer_done = false;
     Bytes carry;  // bytes of a BGZF block cut by the end of a slab
-    // host decoders: the next slab is read (a copy out of the page cache, a quarter of a slab's turnaround) by a
-    // helper thread while this one is inflated; it lands behind HEADROOM bytes so that the carried-over block can be
-    // put in front of it without moving the slab
+    // host decoders, optional (MDG_BAM_READAHEAD=1): the next slab is read (a copy out of the page cache, a quarter of
+    // a slab's turnaround) by a helper thread while this one is inflated; it lands behind HEADROOM bytes so that the
+    // carried-over block can be put in front of it without moving the slab
     Bytes ahead;
     size_t ahead_got = 0;
     bool ahead_valid = false;
@@ -317,7 +317,11 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         return;
     }
     c.inflated.len = out_off;
-    if (!file_done && !on_device && r->inflater == nullptr && r->ahead.reserve(AHEAD_HEADROOM + SLAB)) {
+    // off unless MDG_BAM_READAHEAD=1: the decoder alone gains 7-12 % from it on the GPU box, file -> tables loses
+    // (the helper competes with the thread that builds and submits the batches)
+    const char *ra_env = getenv("MDG_BAM_READAHEAD");
+    const bool read_ahead = ra_env && ra_env[0] == '1';
+    if (read_ahead && !file_done && !on_device && r->inflater == nullptr && r->ahead.reserve(AHEAD_HEADROOM + SLAB)) {
         r->ahead_valid = true;
         r->ahead_thread = std::thread([r, SLAB] { r->ahead_got = fread(r->ahead.p + AHEAD_HEADROOM, 1, SLAB, r->fp); });
     }

@@ -153,10 +153,11 @@ def test_soa_encoder(tmp_path):
     assert_same_batch(got, batch)
 
 
+@pytest.mark.parametrize("read_ahead", ["0", "1"])
 @pytest.mark.parametrize("slab", ["65536", "70001", "250000"])
-def test_many_slabs_and_read_ahead(tmp_path, monkeypatch, slab):
-    """Slabs a little larger than a block: every slab ends inside a block (carried over) and, from the second on,
-    is read ahead by the helper thread while the previous one is inflated."""
+def test_many_slabs_and_read_ahead(tmp_path, monkeypatch, slab, read_ahead):
+    """Slabs a little larger than a block (MDG_BAM_SLAB): every slab ends inside a block, which is carried over; with
+    MDG_BAM_READAHEAD=1 the slabs from the second on are read by the helper thread while the previous one is inflated."""
     import numpy as np
 
     from conftest import GOLDEN
@@ -166,6 +167,7 @@ def test_many_slabs_and_read_ahead(tmp_path, monkeypatch, slab):
     with BamReader(tmp_path / "in.bam", merge_libraries=True) as reader:
         want = reader.read_batch()
     monkeypatch.setenv("MDG_BAM_SLAB", slab)
+    monkeypatch.setenv("MDG_BAM_READAHEAD", read_ahead)
     with BamReader(tmp_path / "in.bam", merge_libraries=True, threads=3) as reader:
         parts = []
         while True:
