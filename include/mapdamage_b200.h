@@ -296,6 +296,16 @@ int mdg_bam_set_libraries(mdg_bam_reader *reader, const char *const *read_groups
 int64_t mdg_bam_read_batch(mdg_bam_reader *reader, const mdg_batch *out, int64_t max_reads, int64_t max_cigar,
                            int64_t max_bases, uint32_t drop_flags, uint8_t *raw, int64_t raw_cap, uint64_t *raw_off,
                            uint8_t *has_mr, int64_t *n_cigar, int64_t *n_bases);
+/*
+ * Reads without a usable read group (reader.py:63-81).  By default the first one fails mdg_bam_read_batch with
+ * MDG_ERR_DATA and the reference's BAMError text ("Read 'name' has no read-group. ...").  Lenient: such reads get
+ * library 0xFFFF instead and the batch succeeds -- the reference looks the library up only for the reads its
+ * down-sampler yields (reader.py:134-164), so a caller that down-samples decides after drawing.
+ * mdg_bam_library_failure: k-th failing read of the last batch in batch order (at most 4096 are kept): returns its
+ * index in the batch (or -1 past the end) and copies the message.
+ */
+int mdg_bam_lenient_libraries(mdg_bam_reader *reader, int32_t on);
+int64_t mdg_bam_library_failure(const mdg_bam_reader *reader, int64_t k, char *buf, int64_t cap);
 /* Records walked so far, dropped ones included. */
 int64_t mdg_bam_records_seen(const mdg_bam_reader *reader);
 /*

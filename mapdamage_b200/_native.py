@@ -88,6 +88,8 @@ SYMBOLS = {
     "mdg_bam_read_batch": (C.c_int64, [C.c_void_p, C.POINTER(Batch), C.c_int64, C.c_int64, C.c_int64, C.c_uint32,
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]),
+    "mdg_bam_lenient_libraries": (C.c_int, [C.c_void_p, C.c_int32]),
+    "mdg_bam_library_failure": (C.c_int64, [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]),
     "mdg_bam_records_seen": (C.c_int64, [C.c_void_p]),
     "mdg_bam_open_on": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "mdg_bam_use_device": (C.c_int, [C.c_void_p, C.c_int32]),

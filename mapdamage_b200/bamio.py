@@ -23,8 +23,10 @@ class BamReader:
     ``libraries`` is the sorted ``(sample, library)`` list indexing the count slabs.
     """
 
-    def __init__(self, path, threads=0, merge_libraries=False, apply_filter=True, device=None):
-        """``device``: inflate the BGZF blocks on that GPU (``mdg_bam_use_device``) instead of on host threads."""
+    def __init__(self, path, threads=0, merge_libraries=False, apply_filter=True, device=None, lenient_libraries=False):
+        """``device``: inflate the BGZF blocks on that GPU (``mdg_bam_use_device``) instead of on host threads.
+        ``lenient_libraries``: a read without a usable read group does not fail its batch; it gets library 0xFFFF and
+        :meth:`library_failures` lists such reads (the caller down-samples first, then decides: ``reader.py:134-164``)."""
         self._lib = _native.load()
         self._reader = C.c_void_p()
         code = self._lib.mdg_bam_open_on(str(path).encode(), threads, -1 if device is None else int(device),
@@ -48,6 +50,8 @@ class BamReader:
         self.header.set_references(names, lengths)
         self.apply_filter = apply_filter
         self.merge_libraries = merge_libraries
+        if lenient_libraries:
+            self._lib.mdg_bam_lenient_libraries(self._reader, 1)
         if merge_libraries:
             self.libraries = [("*", "*")]
             self._lib.mdg_bam_set_libraries(self._reader, None, None, 0)
@@ -75,6 +79,15 @@ class BamReader:
     def __exit__(self, *exc):
         self.close()
         return False
+
+    def library_failures(self):
+        """``[(index in the last batch, BAMError text)]`` of the reads without a usable read group."""
+        out, buf = [], C.create_string_buffer(1024)
+        while True:
+            index = self._lib.mdg_bam_library_failure(self._reader, len(out), buf, len(buf))
+            if index < 0:
+                return out
+            out.append((int(index), buf.value.decode("utf-8", "replace")))
 
     @property
     def device_blocks(self):
@@ -123,10 +136,7 @@ class BamReader:
             None if raw is None else raw.ctypes.data, raw_cap, None if raw_off is None else raw_off.ctypes.data,
             None if has_mr is None else has_mr.ctypes.data, C.byref(n_cigar), C.byref(n_bases))
         if n < 0:
-            message = (self._lib.mdg_bam_error(self._reader) or b"").decode()
-            if n == _native.ERR_DATA and "read-group" in message:
-                raise BAMError(message[0].upper() + message[1:])
-            raise BAMError(message)
+            raise BAMError((self._lib.mdg_bam_error(self._reader) or b"").decode("utf-8", "replace"))
         if n == 0:
             return None
         trimmed = {name: arrays[name][:n] for name, _ in ReadBatch.FIELDS if name != "cigar_off"}

@@ -21,7 +21,7 @@ import numpy as np
 
 from . import downsample as _downsample
 from . import statistics
-from .batch import FILTERED_FLAGS, BatchBuilder
+from .batch import BAMError, FILTERED_FLAGS, BatchBuilder
 from .engine import DamageEngine
 from .refgenome import Reference
 from .samtext import iter_sam
@@ -63,7 +63,7 @@ def count_alignments(filename, ref, length=70, around=10, min_basequal=0, merge_
     if sampler is not None:
         records = _drawn(records, sampler)
     reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
-    reference = reference.reordered(header.references)
+    reference = reference.reordered(header.references, header.lengths)
     builder = BatchBuilder(readgroups=None if merge_libraries else header.libraries(),
                            merge_libraries=merge_libraries, apply_filter=True)
     libraries = builder.libraries
@@ -125,7 +125,7 @@ def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, fol
 
     log = logging.getLogger(__name__)
     if isinstance(sampler, _downsample.ReservoirSampler):
-        with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True) as reader:
+        with BamReader(filename, merge_libraries=True, apply_filter=True) as reader:  # flags only: no library lookup
             buffers = reader.buffers(batch_reads, with_qual=False)
             while True:
                 batch = reader.read_batch(buffers=buffers)
@@ -136,9 +136,10 @@ def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, fol
     # MDG_BAM_GPU=1: BGZF blocks are inflated on the GPU the kernels run on instead of on the host threads (measured
     # slower than sixteen host threads for files of a few GB: see DESIGN.md, section 4.2)
     inflate_on = device if os.environ.get("MDG_BAM_GPU") == "1" else None
-    with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True, device=inflate_on) as reader:
+    with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True, device=inflate_on,
+                   lenient_libraries=sampler is not None) as reader:
         reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
-        reference = reference.reordered(reader.header.references)
+        reference = reference.reordered(reader.header.references, reader.header.lengths)
         libraries = reader.libraries
         own_engine = engine is None
         if own_engine:
@@ -157,7 +158,13 @@ def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, fol
                     break
                 if sampler is not None:
                     # every read of the batch passed the flag filter; those not drawn get a filtered flag
-                    _downsample.apply_mask(batch, np.ones(batch.n, dtype=np.bool_), sampler.mask(batch.n))
+                    drawn = sampler.mask(batch.n)
+                    _downsample.apply_mask(batch, np.ones(batch.n, dtype=np.bool_), drawn)
+                    # the reference looks up the library of the reads it yields only (reader.py:134-164, main.py:165-170)
+                    for index, message in reader.library_failures():
+                        if drawn[index]:
+                            raise BAMError(message)
+                        batch.lib[index] = 0
                 engine.count(batch, compact=False)
                 n_kept += batch.n
                 turn += 1

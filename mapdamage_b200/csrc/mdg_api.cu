@@ -954,7 +954,9 @@ int mdg_set_rescale_model(mdg_ctx *ctx, const uint8_t *lut, const double *inc, i
     ctx->rescale_hist = (unsigned long long *)(p + inc_bytes + lut_bytes);
     MDG_CUDA(ctx, cudaMemset(ctx->rescale_hist, 0, ctx->n_hist * 8));
     MDG_CUDA(ctx, cudaMemcpy(p, inc, (size_t)2 * n_slots * 8, cudaMemcpyHostToDevice));
-    MDG_CUDA(ctx, cudaMemcpy(p + inc_bytes, lut, lut_bytes, cudaMemcpyHostToDevice));
+    // the host table holds exactly 2 * n_slots * 94 bytes; the rounded-up tail of the device copy is zeroed
+    MDG_CUDA(ctx, cudaMemset(p + inc_bytes, 0, lut_bytes));
+    MDG_CUDA(ctx, cudaMemcpy(p + inc_bytes, lut, (size_t)2 * n_slots * 94, cudaMemcpyHostToDevice));
     ctx->model.inc = (const double *)p;
     ctx->model.lut = (const uint8_t *)(p + inc_bytes);
     ctx->model.len5p = len5p;

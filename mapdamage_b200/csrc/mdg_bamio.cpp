@@ -134,6 +134,10 @@ struct mdg_bam_reader {
     std::vector<uint32_t> ref_lengths;
     std::unordered_map<std::string, int32_t> library_of;  // read group id -> library index
     bool merge_libraries = true;
+    // reads of the last batch without a usable read group: (index in the batch, the reference's BAMError text).
+    // lenient: they get library 0xFFFF and the caller decides (down-sampling: only drawn reads are looked up, reader.py:139-164)
+    bool lenient_libraries = false;
+    std::vector<std::pair<int64_t, std::string>> library_failures;
     // decompressed bytes not yet consumed
     Bytes stream;
     size_t stream_pos = 0;  // next unread byte
@@ -150,13 +154,6 @@ struct mdg_bam_reader {
     int produce_at = 0, consume_at = 0;
     bool stop = false, producer_done = false;
     Bytes carry;  // bytes of a BGZF block cut by the end of a slab
-    // host decoders, optional (MDG_BAM_READAHEAD=1): the next slab is read (a copy out of the page cache, a quarter of
-    // a slab's turnaround) by a helper thread while this one is inflated; it lands behind HEADROOM bytes so that the
-    // carried-over block can be put in front of it without moving the slab
-    Bytes ahead;
-    size_t ahead_got = 0;
-    bool ahead_valid = false;
-    std::thread ahead_thread;
     size_t slab_bytes = 0;  // MDG_BAM_SLAB: slab size of the host decoders (tests: many slabs from small files)
 };
 
@@ -190,7 +187,6 @@ static double now_s()
 }
 
 constexpr size_t SLAB_BYTES = 32u << 20;
-constexpr size_t AHEAD_HEADROOM = 1u << 16;  // a carried-over piece of a BGZF block is shorter than a block: 64 KB
 constexpr size_t SLAB_BYTES_DEVICE = 256u << 20;  // the GPU inflates a slab in one launch: the more blocks the better
 
 // Producer side: reads one slab of the file, cuts it into BGZF blocks and inflates them in parallel.
@@ -208,9 +204,7 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
             r->inflater_failed = true;  // no device: the host decoders do all of it
         }
     }
-    if (r->ahead_thread.joinable()) r->ahead_thread.join();
-    const bool use_ahead = r->ahead_valid;
-    const bool on_device = r->inflater != nullptr && !use_ahead;
+    const bool on_device = r->inflater != nullptr;
     size_t SLAB = on_device ? SLAB_BYTES_DEVICE : r->slab_bytes;
     if (on_device) {
         // no more than what is left of a regular file: the slab is page-locked memory
@@ -235,22 +229,11 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         c.message = "out of host memory";
         return;
     }
-    size_t base = 0, got;
+    const size_t base = 0;
     const double t1 = now_s();
-    if (use_ahead) {
-        // read while the previous slab was inflated: take that buffer, the carried-over block goes in front of it
-        std::swap(c.compressed.p, r->ahead.p);
-        std::swap(c.compressed.cap, r->ahead.cap);
-        base = AHEAD_HEADROOM - r->carry.len;
-        memcpy(c.compressed.p + base, r->carry.p, r->carry.len);
-        got = r->ahead_got;
-        r->ahead_valid = false;
-        c.compressed.len = AHEAD_HEADROOM + got;
-    } else {
-        memcpy(c.compressed.p, r->carry.p, r->carry.len);
-        got = fread(c.compressed.p + r->carry.len, 1, SLAB, r->fp);
-        c.compressed.len = r->carry.len + got;
-    }
+    memcpy(c.compressed.p, r->carry.p, r->carry.len);
+    const size_t got = fread(c.compressed.p + r->carry.len, 1, SLAB, r->fp);
+    c.compressed.len = r->carry.len + got;
     const double t2 = now_s();
     r->carry.len = 0;
     const bool file_done = got < SLAB;
@@ -291,6 +274,11 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
                     b.in_off = at + 12 + xlen;
                     b.in_len = (size_t)total - 12 - xlen - 8;
                     b.isize = le32(in + at + total - 4);
+                    if (b.isize > 65536) {  // SAM specification 4.1: a block inflates to at most 64 KB
+                        c.error = MDG_ERR_DATA;
+                        c.message = "BGZF block claims more than 65536 bytes of data";
+                        return;
+                    }
                     b.out_off = out_off;
                     out_off += b.isize;
                     c.blocks.push_back(b);
@@ -317,14 +305,6 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         return;
     }
     c.inflated.len = out_off;
-    // off unless MDG_BAM_READAHEAD=1: the decoder alone gains 7-12 % from it on the GPU box, file -> tables loses
-    // (the helper competes with the thread that builds and submits the batches)
-    const char *ra_env = getenv("MDG_BAM_READAHEAD");
-    const bool read_ahead = ra_env && ra_env[0] == '1';
-    if (read_ahead && !file_done && !on_device && r->inflater == nullptr && r->ahead.reserve(AHEAD_HEADROOM + SLAB)) {
-        r->ahead_valid = true;
-        r->ahead_thread = std::thread([r, SLAB] { r->ahead_got = fread(r->ahead.p + AHEAD_HEADROOM, 1, SLAB, r->fp); });
-    }
     const double t3 = now_s();
     // on the GPU, all blocks of the slab in one launch; what it could not do (status != 0) or got wrong (CRC) is
     // done again below by the host decoders
@@ -476,7 +456,6 @@ void stop_producer(mdg_bam_reader *r)
     }
     r->cond.notify_all();
     if (r->producer.joinable()) r->producer.join();
-    if (r->ahead_thread.joinable()) r->ahead_thread.join();
 }
 
 int read_header(mdg_bam_reader *r)
@@ -723,7 +702,8 @@ int64_t mdg_bam_read_batch(mdg_bam_reader *r, const mdg_batch *out, int64_t max_
     }
     const uint8_t *const origin = r->stream.data() + r->keep_from;
     const int64_t n = (int64_t)recs.size();
-    std::atomic<int> failure{0};
+    std::mutex failure_mutex;
+    r->library_failures.clear();
     const int64_t chunk = 4096, n_chunks = (n + chunk - 1) / chunk;
     parallel_for(n_chunks, r->n_threads, [&](int64_t c) {
         for (int64_t i = c * chunk; i < std::min(n, (c + 1) * chunk); ++i) {
@@ -753,8 +733,14 @@ int64_t mdg_bam_read_batch(mdg_bam_reader *r, const mdg_batch *out, int64_t max_
                 const char *rg = find_read_group(aux, end);
                 auto it = rg ? r->library_of.find(rg) : r->library_of.end();
                 if (it == r->library_of.end()) {
-                    failure = rg ? 2 : 1;
-                    lib = 0;
+                    // reader.py:67-81, with the read's name (and group) as the reference prints them with %r
+                    const std::string name((const char *)p + 32, l_name ? l_name - 1 : 0);
+                    std::string text = "Read '" + name + "' has ";
+                    if (rg) text += std::string("read-group not listed in BAM header ('") + rg + "'); either fix BAM or use --merge-libraries";
+                    else text += "no read-group. Either fix BAM or use --merge-libraries";
+                    std::lock_guard<std::mutex> lock(failure_mutex);
+                    if (r->library_failures.size() < 4096) r->library_failures.emplace_back(i, text);
+                    lib = 0xFFFF;
                 } else {
                     lib = (uint16_t)it->second;
                 }
@@ -772,11 +758,26 @@ int64_t mdg_bam_read_batch(mdg_bam_reader *r, const mdg_batch *out, int64_t max_
     if (raw) raw_off[n] = raw_used;
     if (n_cigar_out) *n_cigar_out = (int64_t)cigars;
     if (n_bases_out) *n_bases_out = (int64_t)bases;
-    if (failure)
-        return rfail(r, MDG_ERR_DATA, failure == 1 ? "a read has no read-group. Either fix BAM or use --merge-libraries"
-                                                   : "a read has a read-group not listed in the BAM header; either fix BAM or use "
-                                                     "--merge-libraries");
+    if (!r->library_failures.empty()) {
+        std::sort(r->library_failures.begin(), r->library_failures.end());
+        if (!r->lenient_libraries) return rfail(r, MDG_ERR_DATA, "%s", r->library_failures[0].second.c_str());
+    }
     return n;
+}
+
+int mdg_bam_lenient_libraries(mdg_bam_reader *r, int32_t on)
+{
+    if (!r) return MDG_ERR_ARGUMENT;
+    r->lenient_libraries = on != 0;
+    return MDG_OK;
+}
+
+int64_t mdg_bam_library_failure(const mdg_bam_reader *r, int64_t k, char *buf, int64_t cap)
+{
+    if (!r || k < 0) return MDG_ERR_ARGUMENT;
+    if (k >= (int64_t)r->library_failures.size()) return -1;
+    if (buf && cap > 0) snprintf(buf, (size_t)cap, "%s", r->library_failures[(size_t)k].second.c_str());
+    return r->library_failures[(size_t)k].first;
 }
 
 int64_t mdg_bam_records_seen(const mdg_bam_reader *r) { return r ? r->records_seen : 0; }

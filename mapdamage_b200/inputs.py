@@ -12,7 +12,7 @@ def load_alignments(sam_path, fasta_path, merge_libraries=False, apply_filter=Tr
     ``(sample, library)`` list that indexes the count slabs.
     """
     header, records = read_sam(sam_path)
-    reference = Reference.from_fasta(fasta_path).reordered(header.references)
+    reference = Reference.from_fasta(fasta_path).reordered(header.references, header.lengths)
     builder = BatchBuilder(
         readgroups=None if merge_libraries else header.libraries(),
         merge_libraries=merge_libraries, apply_filter=apply_filter,

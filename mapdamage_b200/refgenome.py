@@ -22,6 +22,11 @@ for _code, _ch in enumerate("ACGT"):
     _CODE_OF[ord(_ch.lower())] = _code
 
 
+class ReferenceMismatch(ValueError):
+    """The FASTA does not hold the contigs of the alignment file (``seq.compare_sequence_dicts`` returning False,
+    ``main.py:139-145``)."""
+
+
 class Reference:
     """Ordered contigs as ASCII ``uint8`` arrays plus the packed device image."""
 
@@ -42,9 +47,50 @@ class Reference:
         seqs = read_fasta(path)
         return cls(list(seqs), list(seqs.values()))
 
-    def reordered(self, names):
-        """Contigs in the order of the BAM header (tid order)."""
+    def reordered(self, names, lengths=None):
+        """Contigs in the order of the BAM header (tid order).
+
+        With ``lengths`` (the header's ``LN`` values) the two sequence dictionaries are compared the way
+        ``main.py:139-145`` does through ``seq.compare_sequence_dicts`` (``seq.py:75-112``): a contig of the
+        alignment file that the FASTA lacks, or whose length differs, is logged with the reference's messages
+        and raises :class:`ReferenceMismatch` (the reference's ``main`` returns 1 there); FASTA-only contigs
+        only draw the reference's warning.
+        """
         index = {name: i for i, name in enumerate(self.names)}
+        if lengths is not None:
+            import logging
+
+            log = logging.getLogger(__name__)
+            bam = dict(zip(names, (int(x) for x in lengths)))
+            fasta = dict(zip(self.names, self.lengths))
+            if fasta != bam:
+                common = set(fasta) & set(bam)
+                if not common:
+                    log.error("BAM and FASTA file have no sequence names in common")
+                    raise ReferenceMismatch("BAM and FASTA file have no sequence names in common")
+                different = [(key, fasta[key], bam[key]) for key in sorted(common) if fasta[key] != bam[key]]
+                if different:
+                    log.error("Length of required FASTA sequences differ:")
+                    for values in different:
+                        log.error(" - %s: %i vs %i bp" % values)
+                bam_only = set(bam) - common
+                if bam_only:
+                    log.error("Sequences not found in FASTA:")
+                    for key in bam_only:
+                        log.error("%s (%i bp)", key, bam[key])
+                fasta_only = set(fasta) - common
+                if fasta_only:
+                    log.warning("FASTA file contains extra sequences:")
+                    for key in fasta_only:
+                        log.warning(" - %s = %i bp", key, fasta[key])
+                if different or bam_only:
+                    raise ReferenceMismatch(
+                        "FASTA and alignment file disagree: %s" % "; ".join(
+                            ["%s: %i vs %i bp" % v for v in different]
+                            + ["%s (%i bp) not found in FASTA" % (k, bam[k]) for k in sorted(bam_only)]))
+        missing = [n for n in names if n not in index]
+        if missing:
+            raise ReferenceMismatch("Sequences not found in FASTA: %s" % ", ".join(missing))
         return Reference(names, [self.sequences[index[n]] for n in names])
 
     def packed(self):

@@ -121,7 +121,7 @@ def _rescale_qual_core(ref, options, engine=None, batch_reads=1 << 18):
         return _rescale_bam(ref, options, model, engine, batch_reads, log)
     header, records = iter_sam(filename)
     reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
-    reference = reference.reordered(header.references)
+    reference = reference.reordered(header.references, header.lengths)
 
     own_engine = engine is None
     if own_engine:
@@ -162,7 +162,7 @@ def _rescale_bam(ref, options, model, engine, batch_reads, log):
 
     with BamReader(input_kind(options.filename)[0], merge_libraries=True, apply_filter=False) as reader:
         reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
-        reference = reference.reordered(reader.header.references)
+        reference = reference.reordered(reader.header.references, reader.header.lengths)
         own_engine = engine is None
         if own_engine:
             engine = DamageEngine(max_reads=batch_reads, device=getattr(options, "device", 0))

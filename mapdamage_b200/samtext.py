@@ -65,9 +65,16 @@ class SamHeader:
 
     def libraries(self):
         """Read-group ID -> (sample, library); KeyError text as reader.py:107-116."""
+        from .batch import BAMError
+
         out = {}
         for rg_id, record in self.readgroups.items():
-            out[rg_id] = (record["SM"], record["LB"])
+            try:
+                out[rg_id] = (record["SM"], record["LB"])
+            except KeyError as error:  # reader.py:107-116
+                raise BAMError("Incomplete readgroup found: %s is missing %s. "
+                               "Either fix BAM or use --merge-libraries"
+                               % (rg_id if rg_id is not None else "Unnamed readgroup", error))
         return out
 
 
