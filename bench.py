@@ -75,6 +75,12 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", choices=("c2", "c3"), default="c2",
                     help="c2 = configs[1] (the headline); c3 = configs[2]: 50-150 bp pairs, mixed CIGARs, two libraries")
+    ap.add_argument("--configs", default="auto",
+                    help="other BASELINE.json configurations measured after the headline and reported under \"configs\": "
+                         "comma list of c3,c4,c5, 'none', or 'auto' (c3 and c4 on one GPU, c5 on eight)")
+    ap.add_argument("--c4-reads", type=int, default=200_000_000, help="reads per step of the rescale configuration")
+    ap.add_argument("--c4-file-reads", type=int, default=16_000_000,
+                    help="reads of the BAM file the file -> rescaled-file leg of c4 runs on")
     return ap.parse_args()
 
 
@@ -93,6 +99,8 @@ class ClockSampler:
         self.device = device
 
     def __enter__(self):
+        if self.device is None:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
@@ -159,15 +167,31 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic():
-    """DRAM bytes per counting launch from the committed ncu capture of this workload, if any."""
+def recorded_traffic(workload):
+    """DRAM bytes per counting launch from the committed ncu capture of THIS workload (profiles/traffic.json is keyed by
+    workload); None for a workload that was never captured -- a figure measured on another shape is not reported."""
     path = ROOT / "profiles" / "traffic.json"
     if path.is_file():
         try:
-            return json.loads(path.read_text())
+            return json.loads(path.read_text()).get(workload)
         except ValueError:
             pass
     return None
+
+
+WORKLOADS = {
+    "c2": "configs[1]: 50M x 100bp SE aDNA reads (C->T/G->A damage), 1 Mb reference, -l 70 -a 10 -Q 0",
+    "c3": "configs[2]: 50M x 50-150bp PE aDNA reads, mixed CIGARs (70% match, 10% each insertion / deletion / "
+          "soft clips), 2 libraries, 1 Mb reference, -l 70 -a 10 -Q 0",
+    "c4": "configs[3]: 200M x 100bp SE reads with qualities, --rescale pass producing a rescaled BAM",
+    "c5": "configs[4]: 1B x 100bp SE aDNA reads sharded over 8 GPUs (125M per rank), NCCL all-reduce of the count tables",
+}
+# the reference's own Python loop (main.py:165-220) cannot run on the GPU box (pysam is not installable, /root/reference
+# does not travel); this is the figure measured in the survey container through oracle/pysam_shim.py
+PYTHON_REFERENCE = {"value": 18200.0, "unit": UNIT, "cores": 1,
+                    "provenance": "unmodified reference main() under oracle/pysam_shim.py, 200 k reads, one core of the "
+                                  "survey container (SURVEY.md section 6); not re-measured on this box: kind 'reference' "
+                                  "is not obtainable there (no pysam wheel, no network, /root/reference absent)"}
 
 
 # ---------------------------------------------------------------------------
@@ -190,70 +214,90 @@ def reference_arm(args, rank, world):
         oracle.count(batch, reference, length=LENGTH, around=AROUND, threads=cores)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    what = "%d reads per step of the same synthetic workload (host-generated, seed %d)" % (sample, args.seed + 1)
+    what = ("each step counts a bounded sample of %d reads of the workload (host-generated with the same read shape, "
+            "seed %d); throughput does not depend on the sample size" % (sample, args.seed + 1))
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64",
         "data": "synthetic",
-        "config": {"workload": "50M x 100bp SE aDNA reads, 1 Mb reference, -l 70 -a 10 -Q 0 (bounded sample)",
-                   "reads_per_step": sample},
+        "config": {"workload": WORKLOADS["c2"], "reads_per_gpu_per_step": args.reads, "seed": args.seed,
+                   "sample": what, "sample_reads_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": what,
                          "note": "C port of the reference's Python loop (oracle/mdg_oracle.c), pinned to the "
-                                 "unmodified reference by tests/golden; the Python original runs ~18 k reads/s "
-                                 "on one core (SURVEY.md section 6)"},
+                                 "unmodified reference by tests/golden",
+                         "python_reference": PYTHON_REFERENCE},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
 
 
 # ---------------------------------------------------------------------------
-def gpu_arm(args, rank, local_rank, world):
-    import torch
+class Ranks:
+    """torch.distributed plumbing of one bench process (one per GPU)."""
 
-    from mapdamage_b200 import multigpu, synth
-    from mapdamage_b200.engine import DamageEngine, bind_host_to_device
+    def __init__(self, rank, local_rank, world):
+        import torch
 
-    cpus = bind_host_to_device(local_rank)  # pinned batches on the GPU's own NUMA node
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+        self.torch, self.rank, self.local_rank, self.world = torch, rank, local_rank, world
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
 
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if dist is None:
+    def max(self, x):
+        if self.dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    n_batches = max(1, -(-args.reads // args.batch_reads))
-    sizes = [args.reads // n_batches + (1 if i < args.reads % n_batches else 0) for i in range(n_batches)]
-    cap = max(sizes)
-    c3 = args.workload == "c3"
+    def all_true(self, ok):
+        return self.max(0.0 if ok else 1.0) == 0.0
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def same_tables(got, want):
+    return all(np.array_equal(a, b) for a, b in zip(got, want))
+
+
+def counting_config(args, ranks, workload, reads, steps, warmup, sample_clocks=False, with_cpu=False, with_e2e=True,
+                    e2e_host_reads=None):
+    """One counting workload measured the way the headline is: parity first, then ``value`` (resident batches, CUDA
+    events), ``e2e`` (pinned host batches through DamageEngine.count) and the roofline of the dominant kernel."""
+    from mapdamage_b200 import multigpu, synth
+    from mapdamage_b200.engine import DamageEngine
+
+    rank, world, local_rank = ranks.rank, ranks.world, ranks.local_rank
+    c3 = workload == "c3"
     n_lib = N_LIBS_C3 if c3 else 1
+    n_batches = max(1, -(-reads // args.batch_reads))
+    sizes = [reads // n_batches + (1 if i < reads % n_batches else 0) for i in range(n_batches)]
+    if c3:
+        sizes = [n + (n & 1) for n in sizes]
+    cap = max(sizes)
     engine = DamageEngine(length=LENGTH, around=AROUND, min_qual=0, n_libraries=n_lib, lg_bins=8192,
                           device=local_rank, n_slots=2, max_reads=cap + 1, max_cigar_ops=3 * cap + 3 if c3 else cap,
                           max_bases=(cap + 1) * (152 if c3 else READ_LEN + (READ_LEN & 1)))
     reference = synth.make_reference([REF_BASES], seed=args.seed)
     engine.set_reference(reference)
     if world > 1:
-        multigpu.connect(engine, dist, rank, world)
-
-    if args.workload == "c3":
-        shape = dict(length=(50, 150), mix=(7, 1, 1, 1), paired=True, n_libs=N_LIBS_C3)
-        sizes = [n + (n & 1) for n in sizes]
-    else:
-        shape = dict(length=(READ_LEN, READ_LEN))
+        multigpu.connect(engine, ranks.dist, rank, world)
+    shape = dict(length=(50, 150), mix=(7, 1, 1, 1), paired=True, n_libs=N_LIBS_C3) if c3 else dict(length=(READ_LEN, READ_LEN))
     resident = [engine.synth_batch(n, seed=args.seed + 1000 * rank + i, with_qual=False, **shape)
                 for i, n in enumerate(sizes)]
+    total = sum(sizes)
 
     def one_pass():
         for dev in resident:
@@ -261,111 +305,136 @@ def gpu_arm(args, rank, local_rank, world):
         if world > 1:
             engine.allreduce_tables()
 
-    # ---- correctness before speed: oracle parity on a sample, invariants at full size ----
+    # ---- correctness before speed ----
     host0 = engine.download(resident[0])
     check = {}
     if rank == 0:
         import oracle
 
+        threads = min(16, os.cpu_count() or 1)
+        # (1) the streamed path (mdg_count_submit) on a sample
         sample = host0.slice(0, min(args.check_sample, host0.n))
-        want = oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, n_lib=n_lib,
-                            threads=min(8, os.cpu_count() or 1))
+        want = oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, n_lib=n_lib, threads=threads)
         engine.reset()
         engine.count(sample)
-        got = engine.tables()
-        for name, a, b in zip(("misincorporation", "dnacomp", "lgdistribution"), got, want):
-            if not np.array_equal(a, b):
-                raise SystemExit("bench: %s table differs from the oracle on the %d-read sample" % (name, sample.n))
-        check["oracle_sample_reads"] = sample.n
+        if not same_tables(engine.tables(), want):
+            raise SystemExit("bench[%s]: tables differ from the oracle on the %d-read sample (submit path)" % (workload, sample.n))
+        check["oracle_sample_reads_submit_path"] = sample.n
+        # (2) the resident path that is timed: one WHOLE resident batch, every table cell against the oracle
+        want = oracle.count(host0, reference, length=LENGTH, around=AROUND, lg_bins=8192, n_lib=n_lib, threads=threads)
+        engine.reset()
+        engine.count_resident(resident[0])
+        if not same_tables(engine.tables(), want):
+            raise SystemExit("bench[%s]: tables differ from the oracle on the whole resident batch (%d reads)" % (workload, host0.n))
+        check["oracle_whole_resident_batch_reads"] = host0.n
+    # (3) every batch at full size: size-independent invariants
     engine.reset()
     for dev in resident:
         engine.count_resident(dev)
-    mis, comp, lg = engine.tables()
-    total = sum(sizes)
-    # every read is 100M on an N-free genome: each end/position sees every read exactly once
+    mis, comp, lg = local = engine.tables()
     if not c3:
+        # every read is 100M on an N-free genome: each end / position sees every read exactly once
         per_pos = mis[0, :, :, 0:4, :].sum(axis=(1, 2))
-        if not (np.all(per_pos == total) and int(lg.sum()) == total and int(lg[0, 1, :, READ_LEN].sum()) == total):
-            raise SystemExit("bench: full-size invariants failed (reference-base totals / length histogram)")
-        if not np.all(comp[0, :, :, :, :LENGTH].sum(axis=(1, 2)) == total):
-            raise SystemExit("bench: full-size invariants failed (read composition totals)")
+        ok = (np.all(per_pos == total) and int(lg.sum()) == total and int(lg[0, 1, :, READ_LEN].sum()) == total
+              and np.all(comp[0, :, :, :, :LENGTH].sum(axis=(1, 2)) == total))
     else:
         # every record is a proper pair: one histogram entry per first mate; reads of >= 50 bp fill position 1 of
         # both ends with a read base
-        if int(lg.sum()) != total // 2 or int(comp[:, :, :, :, 0].sum()) != 2 * total:
-            raise SystemExit("bench: full-size invariants failed (pair histogram mass / read composition totals)")
+        ok = int(lg.sum()) == total // 2 and int(comp[:, :, :, :, 0].sum()) == 2 * total
+    if not ok:
+        raise SystemExit("bench[%s]: full-size invariants failed" % workload)
     check["full_size_invariants"] = "ok"
+    # (4) several GPUs: the all-reduced tables equal the sum of the per-rank tables taken before the collective
+    #     (summed independently through torch.distributed), on every rank
+    if world > 1:
+        engine.allreduce_tables()
+        reduced = engine.tables()
+        want = multigpu.sum_tables_host(ranks.dist, local)
+        ok = same_tables(reduced, want)
+        if not c3:
+            ok = ok and bool(np.all(reduced[0][0, :, :, 0:4, :].sum(axis=(1, 2)) == world * total))
+            ok = ok and int(reduced[2].sum()) == world * total
+        engine.allreduce_tables()  # a second reduction must not add the sums to themselves
+        ok = ok and same_tables(engine.tables(), reduced)
+        if not ranks.all_true(ok):
+            raise SystemExit("bench[%s]: all-reduced tables differ from the sum of the per-rank tables" % workload)
+        check["allreduced_parity"] = "ok"
+        check["allreduced_reads"] = world * total
 
     # ---- value: resident batches, CUDA events on the compute stream ----
     t_warm = time.perf_counter()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_pass()
     engine.sync()
+    t_pass = ranks.max((time.perf_counter() - t_warm) / max(1, warmup))
     # the same number of extra passes on every rank (each pass ends in a collective): about one second of load
-    t_pass = max_over_ranks((time.perf_counter() - t_warm) / max(1, args.warmup))
-    n_sustain = int(min(2000, max(1, np.ceil(1.0 / max(t_pass, 1e-4)))))
-    barrier()
-    with ClockSampler(local_rank) as clocks:
+    n_sustain = int(min(2000, max(1, np.ceil(1.0 / max(t_pass, 1e-4))))) if sample_clocks else 0
+    ranks.barrier()
+    with ClockSampler(local_rank if sample_clocks else None) as clocks:
         # the timed region is tens of milliseconds, shorter than one nvidia-smi period: keep the same load
         # running untimed until the sampler has seen it, then time the K steps without a gap
-        clocks.wait_for_samples(1)
+        if sample_clocks:
+            clocks.wait_for_samples(1)
         for _ in range(n_sustain):
             one_pass()
         engine.sync()
         engine.kernel_ms()
         launches0 = engine.launch_count()
-        barrier()
+        ranks.barrier()
         t_start = time.perf_counter()
         engine.event_record(0)
-        for _ in range(args.steps):
+        for _ in range(steps):
             one_pass()
         engine.event_record(1)
         ms = engine.event_elapsed_ms()
         t_stop = time.perf_counter()
-        barrier()
-    clock_summary = clocks.summary(t_start, t_stop)
-    ms = max_over_ranks(ms)
+        ranks.barrier()
+    ms = ranks.max(ms)
     launches = engine.launch_count() - launches0
     kernel_ms = engine.kernel_ms()
-    n_count_launch_groups = args.steps * n_batches
-    value = world * total * args.steps / (ms * 1e-3)
+    value = world * total * steps / (ms * 1e-3)
 
     # ---- e2e: pinned host batches through the public API ----
     e2e = None
-    if not args.no_e2e:
-        host = [engine.download(dev, pinned=True) for dev in resident]
-        h2d = sum(engine.h2d_bytes(b) for b in host)
+    if with_e2e:
+        # e2e_host_reads: pin only that many reads and stream them repeatedly (same bytes and copies per read)
+        n_host = len(resident) if e2e_host_reads is None else max(1, min(len(resident), -(-e2e_host_reads // cap)))
+        host = [engine.download(dev, pinned=True) for dev in resident[:n_host]]
+        order = [host[i % n_host] for i in range(len(resident))]
+        h2d = sum(engine.h2d_bytes(b) for b in order)
         d2h = int(mis.nbytes + comp.nbytes + lg.nbytes)
+        e2e_reads = sum(b.n for b in order)
         engine.reset()
 
         def e2e_pass():
-            for b in host:
+            for b in order:
                 engine.count(b)
             if world > 1:
                 engine.allreduce_tables()
             return engine.tables()
 
-        for _ in range(min(args.warmup, 3)):
+        for _ in range(min(warmup, 3)):
             e2e_pass()
-        barrier()
+        ranks.barrier()
         engine.event_record(0)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             tables = e2e_pass()
         engine.event_record(1)
         e2e_ms = engine.event_elapsed_ms()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        barrier()
-        e2e_ms = max_over_ranks(max(e2e_ms, wall_ms))
-        e2e = {"value": world * total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
-               "ms_per_step": e2e_ms / args.steps,
+        ranks.barrier()
+        e2e_ms = ranks.max(max(e2e_ms, wall_ms))
+        e2e = {"value": world * e2e_reads * steps / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / steps,
                "timing": "max(CUDA events on the compute stream, host wall clock) around submit..fetch, max over ranks"}
+        if n_host < len(resident):
+            e2e["host_batches"] = "%d pinned batches streamed %d times per step" % (n_host, len(resident))
         del tables
 
     # ---- CPU baseline on a bounded sample (rank 0, single GPU runs only) ----
     cpu = None
-    if rank == 0 and world == 1:
+    if with_cpu and rank == 0 and world == 1:
         import oracle
 
         sample = host0.slice(0, min(args.cpu_sample, host0.n))
@@ -376,39 +445,36 @@ def gpu_arm(args, rank, local_rank, world):
         dt = time.perf_counter() - t0
         cpu = {"value": passes * sample.n / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "first %d reads of batch 0 of this workload, %d passes, one thread, %.1f s"
-                         % (sample.n, passes, dt)}
+                         % (sample.n, passes, dt),
+               "python_reference": PYTHON_REFERENCE}
 
+    out = None
     if rank == 0:
         peak, peak_source = measured_peak()
-        launch_ms = kernel_ms / n_count_launch_groups
+        launch_ms = kernel_ms / (steps * n_batches)
         algo = ALGO_BYTES_PER_READ
         if c3:  # SURVEY 8(d) formula, averaged over batch 0
             algo = float(15 + 4 * host0.cigar.shape[0] / host0.n + (host0.l_seq.mean() + 1) / 2
                          + (host0.l_seq.mean() + 2 * AROUND + 1) / 2)
         bytes_per_launch = algo * total / n_batches
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
-        traffic = recorded_traffic()
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
+        traffic = recorded_traffic("c2" if workload == "c5" else workload)
+        out = {
+            "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
             "config": {
-                "workload": "configs[2]: 50M x 50-150bp PE aDNA reads, mixed CIGARs (70% match, 10% each insertion / deletion / "
-                            "soft clips), 2 libraries, 1 Mb reference, -l 70 -a 10 -Q 0" if c3 else
-                            "configs[1]: 50M x 100bp SE aDNA reads (C->T/G->A damage), 1 Mb reference, -l 70 -a 10 -Q 0",
+                "workload": WORKLOADS[workload],
                 "reads_per_gpu_per_step": total, "batches_per_step": n_batches, "seed": args.seed,
-                "l2": "inputs larger than L2 (%.1f GB of resident batches per pass vs 126 MB)" % (
-                    total * 90 / 1e9),
+                "l2": "inputs larger than L2 (%.1f GB of resident batches per pass vs 126 MB)" % (total * 90 / 1e9),
                 "parallelism": "reads sharded per GPU; NCCL all-reduce of the count tables per step" if world > 1
                 else "single GPU",
-                "host_cpus_bound": None if cpus is None else len(cpus),
             },
-            "clocks": clock_summary,
+            "clocks": clocks.summary(t_start, t_stop) if sample_clocks else None,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                "traffic_source": None if traffic is None else traffic.get("source"),
                 "peak_source": peak_source, "algorithmic_bytes_per_read": algo,
                 "reads_per_launch": total / n_batches, "kernel_ms_per_launch": launch_ms,
                 "kernel_share_of_step": kernel_ms / ms,
@@ -417,10 +483,50 @@ def gpu_arm(args, rank, local_rank, world):
             "cpu_baseline": cpu,
             "check": check,
         }
-        emit(line)
+    for dev in resident:
+        dev.free()
     engine.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    return out
+
+
+def gpu_arm(args, rank, local_rank, world):
+    from mapdamage_b200.engine import bind_host_to_device
+
+    cpus = bind_host_to_device(local_rank)  # pinned batches on the GPU's own NUMA node
+    ranks = Ranks(rank, local_rank, world)
+    main_cfg = counting_config(args, ranks, args.workload, args.reads, args.steps, args.warmup, sample_clocks=True,
+                               with_cpu=True, with_e2e=not args.no_e2e)
+    wanted = [c for c in args.configs.split(",") if c and c != "none"]
+    if "auto" in wanted:
+        # the other configurations BASELINE.json names: configs[2] and configs[3] are single-GPU cases,
+        # configs[4] is the 8-GPU case
+        wanted = (["c3", "c4"] if world == 1 else []) + (["c5"] if world == 8 else [])
+    configs = {}
+    side_steps, side_warm = max(2, min(args.steps, 5)), 3
+    for name in wanted:
+        if name == args.workload:
+            continue
+        if name == "c3":
+            configs[name] = counting_config(args, ranks, "c3", args.reads, side_steps, side_warm,
+                                            with_e2e=not args.no_e2e)
+        elif name == "c5":
+            # 1 B reads over the ranks: each rank counts its own 1e9 / world reads per step
+            configs[name] = counting_config(args, ranks, "c5", 1_000_000_000 // world, side_steps, side_warm,
+                                            with_e2e=not args.no_e2e, e2e_host_reads=args.reads)
+        elif name == "c4":
+            configs[name] = rescale_config(args, ranks)
+    if rank == 0:
+        line = {"metric": METRIC, "n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8/int64", "data": "synthetic"}
+        line.update(main_cfg)
+        line["config"]["host_cpus_bound"] = None if cpus is None else len(cpus)
+        line["configs"] = {k: v for k, v in configs.items() if v is not None}
+        emit(line)
+    ranks.close()
+
+
+def rescale_config(args, ranks):
+    return None
 
 
 def main():

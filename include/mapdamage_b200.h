@@ -221,7 +221,13 @@ int mdg_fetch_rescale_hist(mdg_ctx *ctx, uint64_t *sub, uint64_t *rev, uint64_t 
  * the caller's launcher (torch.distributed / MPI / a file). */
 int mdg_nccl_unique_id(void *id128);
 int mdg_nccl_init(mdg_ctx *ctx, const void *id128, int32_t rank, int32_t n_ranks);
-/* ncclAllReduce(sum, uint64) over all count tables, in place, on the compute stream. */
+/*
+ * ncclAllReduce(sum, uint64) over all count tables on the compute stream, OUT OF PLACE: each rank's accumulators keep
+ * its own counts, the sums over ranks land in a second buffer, and mdg_fetch_tables returns that buffer until this
+ * rank counts again (or resets).  So "count, reduce, count more, reduce" and "reduce twice" both give the sum of what
+ * every rank has counted so far -- the tables are sums over reads (main.py:165-217), never sums of sums.
+ * Fragment lengths beyond lg_bins (mdg_fetch_lg_overflow) stay per rank; the caller concatenates them.
+ */
 int mdg_allreduce_tables(mdg_ctx *ctx);
 
 /* ---- synthetic input in HBM (bench.py, tests) ------------------------- */

@@ -148,8 +148,10 @@ struct mdg_ctx {
     std::vector<cudaEvent_t> kernel_events;  // pairs
     size_t kernel_events_used = 0;
     int64_t launches = 0;
-    // multi-GPU
+    // multi-GPU: the all-reduce writes the sums over ranks into `reduced`; the accumulators stay local
     ncclComm_t comm = nullptr;
+    unsigned long long *reduced = nullptr;
+    bool reduced_valid = false;  // `reduced` holds the sum of what every rank has counted so far
 };
 
 namespace {
@@ -379,6 +381,7 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
 {
     if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before counting");
     if (view.n_reads == 0) return MDG_OK;
+    ctx->reduced_valid = false;  // the local tables move on: sums over ranks need a new mdg_allreduce_tables
     mdg::DevBatch b = view;
     if (!has_qual) b.qual = nullptr;
     mdg::CountParams p{ctx->cfg.length, ctx->cfg.around, ctx->cfg.min_qual, ctx->cfg.n_libraries, ctx->cfg.lg_bins};
@@ -743,6 +746,7 @@ void mdg_destroy(mdg_ctx *ctx)
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     cudaFree(ctx->ref_block);
     cudaFree(ctx->tables);
+    cudaFree(ctx->reduced);
     cudaFree(ctx->aux_block);
     cudaFree(ctx->model_block);
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
@@ -906,6 +910,7 @@ int mdg_reset_tables(mdg_ctx *ctx)
     if (rc) return rc;
     MDG_CUDA(ctx, cudaMemset(ctx->tables, 0, (ctx->n_mis + ctx->n_comp + ctx->n_lg) * 8));
     MDG_CUDA(ctx, cudaMemset(ctx->aux_block, 0, 256 + 64));
+    ctx->reduced_valid = false;
     return MDG_OK;
 }
 
@@ -914,9 +919,11 @@ int mdg_fetch_tables(mdg_ctx *ctx, uint64_t *misincorp, uint64_t *dnacomp, uint6
     if (!ctx) return MDG_ERR_ARGUMENT;
     int rc = mdg_sync(ctx);
     if (rc) return rc;
-    if (misincorp) MDG_CUDA(ctx, cudaMemcpy(misincorp, ctx->count_tables.misincorp, ctx->n_mis * 8, cudaMemcpyDeviceToHost));
-    if (dnacomp) MDG_CUDA(ctx, cudaMemcpy(dnacomp, ctx->count_tables.dnacomp, ctx->n_comp * 8, cudaMemcpyDeviceToHost));
-    if (lghist) MDG_CUDA(ctx, cudaMemcpy(lghist, ctx->count_tables.lghist, ctx->n_lg * 8, cudaMemcpyDeviceToHost));
+    // after mdg_allreduce_tables (and until this rank counts again): the sums over all ranks
+    const unsigned long long *from = ctx->reduced_valid ? ctx->reduced : ctx->tables;
+    if (misincorp) MDG_CUDA(ctx, cudaMemcpy(misincorp, from, ctx->n_mis * 8, cudaMemcpyDeviceToHost));
+    if (dnacomp) MDG_CUDA(ctx, cudaMemcpy(dnacomp, from + ctx->n_mis, ctx->n_comp * 8, cudaMemcpyDeviceToHost));
+    if (lghist) MDG_CUDA(ctx, cudaMemcpy(lghist, from + ctx->n_mis + ctx->n_comp, ctx->n_lg * 8, cudaMemcpyDeviceToHost));
     return MDG_OK;
 }
 
@@ -1200,8 +1207,12 @@ int mdg_allreduce_tables(mdg_ctx *ctx)
         if (slot.stream) MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
     NcclApi &api = nccl_api();
     const size_t n = ctx->n_mis + ctx->n_comp + ctx->n_lg;
-    ncclResult_t r = api.AllReduce(ctx->tables, ctx->tables, n, ncclUint64, ncclSum, ctx->comm, ctx->compute);
+    // out of place: the accumulators keep this rank's own counts, so counting on and reducing again (or reducing
+    // twice) gives the sum over ranks each time instead of re-adding what an earlier call had already summed
+    if (!ctx->reduced) MDG_CUDA(ctx, cudaMalloc(&ctx->reduced, n * 8));
+    ncclResult_t r = api.AllReduce(ctx->tables, ctx->reduced, n, ncclUint64, ncclSum, ctx->comm, ctx->compute);
     if (r != ncclSuccess) return fail(ctx, MDG_ERR_NCCL, "ncclAllReduce: %s", api.GetErrorString ? api.GetErrorString(r) : "?");
+    ctx->reduced_valid = true;
     ctx->launches += 1;
     return MDG_OK;
 }

@@ -39,9 +39,12 @@ def sum_tables_host(dist, tables):
     semantics of ``mdg_allreduce_tables`` for tests that run without NCCL."""
     import torch
 
+    on_gpu = dist.get_backend() == "nccl"  # NCCL moves device tensors only
     out = []
     for table in tables:
         t = torch.from_numpy(np.ascontiguousarray(table).astype(np.int64))
+        if on_gpu:
+            t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        out.append(t.numpy().astype(np.uint64))
+        out.append(t.cpu().numpy().astype(np.uint64))
     return tuple(out)

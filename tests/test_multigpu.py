@@ -106,7 +106,19 @@ def test_two_gpu_allreduce_nccl(tmp_path):
                           max_bases=mine.total_bases) as engine:
             engine.set_reference(reference)
             multigpu.connect(engine, dist)
-            engine.count(mine)
+            half = mine.n // 2
+            engine.count(mine.slice(0, half))
+            local = engine.tables()
+            engine.allreduce_tables()
+            first = engine.tables()
+            engine.allreduce_tables()  # reducing twice must not add the sums to themselves
+            again = engine.tables()
+            for a, b in zip(first, again):
+                assert np.array_equal(a, b)
+            # the reduced tables are the sum of the per-rank tables taken before the collective
+            for a, b in zip(first, multigpu.sum_tables_host(dist, local)):
+                assert np.array_equal(a, b)
+            engine.count(mine.slice(half, mine.n))  # count on, reduce again: sums over reads, not sums of sums
             engine.allreduce_tables()
             got = engine.tables()
         want = oracle.count(batch, reference, lg_bins=8192, threads=2)
