@@ -201,6 +201,22 @@ int mdg_set_rescale_model(mdg_ctx *ctx, const uint8_t *lut, const double *inc, i
  */
 int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, float *mr_out,
                        uint8_t *status_out);
+/*
+ * The same pass returning only what changed.  A read has a handful of C->T / G->A bases, so instead of the whole quality
+ * array (l_seq bytes per read back over PCIe) the device lists the bytes it rewrote: after mdg_rescale_collect(ticket),
+ * qual[change_at[k]] = change_q[k] for k < the returned count patches the caller's own array (indices into the batch's
+ * qual array).  mr_out / status_out as above.  `ticket` names the staging slot; collect it before n_slots further
+ * submits.  Returns MDG_ERR_CAPACITY when more than a quarter of all bases changed (use mdg_rescale_submit) or the
+ * caller's arrays are too small.
+ */
+int mdg_rescale_submit_sparse(mdg_ctx *ctx, const mdg_batch *host, float *mr_out, uint8_t *status_out, int32_t *ticket);
+int64_t mdg_rescale_collect(mdg_ctx *ctx, int32_t ticket, uint32_t *change_at, uint8_t *change_q, int64_t cap);
+/*
+ * Rescales a batch resident in HBM in place (its quality array is rewritten on the device), on the compute stream:
+ * batches made by mdg_bam_stream_next (file -> device) or mdg_batch_upload.  mr_out / status_out (host, optional) are
+ * filled by asynchronous copies; the device copies stay with the batch for mdg_bam_encode_batch.
+ */
+int mdg_rescale_resident(mdg_ctx *ctx, mdg_dev_batch *batch, float *mr_out, uint8_t *status_out);
 /* The counters behind the log lines of rescale.py:303-304,335-343,255-261 (see mdg_rescale_submit). */
 int mdg_fetch_rescale_stats(mdg_ctx *ctx, uint64_t *stats8);
 /*
@@ -325,6 +341,36 @@ int mdg_bam_use_device(mdg_bam_reader *reader, int32_t device);
 int64_t mdg_bam_device_blocks(const mdg_bam_reader *reader);
 
 /*
+ * The same file decoded on the GPU of a context (csrc/mdg_bamdev.cuh): the host only reads the file, slab by slab, into
+ * page-locked memory; BGZF inflate, CRC32 check, record boundaries (guessed per 32 KB segment, then verified against the
+ * true chain of length prefixes, so the result is exact), the scatter into the struct-of-arrays batch, read group ->
+ * library and the MR-tag test all run on the device, one slab ahead of the caller.  What pysam.AlignmentFile iteration
+ * is to the reference (reader.py:38,121-132; rescale.py:298-300).
+ *   data_start / n_references: uncompressed offset of the first record and the number of reference sequences, as the
+ *     host reader found them in the header (mdg_bam_data_start, mdg_bam_n_references);
+ *   slab_bytes: compressed bytes per step (0 = 512 MB, never more than the file).
+ * mdg_bam_stream_next returns the number of records of the next batch (0 at the end of the file, < 0 on error) and a
+ * batch resident in HBM that belongs to the stream: valid for mdg_count_resident / mdg_rescale_resident until the next
+ * call.  Records with flag & drop_flags are skipped (0xF04 for the counting pass, 0 for the rescale pass).  A read
+ * without a usable read group fails the batch with the reference's BAMError text (reader.py:67-81).
+ */
+typedef struct mdg_bam_stream mdg_bam_stream;
+uint64_t mdg_bam_data_start(const mdg_bam_reader *reader);
+int mdg_bam_stream_open(mdg_ctx *ctx, const char *path, uint64_t data_start, int32_t n_references, int64_t slab_bytes,
+                        mdg_bam_stream **out);
+void mdg_bam_stream_close(mdg_bam_stream *stream);
+const char *mdg_bam_stream_error(const mdg_bam_stream *stream);
+int mdg_bam_stream_set_libraries(mdg_bam_stream *stream, const char *const *read_groups, const uint16_t *library, int32_t n);
+int64_t mdg_bam_stream_next(mdg_bam_stream *stream, uint32_t drop_flags, int32_t with_qual, int32_t want_mr,
+                            mdg_dev_batch **out);
+/* "already has an MR tag" flags (rescale.py:277-278) of the batch handed out last (needs want_mr). */
+int mdg_bam_stream_has_mr(mdg_bam_stream *stream, uint8_t *has_mr, int64_t n);
+/* Records walked (dropped ones included), BGZF blocks inflated on the device / redone on the host, segments whose
+ * first-record guess the verification pass corrected, seconds spent {reading, decoding, waiting for a batch}. */
+int mdg_bam_stream_stats(const mdg_bam_stream *stream, int64_t *records_seen, int64_t *blocks_device, int64_t *blocks_host,
+                         int64_t *guesses_wrong, double *seconds3);
+
+/*
  * Raw DEFLATE (RFC 1951) stream -> out; returns the number of bytes written, or a negative code when the stream is
  * damaged, does not fit out_cap, or uses a form this decoder leaves to zlib.  What mdg_bam_read_batch inflates BGZF
  * blocks with (htslib / zlib under pysam.AlignmentFile in the reference, reader.py:38); every block's CRC32 is
@@ -379,6 +425,18 @@ int mdg_bam_write_batch(mdg_bam_writer *writer, const uint8_t *raw, const uint64
  */
 int mdg_bam_write_soa(mdg_bam_writer *writer, const mdg_batch *batch, int64_t first_index, const char *name_prefix,
                       const char *const *read_group_of_library, int32_t n_libraries);
+/* Appends finished BGZF blocks behind whatever is pending (mdg_bam_encode_batch uses it). */
+int mdg_bam_write_raw(mdg_bam_writer *writer, const uint8_t *blocks, int64_t n_bytes);
+/*
+ * The writer on the GPU, for batches made by mdg_bam_stream_next with drop_flags = 0: every record of the slab is
+ * re-emitted in input order (rescale.py:344), a record mdg_rescale_resident marked with its rewritten qualities and
+ * an MR:f tag (rescale.py:273-280); the byte stream is cut into 0xff00-byte BGZF blocks, each deflated by one thread
+ * block (literal-only dynamic Huffman, or stored when smaller) with its CRC32, packed and copied to the host.  The
+ * file write of one batch overlaps the GPU work of the next; mdg_bam_encode_flush waits for the last one (call it before
+ * mdg_bam_finish) and reports uncompressed / compressed bytes and seconds {encoding, waiting for the file}.
+ */
+int mdg_bam_encode_batch(mdg_bam_stream *stream, mdg_dev_batch *batch, mdg_bam_writer *writer);
+int mdg_bam_encode_flush(mdg_bam_stream *stream, int64_t *bytes_in, int64_t *bytes_out, double *seconds2);
 /* Flushes, writes the BGZF end-of-file block and closes the file. */
 int mdg_bam_finish(mdg_bam_writer *writer);
 void mdg_bam_writer_free(mdg_bam_writer *writer);

@@ -91,6 +91,21 @@ SYMBOLS = {
     "mdg_bam_lenient_libraries": (C.c_int, [C.c_void_p, C.c_int32]),
     "mdg_bam_library_failure": (C.c_int64, [C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]),
     "mdg_bam_records_seen": (C.c_int64, [C.c_void_p]),
+    "mdg_bam_data_start": (C.c_uint64, [C.c_void_p]),
+    "mdg_bam_stream_open": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
+    "mdg_bam_stream_close": (None, [C.c_void_p]),
+    "mdg_bam_stream_error": (C.c_char_p, [C.c_void_p]),
+    "mdg_bam_stream_set_libraries": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32]),
+    "mdg_bam_stream_next": (C.c_int64, [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "mdg_bam_stream_has_mr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "mdg_bam_stream_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "mdg_bam_write_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "mdg_bam_encode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mdg_bam_encode_flush": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "mdg_rescale_submit_sparse": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "mdg_rescale_collect": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
+    "mdg_rescale_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdg_bam_open_on": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "mdg_bam_use_device": (C.c_int, [C.c_void_p, C.c_int32]),
     "mdg_bam_device_blocks": (C.c_int64, [C.c_void_p]),

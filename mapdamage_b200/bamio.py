@@ -157,6 +157,105 @@ class BamReader:
             yield batch
 
 
+class DeviceBamStream:
+    """A BAM file decoded on the GPU of ``engine`` (``mdg_bam_stream_*``, ``csrc/mdg_bamdev.cuh``).
+
+    The host only reads the file; BGZF inflate, CRC check, record boundaries, the struct-of-arrays scatter and the read
+    group -> library lookup run on the device, one slab ahead of the caller.  Iterating yields
+    :class:`~mapdamage_b200.engine.DeviceBatch` objects resident in HBM (valid until the next one is asked for): feed
+    them to ``engine.count_resident`` / ``engine.rescale_resident``.  The header comes from a host :class:`BamReader`.
+    """
+
+    def __init__(self, engine, path, merge_libraries=False, apply_filter=True, with_qual=True, want_mr=False,
+                 slab_bytes=0):
+        from .engine import DeviceBatch
+
+        self._DeviceBatch = DeviceBatch
+        self._lib = _native.load()
+        self.engine = engine
+        with BamReader(path, threads=2, merge_libraries=merge_libraries, apply_filter=apply_filter) as reader:
+            self.header = reader.header
+            self.libraries = reader.libraries
+            data_start = int(self._lib.mdg_bam_data_start(reader._reader))
+            groups = {} if merge_libraries else self.header.libraries()
+        self.path = path
+        self._stream = C.c_void_p()
+        code = self._lib.mdg_bam_stream_open(engine._ctx, str(path).encode(), data_start, len(self.header.references),
+                                             int(slab_bytes), C.byref(self._stream))
+        if code < 0:
+            raise BAMError((self._lib.mdg_bam_stream_error(None) or b"").decode())
+        if not merge_libraries:
+            index = {key: i for i, key in enumerate(self.libraries)}
+            if groups:
+                ids = (C.c_char_p * len(groups))(*[rg.encode() for rg in groups])
+                libs = np.array([index[groups[rg]] for rg in groups], dtype=np.uint16)
+                self._lib.mdg_bam_stream_set_libraries(self._stream, ids, libs.ctypes.data, len(groups))
+            else:
+                # no read groups in the header: every read fails, as in the reference (reader.py:67-73)
+                ids = (C.c_char_p * 1)(b"\x00")
+                self._lib.mdg_bam_stream_set_libraries(self._stream, ids, np.zeros(1, np.uint16).ctypes.data, 1)
+        self._drop = FILTERED_FLAGS if apply_filter else 0
+        self._with_qual, self._want_mr = bool(with_qual), bool(want_mr)
+
+    def next_batch(self):
+        """The next slab's records as a resident batch, or ``None`` at the end of the file."""
+        handle = C.c_void_p()
+        n = self._lib.mdg_bam_stream_next(self._stream, self._drop, int(self._with_qual), int(self._want_mr),
+                                          C.byref(handle))
+        if n < 0:
+            raise BAMError((self._lib.mdg_bam_stream_error(self._stream) or b"").decode("utf-8", "replace"))
+        if n == 0:
+            return None
+        batch = self._DeviceBatch(self.engine, handle, int(n), has_qual=self._with_qual)
+        batch.free = lambda: None  # owned by the stream
+        return batch
+
+    def __iter__(self):
+        while True:
+            batch = self.next_batch()
+            if batch is None:
+                return
+            yield batch
+
+    def has_mr(self, batch):
+        flags = np.empty(batch.n, dtype=np.uint8)
+        if self._lib.mdg_bam_stream_has_mr(self._stream, flags.ctypes.data, batch.n) < 0:
+            raise BAMError((self._lib.mdg_bam_stream_error(self._stream) or b"").decode())
+        return flags
+
+    def encode(self, batch, writer):
+        """Re-emits the records of ``batch`` (the one handed out last) through ``writer`` (``mdg_bam_encode_batch``)."""
+        if self._lib.mdg_bam_encode_batch(self._stream, batch.handle, writer._writer) < 0:
+            raise OSError((self._lib.mdg_bam_stream_error(self._stream) or b"").decode())
+
+    def flush(self):
+        """Waits for the last file write; returns ``(uncompressed bytes, compressed bytes, encode s, write-wait s)``."""
+        a, b = C.c_int64(), C.c_int64()
+        t = (C.c_double * 2)()
+        if self._lib.mdg_bam_encode_flush(self._stream, C.byref(a), C.byref(b), t) < 0:
+            raise OSError((self._lib.mdg_bam_stream_error(self._stream) or b"").decode())
+        return a.value, b.value, t[0], t[1]
+
+    def stats(self):
+        seen, dev, host, wrong = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        t = (C.c_double * 3)()
+        self._lib.mdg_bam_stream_stats(self._stream, C.byref(seen), C.byref(dev), C.byref(host), C.byref(wrong), t)
+        return {"records_seen": seen.value, "blocks_on_device": dev.value, "blocks_redone_on_host": host.value,
+                "segment_guesses_corrected": wrong.value, "read_s": t[0], "decode_s": t[1], "wait_s": t[2]}
+
+    def close(self):
+        if self._stream:
+            self._lib.mdg_bam_stream_close(self._stream)
+            self._stream = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
 class BamWriter:
     """Writes the records of batches read with ``keep_raw`` (``rescale.py:299,344``)."""
 

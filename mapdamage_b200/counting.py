@@ -133,10 +133,12 @@ def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, fol
                     break
                 sampler.feed(batch.n)
         sampler = _downsample.Selection(sampler.selected())
-    # MDG_BAM_GPU=1: BGZF blocks are inflated on the GPU the kernels run on instead of on the host threads (measured
-    # slower than sixteen host threads for files of a few GB: see DESIGN.md, section 4.2)
-    inflate_on = device if os.environ.get("MDG_BAM_GPU") == "1" else None
-    with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True, device=inflate_on,
+    if sampler is None and not Path(filename).is_fifo() and not Path(filename).is_char_device() \
+            and os.environ.get("MDG_BAM_HOST") != "1":
+        return _count_bam_on_device(filename, ref, length, around, min_basequal, merge_libraries, folder, device, lg_bins,
+                                    engine)
+    # the host decoder: pipes, down-sampling (the draws need every kept read's turn on the host), MDG_BAM_HOST=1
+    with BamReader(filename, merge_libraries=merge_libraries, apply_filter=True,
                    lenient_libraries=sampler is not None) as reader:
         reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
         reference = reference.reordered(reader.header.references, reader.header.lengths)
@@ -174,6 +176,39 @@ def _count_bam(filename, ref, length, around, min_basequal, merge_libraries, fol
         finally:
             if own_engine:
                 engine.close()
+    log.debug("Counted %d of %d alignments", n_kept, n_seen)
+    return _finish(libraries, length, around, mis, comp, lg, overflow, folder)
+
+
+def _count_bam_on_device(filename, ref, length, around, min_basequal, merge_libraries, folder, device, lg_bins, engine):
+    """BAM input decoded on the GPU (``bamio.DeviceBamStream``): the host reads the file and nothing else; slabs are
+    inflated, cut into records, scattered into the batch layout and counted in HBM."""
+    from .bamio import BamReader, DeviceBamStream
+
+    log = logging.getLogger(__name__)
+    with BamReader(filename, threads=2, merge_libraries=merge_libraries, apply_filter=True) as reader:
+        header, libraries = reader.header, reader.libraries
+    reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
+    reference = reference.reordered(header.references, header.lengths)
+    own_engine = engine is None
+    if own_engine:
+        engine = DamageEngine(length=length, around=around, min_qual=min_basequal, n_libraries=max(1, len(libraries)),
+                              lg_bins=lg_bins, device=device, max_reads=0)
+    try:
+        engine.set_reference(reference)
+        n_kept = 0
+        with DeviceBamStream(engine, filename, merge_libraries=merge_libraries, apply_filter=True,
+                             with_qual=min_basequal > 0) as stream:
+            for batch in stream:
+                engine.count_resident(batch)
+                n_kept += batch.n
+            engine.sync()
+            n_seen = stream.stats()["records_seen"]
+        mis, comp, lg = engine.tables()
+        overflow = engine.lg_overflow()
+    finally:
+        if own_engine:
+            engine.close()
     log.debug("Counted %d of %d alignments", n_kept, n_seen)
     return _finish(libraries, length, around, mis, comp, lg, overflow, folder)
 

@@ -78,6 +78,12 @@ struct Slot {
     // rescale outputs
     float *mr_out = nullptr;
     uint8_t *status_out = nullptr;
+    // sparse mode (mdg_rescale_submit_sparse): the quality bytes that changed, instead of the whole array
+    uint32_t *change_at = nullptr;
+    uint8_t *change_q = nullptr;
+    unsigned long long *n_changes = nullptr;       // device counter
+    unsigned long long *n_changes_host = nullptr;  // page-locked copy, filled behind the kernels
+    int64_t change_cap = 0;
 };
 
 }  // namespace
@@ -95,6 +101,10 @@ struct WorkList {
 
 struct mdg_dev_batch {
     DeviceArrays arrays;
+    // results of mdg_rescale_resident (one entry per read), kept with the batch for the BAM writer
+    float *res_mr = nullptr;
+    uint8_t *res_status = nullptr;
+    int64_t res_cap = 0;
 };
 
 struct mdg_ctx {
@@ -732,6 +742,10 @@ void mdg_destroy(mdg_ctx *ctx)
         cudaFree(slot.arrays.block);
         cudaFree(slot.mr_out);
         cudaFree(slot.status_out);
+        cudaFree(slot.change_at);
+        cudaFree(slot.change_q);
+        cudaFree(slot.n_changes);
+        if (slot.n_changes_host) cudaFreeHost(slot.n_changes_host);
     }
     cudaFree(ctx->indel_seen_dev);
     if (ctx->indel_seen_host) cudaFreeHost(ctx->indel_seen_host);
@@ -868,6 +882,8 @@ int mdg_batch_free(mdg_ctx *ctx, mdg_dev_batch *batch)
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(batch->arrays.block);
+    cudaFree(batch->res_mr);
+    cudaFree(batch->res_status);
     delete batch;
     return MDG_OK;
 }
@@ -972,38 +988,27 @@ int mdg_set_rescale_model(mdg_ctx *ctx, const uint8_t *lut, const double *inc, i
     return MDG_OK;
 }
 
-int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, float *mr_out, uint8_t *status_out)
+// The rescale kernels over one device batch whose qualities are rewritten in place; mr / status (device, one entry per
+// read) and the optional change list are filled on `stream`.
+static int launch_rescale(mdg_ctx *ctx, const mdg::DevBatch &view, float *d_mr, uint8_t *d_status, uint32_t *change_at,
+                          uint8_t *change_q, unsigned long long *n_changes, int64_t change_cap, cudaStream_t stream)
 {
-    if (!ctx) return MDG_ERR_ARGUMENT;
-    int rc = check_batch(ctx, host);
-    if (rc) return rc;
-    if (!qual_out || !mr_out || !status_out) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_rescale_submit: NULL output");
-    if (!host->qual) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_rescale_submit: batch has no quality array");
-    if (!ctx->model.lut) return fail(ctx, MDG_ERR_STATE, "mdg_set_rescale_model must be called before rescaling");
-    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before rescaling");
-    if (ctx->slots.empty() || !ctx->slots[0].stream)
-        return fail(ctx, MDG_ERR_STATE, "context was created without staging slots (max_reads = 0)");
-    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    Slot &slot = ctx->slots[ctx->next_slot];
-    ctx->next_slot = (ctx->next_slot + 1) % (int)ctx->slots.size();
-    MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
-    rc = copy_batch(ctx, slot.arrays, host, slot.stream, true, true);
-    if (rc) return rc;
-    const int64_t n = host->n_reads;
+    const int64_t n = view.n_reads;
     if (n == 0) return MDG_OK;
     const size_t n_sub = (size_t)2 * ctx->model.n_slots * 94;
-    // qualities are rewritten in place in the slot's copy of the batch and read back from there
-    uint8_t *const dev_qual = const_cast<uint8_t *>(slot.arrays.view.qual);
-    mdg::RescaleOut out{dev_qual, slot.mr_out, slot.status_out, ctx->rescale_stats, ctx->count_tables.error_flag,
-                        ctx->rescale_hist, ctx->rescale_hist + n_sub, ctx->rescale_hist + n_sub + 2 * 94};
+    uint8_t *const dev_qual = const_cast<uint8_t *>(view.qual);
+    mdg::RescaleOut out{dev_qual, d_mr, d_status, ctx->rescale_stats, ctx->count_tables.error_flag,
+                        ctx->rescale_hist, ctx->rescale_hist + n_sub, ctx->rescale_hist + n_sub + 2 * 94,
+                        change_at, change_q, n_changes, (unsigned long long)change_cap};
     WorkList *wl = nullptr;
-    rc = worklist_for(ctx, slot.stream, n, &wl);
+    int rc = worklist_for(ctx, stream, n, &wl);
     if (rc) return rc;
-    MDG_CUDA(ctx, cudaMemsetAsync(wl->count, 0, 8, slot.stream));
+    MDG_CUDA(ctx, cudaMemsetAsync(wl->count, 0, 8, stream));
+    if (n_changes) MDG_CUDA(ctx, cudaMemsetAsync(n_changes, 0, 8, stream));
     cudaEvent_t e0, e1;
     rc = next_kernel_events(ctx, &e0, &e1);
     if (rc) return rc;
-    MDG_CUDA(ctx, cudaEventRecord(e0, slot.stream));
+    MDG_CUDA(ctx, cudaEventRecord(e0, stream));
     const bool general_only = getenv("MDG_RESCALE_GENERAL") != nullptr;  // A/B and tests: every record by the warp kernel
     const int warp_grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 7) / 8);
     if (!general_only) {
@@ -1011,20 +1016,126 @@ int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, f
         const size_t hist_words = n_sub + 2 * 94;
         const bool shared_hist = hist_words * 4 <= 48 * 1024;
         const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 8, (n + 255) / 256);
-        mdg::rescale_gapfree_kernel<<<grid, 256, shared_hist ? hist_words * 4 : 0, slot.stream>>>(
-            slot.arrays.view, ctx->ref, ctx->model, out, wl->reads, wl->count, shared_hist ? (int)hist_words : 0);
+        mdg::rescale_gapfree_kernel<<<grid, 256, shared_hist ? hist_words * 4 : 0, stream>>>(
+            view, ctx->ref, ctx->model, out, wl->reads, wl->count, shared_hist ? (int)hist_words : 0);
         MDG_CUDA(ctx, cudaGetLastError());
-        mdg::rescale_kernel<<<warp_grid, 256, 0, slot.stream>>>(slot.arrays.view, ctx->ref, ctx->model, out, wl->reads, wl->count);
+        mdg::rescale_kernel<<<warp_grid, 256, 0, stream>>>(view, ctx->ref, ctx->model, out, wl->reads, wl->count);
         ctx->launches += 2;
     } else {
-        mdg::rescale_kernel<<<warp_grid, 256, 0, slot.stream>>>(slot.arrays.view, ctx->ref, ctx->model, out, nullptr, nullptr);
+        mdg::rescale_kernel<<<warp_grid, 256, 0, stream>>>(view, ctx->ref, ctx->model, out, nullptr, nullptr);
         ctx->launches += 1;
     }
     MDG_CUDA(ctx, cudaGetLastError());
-    MDG_CUDA(ctx, cudaEventRecord(e1, slot.stream));
-    MDG_CUDA(ctx, cudaMemcpyAsync(qual_out, dev_qual, (size_t)host->n_bases, cudaMemcpyDeviceToHost, slot.stream));
+    MDG_CUDA(ctx, cudaEventRecord(e1, stream));
+    return MDG_OK;
+}
+
+static int rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, float *mr_out, uint8_t *status_out, int32_t *ticket)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    int rc = check_batch(ctx, host);
+    if (rc) return rc;
+    const bool sparse = ticket != nullptr;
+    if ((!sparse && !qual_out) || !mr_out || !status_out) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_rescale_submit: NULL output");
+    if (!host->qual) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_rescale_submit: batch has no quality array");
+    if (!ctx->model.lut) return fail(ctx, MDG_ERR_STATE, "mdg_set_rescale_model must be called before rescaling");
+    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before rescaling");
+    if (ctx->slots.empty() || !ctx->slots[0].stream)
+        return fail(ctx, MDG_ERR_STATE, "context was created without staging slots (max_reads = 0)");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const int slot_index = ctx->next_slot;
+    Slot &slot = ctx->slots[slot_index];
+    ctx->next_slot = (ctx->next_slot + 1) % (int)ctx->slots.size();
+    MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
+    if (sparse) {
+        *ticket = slot_index;
+        // a batch in which more than a quarter of all bases change is not sequencing data
+        const int64_t want = host->n_bases / 4 + 4096;
+        if (slot.change_cap < want) {
+            cudaFree(slot.change_at);
+            cudaFree(slot.change_q);
+            slot.change_at = nullptr; slot.change_q = nullptr; slot.change_cap = 0;
+            const int64_t cap = std::max<int64_t>(want, ctx->cfg.max_bases / 4 + 4096);
+            MDG_CUDA(ctx, cudaMalloc(&slot.change_at, (size_t)cap * 4));
+            MDG_CUDA(ctx, cudaMalloc(&slot.change_q, (size_t)cap));
+            slot.change_cap = cap;
+        }
+        if (!slot.n_changes) {
+            MDG_CUDA(ctx, cudaMalloc(&slot.n_changes, 8));
+            MDG_CUDA(ctx, cudaHostAlloc((void **)&slot.n_changes_host, 8, cudaHostAllocDefault));
+        }
+        *slot.n_changes_host = 0;
+    }
+    rc = copy_batch(ctx, slot.arrays, host, slot.stream, true, true);
+    if (rc) return rc;
+    const int64_t n = host->n_reads;
+    if (n == 0) return MDG_OK;
+    // qualities are rewritten in place in the slot's copy of the batch
+    rc = launch_rescale(ctx, slot.arrays.view, slot.mr_out, slot.status_out, sparse ? slot.change_at : nullptr,
+                        sparse ? slot.change_q : nullptr, sparse ? slot.n_changes : nullptr, sparse ? slot.change_cap : 0, slot.stream);
+    if (rc) return rc;
+    if (sparse)
+        MDG_CUDA(ctx, cudaMemcpyAsync(slot.n_changes_host, slot.n_changes, 8, cudaMemcpyDeviceToHost, slot.stream));
+    else
+        MDG_CUDA(ctx, cudaMemcpyAsync(qual_out, slot.arrays.view.qual, (size_t)host->n_bases, cudaMemcpyDeviceToHost, slot.stream));
     MDG_CUDA(ctx, cudaMemcpyAsync(mr_out, slot.mr_out, (size_t)n * 4, cudaMemcpyDeviceToHost, slot.stream));
     MDG_CUDA(ctx, cudaMemcpyAsync(status_out, slot.status_out, (size_t)n, cudaMemcpyDeviceToHost, slot.stream));
+    return MDG_OK;
+}
+
+int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, float *mr_out, uint8_t *status_out)
+{
+    return rescale_submit(ctx, host, qual_out, mr_out, status_out, nullptr);
+}
+
+int mdg_rescale_submit_sparse(mdg_ctx *ctx, const mdg_batch *host, float *mr_out, uint8_t *status_out, int32_t *ticket)
+{
+    if (!ticket) return ctx ? fail(ctx, MDG_ERR_ARGUMENT, "mdg_rescale_submit_sparse: NULL ticket") : MDG_ERR_ARGUMENT;
+    return rescale_submit(ctx, host, nullptr, mr_out, status_out, ticket);
+}
+
+int64_t mdg_rescale_collect(mdg_ctx *ctx, int32_t ticket, uint32_t *change_at, uint8_t *change_q, int64_t cap)
+{
+    if (!ctx || ticket < 0 || ticket >= (int32_t)ctx->slots.size()) return MDG_ERR_ARGUMENT;
+    Slot &slot = ctx->slots[(size_t)ticket];
+    if (!slot.n_changes_host) return fail(ctx, MDG_ERR_STATE, "mdg_rescale_collect: no sparse submit on this ticket");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
+    const int64_t n = (int64_t)*slot.n_changes_host;
+    if (n > slot.change_cap)
+        return fail(ctx, MDG_ERR_CAPACITY, "%lld quality bytes changed, more than the change list holds (%lld): use mdg_rescale_submit",
+                    (long long)n, (long long)slot.change_cap);
+    if (n > cap || (n && (!change_at || !change_q)))
+        return fail(ctx, MDG_ERR_CAPACITY, "mdg_rescale_collect: %lld changes do not fit the caller's arrays (%lld)", (long long)n, (long long)cap);
+    if (n) {
+        MDG_CUDA(ctx, cudaMemcpyAsync(change_at, slot.change_at, (size_t)n * 4, cudaMemcpyDeviceToHost, slot.stream));
+        MDG_CUDA(ctx, cudaMemcpyAsync(change_q, slot.change_q, (size_t)n, cudaMemcpyDeviceToHost, slot.stream));
+        MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
+    }
+    return n;
+}
+
+int mdg_rescale_resident(mdg_ctx *ctx, mdg_dev_batch *batch, float *mr_out, uint8_t *status_out)
+{
+    if (!ctx || !batch) return MDG_ERR_ARGUMENT;
+    if (!batch->arrays.has_qual || !batch->arrays.view.qual) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_rescale_resident: batch has no quality array");
+    if (!ctx->model.lut) return fail(ctx, MDG_ERR_STATE, "mdg_set_rescale_model must be called before rescaling");
+    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "mdg_set_reference must be called before rescaling");
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const int64_t n = batch->arrays.view.n_reads;
+    if (n > batch->res_cap) {
+        MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+        cudaFree(batch->res_mr);
+        cudaFree(batch->res_status);
+        batch->res_mr = nullptr; batch->res_status = nullptr; batch->res_cap = 0;
+        MDG_CUDA(ctx, cudaMalloc(&batch->res_mr, (size_t)batch->arrays.cap_reads * 4 + 8));
+        MDG_CUDA(ctx, cudaMalloc(&batch->res_status, (size_t)batch->arrays.cap_reads + 8));
+        batch->res_cap = batch->arrays.cap_reads;
+    }
+    int rc = launch_rescale(ctx, batch->arrays.view, batch->res_mr, batch->res_status, nullptr, nullptr, nullptr, 0, ctx->compute);
+    if (rc) return rc;
+    if (mr_out) MDG_CUDA(ctx, cudaMemcpyAsync(mr_out, batch->res_mr, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->compute));
+    if (status_out) MDG_CUDA(ctx, cudaMemcpyAsync(status_out, batch->res_status, (size_t)n, cudaMemcpyDeviceToHost, ctx->compute));
     return MDG_OK;
 }
 
@@ -1252,3 +1363,6 @@ int mdg_last_kernel_ms(mdg_ctx *ctx, float *ms)
 }
 
 }  // extern "C"
+
+#include <chrono>
+#include "mdg_bamdev.cuh"

@@ -144,6 +144,7 @@ struct mdg_bam_reader {
     size_t keep_from = 0;   // bytes before this may be dropped by the next refill (a batch under construction
                             // keeps its first record here; offsets relative to keep_from survive refills)
     bool eof = false;
+    uint64_t data_start = 0;  // uncompressed bytes in front of the first record (magic, header text, reference list)
     int64_t records_seen = 0;
     // read-ahead: a producer thread reads and inflates the next chunk while the caller works on this one
     Chunk chunks[2];
@@ -471,6 +472,7 @@ int read_header(mdg_bam_reader *r)
     while (!r->header_text.empty() && r->header_text.back() == '\0') r->header_text.pop_back();
     const uint32_t n_ref = le32(r->stream.data() + r->stream_pos + 8 + l_text);
     r->stream_pos += 12 + (size_t)l_text;
+    r->data_start = r->stream_pos;
     r->keep_from = r->stream_pos;
     for (uint32_t i = 0; i < n_ref; ++i) {
         rc = ensure(r, 4, &ok);
@@ -482,6 +484,7 @@ int read_header(mdg_bam_reader *r)
         r->ref_names.emplace_back(name, l_name ? l_name - 1 : 0);
         r->ref_lengths.push_back(le32(r->stream.data() + r->stream_pos + 4 + l_name));
         r->stream_pos += 8 + (size_t)l_name;
+        r->data_start += r->stream_pos - r->keep_from;
         r->keep_from = r->stream_pos;
     }
     return MDG_OK;
@@ -782,6 +785,8 @@ int64_t mdg_bam_library_failure(const mdg_bam_reader *r, int64_t k, char *buf, i
 
 int64_t mdg_bam_records_seen(const mdg_bam_reader *r) { return r ? r->records_seen : 0; }
 
+uint64_t mdg_bam_data_start(const mdg_bam_reader *r) { return r ? r->data_start : 0; }
+
 // ---- writer ---------------------------------------------------------------------------------
 
 static int wfail(mdg_bam_writer *w, int code, const char *msg)
@@ -974,6 +979,16 @@ int mdg_bam_write_soa(mdg_bam_writer *w, const mdg_batch *b, int64_t first_index
         int rc = flush_blocks(w, false);
         if (rc) return rc;
     }
+    return MDG_OK;
+}
+
+// Appends finished BGZF blocks (mdg_bam_encode_batch makes them on the GPU) behind whatever is pending.
+int mdg_bam_write_raw(mdg_bam_writer *w, const uint8_t *blocks, int64_t n_bytes)
+{
+    if (!w || n_bytes < 0 || (n_bytes && !blocks)) return wfail(w, MDG_ERR_ARGUMENT, "mdg_bam_write_raw: bad argument");
+    int rc = flush_blocks(w, true);
+    if (rc) return rc;
+    if (n_bytes && fwrite(blocks, 1, (size_t)n_bytes, w->fp) != (size_t)n_bytes) return wfail(w, MDG_ERR_DATA, "write failed");
     return MDG_OK;
 }
 

@@ -33,7 +33,41 @@ struct RescaleOut {
     unsigned long long *hist_sub;   // [type C>T, G>A][slot][94]: rescaled columns by position slot and old Phred
     unsigned long long *hist_rev;   // [type T>C, A>G][94]: the reverse transitions by Phred (never rescaled)
     unsigned long long *ref_count;  // [A, C, G, T]: reference bases over all walked columns
+    // optional list of the quality bytes that changed: change_at[k] = index into `qual`, change_q[k] = the new score
+    // (what crosses PCIe instead of the whole quality array); entries beyond change_cap are counted, not stored
+    uint32_t *change_at;
+    uint8_t *change_q;
+    unsigned long long *n_changes;
+    unsigned long long change_cap;
 };
+
+// Appends this lane's pending changes (at most RESCALE_PENDING, packed index << 8 | score is too narrow, so two arrays)
+// with one atomic per warp.  Call with the whole warp converged.
+constexpr int RESCALE_PENDING = 6;
+__device__ __forceinline__ void flush_changes(const RescaleOut &out, const uint32_t (&at)[RESCALE_PENDING],
+                                              const uint8_t (&q)[RESCALE_PENDING], int &n_mine, int lane)
+{
+    const uint32_t any = __ballot_sync(0xffffffffu, n_mine > 0);
+    if (!any) return;
+    uint32_t inc = (uint32_t)n_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(out.n_changes, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0) + (inc - (uint32_t)n_mine);
+#pragma unroll
+    for (int k = 0; k < RESCALE_PENDING; ++k) {
+        if (k < n_mine && base + k < out.change_cap) {
+            out.change_at[base + k] = at[k];
+            out.change_q[base + k] = q[k];
+        }
+    }
+    n_mine = 0;
+}
 
 // float(("%.5f" % x)) narrowed to float32: exact decimal rounding, half to even.
 __device__ inline float round_5_decimals(double x)
@@ -118,8 +152,9 @@ __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const Rescale
     for (uint32_t base = 0; base < C; base += 32) {
         const uint32_t i = base + lane;
         double add = 0.0;
-        bool contributes = false;
-        uint32_t ref_here = CODE_OTHER;
+        bool contributes = false, changed = false;
+        uint32_t ref_here = CODE_OTHER, changed_at = 0;
+        uint8_t changed_q = 0;
         if (i < C) {
             const uint32_t col = strand ? C - 1 - i : i;
             uint32_t op = OP_M, j = col, refidx = col;
@@ -167,7 +202,13 @@ __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const Rescale
                         if (q > 93) {
                             atomicCAS(out.error_flag, 0, DATA_ERR_QUAL);
                         } else {
-                            out.qual[qbase + j] = m.lut[((size_t)type * m.n_slots + slot) * 94 + q];
+                            const uint8_t new_q = m.lut[((size_t)type * m.n_slots + slot) * 94 + q];
+                            out.qual[qbase + j] = new_q;
+                            if (new_q != q) {
+                                changed_at = (uint32_t)(qbase + j);
+                                changed_q = new_q;
+                                changed = true;
+                            }
                             add = m.inc[type * m.n_slots + slot];
                             contributes = slot != 0;  // slot 0 adds exactly 0.0
                             atomicAdd(out.hist_sub + ((size_t)type * m.n_slots + slot) * 94 + q, 1ull);
@@ -182,6 +223,18 @@ __device__ void rescale_read(const DevBatch &b, const DevRef &ref, const Rescale
         }
 #pragma unroll
         for (uint32_t g = 0; g < 4; ++g) ref_seen[g] += __popc(__ballot_sync(0xffffffffu, ref_here == g));
+        if (out.change_at) {
+            const uint32_t ch = __ballot_sync(0xffffffffu, changed);
+            if (ch) {
+                unsigned long long base = 0;
+                if (lane == __ffs(ch) - 1) base = atomicAdd(out.n_changes, (unsigned long long)__popc(ch));
+                base = __shfl_sync(0xffffffffu, base, __ffs(ch) - 1) + __popc(ch & ((1u << lane) - 1u));
+                if (changed && base < out.change_cap) {
+                    out.change_at[base] = changed_at;
+                    out.change_q[base] = changed_q;
+                }
+            }
+        }
         uint32_t mask = __ballot_sync(0xffffffffu, contributes);
         while (mask) {  // sequential fp64 sum in read order (rescale.py:244)
             int src = __ffs(mask) - 1;
@@ -245,6 +298,9 @@ __global__ void __launch_bounds__(256) rescale_gapfree_kernel(DevBatch b, DevRef
     for (int64_t round = 0; round < rounds; ++round) {
         const int64_t r = round * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         bool complex = false;
+        uint32_t pending_at[RESCALE_PENDING];
+        uint8_t pending_q[RESCALE_PENDING];
+        int n_pending = 0;
         if (r < b.n_reads) do {
             const uint32_t flag = b.flag[r];
             const uint32_t l_seq = b.l_seq[r];
@@ -361,7 +417,27 @@ __global__ void __launch_bounds__(256) rescale_gapfree_kernel(DevBatch b, DevRef
                                 atomicCAS(out.error_flag, 0, DATA_ERR_QUAL);
                             } else {
                                 const int cell = (type * m.n_slots + slot) * 94 + (int)q;
-                                out.qual[q0 + j] = m.lut[cell];
+                                const uint8_t new_q = m.lut[cell];
+                                out.qual[q0 + j] = new_q;
+                                if (new_q != q && out.change_at) {
+                                    if (n_pending == RESCALE_PENDING) {
+                                        // more changes in one read than a lane holds: this lane appends on its own
+                                        const unsigned long long base = atomicAdd(out.n_changes, (unsigned long long)RESCALE_PENDING);
+                                        for (int k = 0; k < RESCALE_PENDING; ++k)
+                                            if (base + k < out.change_cap) {
+                                                out.change_at[base + k] = pending_at[k];
+                                                out.change_q[base + k] = pending_q[k];
+                                            }
+                                        n_pending = 0;
+                                    }
+#pragma unroll
+                                    for (int k = 0; k < RESCALE_PENDING; ++k)
+                                        if (k == n_pending) {
+                                            pending_at[k] = (uint32_t)(q0 + j);
+                                            pending_q[k] = new_q;
+                                        }
+                                    ++n_pending;
+                                }
                                 if (slot) mr += m.inc[type * m.n_slots + slot];  // slot 0 adds exactly 0.0
                                 if (shared_hist) atomicAdd(s_hist + cell, 1u);
                                 else atomicAdd(out.hist_sub + cell, 1ull);
@@ -407,6 +483,7 @@ __global__ void __launch_bounds__(256) rescale_gapfree_kernel(DevBatch b, DevRef
             out.mr[r] = round_5_decimals(mr);
             ++n_rescaled;
         } while (false);
+        if (out.change_at) flush_changes(out, pending_at, pending_q, n_pending, lane);
         // warp-aggregated append of the records left to rescale_kernel
         const uint32_t cx = __ballot_sync(0xffffffffu, complex);
         if (cx) {

@@ -290,6 +290,45 @@ class DamageEngine:
             self._ctx, C.byref(s), qual_out.ctypes.data, mr.ctypes.data, status.ctypes.data))
         return qual_out[:s.n_bases], mr[:batch.n], status[:batch.n]
 
+    def rescale_sparse(self, batch, out=None, compact=True):
+        """Queues the rescale of one batch; only what changed comes back (``mdg_rescale_submit_sparse``).
+        Returns ``(mr, status, ticket)``; after :meth:`rescale_collect` ``(ticket)`` the batch's own ``qual`` array has
+        been patched in place and ``mr`` / ``status`` are valid."""
+        s = batch_struct(batch, compact)
+        if out is None:
+            out = (np.empty(max(1, batch.n), dtype=np.float32), np.empty(max(1, batch.n), dtype=np.uint8))
+        mr, status = out
+        ticket = C.c_int32(-1)
+        self._keepalive.append((batch, s, out))
+        self._check(self._lib.mdg_rescale_submit_sparse(self._ctx, C.byref(s), mr.ctypes.data, status.ctypes.data,
+                                                        C.byref(ticket)))
+        return mr[:batch.n], status[:batch.n], ticket.value
+
+    def rescale_collect(self, ticket, batch, scratch=None):
+        """Waits for the sparse submit ``ticket`` and writes the changed quality bytes into ``batch.qual``.
+        Returns the number of bytes that changed."""
+        cap = batch.total_bases // 4 + 4096
+        if scratch is None or scratch[0].shape[0] < cap:
+            scratch = (np.empty(cap, dtype=np.uint32), np.empty(cap, dtype=np.uint8))
+        at, q = scratch
+        n = self._check(self._lib.mdg_rescale_collect(self._ctx, ticket, at.ctypes.data, q.ctypes.data, at.shape[0]))
+        if n:
+            batch.qual[at[:n]] = q[:n]
+        return int(n)
+
+    def rescale_resident(self, device_batch, want_results=False):
+        """Rescales a resident batch in place (``mdg_rescale_resident``); with ``want_results`` returns ``(mr, status)``
+        host arrays that are valid after :meth:`sync`."""
+        handle = device_batch.handle
+        if want_results:
+            mr = np.empty(max(1, device_batch.n), dtype=np.float32)
+            status = np.empty(max(1, device_batch.n), dtype=np.uint8)
+            self._keepalive.append((mr, status))
+            self._check(self._lib.mdg_rescale_resident(self._ctx, handle, mr.ctypes.data, status.ctypes.data))
+            return mr[:device_batch.n], status[:device_batch.n]
+        self._check(self._lib.mdg_rescale_resident(self._ctx, handle, None, None))
+        return None
+
     def rescale_stats(self):
         stats = np.zeros(8, dtype=np.uint64)
         self._check(self._lib.mdg_fetch_rescale_stats(self._ctx, stats.ctypes.data))

@@ -154,11 +154,90 @@ def _rescale_qual_core(ref, options, engine=None, batch_reads=1 << 18):
     return _report(log, stats, summary)
 
 
+def _rescale_bam_on_device(ref, options, model, engine, log):
+    """BAM in, BAM out, on the GPU: the host reads one file and writes the other; inflate, record scatter, the
+    rescale kernels, record re-emission (new qualities, ``MR:f``) and BGZF deflate all run in HBM
+    (``bamio.DeviceBamStream``).  Every record is written, in input order, under the input's header
+    (``rescale.py:298-300,344``)."""
+    import os
+
+    from .bamio import BamReader, BamWriter, DeviceBamStream
+    from .counting import input_kind
+
+    path = input_kind(options.filename)[0]
+    with BamReader(path, threads=2, merge_libraries=True, apply_filter=False) as reader:
+        header = reader.header
+    reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
+    reference = reference.reordered(header.references, header.lengths)
+    own_engine = engine is None
+    if own_engine:
+        engine = DamageEngine(max_reads=0, device=getattr(options, "device", 0))
+    timings = getattr(options, "timings", None)
+    try:
+        engine.set_reference(reference)
+        engine.set_rescale_model(model)
+        too_long, first = 0, 0
+        with DeviceBamStream(engine, path, merge_libraries=True, apply_filter=False, with_qual=True, want_mr=True,
+                             slab_bytes=int(os.environ.get("MDG_RESCALE_SLAB", "0"))) as stream, \
+                BamWriter(options.rescale_out, header) as writer:
+            for batch in stream:
+                _, status = engine.rescale_resident(batch, want_results=True)
+                engine.sync()  # raises the "quality and sequence mismatch" data error (rescale.py:266-273)
+                clash = np.flatnonzero(stream.has_mr(batch) & (status & 1))
+                if clash.size:  # rescale.py:277-278
+                    raise SystemExit("Read: %s already has a MR tag, can't rescale"
+                                     % _names_at(path, [first + int(clash[0])])[0])
+                now = engine.rescale_stats()["alignment_longer_than_read"]
+                if now != too_long:  # rescale.py:255-261; rare, so the names are dug out of the file again
+                    host = engine.download(batch)
+                    hits = []
+                    for i in np.flatnonzero(status & 1):
+                        columns = [op for op, n in host.cigar_of(int(i)) if op in (0, 1, 2, 7, 8) and n > 0]
+                        if columns and (columns[0] if host.flag[i] & 0x10 else columns[-1]) == 2:
+                            hits.append(first + int(i))
+                    for name in _names_at(path, hits):
+                        log.warning("The aligment of the read is longer than the actual read %s", name)
+                    too_long = now
+                stream.encode(batch, writer)
+                first += batch.n
+            flushed = stream.flush()
+            if timings is not None:
+                timings.update(stream.stats())
+                timings.update(zip(("bytes_uncompressed", "bytes_compressed", "encode_s", "write_wait_s"), flushed))
+        stats = engine.rescale_stats()
+        summary = SubstitutionSummary(model, *engine.rescale_hist(model.n_slots))
+    finally:
+        if own_engine:
+            engine.close()
+    return _report(log, stats, summary)
+
+
+def _names_at(path, indices):
+    """Names of the records at the given positions of a BAM file (error / warning texts only)."""
+    from .bamio import BamReader
+
+    wanted, names, at = sorted(set(indices)), {}, 0
+    with BamReader(path, merge_libraries=True, apply_filter=False) as reader:
+        while wanted:
+            batch = reader.read_batch(max_reads=1 << 18, keep_raw=True)
+            if batch is None:
+                break
+            while wanted and wanted[0] < at + batch.n:
+                names[wanted[0]] = _record_name(batch, wanted.pop(0) - at)
+            at += batch.n
+    return [names.get(i, "?") for i in indices]
+
+
 def _rescale_bam(ref, options, model, engine, batch_reads, log):
     """BAM in, BAM out: batches from the native decoder, records re-emitted by the native encoder."""
+    import os
+
     from .bamio import BamReader, BamWriter
 
     from .counting import input_kind
+
+    if os.environ.get("MDG_BAM_HOST") != "1" and not input_kind(options.filename)[2]:
+        return _rescale_bam_on_device(ref, options, model, engine, log)
 
     with BamReader(input_kind(options.filename)[0], merge_libraries=True, apply_filter=False) as reader:
         reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)

@@ -105,8 +105,18 @@ def _as_bam(sam, path, block_bytes=0xff00):
     return header, records
 
 
+@pytest.fixture(params=["device", "host"])
+def bam_path(request, monkeypatch):
+    """BAM files go through the GPU decoder / encoder (bamio.DeviceBamStream) unless MDG_BAM_HOST=1."""
+    if request.param == "host":
+        monkeypatch.setenv("MDG_BAM_HOST", "1")
+    monkeypatch.setenv("MDG_BAM_DEVICE_SLAB", "200000")  # several slabs even from small files
+    monkeypatch.setenv("MDG_RESCALE_SLAB", "200000")
+    return request.param
+
+
 @pytest.mark.parametrize("case_dir,params", [c for c in golden_cases("counting") if not c.values[1]["exception"]])
-def test_count_alignments_from_bam(case_dir, params, tmp_path):
+def test_count_alignments_from_bam(case_dir, params, tmp_path, bam_path):
     sam, fasta = materialise_inputs(case_dir, params, tmp_path)
     _as_bam(sam, tmp_path / "input.bam", block_bytes=4096)
     counting.count_alignments(tmp_path / "input.bam", fasta, length=params["length"], around=params["around"],
@@ -163,7 +173,7 @@ def test_count_alignments_downsampled(case_dir, params, as_bam, tmp_path):
 
 
 @pytest.mark.parametrize("case_dir,params", [c for c in golden_cases("rescale")])
-def test_rescale_qual_bam_to_bam(case_dir, params, tmp_path, caplog):
+def test_rescale_qual_bam_to_bam(case_dir, params, tmp_path, caplog, bam_path):
     import bam_py
     from mapdamage_b200.samtext import read_sam
 
