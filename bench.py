@@ -525,8 +525,192 @@ def gpu_arm(args, rank, local_rank, world):
     ranks.close()
 
 
+def rescale_model_terms():
+    """The synthetic damage model of configs[3] (24 rows of the shape rescale.py:23-46 reads)."""
+    corr = {("C", "T", p): 0.9 * 0.67 ** (p - 1) for p in range(1, 13)}
+    corr.update({("G", "A", -p): 0.85 * 0.6 ** (p - 1) for p in range(1, 13)})
+    corr.update({("G", "A", p): 0.013 for p in range(1, 13)})
+    corr.update({("C", "T", -p): 0.021 for p in range(1, 13)})
+    return corr
+
+
 def rescale_config(args, ranks):
-    return None
+    """configs[3]: the rescale pass (rescale.py:285-365) over 200 M reads, three ways:
+    kernels alone on resident batches, through the public API from pinned host batches (only the changed quality
+    bytes come back), and BAM file -> rescaled BAM file through ``rescale.rescale_qual`` (decode, rescale, re-emission
+    and BGZF deflate on the GPU; the host reads one file and writes the other)."""
+    import argparse as _argparse
+    import shutil
+    import tempfile
+
+    from mapdamage_b200 import rescale, synth
+    from mapdamage_b200.bamio import BamReader, BamWriter
+    from mapdamage_b200.engine import DamageEngine
+    from mapdamage_b200.rescale_model import RescaleModel
+    from mapdamage_b200.samtext import SamHeader
+
+    if ranks.rank != 0:
+        return None
+    import oracle
+
+    corr = rescale_model_terms()
+    model = RescaleModel(corr, 12, 12)
+    reference = synth.make_reference([REF_BASES], seed=args.seed)
+    n_batches = max(1, -(-args.c4_reads // args.batch_reads))
+    per = args.c4_reads // n_batches
+    total = per * n_batches
+    out = {"unit": UNIT, "config": {"workload": WORKLOADS["c4"], "reads_per_step": total, "batches_per_step": n_batches,
+                                    "model": "synthetic Stats_out_MCMC_correct_prob.csv, 12 positions per end"}}
+    check = {}
+    with DamageEngine(device=ranks.local_rank, n_slots=2, max_reads=per + 1, max_cigar_ops=per + 1,
+                      max_bases=(per + 1) * READ_LEN) as engine:
+        engine.set_reference(reference)
+        engine.set_rescale_model(model)
+        resident = [engine.synth_batch(per, seed=args.seed + 7000 + i, length=(READ_LEN, READ_LEN), with_qual=True)
+                    for i in range(n_batches)]
+        host0 = engine.download(resident[0])
+        # parity first: 100 k reads, exact qualities, MR and status (the contract allows +-1 Phred; the LUT is exact)
+        sample = host0.slice(0, min(100_000, host0.n))
+        want_qual, want_mr, want_status, _, rc = oracle.rescale(sample, reference, corr)
+        sub = engine.upload(sample)
+        mr, status = engine.rescale_resident(sub, want_results=True)
+        engine.sync()
+        got = engine.download(sub)
+        sub.free()
+        n_b = sample.total_bases
+        if rc != 0 or not (np.array_equal(status, want_status) and np.array_equal(mr[status == 1], want_mr[status == 1])
+                           and np.array_equal(got.qual[:n_b], want_qual[:n_b])):
+            raise SystemExit("bench[c4]: rescaled qualities / MR differ from the oracle on the %d-read sample" % sample.n)
+        check["oracle_sample_reads"] = sample.n
+        check["qualities"] = "exact"
+        # ---- kernels alone: resident batches, CUDA events on the compute stream ----
+        for dev in resident[:2]:
+            engine.rescale_resident(dev)
+        engine.sync()
+        engine.kernel_ms()
+        launches0 = engine.launch_count()
+        engine.event_record(0)
+        for dev in resident:
+            engine.rescale_resident(dev)
+        engine.event_record(1)
+        ms = engine.event_elapsed_ms()
+        kernel_ms = engine.kernel_ms()
+        launches = engine.launch_count() - launches0
+        peak, peak_source = measured_peak()
+        algo = 15 + 8 + 4 + (READ_LEN + 1) // 2 + READ_LEN + (READ_LEN + 1) // 2 + READ_LEN + 4  # SURVEY 8(d): 331 B at 100 bp
+        achieved = algo * total / (kernel_ms * 1e-3) / 1e9
+        out.update({"value": total / (ms * 1e-3), "ms_per_step": ms, "steps": 1, "gpu_launches": int(launches),
+                    "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                 "traffic": None, "peak_source": peak_source, "algorithmic_bytes_per_read": algo,
+                                 "kernel_ms_per_launch": kernel_ms / n_batches, "reads_per_launch": per,
+                                 "note": "qualities are rewritten in place: after the first pass the inputs are the "
+                                         "rescaled qualities (the same columns are looked up)"}})
+        for dev in resident:
+            dev.free()
+        # ---- e2e: pinned host batches through DamageEngine.rescale_sparse / rescale_collect ----
+        if not args.no_e2e:
+            n_host = min(4, n_batches)
+            devs = [engine.synth_batch(per, seed=args.seed + 7000 + i, length=(READ_LEN, READ_LEN), with_qual=True)
+                    for i in range(n_host)]
+            host = [engine.download(dev, pinned=True) for dev in devs]
+            for dev in devs:
+                dev.free()
+            outs = [(engine.arena.empty(per + 1, np.float32), engine.arena.empty(per + 1, np.uint8)) for _ in range(2)]
+            scratch = (np.empty(host[0].total_bases // 4 + 4096, np.uint32), np.empty(host[0].total_bases // 4 + 4096, np.uint8))
+            h2d = n_batches * engine.h2d_bytes(host[0], rescale=True)
+
+            def e2e_pass():
+                pending, changed = None, 0
+                for i in range(n_batches):
+                    batch = host[i % n_host]
+                    _, _, ticket = engine.rescale_sparse(batch, out=outs[i & 1])
+                    if pending is not None:
+                        changed += engine.rescale_collect(pending[0], pending[1], scratch)
+                    pending = (ticket, batch)
+                changed += engine.rescale_collect(pending[0], pending[1], scratch)
+                return changed
+
+            e2e_pass()
+            t0 = time.perf_counter()
+            changed = e2e_pass()
+            dt = time.perf_counter() - t0
+            out["e2e"] = {"value": total / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                          "d2h_bytes_per_step": int(5 * total + 5 * changed), "ms_per_step": dt * 1e3,
+                          "changed_quality_bytes_per_step": int(changed),
+                          "host_batches": "%d pinned batches streamed %d times per step; only the quality bytes that "
+                                          "changed come back (index + score), patched into the host array" % (n_host, n_batches),
+                          "timing": "host wall clock around submit..collect of every batch"}
+    # ---- BAM file -> rescaled BAM file ----
+    n_file = int(args.c4_file_reads)
+    if n_file > 0:
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 600 * n_file else None
+        tmp = Path(tempfile.mkdtemp(prefix="mdg_c4_", dir=base))
+        try:
+            bam, fasta = tmp / "reads.bam", tmp / "ref.fa"
+            reference.write_fasta(fasta)
+            rows = ['"","Position","C.T","G.A"']
+            for k, pos in enumerate(list(range(1, 13)) + list(range(-12, 0))):
+                rows.append('"%d",%d,%r,%r' % (k + 1, pos, corr[("C", "T", pos)], corr[("G", "A", pos)]))
+            (tmp / "Stats_out_MCMC_correct_prob.csv").write_text("\n".join(rows) + "\n")
+            header = SamHeader()
+            header.add("@HD\tVN:1.6\tSO:unsorted")
+            header.add("@SQ\tSN:%s\tLN:%d" % (reference.names[0], REF_BASES))
+            with DamageEngine(device=ranks.local_rank, max_reads=1024) as engine:
+                engine.set_reference(reference)
+                with BamWriter(bam, header) as writer:
+                    done = 0
+                    while done < n_file:
+                        n = min(1 << 21, n_file - done)
+                        dev = engine.synth_batch(n, seed=args.seed + 9000 + done, length=(READ_LEN, READ_LEN), with_qual=True)
+                        writer.write_soa(engine.download(dev), first_index=done)
+                        dev.free()
+                        done += n
+
+            def run(name):
+                timings = {}
+                options = _argparse.Namespace(folder=tmp, filename=bam, rescale_out=tmp / name, rescale_length_5p=12,
+                                              rescale_length_3p=12, timings=timings, device=ranks.local_rank)
+                t0 = time.perf_counter()
+                rc = rescale.rescale_qual(fasta, options)
+                dt = time.perf_counter() - t0
+                if rc != 0:
+                    raise SystemExit("bench[c4]: rescale_qual failed on the synthetic BAM")
+                return dt, timings
+
+            run("warm.bam")  # CUDA context, page-locked buffers, page cache
+            (tmp / "warm.bam").unlink()
+            dt, timings = run("rescaled.bam")
+            # round trip: the output re-read by the host decoder; every record there, in order; the first 100 k against the oracle
+            with BamReader(bam, merge_libraries=True, apply_filter=False) as a, \
+                    BamReader(tmp / "rescaled.bam", merge_libraries=True, apply_filter=False) as b:
+                first_in = a.read_batch(max_reads=100_000, keep_raw=True)
+                first_out = b.read_batch(max_reads=100_000, keep_raw=True)
+                n_out, n_mr = first_out.n, int(first_out.has_mr.sum())
+                while True:
+                    part = b.read_batch(max_reads=1 << 20, keep_raw=True)
+                    if part is None:
+                        break
+                    n_out += part.n
+                    n_mr += int(part.has_mr.sum())
+            want_qual, _, want_status, _, rc = oracle.rescale(first_in, reference, corr)
+            n_b = first_in.total_bases
+            same = (rc == 0 and n_out == n_file and np.array_equal(first_out.qual[:n_b], want_qual[:n_b])
+                    and np.array_equal(first_out.has_mr.astype(np.uint8), want_status & 1)
+                    and np.array_equal(first_out.flag, first_in.flag) and np.array_equal(first_out.pos, first_in.pos)
+                    and np.array_equal(first_out.seq4, first_in.seq4))
+            if not same:
+                raise SystemExit("bench[c4]: the rescaled BAM does not read back as the input with the oracle's qualities")
+            check["file_round_trip"] = "ok: %d records re-read by BamReader, %d with MR; first %d against the oracle" % (
+                n_out, n_mr, first_in.n)
+            out["file_to_file"] = {"value": n_file / dt, "unit": UNIT, "reads": n_file, "seconds": dt,
+                                   "input_bam_bytes": bam.stat().st_size,
+                                   "output_bam_bytes": (tmp / "rescaled.bam").stat().st_size, "stages": timings,
+                                   "projected_seconds_for_200M_reads": 200e6 / (n_file / dt),
+                                   "where": str(base or tempfile.gettempdir())}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    out["check"] = check
+    return out
 
 
 def main():

@@ -17,6 +17,7 @@
 #include "mdg_count.cuh"
 #include "mdg_swar.cuh"
 #include "mdg_stage.cuh"
+#include "mdg_planes.cuh"
 #include "mdg_rescale.cuh"
 #include "mdg_synth.cuh"
 #include "mdg_inflate_dev.cuh"
@@ -97,6 +98,9 @@ struct WorkList {
     // several libraries: reads grouped by library
     uint32_t *by_library = nullptr;         // [cap]
     unsigned long long *lib_scratch = nullptr;  // counts [n_lib] | offsets [n_lib + 1] | cursors [n_lib]
+    // reads with one short indel, left by the bit-plane kernel to count_staged_kernel's indel variant
+    uint32_t *indel_reads = nullptr;            // [cap], library l from offsets[l] on
+    unsigned long long *indel_count = nullptr;  // [n_lib] | bounds [2 n_lib] = {first, last} of every library's stretch
 };
 
 struct mdg_dev_batch {
@@ -152,6 +156,11 @@ struct mdg_ctx {
     int64_t reads_launched = 0;
     mdg::SwarGeom swar{};
     size_t swar_smem = 0;
+    // bit-plane kernel (mdg_planes.cuh): the default for gap-free reads when no quality mask is asked for
+    bool planes_enabled = false;
+    mdg::PlaneGeom planes{};
+    size_t planes_smem = 0;
+    void *planes_block = nullptr;  // genome as bit planes
     std::vector<WorkList> worklists;
     // measurement
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -355,15 +364,19 @@ int worklist_for(mdg_ctx *ctx, cudaStream_t stream, int64_t n_reads, WorkList **
         wl = &ctx->worklists.back();
         wl->stream = stream;
         MDG_CUDA(ctx, cudaMalloc(&wl->count, (size_t)ctx->cfg.n_libraries * 8));
+        MDG_CUDA(ctx, cudaMalloc(&wl->indel_count, (size_t)ctx->cfg.n_libraries * 24));
         if (ctx->cfg.n_libraries > 1)
             MDG_CUDA(ctx, cudaMalloc(&wl->lib_scratch, ((size_t)3 * ctx->cfg.n_libraries + 1) * 8));
     }
     if (wl->cap < n_reads) {
         MDG_CUDA(ctx, cudaStreamSynchronize(stream));
         cudaFree(wl->reads);
+        cudaFree(wl->indel_reads);
         wl->reads = nullptr;
+        wl->indel_reads = nullptr;
         wl->cap = 0;
         MDG_CUDA(ctx, cudaMalloc(&wl->reads, (size_t)n_reads * 4));
+        MDG_CUDA(ctx, cudaMalloc(&wl->indel_reads, (size_t)n_reads * 4));
         if (ctx->cfg.n_libraries > 1) {
             cudaFree(wl->by_library);
             wl->by_library = nullptr;
@@ -413,9 +426,20 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             const unsigned long long seen = *(volatile unsigned long long *)ctx->indel_seen_host;
             if (seen * 50 > (unsigned long long)ctx->reads_launched && seen > 1000) ctx->staged_indels = true;
         }
+        // the bit-plane kernel counts the gap-free reads (no quality mask); reads with one short indel come back in
+        // a list for the staged kernel's indel variant
+        const bool use_planes = ctx->planes_enabled && !q;
+        if (use_planes) MDG_CUDA(ctx, cudaMemsetAsync(wl->indel_count, 0, (size_t)nl * 24, stream));
         // one launch of the bit-sliced kernel over a library's reads (or all reads) into the tables `tl`
         auto launch_bitsliced = [&](const mdg::CountTables &tl, const mdg::SwarSubset &subset) {
-            if (ctx->staged_enabled) {
+            if (use_planes) {
+                mdg::PlaneGeom pg = ctx->planes;
+                pg.indel_seen = ctx->indel_seen_dev;
+                const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
+                const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, tiles);
+                mdg::count_planes_kernel<512><<<pgrid, pg.threads, ctx->planes_smem, stream>>>(b, ctx->ref, p, tl, pg, wl->reads, wl->count,
+                                                                                               wl->indel_reads, wl->indel_count, subset);
+            } else if (ctx->staged_enabled) {
                 // three planes (quality mask or indel reads staged) leave room for fewer reads per tile
                 const bool three = q || ctx->staged_indels;
                 mdg::StagedGeom sg = ctx->staged;
@@ -447,6 +471,22 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             ctx->launches += 3 + nl;
         }
         MDG_CUDA(ctx, cudaGetLastError());
+        if (use_planes) {
+            // the one-indel reads: count_staged_kernel's three-plane variant over each library's stretch of the list
+            unsigned long long *const bounds = wl->indel_count + nl;
+            mdg::indel_bounds_kernel<<<1, 64, 0, stream>>>(wl->indel_count, nl > 1 ? wl->lib_scratch + nl : nullptr, nl, bounds);
+            mdg::StagedGeom sg = ctx->staged;
+            sg.indel_seen = nullptr;
+            sg.tile = ctx->staged_tile_qual;
+            const int64_t tiles = (b.n_reads + sg.tile - 1) / sg.tile;
+            const int sgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->staged_blocks_per_sm, tiles);
+            for (int lib = 0; lib < nl; ++lib)
+                staged_kernel(false, true, ctx->staged_threads)<<<sgrid, sg.threads, ctx->staged_smem_qual, stream>>>(
+                    b, ctx->ref, p, nl == 1 ? ctx->count_tables : lib_tables(ctx, lib), sg, wl->reads, wl->count,
+                    mdg::SwarSubset{wl->indel_reads, bounds + lib, lib});
+            MDG_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 1 + nl;
+        }
         ctx->reads_launched += b.n_reads;
         if (ctx->staged_enabled && ctx->staged_indels_auto && !ctx->staged_indels && ctx->indel_seen_host)
             MDG_CUDA(ctx, cudaMemcpyAsync(ctx->indel_seen_host, ctx->indel_seen_dev, 8, cudaMemcpyDeviceToHost, stream));
@@ -711,6 +751,31 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 }
             }
         }
+        // bit-plane kernel geometry
+        {
+            mdg::PlaneGeom &pg = ctx->planes;
+            const char *kenv = getenv("MDG_KERNEL");
+            pg.threads = 512;
+            pg.uniform = g.uniform;
+            pg.flush_tiles = g.flush_tiles;
+            pg.nw_anchor = (cfg->length + cfg->around + 31) / 32;
+            pg.row_words = 16 * pg.nw_anchor + 4;
+            const int pairs = (pg.threads >> 7) * 32;
+            const size_t fixed = ((size_t)mdg::PL_WIDE * mdg::PL_CLASSES * pg.threads + 4 * pg.nw_anchor + 4 * MDG_LG_SMEM_BINS + 4 * L + 32) * 4;
+            const size_t per_read = ((size_t)pg.row_words + 4 + 2) * 4;
+            int tile = 0;
+            if (fixed + 192 * per_read <= ctx->smem_optin) tile = (int)std::min<size_t>(1024, (ctx->smem_optin - fixed) / per_read / 32 * 32);
+            if (const char *tile_env3 = getenv("MDG_PLANES_TILE")) tile = std::min(tile, std::max(32, atoi(tile_env3)));
+            pg.tile = tile;
+            ctx->planes_smem = fixed + (size_t)tile * per_read;
+            const bool fits = ctx->staged_enabled && 2 * pg.nw_anchor * 2 <= pairs && cfg->around <= 64 && tile >= 192 &&
+                              (size_t)tile * pg.row_words >= (size_t)2 * 20 * 64 * pg.nw_anchor;
+            if (fits && !(kenv && (!strcmp(kenv, "swar") || !strcmp(kenv, "staged")))) {
+                MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_planes_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)ctx->planes_smem));
+                ctx->planes_enabled = true;
+            }
+        }
         const char *env = getenv("MDG_FORCE_GENERAL");
         ctx->force_general = env && env[0] == '1';
     }
@@ -751,6 +816,8 @@ void mdg_destroy(mdg_ctx *ctx)
     if (ctx->indel_seen_host) cudaFreeHost(ctx->indel_seen_host);
     for (auto &w : ctx->worklists) {
         cudaFree(w.reads);
+        cudaFree(w.indel_reads);
+        cudaFree(w.indel_count);
         cudaFree(w.count);
         cudaFree(w.by_library);
         cudaFree(w.lib_scratch);
@@ -759,6 +826,7 @@ void mdg_destroy(mdg_ctx *ctx)
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     cudaFree(ctx->ref_block);
+    cudaFree(ctx->planes_block);
     cudaFree(ctx->tables);
     cudaFree(ctx->reduced);
     cudaFree(ctx->aux_block);
@@ -798,10 +866,18 @@ int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, cons
     mdg::ref_to_one_hot_kernel<<<ctx->sm_count * 8, 256, 0, ctx->compute>>>((uint32_t *)ctx->ref_block,
                                                                              (int64_t)((pad + words_bytes) / 4));
     MDG_CUDA(ctx, cudaGetLastError());
+    // the same image as bit planes (32 bases per uint4), padding included
+    cudaFree(ctx->planes_block);
+    ctx->planes_block = nullptr;
+    MDG_CUDA(ctx, cudaMalloc(&ctx->planes_block, pad + words_bytes));
+    mdg::ref_planes_kernel<<<ctx->sm_count * 8, 256, 0, ctx->compute>>>((const uint32_t *)ctx->ref_block, (int64_t)((pad + words_bytes) / 16),
+                                                                         (uint4 *)ctx->planes_block);
+    MDG_CUDA(ctx, cudaGetLastError());
     MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     MDG_CUDA(ctx, cudaMemcpy(p + words_bytes, contig_off, (size_t)n_contigs * 8, cudaMemcpyHostToDevice));
     MDG_CUDA(ctx, cudaMemcpy(p + words_bytes + off_bytes, contig_len, (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
     ctx->ref.words = (const uint32_t *)p;
+    ctx->ref.planes = (const uint4 *)((char *)ctx->planes_block + pad);
     ctx->ref.contig_off = (const uint64_t *)(p + words_bytes);
     ctx->ref.contig_len = (const uint32_t *)(p + words_bytes + off_bytes);
     ctx->ref.n_contigs = n_contigs;

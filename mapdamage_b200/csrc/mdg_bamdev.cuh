@@ -541,6 +541,46 @@ namespace {
 
 thread_local std::string g_stream_error;
 
+// Page-locked buffers are expensive to make (the kernel locks every page: ~0.4 s per GB) and cheap to keep: a stream
+// hands its slab and output buffers back to this pool when it closes, and the next stream of the process takes them.
+struct PinnedPool {
+    std::mutex mutex;
+    std::vector<std::pair<uint8_t *, size_t>> free_list;
+    uint8_t *take(size_t want, size_t *cap)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mutex);
+            size_t best = free_list.size();
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].second >= want && (best == free_list.size() || free_list[i].second < free_list[best].second)) best = i;
+            if (best < free_list.size() && free_list[best].second <= 2 * want + (64u << 20)) {
+                uint8_t *p = free_list[best].first;
+                *cap = free_list[best].second;
+                free_list.erase(free_list.begin() + (ptrdiff_t)best);
+                return p;
+            }
+        }
+        uint8_t *p = nullptr;
+        if (cudaHostAlloc((void **)&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        *cap = want;
+        return p;
+    }
+    void give(uint8_t *p, size_t cap)
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> lock(mutex);
+        free_list.emplace_back(p, cap);
+    }
+};
+PinnedPool &pinned_pool()
+{
+    static PinnedPool *pool = new PinnedPool();  // never destroyed: the CUDA context may be gone by then
+    return *pool;
+}
+
 int sfail(mdg_bam_stream *s, int code, const char *fmt, ...)
 {
     char buf[512];
@@ -713,6 +753,9 @@ void bamdev_decode(mdg_bam_stream *s, BamDevSlab &slab, BamDevDecoded &out)
         return;
     }
     MDG_S_CUDA(s, out, cudaSetDevice(s->ctx->cfg.device));
+    static const bool timing = getenv("MDG_BAM_TIMING") != nullptr;  // per-slab stage times on stderr
+    const double tt0 = stream_now();
+    double tt1 = tt0, tt2 = tt0, tt3 = tt0, tt4 = tt0;
     const int nb = (int)slab.in_off.size();
     const uint64_t carry = s->carry_len;
     const uint64_t stream_len = carry + slab.inflated;
@@ -753,6 +796,7 @@ void bamdev_decode(mdg_bam_stream *s, BamDevSlab &slab, BamDevDecoded &out)
     uint32_t *d_in_len = (uint32_t *)(d_out_off + cap), *d_isize = d_in_len + cap, *d_crc = d_isize + cap;
     int32_t *d_status = (int32_t *)(d_crc + cap);
     cudaStream_t st = s->stream;
+    tt1 = stream_now();
     // the carried-over tail of the previous stream goes in front
     if (carry) {
         MDG_S_CUDA(s, out, cudaMemcpyAsync(out.stream, s->decoded[s->carry_from].stream + s->carry_at, (size_t)carry,
@@ -801,6 +845,7 @@ void bamdev_decode(mdg_bam_stream *s, BamDevSlab &slab, BamDevDecoded &out)
         MDG_S_CUDA(s, out, cudaStreamSynchronize(st));
     }
     out.stream_len = stream_len;
+    tt2 = stream_now();
     // ---- record boundaries ----
     const uint64_t start0 = s->records_seen == 0 && s->carry_from < 0 ? s->data_start : 0;
     const int64_t n_seg = (int64_t)((stream_len + mdg::BAM_SEGMENT - 1) / mdg::BAM_SEGMENT);
@@ -842,6 +887,7 @@ void bamdev_decode(mdg_bam_stream *s, BamDevSlab &slab, BamDevDecoded &out)
         s->h_totals->tail = stream_len;
     }
     const mdg::BamTotals walked = *s->h_totals;
+    tt3 = stream_now();
     if (walked.malformed) {
         out.error = MDG_ERR_DATA;
         char buf[128];
@@ -923,6 +969,10 @@ void bamdev_decode(mdg_bam_stream *s, BamDevSlab &slab, BamDevDecoded &out)
     MDG_S_CUDA(s, out, cudaStreamSynchronize(st));
     s->ctx->launches += 5;
     const mdg::BamTotals laid = *s->h_totals;
+    tt4 = stream_now();
+    if (timing)
+        fprintf(stderr, "device slab: %d blocks, %lld records, buffers %.3f s, copy + inflate + crc %.3f s, walk %.3f s, fields + layout + scatter %.3f s (with allocations)\n",
+                nb, (long long)n, tt1 - tt0, tt2 - tt1, tt3 - tt2, tt4 - tt3);
     if (laid.bases >= (1ull << 32) || laid.cigars >= (1ull << 32)) {
         out.error = MDG_ERR_CAPACITY;
         out.message = "a slab holds more than 2^32 bases: use a smaller slab";
@@ -1044,8 +1094,9 @@ int mdg_bam_stream_open(mdg_ctx *ctx, const char *path, uint64_t data_start, int
     s->slabs.resize((size_t)n_slabs);
     s->slab_state.assign((size_t)n_slabs, 0);
     for (auto &slab : s->slabs) {
-        slab.cap = s->slab_bytes + (1u << 17);  // room for the piece of a block carried over from the slab before
-        if (cudaHostAlloc((void **)&slab.data, slab.cap, cudaHostAllocDefault) != cudaSuccess) return bail(MDG_ERR_CUDA, "cudaHostAlloc failed");
+        // room for the piece of a block carried over from the slab before
+        slab.data = pinned_pool().take(s->slab_bytes + (1u << 17), &slab.cap);
+        if (!slab.data) return bail(MDG_ERR_CUDA, "cudaHostAlloc failed");
     }
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(MDG_ERR_CUDA, "cudaStreamCreate failed");
     if (cudaMalloc(&s->d_totals, sizeof(mdg::BamTotals)) != cudaSuccess ||
@@ -1096,7 +1147,7 @@ void mdg_bam_stream_close(mdg_bam_stream *s)
     if (s->ctx) cudaSetDevice(s->ctx->cfg.device);
     if (s->ctx) cudaStreamSynchronize(s->ctx->compute);
     if (s->fd >= 0) close(s->fd);
-    for (auto &slab : s->slabs) cudaFreeHost(slab.data);
+    for (auto &slab : s->slabs) pinned_pool().give(slab.data, slab.cap);
     for (auto &d : s->decoded) {
         cudaFree(d.stream);
         cudaFree(d.arrays.block);
@@ -1124,7 +1175,7 @@ void mdg_bam_stream_close(mdg_bam_stream *s)
     cudaFree(s->e_prefix);
     cudaFree(s->e_scan);
     if (s->e_total_host) cudaFreeHost(s->e_total_host);
-    for (auto *p : s->e_host) if (p) cudaFreeHost(p);
+    for (int i = 0; i < 2; ++i) pinned_pool().give(s->e_host[i], s->e_host_cap[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -1688,12 +1739,10 @@ int mdg_bam_encode_batch(mdg_bam_stream *s, mdg_dev_batch *batch, mdg_bam_writer
     const uint64_t packed = s->e_total_host[1];
     const int turn = s->e_turn;
     if (s->e_host_cap[turn] < packed) {
-        if (s->e_host[turn]) cudaFreeHost(s->e_host[turn]);
-        s->e_host[turn] = nullptr;
+        pinned_pool().give(s->e_host[turn], s->e_host_cap[turn]);
         s->e_host_cap[turn] = 0;
-        const size_t cap = (size_t)packed * 5 / 4 + (1u << 20);
-        MDG_E_CUDA(cudaHostAlloc((void **)&s->e_host[turn], cap, cudaHostAllocDefault));
-        s->e_host_cap[turn] = cap;
+        s->e_host[turn] = pinned_pool().take((size_t)packed * 9 / 8 + (1u << 20), &s->e_host_cap[turn]);
+        if (!s->e_host[turn]) return sfail(s, MDG_ERR_CUDA, "cudaHostAlloc failed (encoder output)");
     }
     MDG_E_CUDA(cudaMemcpyAsync(s->e_host[turn], s->e_packed, (size_t)packed, cudaMemcpyDeviceToHost, st));
     MDG_E_CUDA(cudaStreamSynchronize(st));

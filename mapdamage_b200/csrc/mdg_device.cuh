@@ -37,6 +37,7 @@ struct DevBatch {
 };
 
 struct DevRef {
+    const uint4 *planes;         // the same genome as bit planes: 32 bases per entry, {A, C, G, T} words (mdg_planes.cuh)
     const uint32_t *words;       // 8 bases per word, low nibble first, one-hot
     const uint64_t *contig_off;  // first base of each contig in the packed stream
     const uint32_t *contig_len;

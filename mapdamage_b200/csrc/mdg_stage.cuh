@@ -73,13 +73,14 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     uint32_t *const s_ctl_base = s_clip + 4 * L;                  // two sets of {n_fwd, n_rev, n_cx, min / max columns, -, -, -}
 
     const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t *const subset = sub.list ? sub.list + sub.offsets[sub.lib] : nullptr;
+    const int64_t n_todo = sub.list ? (int64_t)(sub.offsets[sub.lib + 1] - sub.offsets[sub.lib]) : b.n_reads;
+    if ((int64_t)blockIdx.x * T >= n_todo) return;  // no tile for this block (an empty list costs a launch, nothing more)
     for (int i = tid; i < l2_words + sub_words; i += nthreads) s_l2[i] = 0;
     for (int i = tid; i < 4 * MDG_LG_SMEM_BINS + 4 * L; i += nthreads) s_lg[i] = 0;
 
     const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
     const uint32_t *__restrict__ ref32 = ref.words;
-    const uint32_t *const subset = sub.list ? sub.list + sub.offsets[sub.lib] : nullptr;
-    const int64_t n_todo = sub.list ? (int64_t)(sub.offsets[sub.lib + 1] - sub.offsets[sub.lib]) : b.n_reads;
 
     // Block mode: 0 = two anchors per read (window words 0..W-1 left, W..2W-1 right); C > 0 = every gap-free read
     // of the tile has C columns and one window [-A, C + A) per read serves both tables (see mdg_swar.cuh).
@@ -878,6 +879,18 @@ count_staged_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Staged
     for (int i = tid; i < 4 * L; i += nthreads) {
         const uint32_t v = s_clip[i];
         if (v) atomicAdd(t.misincorp + ((size_t)(i / L) * MDG_N_CLASSES + MDG_CLASS_SOFTCLIP) * L + i % L, (unsigned long long)v);
+    }
+}
+
+// {first, last} of every library's stretch of the one-indel list (count_planes_kernel appends library l from
+// offsets[l] on): bounds[2 l], bounds[2 l + 1]
+__global__ void indel_bounds_kernel(const unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ offsets, int n_lib,
+                                    unsigned long long *__restrict__ bounds)
+{
+    for (int l = threadIdx.x; l < n_lib; l += blockDim.x) {
+        const unsigned long long first = offsets ? offsets[l] : 0ull;
+        bounds[2 * l] = first;
+        bounds[2 * l + 1] = first + counts[l];
     }
 }
 

@@ -223,7 +223,8 @@ def _names_at(path, indices):
             if batch is None:
                 break
             while wanted and wanted[0] < at + batch.n:
-                names[wanted[0]] = _record_name(batch, wanted.pop(0) - at)
+                index = wanted.pop(0)
+                names[index] = _record_name(batch, index - at)
             at += batch.n
     return [names.get(i, "?") for i in indices]
 

@@ -85,7 +85,8 @@ def test_stream_on_python_made_files(case, tmp_path):
             assert_same_arrays(concatenate(parts), want)
 
 
-def test_stream_errors(tmp_path):
+def test_stream_errors(tmp_path, monkeypatch):
+    monkeypatch.setenv("MDG_BAM_SLAB", "65536")  # host reader (header only): small slabs, so that a cut further on is not met at once
     header, records = read_sam(GOLDEN / "a06_no_readgroup" / "input.sam")
     bam = tmp_path / "in.bam"
     bam_py.write_bam(bam, header, records)
@@ -98,13 +99,21 @@ def test_stream_errors(tmp_path):
         synthetic_bam(good, 20_000, seed=5)
         data = good.read_bytes()
         (tmp_path / "cut.bam").write_bytes(data[:len(data) // 2])
-        with DeviceBamStream(engine, tmp_path / "cut.bam", merge_libraries=True) as stream:
-            with pytest.raises(BAMError):
+        with pytest.raises(BAMError):  # a file this small is seen to be cut short as soon as it is opened
+            with DeviceBamStream(engine, tmp_path / "cut.bam", merge_libraries=True) as stream:
                 list(stream)
         corrupt = bytearray(data)
         corrupt[len(data) // 2] ^= 0x55
         (tmp_path / "corrupt.bam").write_bytes(bytes(corrupt))
-        with DeviceBamStream(engine, tmp_path / "corrupt.bam", merge_libraries=True) as stream:
+        with pytest.raises(BAMError):
+            with DeviceBamStream(engine, tmp_path / "corrupt.bam", merge_libraries=True) as stream:
+                list(stream)
+        # a larger file cut inside a later slab: the header reads fine, the stream fails when it gets there
+        big = tmp_path / "big.bam"
+        synthetic_bam(big, 120_000, seed=6)
+        data = big.read_bytes()
+        (tmp_path / "big_cut.bam").write_bytes(data[:len(data) * 3 // 4])
+        with DeviceBamStream(engine, tmp_path / "big_cut.bam", merge_libraries=True, slab_bytes=1 << 20) as stream:
             with pytest.raises(BAMError):
                 list(stream)
 
