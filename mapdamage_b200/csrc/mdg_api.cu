@@ -761,12 +761,18 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             pg.nw_anchor = (cfg->length + cfg->around + 31) / 32;
             pg.row_words = 16 * pg.nw_anchor + 4;
             const int pairs = (pg.threads >> 7) * 32;
-            const size_t fixed = ((size_t)mdg::PL_WIDE * mdg::PL_CLASSES * pg.threads + 4 * pg.nw_anchor + 4 * MDG_LG_SMEM_BINS + 4 * L + 32) * 4;
-            const size_t per_read = ((size_t)pg.row_words + 4 + 2) * 4;
+            const size_t fixed = ((size_t)mdg::PL_WIDE * mdg::PL_CLASSES * pg.threads + 4 * pg.nw_anchor + 4 * MDG_LG_SMEM_BINS + 4 * L + 64 +
+                                  (size_t)2 * 12 * 64 * pg.nw_anchor) * 4 + 256;
+            // per read: the staged row, the record, two list slots, and 56 bytes of the tile's seq4 stretch (reads of up
+            // to about 110 bases on average; a tile of longer reads takes its bases from global memory)
+            const char *slab_env = getenv("MDG_PLANES_SLAB");
+            const size_t seq_per_read = slab_env && slab_env[0] == '0' ? 0 : 56;
+            const size_t per_read = ((size_t)pg.row_words + 4 + 2) * 4 + seq_per_read;
             int tile = 0;
             if (fixed + 192 * per_read <= ctx->smem_optin) tile = (int)std::min<size_t>(1024, (ctx->smem_optin - fixed) / per_read / 32 * 32);
             if (const char *tile_env3 = getenv("MDG_PLANES_TILE")) tile = std::min(tile, std::max(32, atoi(tile_env3)));
             pg.tile = tile;
+            pg.seq_words = (int)((size_t)tile * seq_per_read / 4 / 4 * 4);
             ctx->planes_smem = fixed + (size_t)tile * per_read;
             const bool fits = ctx->staged_enabled && 2 * pg.nw_anchor * 2 <= pairs && cfg->around <= 64 && tile >= 192 &&
                               (size_t)tile * pg.row_words >= (size_t)2 * 20 * 64 * pg.nw_anchor;
@@ -979,6 +985,12 @@ int mdg_sync(mdg_ctx *ctx)
         if (slot.stream) MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
     MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
 #ifdef MDG_PHASE_CLOCKS
+    {
+        unsigned int pp[16];
+        if (cudaMemcpyFromSymbol(pp, mdg::mdg_plane_phase_dump, sizeof(pp)) == cudaSuccess && pp[0])
+            fprintf(stderr, "plane kernel phase clocks (block 3, thread 0): parse %u sync %u stage %u sync %u count %u sync+flush %u\n", pp[0], pp[1],
+                    pp[2], pp[3], pp[4], pp[5]);
+    }
     {
         unsigned int pc[24];
         if (cudaMemcpyFromSymbol(pc, mdg::mdg_phase_dump, sizeof(pc)) == cudaSuccess) {

@@ -541,6 +541,9 @@ namespace {
 
 thread_local std::string g_stream_error;
 
+// inflated bytes one slab may hold: the batch arrays index bases (and this stream) with 32 bits
+constexpr uint64_t BAMDEV_STREAM_LIMIT = 3400ull << 20;
+
 // Page-locked buffers are expensive to make (the kernel locks every page: ~0.4 s per GB) and cheap to keep: a stream
 // hands its slab and output buffers back to this pool when it closes, and the next stream of the process takes them.
 struct PinnedPool {
@@ -601,9 +604,10 @@ double stream_now()
 // reader thread: slabs of the file into page-locked memory, cut into BGZF blocks
 void bamdev_reader_loop(mdg_bam_stream *s)
 {
-    std::vector<uint8_t> carry;  // the piece of a BGZF block cut by the end of the previous slab
+    std::vector<uint8_t> carry;  // what the previous slab left over: the piece of a BGZF block cut by its end, or
+                                 // the blocks that would have inflated past BAMDEV_STREAM_LIMIT
     uint64_t file_at = 0;
-    bool done = false;
+    bool done = false, file_ended = false;
     while (!done) {
         int k;
         {
@@ -619,8 +623,9 @@ void bamdev_reader_loop(mdg_bam_stream *s)
         slab.last = false;
         memcpy(slab.data, carry.data(), carry.size());
         size_t len = carry.size();
-        // several preads in flight: one thread copies out of the page cache at a few GB/s only
-        const size_t want = s->slab_bytes;
+        // several preads in flight: one thread copies out of the page cache at a few GB/s only.  What was carried over
+        // (the blocks of the slab before that would have inflated past the limit) counts towards this slab.
+        const size_t want = file_ended ? 0 : s->slab_bytes > carry.size() ? s->slab_bytes - carry.size() : 0;
         {
             const int n_io = 4;
             const size_t piece = (want + n_io - 1) / n_io;
@@ -645,9 +650,10 @@ void bamdev_reader_loop(mdg_bam_stream *s)
             }
             file_at += total;
             len += total;
-            slab.last = total < want;
+            if (total < want) file_ended = true;
         }
         carry.clear();
+        bool cut = false;
         slab.len = len;
         size_t at = 0;
         uint64_t out_off = 0;
@@ -684,6 +690,12 @@ void bamdev_reader_loop(mdg_bam_stream *s)
                             slab.message = "BGZF block claims more than 65536 bytes of data";
                             break;
                         }
+                        if (out_off + isize > BAMDEV_STREAM_LIMIT && !slab.in_off.empty()) {
+                            // the batch arrays index bases with 32 bits: the rest of the slab waits for the next one
+                            carry.assign(in + at, in + len);
+                            cut = true;
+                            break;
+                        }
                         if (isize) {
                             slab.in_off.push_back(at + 12 + xlen);
                             slab.in_len.push_back((uint32_t)((size_t)total - 12 - xlen - 8));
@@ -697,7 +709,7 @@ void bamdev_reader_loop(mdg_bam_stream *s)
                     }
                 }
             }
-            if (slab.last) {
+            if (file_ended) {
                 slab.error = MDG_ERR_DATA;
                 slab.message = "truncated BGZF block";
             } else {
@@ -705,6 +717,8 @@ void bamdev_reader_loop(mdg_bam_stream *s)
             }
             break;
         }
+        if (!carry.empty()) slab.len = at;  // what is carried over is not this slab's to copy
+        slab.last = file_ended && carry.empty() && !cut;
         slab.inflated = out_off;
         done = slab.last || slab.error;
         {
@@ -1074,15 +1088,13 @@ int mdg_bam_stream_open(mdg_ctx *ctx, const char *path, uint64_t data_start, int
     size_t file_size = 0;
     if (fstat(s->fd, &st) == 0 && S_ISREG(st.st_mode)) file_size = (size_t)st.st_size;
     if (const char *env = getenv("MDG_BAM_DEVICE_SLAB")) slab_bytes = atoll(env);
-    if (slab_bytes <= 0) slab_bytes = 512ll << 20;
+    if (slab_bytes <= 0) slab_bytes = 2048ll << 20;  // the inflate kernel is latency-bound: the more blocks per launch the better
     if (slab_bytes < (1 << 17)) slab_bytes = 1 << 17;
     // no more page-locked memory than the file needs
-    int n_slabs = 3;
+    int n_slabs = slab_bytes >= (512ll << 20) ? 2 : 3;
     if (file_size && (size_t)slab_bytes >= file_size) {
         slab_bytes = (int64_t)file_size + 1;
-        n_slabs = 1;
-    } else if (file_size && (size_t)slab_bytes * 2 >= file_size) {
-        n_slabs = 2;
+        n_slabs = 2;  // a slab cut short by BAMDEV_STREAM_LIMIT leaves its rest to a second one
     }
     s->slab_bytes = (size_t)slab_bytes;
     auto bail = [&](int code, const char *what) {

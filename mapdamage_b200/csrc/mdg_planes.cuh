@@ -40,12 +40,13 @@ struct PlaneGeom {
     int32_t flush_tiles;  // > 0: reduce the counters every so many tiles (tests)
     int32_t nw_anchor;    // words per anchor window: ceil((L + A) / 32)
     int32_t row_words;    // words per staged read: 8 * (2 * nw_anchor) + 4 (rows land on different banks)
+    int32_t seq_words;    // shared-memory words for the tile's slab of seq4 (bulk-copied ahead); 0: none
     unsigned long long *indel_seen;  // counts the one-indel reads met (steers the host's choice of variants)
 };
 
-constexpr int PL_REG = 6;    // counter planes in registers (counts to 63)
-constexpr int PL_WIDE = 10;  // counter planes in shared memory, weights 2^4 .. 2^13
-constexpr int PL_CLASSES = 5;
+constexpr int PL_REG = 8;    // counter planes in registers (counts to 255)
+constexpr int PL_WIDE = 8;   // counter planes in shared memory, weights 2^4 .. 2^11
+constexpr int PL_CLASSES = 2;  // R_g and H_g; the substitution classes P_g* are rare events and go to a shared table
 
 struct __align__(16) PlaneRecord {
     uint32_t q0;    // base index (nibble) of the first aligned base in seq4: base_off + leading clip
@@ -65,6 +66,23 @@ __device__ __forceinline__ uint32_t nibbles_to_planes(uint32_t x)
     return x;
 }
 
+// The same for a word of seq4 as BAM stores it (first base of a byte in the high nibble).  Logic and funnel shifts
+// issue on the ALU pipe, one warp-instruction per two cycles per scheduler, and this kernel is bound by it; a shift by a
+// constant is also a multiplication (left: x * 2^d, right: the high half of x * 2^(32 - d)), which issues on the FMA
+// pipe next to it.
+__device__ __forceinline__ uint32_t shl_fma(uint32_t x, int d) { return x * (1u << d); }
+__device__ __forceinline__ uint32_t shr_fma(uint32_t x, int d) { return __umulhi(x, 1u << (32 - d)); }
+__device__ __forceinline__ uint32_t bam_word_to_planes(uint32_t w)
+{
+    uint32_t x = (shl_fma(w & 0x0F0F0F0Fu, 4)) | (shr_fma(w, 4) & 0x0F0F0F0Fu);  // nibble j = base j
+    uint32_t t;
+    t = (shr_fma(x, 1) ^ x) & 0x22222222u; x ^= t ^ shl_fma(t, 1);
+    t = (shr_fma(x, 3) ^ x) & 0x0A0A0A0Au; x ^= t ^ shl_fma(t, 3);
+    t = (shr_fma(x, 6) ^ x) & 0x00CC00CCu; x ^= t ^ shl_fma(t, 6);
+    t = (shr_fma(x, 12) ^ x) & 0x0000F0F0u; x ^= t ^ shl_fma(t, 12);
+    return x;
+}
+
 // bits [lo, hi) of a 32-bit word, both clamped to [0, 32]
 __device__ __forceinline__ uint32_t bit_range(int lo, int hi)
 {
@@ -81,7 +99,7 @@ __device__ __forceinline__ uint32_t bit_range(int lo, int hi)
         h = ((a) & (b)) | (u_ & (c));         \
         l = u_ ^ (c);                         \
     }
-// adds eight one-bit masks into a six-plane vertical counter
+// adds eight one-bit masks into an eight-plane vertical counter
 #define MDG_ADD8(c, m0, m1, m2, m3, m4, m5, m6, m7)                 \
     {                                                               \
         uint32_t a1, b1, c1, d1, a2, b2, a4, k;                     \
@@ -94,7 +112,9 @@ __device__ __forceinline__ uint32_t bit_range(int lo, int hi)
         MDG_CSA(a4, c[2], c[2], a2, b2)                             \
         k = c[3] & a4; c[3] ^= a4;                                  \
         a4 = c[4] & k; c[4] ^= k;                                   \
-        c[5] ^= a4;                                                 \
+        k = c[5] & a4; c[5] ^= a4;                                  \
+        a4 = c[6] & k; c[6] ^= k;                                   \
+        c[7] ^= a4;                                                 \
     }
 
 #ifdef MDG_PHASE_CLOCKS
@@ -119,11 +139,26 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
     uint32_t *const s_lg = s_mask + 2 * WPR_MAX;                                // [kind][strand][MDG_LG_SMEM_BINS]
     uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;                       // [end][strand][L]
     uint32_t *const s_ctl_base = s_clip + 4 * L;                                // two sets of {n_fwd, n_rev, n_cx, min cols, max cols, n_ix, -, -}
+    // the tile's stretch of seq4, brought in by one bulk asynchronous copy (cp.async.bulk, completion on an mbarrier)
+    // while the tile before is counted
+    uint32_t *const s_sub = s_ctl_base + 16;                                    // [strand][12 substitution classes][32 * WPR_MAX window bits]
+    uint32_t *const s_seq = (uint32_t *)(((uintptr_t)(s_sub + 2 * 12 * 32 * WPR_MAX) + 15) & ~(uintptr_t)15);
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ int32_t s_slab[2];  // first seq4 word held in s_seq (may be negative: the words in front of the array), words (0: no copy)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < PL_WIDE * PL_CLASSES * nthreads; i += nthreads) s_wide[i] = 0;
     for (int i = tid; i < 4 * MDG_LG_SMEM_BINS + 4 * L; i += nthreads) s_lg[i] = 0;
+    for (int i = tid; i < 2 * 12 * 32 * WPR_MAX; i += nthreads) s_sub[i] = 0;
 
+    const uint32_t mbar_addr = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        s_slab[0] = 0;
+        s_slab[1] = 0;
+    }
+    uint32_t slab_phase = 0;  // bulk copies waited for so far (the mbarrier's phase parity)
     const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
     const uint4 *__restrict__ planes = ref.planes;
     const uint32_t *const subset = sub.list ? sub.list + sub.offsets[sub.lib] : nullptr;
@@ -140,11 +175,12 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
     const int pairs = (nthreads >> 7) * 32;
     auto slots_of = [&](int columns) { return (pairs / words_of(columns)) & ~1; };
     bool active;
-    int ws, slot, strand;
+    int ws, slot, strand, mode_slots;
     auto set_mode = [&](int columns) {
         mode = columns;
         const int wpr = words_of(columns);
-        active = pair < wpr * slots_of(columns);
+        mode_slots = slots_of(columns);
+        active = pair < wpr * mode_slots;
         ws = pair % wpr;
         slot = pair / wpr;
         strand = slot & 1;
@@ -174,27 +210,27 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
     for (int c = 0; c < PL_CLASSES; ++c)
 #pragma unroll
         for (int k = 0; k < PL_REG; ++k) cnt[c][k] = 0;
-    int n_iter = 0;  // eight-read iterations since planes 4 and 5 were moved up
+    int n_iter = 0;  // eight-read iterations since planes 4 .. 7 were moved up
     uint32_t *const my_wide = s_wide + tid;  // plane k of class c at my_wide[(k * PL_CLASSES + c) * nthreads]
 
-    // planes 4 and 5 of the register counters -> the wide counters in shared memory
+    // planes 4 .. 7 of the register counters -> the wide counters in shared memory (a ripple-carry add, plane by plane)
     auto spill = [&]() {
 #pragma unroll
         for (int c = 0; c < PL_CLASSES; ++c) {
             uint32_t *w = my_wide + c * nthreads;
-            const uint32_t w0 = w[0], v4 = cnt[c][4], v5 = cnt[c][5];
-            w[0] = w0 ^ v4;
-            uint32_t carry = w0 & v4;
-            const uint32_t w1 = w[PL_CLASSES * nthreads];
-            w[PL_CLASSES * nthreads] = w1 ^ v5 ^ carry;
-            carry = (w1 & v5) | ((w1 ^ v5) & carry);
-            for (int k = 2; carry && k < PL_WIDE; ++k) {
+            uint32_t carry = 0;
+#pragma unroll
+            for (int k = 0; k < PL_REG - 4; ++k) {
+                const uint32_t wk = w[k * PL_CLASSES * nthreads], v = cnt[c][4 + k];
+                w[k * PL_CLASSES * nthreads] = wk ^ v ^ carry;
+                carry = (wk & v) | ((wk ^ v) & carry);
+                cnt[c][4 + k] = 0;
+            }
+            for (int k = PL_REG - 4; carry && k < PL_WIDE; ++k) {
                 const uint32_t wk = w[k * PL_CLASSES * nthreads];
                 w[k * PL_CLASSES * nthreads] = wk ^ carry;
                 carry &= wk;
             }
-            cnt[c][4] = 0;
-            cnt[c][5] = 0;
         }
         n_iter = 0;
     };
@@ -234,8 +270,8 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
         if (active) {
 #pragma unroll
             for (int c = 0; c < PL_CLASSES; ++c) {
-                // class of the tables: R_g, H_g, P_g*
-                const int cls = c == 0 ? group : c == 1 ? 4 + group : 8 + 3 * group + (c - 2);
+                // class of the tables: R_g, H_g
+                const int cls = c == 0 ? group : 4 + group;
                 uint32_t pl[4 + PL_WIDE];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) pl[k] = cnt[c][k];
@@ -262,9 +298,14 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
         __syncthreads();
         for (int i = tid; i < PL_WIDE * PL_CLASSES * nthreads; i += nthreads) s_wide[i] = 0;
         for (int cell = tid; cell < 2 * 20 * bits; cell += nthreads) {
-            const unsigned long long sum = red[cell];
-            if (!sum) continue;
             const int bit = cell % bits, cls = (cell / bits) % 20, cstrand = cell / (20 * bits);
+            unsigned long long sum = red[cell];
+            if (cls >= 8) {  // substitution classes: counted one event at a time
+                uint32_t *const from = s_sub + ((size_t)cstrand * 12 + (cls - 8)) * 32 * WPR_MAX + bit;
+                sum = *from;
+                *from = 0;
+            }
+            if (!sum) continue;
             if (mode) {
                 const int pos = bit - A;  // column
                 if (pos < 0) add_cell(0, cstrand, cls, pos, sum);                          // left flank
@@ -291,42 +332,40 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
     bool dirty = false;
 
     // ---- stage: the plane words of one window of one read ----
-    // window bit J (word k = J >> 5) is column c_start + J of the alignment
-    auto stage_window = [&](const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side) {
+    // window bit J (word k = J >> 5) is column c_start + J of the alignment.  kNW > 0: the word count is known at
+    // compile time, all loads of the window are issued before the first use; kNW = 0: any count, word by word.
+    auto stage_window = [&](auto nw_tag, const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
+                            int slab_w0, int slab_words) {
+        constexpr int kNW = decltype(nw_tag)::value;
         const int cols = (int)(rec.cols & 0x7FFF);
         const int v = (int)(rec.misc & 0xFFFF);
         const int lf = (int)((rec.cols >> 16) & 0xFF), rf = (int)(rec.cols >> 24);
         const bool typical = lf == A && rf == A && (mode || v == L);
         // read: nibble index of window bit 0, eight bases per seq4 word
         const int64_t qn = (int64_t)rec.q0 + c_start;
-        const uint32_t *qp = seq32 + (qn >> 3);
         const int qs = (int)(qn & 7);
+        // from the tile's copy in shared memory when the window's words all lie inside it, else from global memory
+        const int64_t qw = qn >> 3, in_slab = qw - slab_w0;
+        const bool from_smem = slab_words > 0 && in_slab >= 0 && in_slab + 4 * (kNW > 0 ? kNW : n_words) + 1 <= slab_words;
+        const uint32_t *const qs_ptr = s_seq + (from_smem ? in_slab : 0), *const qg_ptr = seq32 + qw;
+        auto seq_word = [&](int m) { return from_smem ? qs_ptr[m] : __ldg(qg_ptr + m); };
         // genome: 32 bases per uint4
         const int64_t rn = ((int64_t)rec.rg << 5) + (int)((rec.misc >> 16) & 31) + c_start;
         const uint4 *rp = planes + (rn >> 5);
         const int rs = (int)(rn & 31);
-        uint32_t carry_t = nibbles_to_planes(natural_order(__ldg(qp)));
-        uint4 g_lo = __ldg(rp);
-        for (int k = 0; k < n_words; ++k) {
-            const uint32_t t0 = carry_t;
-            const uint32_t t1 = nibbles_to_planes(natural_order(__ldg(qp + 4 * k + 1)));
-            const uint32_t t2 = nibbles_to_planes(natural_order(__ldg(qp + 4 * k + 2)));
-            const uint32_t t3 = nibbles_to_planes(natural_order(__ldg(qp + 4 * k + 3)));
-            const uint32_t t4 = nibbles_to_planes(natural_order(__ldg(qp + 4 * k + 4)));
-            carry_t = t4;
+        // one window word from five transposed seq4 words and two genome entries
+        auto emit = [&](int k, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, const uint4 &g_lo, const uint4 &g_hi) {
             // plane p: bytes p of t0..t3, then eight more bits from t4, shifted to the window
             const uint32_t lo01a = __byte_perm(t0, t1, 0x0040), lo23a = __byte_perm(t2, t3, 0x0040);
             const uint32_t lo01c = __byte_perm(t0, t1, 0x0051), lo23c = __byte_perm(t2, t3, 0x0051);
             const uint32_t lo01g = __byte_perm(t0, t1, 0x0062), lo23g = __byte_perm(t2, t3, 0x0062);
             const uint32_t lo01t = __byte_perm(t0, t1, 0x0073), lo23t = __byte_perm(t2, t3, 0x0073);
-            uint32_t xa = __funnelshift_r(__byte_perm(lo01a, lo23a, 0x5410), t4 & 0xFFu, qs);
-            uint32_t xc = __funnelshift_r(__byte_perm(lo01c, lo23c, 0x5410), (t4 >> 8) & 0xFFu, qs);
-            uint32_t xg = __funnelshift_r(__byte_perm(lo01g, lo23g, 0x5410), (t4 >> 16) & 0xFFu, qs);
-            uint32_t xt = __funnelshift_r(__byte_perm(lo01t, lo23t, 0x5410), t4 >> 24, qs);
-            const uint4 g_hi = __ldg(rp + k + 1);
-            uint32_t ya = __funnelshift_r(g_lo.x, g_hi.x, rs), yc = __funnelshift_r(g_lo.y, g_hi.y, rs);
-            uint32_t yg = __funnelshift_r(g_lo.z, g_hi.z, rs), yt = __funnelshift_r(g_lo.w, g_hi.w, rs);
-            g_lo = g_hi;
+            const uint32_t xa = __funnelshift_r(__byte_perm(lo01a, lo23a, 0x5410), t4 & 0xFFu, qs);
+            const uint32_t xc = __funnelshift_r(__byte_perm(lo01c, lo23c, 0x5410), (t4 >> 8) & 0xFFu, qs);
+            const uint32_t xg = __funnelshift_r(__byte_perm(lo01g, lo23g, 0x5410), (t4 >> 16) & 0xFFu, qs);
+            const uint32_t xt = __funnelshift_r(__byte_perm(lo01t, lo23t, 0x5410), t4 >> 24, qs);
+            const uint32_t ya = __funnelshift_r(g_lo.x, g_hi.x, rs), yc = __funnelshift_r(g_lo.y, g_hi.y, rs);
+            const uint32_t yg = __funnelshift_r(g_lo.z, g_hi.z, rs), yt = __funnelshift_r(g_lo.w, g_hi.w, rs);
             uint32_t aligned, flank;
             if (typical) {
                 aligned = s_mask[2 * (first_word + k)];
@@ -355,6 +394,31 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
             uint4 *out = (uint4 *)(row_at + 8 * (first_word + k));
             out[0] = xs;
             out[1] = ys;
+        };
+        if constexpr (kNW > 0) {
+            uint32_t w[4 * kNW + 1];
+            uint4 gw[kNW + 1];
+#pragma unroll
+            for (int m = 0; m <= 4 * kNW; ++m) w[m] = seq_word(m);
+#pragma unroll
+            for (int k = 0; k <= kNW; ++k) gw[k] = __ldg(rp + k);
+#pragma unroll
+            for (int m = 0; m <= 4 * kNW; ++m) w[m] = bam_word_to_planes(w[m]);
+#pragma unroll
+            for (int k = 0; k < kNW; ++k) emit(k, w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3], w[4 * k + 4], gw[k], gw[k + 1]);
+        } else {
+            uint32_t carry_t = bam_word_to_planes(seq_word(0));
+            uint4 g_lo = __ldg(rp);
+            for (int k = 0; k < n_words; ++k) {
+                uint32_t t[5];
+                t[0] = carry_t;
+#pragma unroll
+                for (int j = 1; j <= 4; ++j) t[j] = bam_word_to_planes(seq_word(4 * k + j));
+                carry_t = t[4];
+                const uint4 g_hi = __ldg(rp + k + 1);
+                emit(k, t[0], t[1], t[2], t[3], t[4], g_lo, g_hi);
+                g_lo = g_hi;
+            }
         }
     };
 
@@ -385,6 +449,11 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
         uint32_t lead = 0, trail = 0, cols = 0, gap_len = 0, gap_del = 0;
         int state = 0, n_lead = 0, n_trail = 0;
         bool simple = h.c1 > h.c0;
+        if (h.c1 - h.c0 == 1 && ((0x181u >> (h.cig0 & 0xF)) & 1u)) {
+            // one match block (M, = or X): nearly every read of an untrimmed library
+            cols = h.cig0 >> 4;
+            state = 1;
+        } else
         for (uint32_t k = h.c0; k < h.c1 && simple; ++k) {
             const uint32_t w = k == h.c0 ? h.cig0 : __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
             const bool match = op == OP_M || op == OP_EQ || op == OP_X;
@@ -548,9 +617,28 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
         const uint32_t live1 = prefetch_listed_headers(blockIdx.x + (int64_t)gridDim.x, boff1, coff1);
         prefetch_listed_bases(live1, boff1, coff1);
     }
+    // one thread: the stretch of seq4 the reads of a tile occupy (reads are laid out in order: a stage thread checks
+    // that its read really lies inside), 32 bytes more in front and 48 behind for the windows' flanks, as one bulk copy
+    auto issue_slab = [&](int64_t tile_index) {
+        s_slab[1] = 0;
+        if (subset || g.seq_words <= 0 || tile_index >= n_tiles) return;
+        const int64_t r0 = tile_index * T, r1 = min(n_todo, r0 + (int64_t)T) - 1;
+        const uint64_t first = b.base_off[r0], last = (uint64_t)b.base_off[r1] + b.l_seq[r1];
+        const int64_t lo = ((int64_t)(first >> 1) - 32) & ~15ll, hi = ((int64_t)((last + 1) >> 1) + 48 + 15) & ~15ll;
+        const int64_t bytes = hi - lo;
+        if (bytes <= 0 || bytes > 4ll * g.seq_words) return;
+        s_slab[0] = (int32_t)(lo >> 2);
+        s_slab[1] = (int32_t)(bytes >> 2);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_seq);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"((uint32_t)bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"((const char *)b.seq4 + lo), "r"((uint32_t)bytes), "r"(mbar_addr)
+                     : "memory");
+    };
     int tile_parity = 0;
     if (tid < 6) s_ctl_base[tid] = tid == 3 ? 0xffffffffu : 0u;
     __syncthreads();
+    if (tid == 0) issue_slab(blockIdx.x);
 #ifdef MDG_PHASE_CLOCKS
     __shared__ unsigned int s_pc[8];
     if (tid < 8) s_pc[tid] = 0;
@@ -678,6 +766,18 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
 
         // ---- stage: one thread per (read, window) ----
         const int n_fwd = (int)s_ctl[0], n_rev = (int)s_ctl[1];
+        const int slab_w0 = s_slab[0], slab_words = s_slab[1];
+        if (slab_words) {
+            // the bulk copy of this tile's seq4 stretch was issued a tile ago: it has long landed
+            uint32_t landed;
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(landed)
+                             : "r"(mbar_addr), "r"(slab_phase & 1u)
+                             : "memory");
+            } while (!landed);
+            ++slab_phase;
+        }
         {
             const int n_windows = mode ? 1 : 2, n_items = (n_fwd + n_rev) * n_windows;
             const int wpr = words_of(mode);
@@ -686,9 +786,11 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
                 const int row = li < n_fwd ? li : T - 1 - (li - n_fwd);
                 const PlaneRecord rec = s_rec[row];
                 uint32_t *const row_at = s_stage + (size_t)row * ROW;
-                if (mode) stage_window(rec, row_at, 0, wpr, -A, 0);
-                else if (side == 0) stage_window(rec, row_at, 0, NWA, -A, 0);
-                else stage_window(rec, row_at, NWA, NWA, (int)(rec.cols & 0x7FFF) + A - 32 * NWA, 1);
+                const int n_words = mode ? wpr : NWA, first_word = side ? NWA : 0;
+                const int c_start = side ? (int)(rec.cols & 0x7FFF) + A - 32 * NWA : -A;
+                if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words);
+                else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words);
+                else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words);
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
@@ -698,10 +800,11 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
         MDG_PPHASE(3)
 
         if (tid < 6) s_ctl_next[tid] = tid == 3 ? 0xffffffffu : 0u;
+        if (tid == 0) issue_slab(tile + gridDim.x);  // lands while this tile is counted and the next one parsed
         // ---- count: this thread's window word and reference base, every stride-th read of its strand ----
         if (active) {
             const int n_mine = strand ? n_rev : n_fwd;
-            const int stride = slots_of(mode) >> 1;
+            const int stride = mode_slots >> 1;
             const int row_step = (strand ? -stride : stride) * ROW;
             const uint32_t *at0 = s_stage + (size_t)(strand ? T - 1 - (slot >> 1) : (slot >> 1)) * ROW + 8 * ws;
             // the class wiring is compile-time: a warp is uniform in the reference base G of its classes
@@ -709,29 +812,51 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
                 constexpr int G = decltype(gtag)::value;
                 constexpr int O0 = 0 + (0 >= G), O1 = 1 + (1 >= G), O2 = 2 + (2 >= G);  // the read bases other than G
                 const uint32_t *at = at0;
+                uint32_t *const my_sub = s_sub + ((size_t)strand * 12 + 3 * G) * 32 * WPR_MAX + 32 * ws;
                 for (int i = slot >> 1; i < n_mine; i += 8 * stride) {
                     uint32_t x[8][4], y[8];
+                    if (i + 7 * stride < n_mine) {  // eight reads in hand: no tests
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (i + u * stride < n_mine) {
+                        for (int u = 0; u < 8; ++u) {
                             const uint4 v = *(const uint4 *)(at + u * row_step);
                             x[u][0] = v.x; x[u][1] = v.y; x[u][2] = v.z; x[u][3] = v.w;
                             y[u] = at[u * row_step + 4 + G];
-                        } else {
-                            x[u][0] = x[u][1] = x[u][2] = x[u][3] = 0;
-                            y[u] = 0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const bool live = i + u * stride < n_mine;
+                            const uint32_t *from = live ? at + u * row_step : at;
+                            const uint4 v = *(const uint4 *)from;
+                            const uint32_t keep = live ? 0xFFFFFFFFu : 0u;
+                            x[u][0] = v.x & keep; x[u][1] = v.y & keep; x[u][2] = v.z & keep; x[u][3] = v.w & keep;
+                            y[u] = from[4 + G] & keep;
                         }
                     }
                     at += 8 * row_step;
                     MDG_ADD8(cnt[0], y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7])  // R_g
                     MDG_ADD8(cnt[1], x[0][G], x[1][G], x[2][G], x[3][G], x[4][G], x[5][G], x[6][G], x[7][G])  // H_g
-                    MDG_ADD8(cnt[2], y[0] & x[0][O0], y[1] & x[1][O0], y[2] & x[2][O0], y[3] & x[3][O0], y[4] & x[4][O0], y[5] & x[5][O0],
-                             y[6] & x[6][O0], y[7] & x[7][O0])
-                    MDG_ADD8(cnt[3], y[0] & x[0][O1], y[1] & x[1][O1], y[2] & x[2][O1], y[3] & x[3][O1], y[4] & x[4][O1], y[5] & x[5][O1],
-                             y[6] & x[6][O1], y[7] & x[7][O1])
-                    MDG_ADD8(cnt[4], y[0] & x[0][O2], y[1] & x[1][O2], y[2] & x[2][O2], y[3] & x[3][O2], y[4] & x[4][O2], y[5] & x[5][O2],
-                             y[6] & x[6][O2], y[7] & x[7][O2])
-                    if (++n_iter == 6) spill();  // planes 0-3 hold at most 15, six more iterations add 48: 63 fits six planes
+                    // substitutions (reference G, read another base) are rare: a word with none costs three
+                    // operations, an event one shared-memory atomic on the block's table
+                    uint32_t d[8], any = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        d[u] = y[u] & (x[u][O0] | x[u][O1] | x[u][O2]);
+                        any |= d[u];
+                    }
+                    if (any) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            uint32_t todo = d[u];
+                            while (todo) {
+                                const int j = __ffs(todo) - 1;
+                                todo &= todo - 1;
+                                const int n = (x[u][O0] >> j) & 1u ? 0 : (x[u][O1] >> j) & 1u ? 1 : 2;
+                                atomicAdd(my_sub + n * 32 * WPR_MAX + j, 1u);
+                            }
+                        }
+                    }
+                    if (++n_iter == 30) spill();  // planes 0-3 hold at most 15, thirty more iterations add 240: 255 fits eight planes
                 }
             };
             switch (group) {
