@@ -770,6 +770,8 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             const size_t per_read = ((size_t)pg.row_words + 4 + 2) * 4 + seq_per_read;
             int tile = 0;
             if (fixed + 192 * per_read <= ctx->smem_optin) tile = (int)std::min<size_t>(1024, (ctx->smem_optin - fixed) / per_read / 32 * 32);
+            // whole rounds of the block: a tile of 576 reads would leave 448 threads idle in the second round of every phase
+            if (tile > pg.threads) tile = tile / pg.threads * pg.threads;
             if (const char *tile_env3 = getenv("MDG_PLANES_TILE")) tile = std::min(tile, std::max(32, atoi(tile_env3)));
             pg.tile = tile;
             pg.seq_words = (int)((size_t)tile * seq_per_read / 4 / 4 * 4);

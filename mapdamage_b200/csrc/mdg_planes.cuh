@@ -335,7 +335,7 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
     // window bit J (word k = J >> 5) is column c_start + J of the alignment.  kNW > 0: the word count is known at
     // compile time, all loads of the window are issued before the first use; kNW = 0: any count, word by word.
     auto stage_window = [&](auto nw_tag, const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
-                            int slab_w0, int slab_words) {
+                            int slab_w0, int slab_words, int rstrand) {
         constexpr int kNW = decltype(nw_tag)::value;
         const int cols = (int)(rec.cols & 0x7FFF);
         const int v = (int)(rec.misc & 0xFFFF);
@@ -353,17 +353,25 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
         const int64_t rn = ((int64_t)rec.rg << 5) + (int)((rec.misc >> 16) & 31) + c_start;
         const uint4 *rp = planes + (rn >> 5);
         const int rs = (int)(rn & 31);
-        // one window word from five transposed seq4 words and two genome entries
-        auto emit = [&](int k, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, const uint4 &g_lo, const uint4 &g_hi) {
-            // plane p: bytes p of t0..t3, then eight more bits from t4, shifted to the window
-            const uint32_t lo01a = __byte_perm(t0, t1, 0x0040), lo23a = __byte_perm(t2, t3, 0x0040);
-            const uint32_t lo01c = __byte_perm(t0, t1, 0x0051), lo23c = __byte_perm(t2, t3, 0x0051);
-            const uint32_t lo01g = __byte_perm(t0, t1, 0x0062), lo23g = __byte_perm(t2, t3, 0x0062);
-            const uint32_t lo01t = __byte_perm(t0, t1, 0x0073), lo23t = __byte_perm(t2, t3, 0x0073);
-            const uint32_t xa = __funnelshift_r(__byte_perm(lo01a, lo23a, 0x5410), t4 & 0xFFu, qs);
-            const uint32_t xc = __funnelshift_r(__byte_perm(lo01c, lo23c, 0x5410), (t4 >> 8) & 0xFFu, qs);
-            const uint32_t xg = __funnelshift_r(__byte_perm(lo01g, lo23g, 0x5410), (t4 >> 16) & 0xFFu, qs);
-            const uint32_t xt = __funnelshift_r(__byte_perm(lo01t, lo23t, 0x5410), t4 >> 24, qs);
+        // one window word from five seq4 words (as BAM stores them) and two genome entries.  Plane p of eight bases:
+        // bit p of every nibble (one AND), the two nibbles of a byte side by side in base order (two shifts, one
+        // OR-AND), and the four bytes' bit pairs gathered into the top byte by one multiplication -- the shifts and the
+        // multiplication issue on the FMA pipe, which this kernel leaves idle, only two operations on the ALU pipe.
+        // q4[] carries the fifth word's plane bytes over to the next window word (its first).
+        auto plane_byte = [](uint32_t w, int pl) {
+            const uint32_t y = (pl ? shr_fma(w, pl) : w) & 0x11111111u;
+            return ((shr_fma(y, 4) | shl_fma(y, 1)) & 0x03030303u) * 0x01041040u;  // the plane's eight bits in bits 24..31
+        };
+        auto emit = [&](int k, uint32_t (&q0)[4], uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, const uint4 &g_lo, const uint4 &g_hi) {
+            uint32_t xp[4];
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl) {
+                const uint32_t q1 = plane_byte(w1, pl), q2 = plane_byte(w2, pl), q3 = plane_byte(w3, pl), q4 = plane_byte(w4, pl);
+                const uint32_t lo = __byte_perm(__byte_perm(q0[pl], q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
+                xp[pl] = __funnelshift_r(lo, q4 >> 24, qs);
+                q0[pl] = q4;
+            }
+            const uint32_t xa = xp[0], xc = xp[1], xg = xp[2], xt = xp[3];
             const uint32_t ya = __funnelshift_r(g_lo.x, g_hi.x, rs), yc = __funnelshift_r(g_lo.y, g_hi.y, rs);
             const uint32_t yg = __funnelshift_r(g_lo.z, g_hi.z, rs), yt = __funnelshift_r(g_lo.w, g_hi.w, rs);
             uint32_t aligned, flank;
@@ -394,6 +402,23 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
             uint4 *out = (uint4 *)(row_at + 8 * (first_word + k));
             out[0] = xs;
             out[1] = ys;
+            // substitutions (reference g read as another base b) are rare events: one shared-memory atomic each on the
+            // block's table, here where one thread sees all of a read's window word; the counting loop keeps the
+            // dense classes R_g and H_g only
+            uint32_t ev = (ys.x | ys.y | ys.z | ys.w) & keep & ~((xs.x & ys.x) | (xs.y & ys.y) | (xs.z & ys.z) | (xs.w & ys.w));
+            if (ev) {
+                // base code of a one-hot quadruple of planes: bit 0 from planes C | T, bit 1 from planes G | T
+                const uint32_t g1 = ys.y | ys.w, g2 = ys.z | ys.w, r1 = xs.y | xs.w, r2 = xs.z | xs.w;
+                uint32_t *const to = s_sub + (size_t)rstrand * 12 * 32 * WPR_MAX + 32 * (first_word + k);
+                do {
+                    const int j = __ffs(ev) - 1;
+                    ev &= ev - 1;
+                    const int gb = (int)((g1 >> j) & 1u) + 2 * (int)((g2 >> j) & 1u);
+                    int rb = (int)((r1 >> j) & 1u) + 2 * (int)((r2 >> j) & 1u);
+                    rb -= rb > gb ? 1 : 0;
+                    atomicAdd(to + (3 * gb + rb) * 32 * WPR_MAX + j, 1u);
+                } while (ev);
+            }
         };
         if constexpr (kNW > 0) {
             uint32_t w[4 * kNW + 1];
@@ -402,21 +427,23 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
             for (int m = 0; m <= 4 * kNW; ++m) w[m] = seq_word(m);
 #pragma unroll
             for (int k = 0; k <= kNW; ++k) gw[k] = __ldg(rp + k);
+            uint32_t q0[4];
 #pragma unroll
-            for (int m = 0; m <= 4 * kNW; ++m) w[m] = bam_word_to_planes(w[m]);
+            for (int pl = 0; pl < 4; ++pl) q0[pl] = plane_byte(w[0], pl);
 #pragma unroll
-            for (int k = 0; k < kNW; ++k) emit(k, w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3], w[4 * k + 4], gw[k], gw[k + 1]);
+            for (int k = 0; k < kNW; ++k) emit(k, q0, w[4 * k + 1], w[4 * k + 2], w[4 * k + 3], w[4 * k + 4], gw[k], gw[k + 1]);
         } else {
-            uint32_t carry_t = bam_word_to_planes(seq_word(0));
+            uint32_t q0[4];
+            {
+                const uint32_t w0 = seq_word(0);
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) q0[pl] = plane_byte(w0, pl);
+            }
             uint4 g_lo = __ldg(rp);
             for (int k = 0; k < n_words; ++k) {
-                uint32_t t[5];
-                t[0] = carry_t;
-#pragma unroll
-                for (int j = 1; j <= 4; ++j) t[j] = bam_word_to_planes(seq_word(4 * k + j));
-                carry_t = t[4];
+                const uint32_t w1 = seq_word(4 * k + 1), w2 = seq_word(4 * k + 2), w3 = seq_word(4 * k + 3), w4 = seq_word(4 * k + 4);
                 const uint4 g_hi = __ldg(rp + k + 1);
-                emit(k, t[0], t[1], t[2], t[3], t[4], g_lo, g_hi);
+                emit(k, q0, w1, w2, w3, w4, g_lo, g_hi);
                 g_lo = g_hi;
             }
         }
@@ -788,9 +815,9 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
                 uint32_t *const row_at = s_stage + (size_t)row * ROW;
                 const int n_words = mode ? wpr : NWA, first_word = side ? NWA : 0;
                 const int c_start = side ? (int)(rec.cols & 0x7FFF) + A - 32 * NWA : -A;
-                if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words);
-                else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words);
-                else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words);
+                if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, li >= n_fwd);
+                else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, li >= n_fwd);
+                else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, li >= n_fwd);
             }
         }
         if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
@@ -810,52 +837,26 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
             // the class wiring is compile-time: a warp is uniform in the reference base G of its classes
             auto count_tile = [&](auto gtag) {
                 constexpr int G = decltype(gtag)::value;
-                constexpr int O0 = 0 + (0 >= G), O1 = 1 + (1 >= G), O2 = 2 + (2 >= G);  // the read bases other than G
                 const uint32_t *at = at0;
-                uint32_t *const my_sub = s_sub + ((size_t)strand * 12 + 3 * G) * 32 * WPR_MAX + 32 * ws;
                 for (int i = slot >> 1; i < n_mine; i += 8 * stride) {
-                    uint32_t x[8][4], y[8];
+                    uint32_t xg[8], y[8];
                     if (i + 7 * stride < n_mine) {  // eight reads in hand: no tests
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const uint4 v = *(const uint4 *)(at + u * row_step);
-                            x[u][0] = v.x; x[u][1] = v.y; x[u][2] = v.z; x[u][3] = v.w;
+                            xg[u] = at[u * row_step + G];
                             y[u] = at[u * row_step + 4 + G];
                         }
                     } else {
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const bool live = i + u * stride < n_mine;
-                            const uint32_t *from = live ? at + u * row_step : at;
-                            const uint4 v = *(const uint4 *)from;
-                            const uint32_t keep = live ? 0xFFFFFFFFu : 0u;
-                            x[u][0] = v.x & keep; x[u][1] = v.y & keep; x[u][2] = v.z & keep; x[u][3] = v.w & keep;
-                            y[u] = from[4 + G] & keep;
+                            xg[u] = live ? at[u * row_step + G] : 0u;
+                            y[u] = live ? at[u * row_step + 4 + G] : 0u;
                         }
                     }
                     at += 8 * row_step;
                     MDG_ADD8(cnt[0], y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7])  // R_g
-                    MDG_ADD8(cnt[1], x[0][G], x[1][G], x[2][G], x[3][G], x[4][G], x[5][G], x[6][G], x[7][G])  // H_g
-                    // substitutions (reference G, read another base) are rare: a word with none costs three
-                    // operations, an event one shared-memory atomic on the block's table
-                    uint32_t d[8], any = 0;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        d[u] = y[u] & (x[u][O0] | x[u][O1] | x[u][O2]);
-                        any |= d[u];
-                    }
-                    if (any) {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            uint32_t todo = d[u];
-                            while (todo) {
-                                const int j = __ffs(todo) - 1;
-                                todo &= todo - 1;
-                                const int n = (x[u][O0] >> j) & 1u ? 0 : (x[u][O1] >> j) & 1u ? 1 : 2;
-                                atomicAdd(my_sub + n * 32 * WPR_MAX + j, 1u);
-                            }
-                        }
-                    }
+                    MDG_ADD8(cnt[1], xg[0], xg[1], xg[2], xg[3], xg[4], xg[5], xg[6], xg[7])  // H_g
                     if (++n_iter == 30) spill();  // planes 0-3 hold at most 15, thirty more iterations add 240: 255 fits eight planes
                 }
             };
