@@ -82,7 +82,8 @@ typedef struct {
  *   lib       NULL: every read is in library 0
  *   tlen      NULL: 0 (only read for proper-pair first mates, statistics.py:121-124)
  *   mtid/mpos NULL: -1 (only read by the rescale pairing rule, rescale.py:318-337)
- *   cigar_off NULL: every read has exactly one CIGAR op, cigar[i] (n_cigar == n_reads)
+ *   cigar_off NULL: every read has exactly one CIGAR op: cigar[i] (n_cigar == n_reads), or the one word cigar[0]
+ *                   all reads share (n_cigar == 1: untrimmed reads of one length, all "100M")
  *   base_off  NULL: reads are packed back to back, each starting on an even base:
  *                   base_off[i] = sum over k < i of (l_seq[k] rounded up to even)
  */

@@ -105,6 +105,8 @@ class ReadBatch:
                     drop.update(("mtid", "mpos"))
                 if self.cigar.shape[0] == n and np.array_equal(self.cigar_off, np.arange(n + 1, dtype=np.uint32)):
                     drop.add("cigar_off")
+                    if n > 1 and (self.cigar == self.cigar[0]).all():
+                        drop.add("cigar")  # one CIGAR word shared by every read: a single word crosses PCIe
                 padded = (self.l_seq.astype(np.int64) + 1) & ~1
                 packed = np.zeros(n, dtype=np.int64)
                 np.cumsum(padded[:-1], out=packed[1:])

@@ -241,8 +241,9 @@ int check_batch(mdg_ctx *ctx, const mdg_batch *h)
         return fail(ctx, MDG_ERR_ARGUMENT, "batch too large: split it (offsets are 32-bit)");
     if (h->n_reads && (!h->flag || !h->pos || (h->n_cigar && !h->cigar) || (h->n_bases && !h->seq4)))
         return fail(ctx, MDG_ERR_ARGUMENT, "batch lacks a required array (flag, pos, cigar, seq4)");
-    if (h->n_reads && !h->cigar_off && h->n_cigar != h->n_reads)
-        return fail(ctx, MDG_ERR_ARGUMENT, "cigar_off may only be NULL when every read has exactly one CIGAR op");
+    if (h->n_reads && !h->cigar_off && h->n_cigar != h->n_reads && h->n_cigar != 1)
+        return fail(ctx, MDG_ERR_ARGUMENT, "cigar_off may only be NULL when every read has exactly one CIGAR op "
+                                           "(n_cigar = n_reads words, or n_cigar = 1: the one word all reads share)");
     return MDG_OK;
 }
 
@@ -266,7 +267,16 @@ int copy_batch(mdg_ctx *ctx, DeviceArrays &a, const mdg_batch *h, cudaStream_t s
     MDG_CUDA(ctx, cudaMemsetAsync((void *)a.view.field, byte, (size_t)(bytes), stream))
     MDG_H2D(flag, n * 2);
     MDG_H2D(pos, n * 4);
-    MDG_H2D(cigar, h->n_cigar * 4);
+    const bool shared_cigar = !h->cigar_off && h->n_cigar == 1 && n > 1;  // one CIGAR word for every read
+    if (shared_cigar) {
+        if (n > a.cap_cigar) return fail(ctx, MDG_ERR_CAPACITY, "batch of %lld reads exceeds the slot's CIGAR capacity (%lld)", (long long)n, (long long)a.cap_cigar);
+        mdg::fill_words<<<(unsigned)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, stream>>>((uint32_t *)a.view.cigar, n, h->cigar[0]);
+        MDG_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        a.n_cigar = n;
+    } else {
+        MDG_H2D(cigar, h->n_cigar * 4);
+    }
     MDG_H2D(seq4, h->n_bases / 2);
     if (h->tid) MDG_H2D(tid, n * 4);
     else MDG_FILL(tid, 0, n * 4);
@@ -946,7 +956,8 @@ int mdg_batch_upload(mdg_ctx *ctx, const mdg_batch *host, mdg_dev_batch **out)
     MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     mdg_dev_batch *d = new (std::nothrow) mdg_dev_batch();
     if (!d) return fail(ctx, MDG_ERR_ARGUMENT, "out of host memory");
-    rc = alloc_arrays(ctx, d->arrays, host->n_reads, host->n_cigar, host->n_bases, host->qual != nullptr);
+    const int64_t cigar_words = !host->cigar_off && host->n_cigar == 1 ? std::max<int64_t>(host->n_reads, 1) : host->n_cigar;
+    rc = alloc_arrays(ctx, d->arrays, host->n_reads, cigar_words, host->n_bases, host->qual != nullptr);
     if (!rc) rc = copy_batch(ctx, d->arrays, host, ctx->compute, true, true);
     if (!rc && cudaStreamSynchronize(ctx->compute) != cudaSuccess)
         rc = fail(ctx, MDG_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -1506,14 +1506,20 @@ __global__ void __launch_bounds__(DEFLATE_THREADS) bgzf_deflate_kernel(const uin
             }
             node_depth[i] = (uint8_t)d;
         }
-        // zlib's gen_bitlen: move leaves up until the code fits 15 bits
-        while (overflow > 0) {
-            int bits = 14;
-            while (bl_count[bits] == 0) --bits;
-            --bl_count[bits];
-            bl_count[bits + 1] += 2;
-            --bl_count[15];
-            overflow -= 2;
+        // leaves deeper than 15 were put at 15, which over-subscribes the code: Kraft sum * 2^15 exceeds 2^15.  As
+        // zlib's gen_bitlen does, a leaf of depth b < 15 is replaced by an inner node whose two children are that leaf
+        // and one of the leaves at 15: -2^(15-b) + 2 * 2^(14-b) - 1, one unit less per step, until the code is complete
+        if (overflow > 0) {
+            int excess = -(1 << 15);
+            for (int bits = 1; bits <= 15; ++bits) excess += bl_count[bits] << (15 - bits);
+            while (excess > 0) {
+                int bits = 14;
+                while (bl_count[bits] == 0) --bits;
+                --bl_count[bits];
+                bl_count[bits + 1] += 2;
+                --bl_count[15];
+                --excess;
+            }
         }
         // lengths by rank: the rarest symbols get the longest codes
         {

@@ -188,6 +188,11 @@ __global__ void __launch_bounds__(256) layout_fill(const uint32_t *__restrict__ 
     }
 }
 
+__global__ void __launch_bounds__(256) fill_words(uint32_t *to, int64_t n, uint32_t word)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) to[i] = word;
+}
+
 // l_seq of a batch passed without it: the bases its CIGAR consumes from the read (M, I, S, =, X).
 // cigar_off == null: one op per read.
 __global__ void __launch_bounds__(256) lseq_from_cigar(const uint32_t *__restrict__ cigar, const uint32_t *__restrict__ cigar_off,

@@ -34,7 +34,9 @@ def batch_struct(batch, compact=False):
     s.n_bases = n_bases
     drop = batch.droppable() if compact else ()
     for name in _FIELDS:
-        setattr(s, name, None if name in drop else getattr(batch, name).ctypes.data)
+        setattr(s, name, None if name in drop and name != "cigar" else getattr(batch, name).ctypes.data)
+    if "cigar" in drop:
+        s.n_cigar = 1  # every read has the CIGAR word cigar[0] (mdg_batch: cigar_off NULL, n_cigar == 1)
     s.qual = None if qual is None else qual.ctypes.data
     return s
 
@@ -216,7 +218,7 @@ class DamageEngine:
         """Bytes ``count`` (or ``rescale``) copies to the device for ``batch`` (see ``copy_batch``)."""
         n = batch.n
         drop = batch.droppable() if compact else ()
-        total = n * (2 + 4) + batch.cigar.nbytes + batch.total_bases // 2  # flag, pos, cigar, seq4
+        total = n * (2 + 4) + (4 if "cigar" in drop else batch.cigar.nbytes) + batch.total_bases // 2  # flag, pos, cigar, seq4
         total += sum(size for name, size in (("tid", 4 * n), ("l_seq", 4 * n), ("lib", 2 * n), ("tlen", 4 * n),
                                              ("base_off", 4 * n), ("cigar_off", 4 * (n + 1))) if name not in drop)
         if rescale:

@@ -185,3 +185,29 @@ def test_sparse_rescale_returns_only_what_changed():
         assert np.array_equal(status, want_status) and np.array_equal(mr[status == 1], want_mr[status == 1])
         assert np.array_equal(patched.qual[:batch.total_bases], want_qual[:batch.total_bases])
         assert 0 < changed == int((want_qual[:batch.total_bases] != batch.qual[:batch.total_bases]).sum())
+
+
+def test_encoder_limits_code_lengths(tmp_path):
+    """Byte frequencies that fall off like Fibonacci numbers make a Huffman tree deeper than DEFLATE's 15 bits: the
+    device encoder has to rebalance it (zlib's gen_bitlen), and every block must still inflate (gzip checks CRC32 and
+    ISIZE of each)."""
+    reference = synth.make_reference([300_000], seed=3)
+    batch = synth.simulate_reads(reference, 40_000, seed=9, length=(150, 150), mix=(1, 0, 0, 0), paired=False)
+    rng = np.random.default_rng(5)
+    weights = np.array([1.618 ** -k for k in range(40)])
+    batch.qual[:] = rng.choice(np.arange(2, 42, dtype=np.uint8), size=batch.qual.shape[0], p=weights / weights.sum())
+    header = SamHeader()
+    header.add("@HD\tVN:1.6\tSO:unsorted")
+    header.add("@SQ\tSN:%s\tLN:%d" % (reference.names[0], reference.lengths[0]))
+    src, out = tmp_path / "in.bam", tmp_path / "out.bam"
+    with BamWriter(src, header, threads=2) as writer:
+        writer.write_soa(batch, first_index=0)
+    with DamageEngine(max_reads=0) as engine:
+        with DeviceBamStream(engine, src, merge_libraries=True, apply_filter=False) as stream, BamWriter(out, stream.header) as writer:
+            for dev in stream:
+                stream.encode(dev, writer)
+            stream.flush()
+    with gzip.open(src, "rb") as a, gzip.open(out, "rb") as b:
+        assert a.read() == b.read()
+    with BamReader(out, merge_libraries=True, apply_filter=False) as reader:  # and the native host decoder agrees
+        assert sum(part.n for part in reader) == batch.n

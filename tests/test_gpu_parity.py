@@ -267,7 +267,7 @@ def test_optional_arrays_default_on_device(name):
     batch = synth.simulate_reads(reference, 30_000, seed=21, **SYNTH[name])
     assert {"base_off", "lib", "l_seq"} <= batch.droppable()
     if name == "se100_noqual":
-        assert {"cigar_off", "tlen"} <= batch.droppable()
+        assert {"cigar_off", "tlen", "cigar"} <= batch.droppable()  # "cigar": one word ("100M") shared by every read
     tables = []
     for compact in (False, True):
         with DamageEngine(max_reads=batch.n, max_cigar_ops=batch.cigar.shape[0], max_bases=batch.total_bases) as engine:
@@ -293,6 +293,8 @@ def test_optional_arrays_default_on_device(name):
 
 @pytest.mark.parametrize("env", [{}, {"MDG_SWAR_FLUSH_TILES": "3"}, {"MDG_SWAR_UNIFORM": "0"}, {"MDG_STAGE_THREADS": "256"},
                                  {"MDG_STAGE_TILE": "96"}, {"MDG_STAGE_INDELS": "1"}, {"MDG_STAGE_INDELS": "0"}, {"MDG_KERNEL": "swar"},
+                                 {"MDG_KERNEL": "staged"}, {"MDG_KERNEL": "staged", "MDG_SWAR_FLUSH_TILES": "3"},
+                                 {"MDG_PLANES_TILE": "224", "MDG_SWAR_FLUSH_TILES": "2"}, {"MDG_PLANES_SLAB": "0"},
                                  {"MDG_KERNEL": "swar", "MDG_SWAR_VARIANT": "512,1", "MDG_SWAR_FLUSH_TILES": "2"}])
 @pytest.mark.parametrize("min_qual", [0, 25])
 def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
