@@ -291,8 +291,6 @@ typedef struct mdg_bam_reader mdg_bam_reader;
 typedef struct mdg_bam_writer mdg_bam_writer;
 
 int mdg_bam_open(const char *path, int32_t n_threads, mdg_bam_reader **out);
-/* The same with mdg_bam_use_device(reader, device) in force from the first slab (device < 0: host decoders). */
-int mdg_bam_open_on(const char *path, int32_t n_threads, int32_t device, mdg_bam_reader **out);
 void mdg_bam_close(mdg_bam_reader *reader);
 /* Message of the last failure (reader may be NULL for mdg_bam_open failures). */
 const char *mdg_bam_error(const mdg_bam_reader *reader);
@@ -331,16 +329,6 @@ int mdg_bam_lenient_libraries(mdg_bam_reader *reader, int32_t on);
 int64_t mdg_bam_library_failure(const mdg_bam_reader *reader, int64_t k, char *buf, int64_t cap);
 /* Records walked so far, dropped ones included. */
 int64_t mdg_bam_records_seen(const mdg_bam_reader *reader);
-/*
- * From the next slab on, BGZF blocks are inflated on GPU `device` (mdg_inflate_blocks: 256 MB slabs, one launch each)
- * instead of on the host threads; blocks the GPU turns down or gets wrong (CRC32, checked on the host for every
- * block) are inflated on the host as before.  device < 0 switches back.  mdg_bam_device_blocks: how many blocks the
- * GPU has delivered so far.  Off unless asked for: one thread per block needs far more blocks in flight than a slab
- * holds before it beats sixteen host threads.
- */
-int mdg_bam_use_device(mdg_bam_reader *reader, int32_t device);
-int64_t mdg_bam_device_blocks(const mdg_bam_reader *reader);
-
 /*
  * The same file decoded on the GPU of a context (csrc/mdg_bamdev.cuh): the host only reads the file, slab by slab, into
  * page-locked memory; BGZF inflate, CRC32 check, record boundaries (guessed per 32 KB segment, then verified against the
@@ -384,7 +372,7 @@ int64_t mdg_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t
  * out[out_off[i]]; one thread decodes one block, so the call is worth it from a few thousand blocks up.  `in` and `out`
  * are host buffers (copied whole: in_bytes, out_bytes); status[i] is 0 where block i came out with the right length.
  * The inflater owns its stream and device buffers and may be used from another thread than the mdg_ctx of the same
- * device.  mdg_bam_use_device() makes a reader inflate its slabs this way.
+ * device.  The same kernel inflates the slabs of mdg_bam_stream_next, which keeps the bytes in HBM.
  */
 typedef struct mdg_inflater mdg_inflater;
 int mdg_inflater_create(int32_t device, mdg_inflater **out);

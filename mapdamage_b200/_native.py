@@ -106,9 +106,6 @@ SYMBOLS = {
     "mdg_rescale_submit_sparse": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "mdg_rescale_collect": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
     "mdg_rescale_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "mdg_bam_open_on": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
-    "mdg_bam_use_device": (C.c_int, [C.c_void_p, C.c_int32]),
-    "mdg_bam_device_blocks": (C.c_int64, [C.c_void_p]),
     "mdg_inflate_raw": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "mdg_inflater_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "mdg_inflater_free": (None, [C.c_void_p]),

@@ -23,14 +23,12 @@ class BamReader:
     ``libraries`` is the sorted ``(sample, library)`` list indexing the count slabs.
     """
 
-    def __init__(self, path, threads=0, merge_libraries=False, apply_filter=True, device=None, lenient_libraries=False):
-        """``device``: inflate the BGZF blocks on that GPU (``mdg_bam_use_device``) instead of on host threads.
-        ``lenient_libraries``: a read without a usable read group does not fail its batch; it gets library 0xFFFF and
+    def __init__(self, path, threads=0, merge_libraries=False, apply_filter=True, lenient_libraries=False):
+        """``lenient_libraries``: a read without a usable read group does not fail its batch; it gets library 0xFFFF and
         :meth:`library_failures` lists such reads (the caller down-samples first, then decides: ``reader.py:134-164``)."""
         self._lib = _native.load()
         self._reader = C.c_void_p()
-        code = self._lib.mdg_bam_open_on(str(path).encode(), threads, -1 if device is None else int(device),
-                                         C.byref(self._reader))
+        code = self._lib.mdg_bam_open(str(path).encode(), threads, C.byref(self._reader))
         if code < 0:
             raise BAMError((self._lib.mdg_bam_error(None) or b"").decode())
         text = C.create_string_buffer(int(self._lib.mdg_bam_header_text(self._reader, None, 0)) + 1)
@@ -88,11 +86,6 @@ class BamReader:
             if index < 0:
                 return out
             out.append((int(index), buf.value.decode("utf-8", "replace")))
-
-    @property
-    def device_blocks(self):
-        """BGZF blocks inflated on the GPU so far."""
-        return int(self._lib.mdg_bam_device_blocks(self._reader))
 
     @property
     def records_seen(self):

@@ -123,11 +123,6 @@ struct mdg_bam_reader {
     FILE *fp = nullptr;
     int n_threads = 1;
     bool native_inflate = true;  // MDG_BAM_ZLIB=1: zlib only (A/B runs, tests)
-    // inflate on the GPU (mdg_bam_use_device): the producer thread makes the inflater the first time it sees the wish
-    std::atomic<int> want_device{-1};
-    mdg_inflater *inflater = nullptr;
-    bool inflater_failed = false;
-    std::atomic<int64_t> blocks_on_device{0}, blocks_on_host{0};
     std::string error;
     std::string header_text;
     std::vector<std::string> ref_names;
@@ -188,7 +183,6 @@ static double now_s()
 }
 
 constexpr size_t SLAB_BYTES = 32u << 20;
-constexpr size_t SLAB_BYTES_DEVICE = 256u << 20;  // the GPU inflates a slab in one launch: the more blocks the better
 
 // Producer side: reads one slab of the file, cuts it into BGZF blocks and inflates them in parallel.
 void fill_chunk(mdg_bam_reader *r, Chunk &c)
@@ -197,34 +191,9 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
     c.error = 0;
     c.last = false;
     c.compressed.len = 0;
-    // the GPU inflater, when asked for: made here, on the thread that uses it
-    const int device = r->want_device.load();
-    if (device >= 0 && !r->inflater && !r->inflater_failed) {
-        if (mdg_inflater_create(device, &r->inflater) != MDG_OK) {
-            r->inflater = nullptr;
-            r->inflater_failed = true;  // no device: the host decoders do all of it
-        }
-    }
-    const bool on_device = r->inflater != nullptr;
-    size_t SLAB = on_device ? SLAB_BYTES_DEVICE : r->slab_bytes;
-    if (on_device) {
-        // no more than what is left of a regular file: the slab is page-locked memory
-        struct stat st;
-        const long at = ftell(r->fp);
-        if (fstat(fileno(r->fp), &st) == 0 && S_ISREG(st.st_mode) && at >= 0 && (size_t)st.st_size >= (size_t)at)
-            SLAB = std::min(SLAB, (size_t)st.st_size - (size_t)at + 1);
-    }
+    const size_t SLAB = r->slab_bytes;
     static const bool timing = getenv("MDG_BAM_TIMING") != nullptr;  // per-slab stage times on stderr
     const double t0 = now_s();
-    c.compressed.set_pinned(on_device);
-    c.inflated.set_pinned(on_device);
-    // page-locked slabs are sized once: room for the carried-over block, and for the inflated side the most DEFLATE
-    // can expand plus slack, so that no later slab makes them grow (growing means locking the pages again)
-    if (on_device && !(c.inflated.reserve(5 * SLAB / 2 + (1u << 20)) && c.compressed.reserve(SLAB + (2u << 20)))) {
-        c.error = MDG_ERR_ARGUMENT;
-        c.message = "out of host memory";
-        return;
-    }
     if (!c.compressed.reserve(r->carry.len + SLAB)) {
         c.error = MDG_ERR_ARGUMENT;
         c.message = "out of host memory";
@@ -307,37 +276,12 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
     }
     c.inflated.len = out_off;
     const double t3 = now_s();
-    // on the GPU, all blocks of the slab in one launch; what it could not do (status != 0) or got wrong (CRC) is
-    // done again below by the host decoders
-    std::vector<int32_t> device_status;
-    if (on_device && c.blocks.size() >= 64) {
-        const size_t nb = c.blocks.size();
-        std::vector<uint64_t> in_off(nb), out_offs(nb);
-        std::vector<uint32_t> in_len(nb), isize(nb);
-        for (size_t i = 0; i < nb; ++i) {
-            in_off[i] = c.blocks[i].in_off;
-            in_len[i] = (uint32_t)c.blocks[i].in_len;
-            out_offs[i] = c.blocks[i].out_off;
-            isize[i] = c.blocks[i].isize;
-        }
-        device_status.assign(nb, 1);
-        if (mdg_inflate_blocks(r->inflater, c.compressed.p, (int64_t)c.compressed.len, in_off.data(), in_len.data(),
-                               c.inflated.p, (int64_t)out_off, out_offs.data(), isize.data(), (int32_t)nb,
-                               device_status.data()) != MDG_OK)
-            device_status.assign(nb, 1);
-    }
     const double t4 = now_s();
     std::atomic<int> bad{0};
-    std::atomic<int64_t> by_device{0};
     parallel_for((int64_t)c.blocks.size(), r->n_threads, [&](int64_t i) {
         const Block &b = c.blocks[(size_t)i];
         if (!b.isize) return;
         const uint32_t want_crc = le32(c.compressed.p + b.in_off + b.in_len);
-        if (!device_status.empty() && device_status[(size_t)i] == 0 &&
-            (uint32_t)crc32(crc32(0L, Z_NULL, 0), c.inflated.p + b.out_off, b.isize) == want_crc) {
-            ++by_device;
-            return;
-        }
         // the native decoder first (mdg_inflate.cpp); zlib for anything it turns down or gets wrong
         if (r->native_inflate &&
             mdg_inflate_raw(c.compressed.p + b.in_off, (int64_t)b.in_len, c.inflated.p + b.out_off, (int64_t)b.isize) == (int64_t)b.isize &&
@@ -360,10 +304,8 @@ void fill_chunk(mdg_bam_reader *r, Chunk &c)
         inflateEnd(&z);
     });
     if (timing)
-        fprintf(stderr, "slab: %zu blocks, reserve %.3f s, read %.3f s, scan + reserve %.3f s, device inflate %.3f s, host crc / inflate %.3f s\n",
-                c.blocks.size(), t1 - t0, t2 - t1, t3 - t2, t4 - t3, now_s() - t4);
-    r->blocks_on_device += by_device.load();
-    r->blocks_on_host += (int64_t)c.blocks.size() - by_device.load();
+        fprintf(stderr, "slab: %zu blocks, reserve %.3f s, read %.3f s, scan + reserve %.3f s, inflate + crc %.3f s\n", c.blocks.size(), t1 - t0,
+                t2 - t1, t3 - t2, now_s() - t4);
     if (bad) {
         c.error = MDG_ERR_DATA;
         c.message = bad == 2 ? "BGZF block fails its CRC32" : "BGZF block does not inflate";
@@ -563,11 +505,6 @@ extern "C" {
 
 int mdg_bam_open(const char *path, int32_t n_threads, mdg_bam_reader **out)
 {
-    return mdg_bam_open_on(path, n_threads, -1, out);
-}
-
-int mdg_bam_open_on(const char *path, int32_t n_threads, int32_t device, mdg_bam_reader **out)
-{
     if (!path || !out) return rfail(nullptr, MDG_ERR_ARGUMENT, "mdg_bam_open: NULL argument");
     *out = nullptr;
     mdg_bam_reader *r = new (std::nothrow) mdg_bam_reader();
@@ -584,7 +521,6 @@ int mdg_bam_open_on(const char *path, int32_t n_threads, int32_t device, mdg_bam
         return MDG_ERR_ARGUMENT;
     }
     setvbuf(r->fp, nullptr, _IONBF, 0);  // slabs are read whole
-    r->want_device.store(device < 0 ? -1 : device);
     {
         const char *env = getenv("MDG_BAM_SLAB");
         const long long want = env ? atoll(env) : 0;
@@ -608,18 +544,8 @@ void mdg_bam_close(mdg_bam_reader *r)
     if (!r) return;
     stop_producer(r);
     if (r->fp) fclose(r->fp);
-    mdg_inflater_free(r->inflater);
     delete r;
 }
-
-int mdg_bam_use_device(mdg_bam_reader *r, int32_t device)
-{
-    if (!r) return MDG_ERR_ARGUMENT;
-    r->want_device.store(device < 0 ? -1 : device);
-    return MDG_OK;
-}
-
-int64_t mdg_bam_device_blocks(const mdg_bam_reader *r) { return r ? r->blocks_on_device.load() : 0; }
 
 const char *mdg_bam_error(const mdg_bam_reader *r) { return r ? r->error.c_str() : g_open_error.c_str(); }
 

@@ -98,43 +98,3 @@ def test_damaged_blocks_are_reported_not_fatal():
     assert status[200] != 0 and status[201] != 0
     # a damaged stream either fails or yields bytes the CRC check of the caller will look at; it never hangs or crashes
     assert all(s in (0, 1) for s in status)
-
-
-def test_reader_inflates_on_the_gpu(tmp_path, golden_dir):
-    """``BamReader(device=0)``: same batches as with the host decoders, and the blocks really came from the GPU."""
-    import bam_py
-    from mapdamage_b200.bamio import BamReader
-    from mapdamage_b200.samtext import read_sam
-
-    header, records = read_sam(golden_dir / "fuzz_0_l70_a10_q0" / "input.sam")
-    bam_py.write_bam(tmp_path / "in.bam", header, records * 3, block_bytes=700)
-    got = {}
-    for device in (None, 0):
-        with BamReader(tmp_path / "in.bam", device=device) as reader:
-            batch = reader.read_batch()
-            assert reader.read_batch() is None
-            got[device] = batch
-            blocks = reader.device_blocks
-        assert (blocks > 100) == (device == 0), blocks
-    assert got[0].n == got[None].n == 3 * sum(1 for r in records if not r.flag & 0xF04)
-    for name in ("flag", "pos", "lib", "l_seq", "cigar", "seq4", "qual", "tlen"):
-        assert np.array_equal(getattr(got[0], name), getattr(got[None], name)), name
-
-
-def test_count_alignments_with_gpu_inflate(tmp_path, golden_dir, monkeypatch):
-    import json
-
-    import bam_py
-    from helpers import assert_tables_equal
-    from mapdamage_b200 import counting
-    from mapdamage_b200.samtext import read_sam
-
-    case = golden_dir / "fuzz_0_l70_a10_q0"
-    params = json.loads((case / "params.json").read_text())
-    header, records = read_sam(case / "input.sam")
-    bam_py.write_bam(tmp_path / "in.bam", header, records, block_bytes=500)
-    monkeypatch.setenv("MDG_BAM_GPU", "1")
-    counting.count_alignments(tmp_path / "in.bam", case / "ref.fa", length=params["length"], around=params["around"],
-                              min_basequal=params["minqual"], merge_libraries=params["merge_libraries"],
-                              folder=tmp_path / "out", batch_reads=256)
-    assert_tables_equal(tmp_path / "out", case)
