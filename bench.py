@@ -77,7 +77,7 @@ def parse_args():
                     help="c2 = configs[1] (the headline); c3 = configs[2]: 50-150 bp pairs, mixed CIGARs, two libraries")
     ap.add_argument("--configs", default="auto",
                     help="other BASELINE.json configurations measured after the headline and reported under \"configs\": "
-                         "comma list of c3,c4,c5, 'none', or 'auto' (c3 and c4 on one GPU, c5 on eight)")
+                         "comma list of c3,c4,c5,g3, 'none', or 'auto' (c3, c4 and g3 on one GPU, c5 on eight)")
     ap.add_argument("--c4-reads", type=int, default=200_000_000, help="reads per step of the rescale configuration")
     ap.add_argument("--c4-file-reads", type=int, default=16_000_000,
                     help="reads of the BAM file the file -> rescaled-file leg of c4 runs on")
@@ -185,6 +185,8 @@ WORKLOADS = {
           "soft clips), 2 libraries, 1 Mb reference, -l 70 -a 10 -Q 0",
     "c4": "configs[3]: 200M x 100bp SE reads with qualities, --rescale pass producing a rescaled BAM",
     "c5": "configs[4]: 1B x 100bp SE aDNA reads sharded over 8 GPUs (125M per rank), NCCL all-reduce of the count tables",
+    "g3": "the reads of configs[1] on a 3.1 Gbp genome (31 contigs of 100 Mbp, made on the device): reference gathers "
+          "come from DRAM instead of L2; reads in random order and in coordinate order",
 }
 # the reference's own Python loop (main.py:165-220) cannot run on the GPU box (pysam is not installable, /root/reference
 # does not travel); this is the figure measured in the survey container through oracle/pysam_shim.py
@@ -500,7 +502,7 @@ def gpu_arm(args, rank, local_rank, world):
     if "auto" in wanted:
         # the other configurations BASELINE.json names: configs[2] and configs[3] are single-GPU cases,
         # configs[4] is the 8-GPU case
-        wanted = (["c3", "c4"] if world == 1 else []) + (["c5"] if world == 8 else [])
+        wanted = (["c3", "c4", "g3"] if world == 1 else []) + (["c5"] if world == 8 else [])
     configs = {}
     side_steps, side_warm = max(2, min(args.steps, 5)), 3
     for name in wanted:
@@ -515,6 +517,8 @@ def gpu_arm(args, rank, local_rank, world):
                                             with_e2e=not args.no_e2e, e2e_host_reads=args.reads)
         elif name == "c4":
             configs[name] = rescale_config(args, ranks)
+        elif name == "g3":
+            configs[name] = big_genome_config(args, ranks)
     if rank == 0:
         line = {"metric": METRIC, "n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/int64", "data": "synthetic"}
@@ -523,6 +527,61 @@ def gpu_arm(args, rank, local_rank, world):
         line["configs"] = {k: v for k, v in configs.items() if v is not None}
         emit(line)
     ranks.close()
+
+
+def big_genome_config(args, ranks):
+    """the synthetic reference of configs[1] is 1 Mb and lives in L2; a human-sized genome does not.
+    12.5 M reads of the configs[1] shape on a 3.1 Gbp genome, drawn uniformly (an unsorted file) and in coordinate
+    order (a sorted one); parity on a sample against the oracle on the downloaded genome."""
+    from mapdamage_b200.engine import DamageEngine
+
+    if ranks.rank != 0:
+        return None
+    import oracle
+
+    reads, n_batches = 12_500_000, 3
+    per = reads // n_batches
+    out = {"unit": UNIT, "config": {"workload": WORKLOADS["g3"], "reads_per_step": per * n_batches, "batches_per_step": n_batches,
+                                    "genome_bases": 31 * 100_000_000}}
+    with DamageEngine(length=LENGTH, around=AROUND, lg_bins=8192, device=ranks.local_rank, max_reads=0) as engine:
+        names, lengths = engine.synth_reference([100_000_000] * 31, seed=args.seed)
+        for order in ("shuffled", "sorted"):
+            resident = [engine.synth_batch(per, seed=args.seed + 3000 + i, length=(READ_LEN, READ_LEN), with_qual=False,
+                                           sorted_positions=order == "sorted") for i in range(n_batches)]
+            if order == "shuffled":
+                # parity: 100 k reads against the oracle on the genome as the device holds it
+                reference = engine.reference_host(names, lengths)
+                sample = engine.download(resident[0]).slice(0, 100_000)
+                want = oracle.count(sample, reference, length=LENGTH, around=AROUND, lg_bins=8192, threads=min(16, os.cpu_count() or 1))
+                sub = engine.upload(sample)
+                engine.reset()
+                engine.count_resident(sub)
+                if not same_tables(engine.tables(), want):
+                    raise SystemExit("bench[g3]: tables differ from the oracle on the 3.1 Gbp genome")
+                sub.free()
+                del reference
+                out["check"] = {"oracle_sample_reads": sample.n}
+            for _ in range(2):
+                for dev in resident:
+                    engine.count_resident(dev)
+            engine.sync()
+            engine.kernel_ms()
+            steps = 5
+            engine.event_record(0)
+            for _ in range(steps):
+                for dev in resident:
+                    engine.count_resident(dev)
+            engine.event_record(1)
+            ms = engine.event_elapsed_ms()
+            kernel_ms = engine.kernel_ms()
+            out[order] = {"value": per * n_batches * steps / (ms * 1e-3), "kernel_ms_per_launch": kernel_ms / (steps * n_batches),
+                          "reads_per_launch": per}
+            for dev in resident:
+                dev.free()
+    out["value"] = out["shuffled"]["value"]
+    traffic = recorded_traffic("g3")
+    out["dram_bytes_per_read"] = None if traffic is None else traffic
+    return out
 
 
 def rescale_model_terms():

@@ -271,7 +271,13 @@ typedef struct {
     float reserved2;
 } mdg_synth_params;
 
-/* Generates a batch directly in device memory (no host copy); needs mdg_set_reference. */
+/* A random genome made on the device instead of uploaded (benchmarks with a genome far larger than L2): contig c has
+ * contig_len[c] uniform A/C/G/T bases, a function of (seed, c, position).  mdg_reference_download copies the image
+ * back (one-hot nibbles 1, 2, 4, 8 = A, C, G, T, low nibble = even base, contigs padded to 8 bases) for the checker. */
+int mdg_synth_reference(mdg_ctx *ctx, const uint32_t *contig_len, int32_t n_contigs, uint64_t seed);
+int mdg_reference_download(mdg_ctx *ctx, uint8_t *one_hot, int64_t n_bytes);
+/* Generates a batch directly in device memory (no host copy); needs mdg_set_reference.  params.reserved = 1: read i
+ * sits at base i / n_reads of the genome (a coordinate-sorted file) instead of at a uniformly drawn base. */
 int mdg_synth_batch(mdg_ctx *ctx, const mdg_synth_params *params, mdg_dev_batch **out);
 int mdg_batch_sizes(mdg_ctx *ctx, const mdg_dev_batch *batch, int64_t *n_reads, int64_t *n_cigar, int64_t *n_bases);
 /* Copies a resident batch into caller-allocated host arrays (sized by

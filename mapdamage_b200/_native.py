@@ -62,6 +62,8 @@ SYMBOLS = {
     "mdg_host_free": (None, [C.c_void_p]),
     "mdg_set_reference": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "mdg_genome_composition": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdg_synth_reference": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64]),
+    "mdg_reference_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "mdg_count_submit": (C.c_int, [C.c_void_p, C.POINTER(Batch)]),
     "mdg_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(C.c_void_p)]),
     "mdg_batch_free": (C.c_int, [C.c_void_p, C.c_void_p]),

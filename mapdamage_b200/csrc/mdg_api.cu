@@ -909,6 +909,70 @@ int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, cons
     return MDG_OK;
 }
 
+// A random genome made on the device (benchmarks with a genome larger than L2: 3.1 Gbp is 1.55 GB here): contig c has
+// contig_len[c] uniform A/C/G/T bases, a pure function of (seed, c, position).
+int mdg_synth_reference(mdg_ctx *ctx, const uint32_t *contig_len, int32_t n_contigs, uint64_t seed)
+{
+    if (!ctx) return MDG_ERR_ARGUMENT;
+    if (!contig_len || n_contigs < 1) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_synth_reference: NULL or empty argument");
+    std::vector<uint64_t> off((size_t)n_contigs);
+    uint64_t total = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+        off[(size_t)c] = total;
+        total += ((uint64_t)contig_len[c] + 7) / 8 * 8;
+    }
+    const int64_t n_bytes = (int64_t)(total / 2);
+    // an all-"not a base" image through the ordinary path, then the contigs are overwritten in place
+    std::vector<uint8_t> blank(1 << 20, 0x77);
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MDG_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(ctx->ref_block);
+    cudaFree(ctx->planes_block);
+    ctx->ref_block = ctx->planes_block = nullptr;
+    ctx->ref = mdg::DevRef{};
+    const size_t pad = 4096;
+    const size_t words_bytes = align_up((size_t)n_bytes + pad), off_bytes = align_up((size_t)n_contigs * 8), len_bytes = align_up((size_t)n_contigs * 4);
+    MDG_CUDA(ctx, cudaMalloc(&ctx->ref_block, pad + words_bytes + off_bytes + len_bytes));
+    MDG_CUDA(ctx, cudaMalloc(&ctx->planes_block, pad + words_bytes));
+    char *p = (char *)ctx->ref_block + pad;
+    MDG_CUDA(ctx, cudaMemset(ctx->ref_block, 0, pad + words_bytes));  // one-hot image: 0 = not a base
+    for (int c = 0; c < n_contigs; ++c) {
+        mdg::synth_reference_kernel<<<ctx->sm_count * 8, 256, 0, ctx->compute>>>((uint32_t *)p + off[(size_t)c] / 8, contig_len[c],
+                                                                                  mdg::mix64(seed + 0x1000003ull * (uint64_t)c));
+        ctx->launches += 1;
+    }
+    mdg::ref_planes_kernel<<<ctx->sm_count * 8, 256, 0, ctx->compute>>>((const uint32_t *)ctx->ref_block, (int64_t)((pad + words_bytes) / 16),
+                                                                         (uint4 *)ctx->planes_block);
+    MDG_CUDA(ctx, cudaGetLastError());
+    MDG_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    MDG_CUDA(ctx, cudaMemcpy(p + words_bytes, off.data(), (size_t)n_contigs * 8, cudaMemcpyHostToDevice));
+    MDG_CUDA(ctx, cudaMemcpy(p + words_bytes + off_bytes, contig_len, (size_t)n_contigs * 4, cudaMemcpyHostToDevice));
+    ctx->ref.words = (const uint32_t *)p;
+    ctx->ref.planes = (const uint4 *)((char *)ctx->planes_block + pad);
+    ctx->ref.contig_off = (const uint64_t *)(p + words_bytes);
+    ctx->ref.contig_len = (const uint32_t *)(p + words_bytes + off_bytes);
+    ctx->ref.n_contigs = n_contigs;
+    ctx->ref_words = (int64_t)((n_bytes + 3) / 4);
+    ctx->ref_total_bases = 0;
+    ctx->ref_min_contig = 0xffffffffu;
+    for (int c = 0; c < n_contigs; ++c) {
+        ctx->ref_total_bases += contig_len[c];
+        ctx->ref_min_contig = std::min(ctx->ref_min_contig, contig_len[c]);
+    }
+    return MDG_OK;
+}
+
+// The genome image as the device holds it (one-hot nibbles, low nibble = even base; 0 = not a base), n_bytes of it.
+int mdg_reference_download(mdg_ctx *ctx, uint8_t *one_hot, int64_t n_bytes)
+{
+    if (!ctx || !one_hot || n_bytes < 0) return MDG_ERR_ARGUMENT;
+    if (!ctx->ref.words) return fail(ctx, MDG_ERR_STATE, "no reference on the device");
+    if (n_bytes > ctx->ref_words * 4) return fail(ctx, MDG_ERR_ARGUMENT, "mdg_reference_download: the image has %lld bytes", (long long)(ctx->ref_words * 4));
+    MDG_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MDG_CUDA(ctx, cudaMemcpy(one_hot, ctx->ref.words, (size_t)n_bytes, cudaMemcpyDeviceToHost));
+    return MDG_OK;
+}
+
 int mdg_genome_composition(mdg_ctx *ctx, uint64_t *counts4)
 {
     if (!ctx || !counts4) return MDG_ERR_ARGUMENT;
@@ -1293,6 +1357,7 @@ int mdg_synth_batch(mdg_ctx *ctx, const mdg_synth_params *sp, mdg_dev_batch **ou
     p.damage0 = sp->damage0;
     p.decay = sp->damage_decay;
     p.genome_bases = ctx->ref_total_bases;
+    p.sorted = sp->reserved != 0;
 
     const int64_t n_blocks = (sp->n_reads + 255) / 256;
     unsigned long long *totals = nullptr;

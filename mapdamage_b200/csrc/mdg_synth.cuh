@@ -26,6 +26,7 @@ struct SynthDev {
     uint32_t error_u24, read_n_u24, filtered_u24;  // thresholds on a 24-bit uniform
     float damage0, decay;
     uint64_t genome_bases;  // sum of contig lengths
+    int32_t sorted;         // 1: positions grow with the read index (a coordinate-sorted file), else uniform at random
 };
 
 struct SynthOut {
@@ -188,6 +189,20 @@ __global__ void __launch_bounds__(256) layout_fill(const uint32_t *__restrict__ 
     }
 }
 
+// a random contig straight into the one-hot genome image: base k of the contig is code mix64(seed, k / 32) bits
+__global__ void __launch_bounds__(256) synth_reference_kernel(uint32_t *words, uint64_t n_bases, uint64_t seed)
+{
+    const uint64_t n_words = (n_bases + 7) / 8;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = mix64(seed ^ mix64(w >> 2)) >> (16 * (w & 3));
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (8 * w + k < n_bases) out |= (1u << ((h >> (2 * k)) & 3)) << (4 * k);
+        words[w] = out;
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_words(uint32_t *to, int64_t n, uint32_t word)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) to[i] = word;
@@ -209,11 +224,12 @@ __global__ void __launch_bounds__(256) lseq_from_cigar(const uint32_t *__restric
     l_seq[i] = len;
 }
 
-__device__ __forceinline__ void place_read(const SynthDev &p, const DevRef &ref, uint64_t h, int32_t rspan,
+__device__ __forceinline__ void place_read(const SynthDev &p, const DevRef &ref, uint64_t h, int64_t i, int32_t rspan,
                                            int32_t *tid, int64_t *pos)
 {
-    // contig chosen in proportion to its length: a uniform base of the genome
-    uint64_t g = (uint64_t)(((unsigned __int128)h * p.genome_bases) >> 64);
+    // contig chosen in proportion to its length: a uniform base of the genome (or, sorted, base i / n of it)
+    uint64_t g = p.sorted ? (uint64_t)(((unsigned __int128)(uint64_t)i * p.genome_bases) / (uint64_t)p.n_reads)
+                          : (uint64_t)(((unsigned __int128)h * p.genome_bases) >> 64);
     int c = 0;
     while (c + 1 < ref.n_contigs && g >= ref.contig_len[c]) {
         g -= ref.contig_len[c];
@@ -257,7 +273,7 @@ __global__ void __launch_bounds__(256) synth_fill(SynthDev p, DevRef ref, const 
         ReadShape sr = right_i < p.n_reads ? (is_left ? shape_of(p, right_i) : s) : sl;
         const uint64_t hp = mix64(p.seed ^ mix64((uint64_t)left_i * 2));
         int64_t pos_l;
-        place_read(p, ref, hp, sl.rspan, &tid, &pos_l);
+        place_read(p, ref, hp, left_i, sl.rspan, &tid, &pos_l);
         const int64_t gap = (int64_t)((mix64(hp) & 0xFFFF) * 301 >> 16);
         int64_t room_r = (int64_t)ref.contig_len[tid] - sr.rspan;
         if (room_r < 0) room_r = 0;
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(256) synth_fill(SynthDev p, DevRef ref, const 
         }
         mtid = tid;
     } else {
-        place_read(p, ref, hr, s.rspan, &tid, &pos);
+        place_read(p, ref, hr, i, s.rspan, &tid, &pos);
         if ((mix64(hr) >> 8) & 1) flag = 16;
     }
     const uint64_t hx = mix64(hr ^ 0xA5A5A5A5ull);

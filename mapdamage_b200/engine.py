@@ -169,6 +169,31 @@ class DamageEngine:
             self._ctx, packed.ctypes.data, packed.shape[0], offsets.ctypes.data,
             lengths.ctypes.data, len(reference.names)))
 
+    def synth_reference(self, lengths, seed=1, names=None):
+        """A random genome made on the device (``mdg_synth_reference``).  Returns the contig names and lengths."""
+        lens = np.array(lengths, dtype=np.uint32)
+        self._check(self._lib.mdg_synth_reference(self._ctx, lens.ctypes.data, len(lens), int(seed)))
+        self._synth_lengths = [int(x) for x in lens]
+        return list(names or ["chr%d" % (i + 1) for i in range(len(lens))]), self._synth_lengths
+
+    def reference_host(self, names, lengths):
+        """The genome the device holds as a host :class:`~mapdamage_b200.refgenome.Reference` (for the checker)."""
+        from .refgenome import Reference
+
+        total = sum((n + 7) // 8 * 8 for n in lengths)
+        image = np.empty(total // 2, dtype=np.uint8)
+        self._check(self._lib.mdg_reference_download(self._ctx, image.ctypes.data, image.shape[0]))
+        letter = np.full(16, ord("N"), dtype=np.uint8)
+        letter[[1, 2, 4, 8]] = np.frombuffer(b"ACGT", dtype=np.uint8)
+        bases = np.empty(total, dtype=np.uint8)
+        bases[0::2] = letter[image & 15]
+        bases[1::2] = letter[image >> 4]
+        sequences, at = [], 0
+        for n in lengths:
+            sequences.append(bases[at:at + n])
+            at += (n + 7) // 8 * 8
+        return Reference(names, sequences)
+
     def genome_composition(self):
         """``[A, C, G, T]`` counts over the uploaded genome (``mdg_genome_composition``)."""
         counts = np.zeros(4, dtype=np.uint64)
@@ -183,13 +208,13 @@ class DamageEngine:
 
     def synth_batch(self, n_reads, seed=1, length=(100, 100), mix=(1, 0, 0, 0), paired=False,
                     with_qual=True, n_libs=1, error_rate=0.002, read_n_rate=0.0, filtered_rate=0.0,
-                    damage0=0.3, damage_decay=0.7):
+                    damage0=0.3, damage_decay=0.7, sorted_positions=False):
         """Seeded synthetic aDNA batch generated directly in HBM (``mdg_synth_batch``)."""
         if isinstance(length, int):
             length = (length, length)
         params = _native.SynthParams(
             seed, n_reads, length[0], length[1], (C.c_int32 * 4)(*mix), int(paired), int(with_qual),
-            n_libs, 0, error_rate, read_n_rate, filtered_rate, damage0, damage_decay, 0.0)
+            n_libs, int(bool(sorted_positions)), error_rate, read_n_rate, filtered_rate, damage0, damage_decay, 0.0)
         handle = C.c_void_p()
         self._check(self._lib.mdg_synth_batch(self._ctx, C.byref(params), C.byref(handle)))
         return DeviceBatch(self, handle, n_reads, has_qual=bool(with_qual))

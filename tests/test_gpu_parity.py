@@ -357,3 +357,25 @@ def test_counting_golden_with_indels_staged(case_dir, params, tmp_path, monkeypa
                                          min_qual=params["minqual"], chunks=2)
     render_tables(tmp_path / "out", libraries, L, A, mis, comp, lg)
     assert_tables_equal(tmp_path / "out", case_dir)
+
+
+@pytest.mark.parametrize("sorted_positions", [False, True])
+def test_device_made_genome_and_sorted_reads(sorted_positions):
+    """mdg_synth_reference / mdg_reference_download (benchmarks with genomes far larger than L2) and reads placed in
+    coordinate order: the tables equal the oracle's on the downloaded genome."""
+    lengths = [700_001, 90_000, 1_234_567]
+    with DamageEngine(max_reads=0) as engine:
+        names, lens = engine.synth_reference(lengths, seed=17)
+        reference = engine.reference_host(names, lens)
+        assert reference.lengths == lengths and set(np.unique(reference.sequences[0])) == set(b"ACGT")
+        dev = engine.synth_batch(120_000, seed=5, length=(40, 130), mix=(7, 1, 1, 1), with_qual=False,
+                                 sorted_positions=sorted_positions)
+        engine.count_resident(dev)
+        got = engine.tables()
+        host = engine.download(dev)
+    if sorted_positions:
+        key = host.tid.astype(np.int64) * (1 << 32) + host.pos
+        assert np.all(np.diff(key) >= 0)
+    want = oracle.count(host, reference, lg_bins=8192, threads=4)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
