@@ -206,12 +206,12 @@ int mdg_rescale_submit(mdg_ctx *ctx, const mdg_batch *host, uint8_t *qual_out, f
  * The same pass returning only what changed.  A read has a handful of C->T / G->A bases, so instead of the whole quality
  * array (l_seq bytes per read back over PCIe) the device lists the bytes it rewrote: after mdg_rescale_collect(ticket),
  * qual[change_at[k]] = change_q[k] for k < the returned count patches the caller's own array (indices into the batch's
- * qual array).  mr_out / status_out as above.  `ticket` names the staging slot; collect it before n_slots further
+ * qual array); with patch_qual the library does that itself, on a few threads.  mr_out / status_out as above.  `ticket` names the staging slot; collect it before n_slots further
  * submits.  Returns MDG_ERR_CAPACITY when more than a quarter of all bases changed (use mdg_rescale_submit) or the
  * caller's arrays are too small.
  */
 int mdg_rescale_submit_sparse(mdg_ctx *ctx, const mdg_batch *host, float *mr_out, uint8_t *status_out, int32_t *ticket);
-int64_t mdg_rescale_collect(mdg_ctx *ctx, int32_t ticket, uint32_t *change_at, uint8_t *change_q, int64_t cap);
+int64_t mdg_rescale_collect(mdg_ctx *ctx, int32_t ticket, uint32_t *change_at, uint8_t *change_q, int64_t cap, uint8_t *patch_qual);
 /*
  * Rescales a batch resident in HBM in place (its quality array is rewritten on the device), on the compute stream:
  * batches made by mdg_bam_stream_next (file -> device) or mdg_batch_upload.  mr_out / status_out (host, optional) are

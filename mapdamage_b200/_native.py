@@ -106,7 +106,7 @@ SYMBOLS = {
     "mdg_bam_encode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdg_bam_encode_flush": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "mdg_rescale_submit_sparse": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
-    "mdg_rescale_collect": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
+    "mdg_rescale_collect": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mdg_rescale_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mdg_inflate_raw": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "mdg_inflater_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),

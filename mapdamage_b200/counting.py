@@ -185,30 +185,45 @@ def _count_bam_on_device(filename, ref, length, around, min_basequal, merge_libr
     inflated, cut into records, scattered into the batch layout and counted in HBM."""
     from .bamio import BamReader, DeviceBamStream
 
+    import time
+
     log = logging.getLogger(__name__)
+    clock = [("start", time.perf_counter())]
     with BamReader(filename, threads=2, merge_libraries=merge_libraries, apply_filter=True) as reader:
         header, libraries = reader.header, reader.libraries
+    clock.append(("header", time.perf_counter()))
     reference = ref if isinstance(ref, Reference) else Reference.from_fasta(ref)
     reference = reference.reordered(header.references, header.lengths)
+    clock.append(("fasta", time.perf_counter()))
     own_engine = engine is None
     if own_engine:
         engine = DamageEngine(length=length, around=around, min_qual=min_basequal, n_libraries=max(1, len(libraries)),
                               lg_bins=lg_bins, device=device, max_reads=0)
     try:
         engine.set_reference(reference)
+        clock.append(("engine + genome upload", time.perf_counter()))
         n_kept = 0
         with DeviceBamStream(engine, filename, merge_libraries=merge_libraries, apply_filter=True,
                              with_qual=min_basequal > 0) as stream:
+            clock.append(("stream open", time.perf_counter()))
             for batch in stream:
                 engine.count_resident(batch)
                 n_kept += batch.n
             engine.sync()
+            clock.append(("decode + count", time.perf_counter()))
             n_seen = stream.stats()["records_seen"]
+        clock.append(("stream close", time.perf_counter()))
         mis, comp, lg = engine.tables()
         overflow = engine.lg_overflow()
     finally:
         if own_engine:
             engine.close()
+    clock.append(("tables + engine close", time.perf_counter()))
+    if os.environ.get("MDG_TIMING"):
+        import sys
+
+        print("count_alignments (device): " + ", ".join("%s %.3f s" % (name, t - clock[i][1]) for i, (name, t) in enumerate(clock[1:])),
+              file=sys.stderr)
     log.debug("Counted %d of %d alignments", n_kept, n_seen)
     return _finish(libraries, length, around, mis, comp, lg, overflow, folder)
 

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -1259,7 +1260,7 @@ int mdg_rescale_submit_sparse(mdg_ctx *ctx, const mdg_batch *host, float *mr_out
     return rescale_submit(ctx, host, nullptr, mr_out, status_out, ticket);
 }
 
-int64_t mdg_rescale_collect(mdg_ctx *ctx, int32_t ticket, uint32_t *change_at, uint8_t *change_q, int64_t cap)
+int64_t mdg_rescale_collect(mdg_ctx *ctx, int32_t ticket, uint32_t *change_at, uint8_t *change_q, int64_t cap, uint8_t *patch_qual)
 {
     if (!ctx || ticket < 0 || ticket >= (int32_t)ctx->slots.size()) return MDG_ERR_ARGUMENT;
     Slot &slot = ctx->slots[(size_t)ticket];
@@ -1276,6 +1277,18 @@ int64_t mdg_rescale_collect(mdg_ctx *ctx, int32_t ticket, uint32_t *change_at, u
         MDG_CUDA(ctx, cudaMemcpyAsync(change_at, slot.change_at, (size_t)n * 4, cudaMemcpyDeviceToHost, slot.stream));
         MDG_CUDA(ctx, cudaMemcpyAsync(change_q, slot.change_q, (size_t)n, cudaMemcpyDeviceToHost, slot.stream));
         MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
+        if (patch_qual) {
+            // scattered single-byte writes over a few hundred MB: a few threads, each its share of the list
+            const int n_parts = n >= (1 << 18) ? 4 : 1;
+            const int64_t piece = (n + n_parts - 1) / n_parts;
+            std::vector<std::thread> pool;
+            for (int t = 1; t < n_parts; ++t)
+                pool.emplace_back([=] {
+                    for (int64_t k = t * piece; k < std::min(n, (t + 1) * piece); ++k) patch_qual[change_at[k]] = change_q[k];
+                });
+            for (int64_t k = 0; k < std::min(n, piece); ++k) patch_qual[change_at[k]] = change_q[k];
+            for (auto &th : pool) th.join();
+        }
     }
     return n;
 }

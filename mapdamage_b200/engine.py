@@ -331,16 +331,15 @@ class DamageEngine:
                                                         C.byref(ticket)))
         return mr[:batch.n], status[:batch.n], ticket.value
 
-    def rescale_collect(self, ticket, batch, scratch=None):
-        """Waits for the sparse submit ``ticket`` and writes the changed quality bytes into ``batch.qual``.
-        Returns the number of bytes that changed."""
+    def rescale_collect(self, ticket, batch, scratch=None, apply=True):
+        """Waits for the sparse submit ``ticket`` and (``apply``) writes the changed quality bytes into ``batch.qual``.
+        Returns the number of bytes that changed; ``scratch[0][:n]`` / ``scratch[1][:n]`` hold their indices and scores."""
         cap = batch.total_bases // 4 + 4096
         if scratch is None or scratch[0].shape[0] < cap:
             scratch = (np.empty(cap, dtype=np.uint32), np.empty(cap, dtype=np.uint8))
         at, q = scratch
-        n = self._check(self._lib.mdg_rescale_collect(self._ctx, ticket, at.ctypes.data, q.ctypes.data, at.shape[0]))
-        if n:
-            batch.qual[at[:n]] = q[:n]
+        n = self._check(self._lib.mdg_rescale_collect(self._ctx, ticket, at.ctypes.data, q.ctypes.data, at.shape[0],
+                                                      batch.qual.ctypes.data if apply else None))
         return int(n)
 
     def rescale_resident(self, device_batch, want_results=False):
