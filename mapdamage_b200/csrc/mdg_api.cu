@@ -1279,7 +1279,7 @@ int64_t mdg_rescale_collect(mdg_ctx *ctx, int32_t ticket, uint32_t *change_at, u
         MDG_CUDA(ctx, cudaStreamSynchronize(slot.stream));
         if (patch_qual) {
             // scattered single-byte writes over a few hundred MB: a few threads, each its share of the list
-            const int n_parts = n >= (1 << 18) ? 4 : 1;
+            const int n_parts = n >= (1 << 18) ? 8 : 1;
             const int64_t piece = (n + n_parts - 1) / n_parts;
             std::vector<std::thread> pool;
             for (int t = 1; t < n_parts; ++t)
