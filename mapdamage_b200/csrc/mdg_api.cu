@@ -447,9 +447,13 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
                 mdg::PlaneGeom pg = ctx->planes;
                 pg.indel_seen = ctx->indel_seen_dev;
                 const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
-                const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, tiles);
-                mdg::count_planes_kernel<512><<<pgrid, pg.threads, ctx->planes_smem, stream>>>(b, ctx->ref, p, tl, pg, wl->reads, wl->count,
-                                                                                               wl->indel_reads, wl->indel_count, subset);
+                const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count * (pg.threads == 256 ? 2 : 1), tiles);
+                if (pg.threads == 256)
+                    mdg::count_planes_kernel<256><<<pgrid, pg.threads, ctx->planes_smem, stream>>>(b, ctx->ref, p, tl, pg, wl->reads, wl->count,
+                                                                                                   wl->indel_reads, wl->indel_count, subset);
+                else
+                    mdg::count_planes_kernel<512><<<pgrid, pg.threads, ctx->planes_smem, stream>>>(b, ctx->ref, p, tl, pg, wl->reads, wl->count,
+                                                                                                   wl->indel_reads, wl->indel_count, subset);
             } else if (ctx->staged_enabled) {
                 // three planes (quality mask or indel reads staged) leave room for fewer reads per tile
                 const bool three = q || ctx->staged_indels;
@@ -766,7 +770,11 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
         {
             mdg::PlaneGeom &pg = ctx->planes;
             const char *kenv = getenv("MDG_KERNEL");
-            pg.threads = 512;
+            const char *pt_env = getenv("MDG_PLANES_THREADS");  // 256: two co-resident blocks per SM (A/B)
+            pg.threads = pt_env && atoi(pt_env) == 256 ? 256 : 512;
+            const size_t smem_budget = pg.threads == 256 ? (ctx->smem_optin + 1024) / 2 - 1024 : ctx->smem_optin;
+            const char *pf_env = getenv("MDG_PLANES_PREFETCH");
+            pg.prefetch_bases = !(pf_env && pf_env[0] == '0');
             pg.uniform = g.uniform;
             pg.flush_tiles = g.flush_tiles;
             pg.nw_anchor = (cfg->length + cfg->around + 31) / 32;
@@ -780,7 +788,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             const size_t seq_per_read = slab_env && slab_env[0] == '0' ? 0 : 56;
             const size_t per_read = ((size_t)pg.row_words + 4 + 2) * 4 + seq_per_read;
             int tile = 0;
-            if (fixed + 192 * per_read <= ctx->smem_optin) tile = (int)std::min<size_t>(1024, (ctx->smem_optin - fixed) / per_read / 32 * 32);
+            if (fixed + 192 * per_read <= smem_budget) tile = (int)std::min<size_t>(1024, (smem_budget - fixed) / per_read / 32 * 32);
             // whole rounds of the block: a tile of 576 reads would leave 448 threads idle in the second round of every phase
             if (tile > pg.threads) tile = tile / pg.threads * pg.threads;
             if (const char *tile_env3 = getenv("MDG_PLANES_TILE")) tile = std::min(tile, std::max(32, atoi(tile_env3)));
@@ -790,8 +798,12 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             const bool fits = ctx->staged_enabled && 2 * pg.nw_anchor * 2 <= pairs && cfg->around <= 64 && tile >= 192 &&
                               (size_t)tile * pg.row_words >= (size_t)2 * 20 * 64 * pg.nw_anchor;
             if (fits && !(kenv && (!strcmp(kenv, "swar") || !strcmp(kenv, "staged")))) {
-                MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_planes_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)ctx->planes_smem));
+                if (pg.threads == 256)
+                    MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_planes_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)ctx->planes_smem));
+                else
+                    MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_planes_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)ctx->planes_smem));
                 ctx->planes_enabled = true;
             }
         }

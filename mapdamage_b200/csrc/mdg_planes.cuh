@@ -42,6 +42,7 @@ struct PlaneGeom {
     int32_t row_words;    // words per staged read: 8 * (2 * nw_anchor) + 4 (rows land on different banks)
     int32_t seq_words;    // shared-memory words for the tile's slab of seq4 (bulk-copied ahead); 0: none
     unsigned long long *indel_seen;  // counts the one-indel reads met (steers the host's choice of variants)
+    int32_t prefetch_bases;  // 1: L2 prefetch of the bases of the tile after next even when the bulk copy brings them in
 };
 
 constexpr int PL_REG = 8;    // counter planes in registers (counts to 255)
@@ -122,7 +123,7 @@ __device__ unsigned int mdg_plane_phase_dump[16];
 #endif
 
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 2 : 1)
 count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneGeom g, uint32_t *__restrict__ worklist,
                     unsigned long long *__restrict__ work_count, uint32_t *__restrict__ indel_list,
                     unsigned long long *__restrict__ indel_count, SwarSubset sub)
@@ -710,6 +711,7 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
             for (int u = 0; u < PREP; ++u) h[u].cig0 = h[u].live && h[u].c1 > h[u].c0 ? __ldg(b.cigar + h[u].c0) : 0;
 #pragma unroll
             for (int u = 0; u < PREP; ++u) {
+                if (q0 + u * nthreads >= T) break;  // the same for every thread: a round nobody has a read in
                 int kind, rstrand;
                 uint32_t columns;
                 PlaneRecord rec{};
@@ -820,7 +822,10 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
                 else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, li >= n_fwd);
             }
         }
-        if (ahead_live) prefetch_bases(ahead_boff, ahead_coff);
+        if (ahead_live) {
+            if (g.prefetch_bases || !slab_words) prefetch_bases(ahead_boff, ahead_coff);
+            else prefetch_l2(b.cigar + ahead_coff);
+        }
         if (listed_live) prefetch_listed_bases(listed_live, listed_boff, listed_coff);
         MDG_PPHASE(2)
         __syncthreads();

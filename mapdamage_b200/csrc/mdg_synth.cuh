@@ -235,7 +235,9 @@ __device__ __forceinline__ void place_read(const SynthDev &p, const DevRef &ref,
         g -= ref.contig_len[c];
         ++c;
     }
-    int64_t room = (int64_t)ref.contig_len[c] - rspan;
+    // sorted: one scale for every read of the contig (the longest reference span a shape can have is len_hi + 3,
+    // a 3-base deletion), else the order would break near the contig end where the room depends on the read
+    int64_t room = (int64_t)ref.contig_len[c] - (p.sorted ? p.len_hi + 3 : rspan);
     if (room < 0) room = 0;
     *tid = c;
     *pos = (int64_t)(g * (uint64_t)(room + 1) / ref.contig_len[c]);

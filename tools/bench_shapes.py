@@ -24,7 +24,10 @@ SHAPES = {
 
 reference = synth.make_reference([1_000_000], seed=5)
 n = 4_000_000
+only = sys.argv[1:]  # shape names; none: all of them
 for name, kw in SHAPES.items():
+    if only and name not in only:
+        continue
     kw = dict(kw)
     min_qual = kw.pop("min_qual", 0)
     with DamageEngine(n_libraries=kw.get("n_libs", 1), max_reads=1024, min_qual=min_qual) as engine:
