@@ -19,6 +19,7 @@
 #include "mdg_swar.cuh"
 #include "mdg_stage.cuh"
 #include "mdg_planes.cuh"
+#include "mdg_planes_ws.cuh"
 #include "mdg_rescale.cuh"
 #include "mdg_synth.cuh"
 #include "mdg_inflate_dev.cuh"
@@ -161,6 +162,10 @@ struct mdg_ctx {
     bool planes_enabled = false;
     mdg::PlaneGeom planes{};
     size_t planes_smem = 0;
+    // its warp-specialised form (mdg_planes_ws.cuh): producer teams stage, consumer warps count
+    int ws_variant = -1;  // index into WS_VARIANTS, -1: off
+    mdg::PlaneGeom ws{};
+    size_t ws_smem = 0;
     void *planes_block = nullptr;  // genome as bit planes
     std::vector<WorkList> worklists;
     // measurement
@@ -410,6 +415,21 @@ mdg::CountTables lib_tables(const mdg_ctx *ctx, int lib)
     return t;
 }
 
+// compiled shapes of the warp-specialised bit-plane kernel: producer teams x warps per team + consumer warps
+using WsKernel = void (*)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::CountTables, mdg::PlaneGeom, uint32_t *, unsigned long long *,
+                          uint32_t *, unsigned long long *, mdg::SwarSubset);
+struct WsVariant {
+    const char *name;
+    int teams, team_warps, cons_warps;
+    WsKernel kernel;
+};
+const WsVariant WS_VARIANTS[] = {
+    {"2x8+8", 2, 8, 8, mdg::count_planes_ws_kernel<2, 8, 8>},
+    {"2x8+4", 2, 8, 4, mdg::count_planes_ws_kernel<2, 8, 4>},
+    {"3x6+8", 3, 6, 8, mdg::count_planes_ws_kernel<3, 6, 8>},
+    {"4x4+8", 4, 4, 8, mdg::count_planes_ws_kernel<4, 4, 8>},
+};
+
 // The counting kernels over one device batch.
 int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStream_t stream)
 {
@@ -443,7 +463,15 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         if (use_planes) MDG_CUDA(ctx, cudaMemsetAsync(wl->indel_count, 0, (size_t)nl * 24, stream));
         // one launch of the bit-sliced kernel over a library's reads (or all reads) into the tables `tl`
         auto launch_bitsliced = [&](const mdg::CountTables &tl, const mdg::SwarSubset &subset) {
-            if (use_planes) {
+            if (use_planes && ctx->ws_variant >= 0) {
+                mdg::PlaneGeom pg = ctx->ws;
+                pg.indel_seen = ctx->indel_seen_dev;
+                const WsVariant &v = WS_VARIANTS[ctx->ws_variant];
+                const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
+                const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, (tiles + v.teams - 1) / v.teams);
+                v.kernel<<<pgrid, pg.threads, ctx->ws_smem, stream>>>(b, ctx->ref, p, tl, pg, wl->reads, wl->count, wl->indel_reads,
+                                                                     wl->indel_count, subset);
+            } else if (use_planes) {
                 mdg::PlaneGeom pg = ctx->planes;
                 pg.indel_seen = ctx->indel_seen_dev;
                 const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
@@ -805,6 +833,28 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                     MDG_CREATE_CUDA(cudaFuncSetAttribute(mdg::count_planes_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)ctx->planes_smem));
                 ctx->planes_enabled = true;
+            }
+        }
+        // warp-specialised bit-plane kernel: MDG_PLANES_WS=<variant name> (or 0: off)
+        if (ctx->planes_enabled) {
+            const char *ws_env = getenv("MDG_PLANES_WS");
+            const char *want = ws_env ? ws_env : "0";
+            for (int i = 0; i < (int)(sizeof(WS_VARIANTS) / sizeof(WS_VARIANTS[0])); ++i) {
+                const WsVariant &v = WS_VARIANTS[i];
+                if (strcmp(want, v.name)) continue;
+                mdg::PlaneGeom wg = ctx->planes;
+                wg.threads = (v.teams * v.team_warps + v.cons_warps) * 32;
+                wg.tile = v.team_warps * 32;
+                const char *slab_env = getenv("MDG_PLANES_SLAB");
+                wg.seq_words = slab_env && slab_env[0] == '0' ? 0 : wg.tile * 56 / 4;
+                const size_t bytes = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, wg.row_words, wg.seq_words);
+                const int pairs = (v.cons_warps * 32 >> 7) * 32;
+                if (bytes <= ctx->smem_optin && 2 * wg.nw_anchor * 2 <= pairs) {
+                    MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                    ctx->ws = wg;
+                    ctx->ws_smem = bytes;
+                    ctx->ws_variant = i;
+                }
             }
         }
         const char *env = getenv("MDG_FORCE_GENERAL");

@@ -259,7 +259,7 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
         }
     };
     // reduces the block's counters into the 64-bit tables (end of the kernel, on mode changes, and before a
-    // thread's 14-bit counters could overflow).  The stage area is free at that point: it holds the block's sums,
+    // thread's 12-bit counters could overflow).  The stage area is free at that point: it holds the block's sums,
     // [strand][class 0..19][window bit].
     auto flush_block = [&]() {
         spill();
@@ -328,7 +328,8 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
     const int min_slots = max(2, (pairs / WPR_MAX) & ~1);
     // a thread counts at most ceil(T / (slots / 2)) reads per tile, rounded up to whole iterations of eight
     const int per_tile = ((T + (min_slots >> 1) - 1) / (min_slots >> 1) + 7) & ~7;
-    const int flush_period = g.flush_tiles > 0 ? g.flush_tiles : max(1, 16000 / per_tile);
+    // twelve counter bits (register planes 0-3, wide planes 4-11): 4095 reads of one class at one position at most
+    const int flush_period = g.flush_tiles > 0 ? g.flush_tiles : max(1, 3800 / per_tile);
     int tiles_since_flush = 0;
     bool dirty = false;
 

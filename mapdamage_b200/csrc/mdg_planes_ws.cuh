@@ -1,0 +1,776 @@
+// Counting pass, bit-plane kernel with specialised warps: producer teams parse and stage tiles, consumer warps count.
+//
+// Same contract and the same arithmetic as count_planes_kernel (mdg_planes.cuh: the loop body of main.py:165-217 for
+// reads whose CIGAR is [H][S] M/=/X+ [S][H]; bit planes, vertical carry-save counters, substitutions as events), but the
+// three block-wide phases of that kernel (parse | stage | count, a barrier after each) are taken apart:
+//
+//   * kTeams producer teams of kTeamWarps warps.  A team owns one stage buffer of T = 32 kTeamWarps reads and walks its
+//     own tiles: parse (filter, CIGAR shape, per-read events, records into lists by strand), then -- once the consumers
+//     have released the buffer -- the plane words of every read's window(s) into the buffer.  The tile's stretch of
+//     seq4 arrives by one bulk asynchronous copy (cp.async.bulk + mbarrier) issued a tile ahead.  Teams run out of step
+//     with each other: while one waits for memory in its parse, another one's transposition keeps the pipes busy.
+//   * kConsWarps consumer warps hold ALL the counters (planes 0-7 in registers, 4-11 in shared memory).  They wait on a
+//     buffer's `full` mbarrier, add its reads into the vertical counters (thread = read slot x window word x reference
+//     base), and arrive on its `empty` mbarrier.  They alone reduce counters into the 64-bit tables.
+//
+// full / empty are mbarriers with one arrival per thread of the side that signals (release / acquire at CTA scope order
+// the staged words); producers synchronise among themselves with a named barrier per team (bar.sync id, T), consumers
+// with their own.  There is no block-wide barrier between the first tile and the last.
+//
+// Substitution events go to a block-wide table indexed by TABLE cell ([anchor][strand][class][position]), so that teams
+// working in different window layouts can share it; it is drained once, at the end.
+#pragma once
+#include "mdg_planes.cuh"
+
+namespace mdg {
+
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+template <int kCount>
+__device__ __forceinline__ void named_barrier(int id)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kCount) : "memory");
+}
+
+// the plane's eight bits of a seq4 word (as BAM stores it) in bits 24..31 -- see count_planes_kernel::plane_byte
+__device__ __forceinline__ uint32_t ws_plane_byte(uint32_t w, int pl)
+{
+    const uint32_t y = (pl ? shr_fma(w, pl) : w) & 0x11111111u;
+    return ((shr_fma(y, 4) | shl_fma(y, 1)) & 0x03030303u) * 0x01041040u;
+}
+
+constexpr int WS_CTL = 8;        // words per tile control block: n_fwd, n_rev, n_cx, min cols, max cols, n_ix, mode, -
+constexpr int WS_CAPACITY = 4000;  // reads a counter may see between two reductions (12 bits: planes 0-3 + wide 4-11)
+
+template <int kTeams, int kTeamWarps, int kConsWarps>
+__global__ void __launch_bounds__((kTeams * kTeamWarps + kConsWarps) * 32, 1)
+count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneGeom g, uint32_t *__restrict__ worklist,
+                       unsigned long long *__restrict__ work_count, uint32_t *__restrict__ indel_list,
+                       unsigned long long *__restrict__ indel_count, SwarSubset sub)
+{
+    constexpr int T = kTeamWarps * 32;   // threads of a producer team = reads per tile
+    constexpr int CT = kConsWarps * 32;  // consumer threads
+    constexpr int PRODUCERS = kTeams * T;
+    constexpr int NTHREADS = PRODUCERS + CT;
+    static_assert(kConsWarps % 4 == 0, "consumer warps come in fours: one per reference base");
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int L = p.L, A = p.A, LA = L + A;
+    const int NWA = g.nw_anchor, WPR_MAX = 2 * NWA, ROW = g.row_words;
+    // ---- shared memory ----
+    uint32_t *const s_wide = smem;                                    // [PL_WIDE][PL_CLASSES][CT]
+    uint32_t *const s_red = s_wide + PL_WIDE * PL_CLASSES * CT;       // [strand][8 classes][32 WPR_MAX]: a reduction's sums
+    uint32_t *const s_sub = s_red + 2 * 8 * 32 * WPR_MAX;             // [anchor][strand][12][L] substitution events
+    uint32_t *const s_lg = s_sub + 4 * 12 * L;                        // [kind][strand][MDG_LG_SMEM_BINS]
+    uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;             // [end][strand][L]
+    uint32_t *const s_teams = (uint32_t *)(((uintptr_t)(s_clip + 4 * L) + 15) & ~(uintptr_t)15);
+    // per team: stage rows [T][ROW], records [T], two index lists [T], masks [WPR_MAX][2], three control blocks, seq4 stretch
+    const int seq_words = (g.seq_words + 3) & ~3;
+    const int team_words = T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + seq_words;
+    __shared__ __align__(8) unsigned long long s_full[kTeams], s_empty[kTeams], s_slab_bar[kTeams];
+    __shared__ int32_t s_slab[kTeams][2];  // first seq4 word held in the team's copy (may be negative), words (0: no copy)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < PL_WIDE * PL_CLASSES * CT; i += NTHREADS) s_wide[i] = 0;
+    for (int i = tid; i < 4 * 12 * L + 4 * MDG_LG_SMEM_BINS + 4 * L; i += NTHREADS) s_sub[i] = 0;
+    if (tid < kTeams) {
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_full[tid]), T);
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_empty[tid]), CT);
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_slab_bar[tid]), 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        s_slab[tid][0] = 0;
+        s_slab[tid][1] = 0;
+    }
+    for (int i = tid; i < kTeams * 3 * WS_CTL; i += NTHREADS) {
+        const int team = i / (3 * WS_CTL), w = i % (3 * WS_CTL);
+        (s_teams + (size_t)team * team_words + T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3))[w] = (w % WS_CTL) == 3 ? 0xffffffffu : 0u;
+    }
+    __syncthreads();
+
+    const uint32_t *const subset = sub.list ? sub.list + sub.offsets[sub.lib] : nullptr;
+    const int64_t n_todo = sub.list ? (int64_t)(sub.offsets[sub.lib + 1] - sub.offsets[sub.lib]) : b.n_reads;
+    const int64_t n_tiles = (n_todo + T - 1) / T;
+    constexpr int PAIRS = (CT >> 7) * 32;  // (slot, word) pairs per reference base on the consumer side
+    auto words_of = [&](int columns) { return columns ? (columns + 2 * A + 31) / 32 : WPR_MAX; };
+    // tile `k` of team `team` of this block
+    auto tile_of = [&](int64_t k, int team) { return (k * gridDim.x + blockIdx.x) * kTeams + team; };
+
+    if (warp < kTeams * kTeamWarps) {
+        // =========================================== producer team ===========================================
+        const int team = warp / kTeamWarps, ptid = tid - team * T, pwarp = ptid >> 5;
+        uint32_t *const s_stage = s_teams + (size_t)team * team_words;
+        PlaneRecord *const s_rec = (PlaneRecord *)(s_stage + T * ROW);  // forward reads from the front, reverse from the back
+        uint32_t *const s_cx = (uint32_t *)(s_rec + T);                 // reads for the general kernel
+        uint32_t *const s_ix = s_cx + T;                                // one-indel reads
+        uint32_t *const s_mask = s_ix + T;                              // [WPR_MAX][2] aligned / flank masks of a typical read
+        uint32_t *const s_ctl_base = s_mask + ((2 * WPR_MAX + 3) & ~3);
+        uint32_t *const s_seq = s_ctl_base + 4 * WS_CTL;
+        const uint32_t full_addr = (uint32_t)__cvta_generic_to_shared(&s_full[team]);
+        const uint32_t empty_addr = (uint32_t)__cvta_generic_to_shared(&s_empty[team]);
+        const uint32_t slab_addr = (uint32_t)__cvta_generic_to_shared(&s_slab_bar[team]);
+        const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
+        const uint4 *__restrict__ planes = ref.planes;
+        uint32_t slab_phase = 0;
+        int mode = -1;  // window layout the team's masks were made for
+
+        auto fill_masks = [&](int columns) {
+            const int wpr = words_of(columns);
+            for (int w = ptid; w < wpr; w += T) {
+                uint32_t aligned, flank;
+                if (columns) {
+                    aligned = bit_range(A - 32 * w, A + columns - 32 * w);
+                    flank = bit_range(-32 * w, A - 32 * w) | bit_range(A + columns - 32 * w, 2 * A + columns - 32 * w);
+                } else if (w < NWA) {
+                    aligned = bit_range(A - 32 * w, A + L - 32 * w);
+                    flank = bit_range(-32 * w, A - 32 * w);
+                } else {
+                    const int k = w - NWA, top = 32 * NWA;
+                    aligned = bit_range(top - A - L - 32 * k, top - A - 32 * k);
+                    flank = bit_range(top - A - 32 * k, top - 32 * k);
+                }
+                s_mask[2 * w] = aligned;
+                s_mask[2 * w + 1] = flank;
+            }
+        };
+
+        // ---- stage: the plane words of one window of one read (see count_planes_kernel::stage_window) ----
+        auto stage_window = [&](auto nw_tag, const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
+                                int slab_w0, int slab_words, int rstrand) {
+            constexpr int kNW = decltype(nw_tag)::value;
+            const int cols = (int)(rec.cols & 0x7FFF);
+            const int v = (int)(rec.misc & 0xFFFF);
+            const int lf = (int)((rec.cols >> 16) & 0xFF), rf = (int)(rec.cols >> 24);
+            const bool typical = lf == A && rf == A && (mode || v == L);
+            const int64_t qn = (int64_t)rec.q0 + c_start;
+            const int qs = (int)(qn & 7);
+            const int64_t qw = qn >> 3, in_slab = qw - slab_w0;
+            const bool from_smem = slab_words > 0 && in_slab >= 0 && in_slab + 4 * (kNW > 0 ? kNW : n_words) + 1 <= slab_words;
+            const uint32_t *const qs_ptr = s_seq + (from_smem ? in_slab : 0), *const qg_ptr = seq32 + qw;
+            auto seq_word = [&](int m) { return from_smem ? qs_ptr[m] : __ldg(qg_ptr + m); };
+            const int64_t rn = ((int64_t)rec.rg << 5) + (int)((rec.misc >> 16) & 31) + c_start;
+            const uint4 *rp = planes + (rn >> 5);
+            const int rs = (int)(rn & 31);
+            uint32_t *const sub_at = s_sub + (size_t)rstrand * 12 * L;
+            auto emit = [&](int k, uint32_t (&q0)[4], uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, const uint4 &g_lo, const uint4 &g_hi) {
+                uint32_t xp[4];
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) {
+                    const uint32_t q1 = ws_plane_byte(w1, pl), q2 = ws_plane_byte(w2, pl), q3 = ws_plane_byte(w3, pl), q4 = ws_plane_byte(w4, pl);
+                    const uint32_t lo = __byte_perm(__byte_perm(q0[pl], q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
+                    xp[pl] = __funnelshift_r(lo, q4 >> 24, qs);
+                    q0[pl] = q4;
+                }
+                const uint32_t xa = xp[0], xc = xp[1], xg = xp[2], xt = xp[3];
+                const uint32_t ya = __funnelshift_r(g_lo.x, g_hi.x, rs), yc = __funnelshift_r(g_lo.y, g_hi.y, rs);
+                const uint32_t yg = __funnelshift_r(g_lo.z, g_hi.z, rs), yt = __funnelshift_r(g_lo.w, g_hi.w, rs);
+                uint32_t aligned, flank;
+                if (typical) {
+                    aligned = s_mask[2 * (first_word + k)];
+                    flank = s_mask[2 * (first_word + k) + 1];
+                } else {
+                    const int base = c_start + 32 * k;  // column of bit 0
+                    if (mode) {
+                        aligned = bit_range(-base, cols - base);
+                        flank = bit_range(-lf - base, -base) | bit_range(cols - base, cols + rf - base);
+                    } else if (side == 0) {
+                        aligned = bit_range(-base, v - base);
+                        flank = bit_range(-lf - base, -base);
+                    } else {
+                        aligned = bit_range(cols - v - base, cols - base);
+                        flank = bit_range(cols - base, cols + rf - base);
+                    }
+                }
+                // statistics.py:27: a column counts only when the read base is A/C/G/T; flank bits carry the reference base alone
+                const uint32_t one = (xa ^ xc ^ xg ^ xt) & ~((xa & xc) | (xg & xt));
+                const uint32_t keep = one & aligned, keep_y = keep | flank;
+                uint4 xs, ys;
+                xs.x = xa & keep; xs.y = xc & keep; xs.z = xg & keep; xs.w = xt & keep;
+                ys.x = ya & keep_y; ys.y = yc & keep_y; ys.z = yg & keep_y; ys.w = yt & keep_y;
+                uint4 *out = (uint4 *)(row_at + 8 * (first_word + k));
+                out[0] = xs;
+                out[1] = ys;
+                // substitutions (reference g read as another base): one shared-memory atomic per event, on the table cell
+                uint32_t ev = (ys.x | ys.y | ys.z | ys.w) & keep & ~((xs.x & ys.x) | (xs.y & ys.y) | (xs.z & ys.z) | (xs.w & ys.w));
+                if (ev) {
+                    const uint32_t g1 = ys.y | ys.w, g2 = ys.z | ys.w, r1 = xs.y | xs.w, r2 = xs.z | xs.w;
+                    const int col0 = c_start + 32 * k;  // column of bit 0 of this word
+                    do {
+                        const int j = __ffs(ev) - 1;
+                        ev &= ev - 1;
+                        const int gb = (int)((g1 >> j) & 1u) + 2 * (int)((g2 >> j) & 1u);
+                        int rb = (int)((r1 >> j) & 1u) + 2 * (int)((r2 >> j) & 1u);
+                        rb -= rb > gb ? 1 : 0;
+                        uint32_t *const cell = sub_at + (3 * gb + rb) * L;
+                        const int col = col0 + j, back = cols - 1 - col;  // distance from the left / right end of the alignment
+                        if (mode) {
+                            if (col < L) atomicAdd(cell + col, 1u);
+                            if (back < L) atomicAdd(cell + 2 * 12 * L + back, 1u);
+                        } else if (side == 0) {
+                            atomicAdd(cell + col, 1u);
+                        } else {
+                            atomicAdd(cell + 2 * 12 * L + back, 1u);
+                        }
+                    } while (ev);
+                }
+            };
+            if constexpr (kNW > 0) {
+                uint4 gw[kNW + 1];
+#pragma unroll
+                for (int k = 0; k <= kNW; ++k) gw[k] = __ldg(rp + k);
+                uint32_t q0[4];
+                {
+                    const uint32_t w0 = seq_word(0);
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) q0[pl] = ws_plane_byte(w0, pl);
+                }
+#pragma unroll
+                for (int k = 0; k < kNW; ++k) {
+                    const uint32_t w1 = seq_word(4 * k + 1), w2 = seq_word(4 * k + 2), w3 = seq_word(4 * k + 3), w4 = seq_word(4 * k + 4);
+                    emit(k, q0, w1, w2, w3, w4, gw[k], gw[k + 1]);
+                }
+            } else {
+                uint32_t q0[4];
+                {
+                    const uint32_t w0 = seq_word(0);
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) q0[pl] = ws_plane_byte(w0, pl);
+                }
+                uint4 g_lo = __ldg(rp);
+                for (int k = 0; k < n_words; ++k) {
+                    const uint32_t w1 = seq_word(4 * k + 1), w2 = seq_word(4 * k + 2), w3 = seq_word(4 * k + 3), w4 = seq_word(4 * k + 4);
+                    const uint4 g_hi = __ldg(rp + k + 1);
+                    emit(k, q0, w1, w2, w3, w4, g_lo, g_hi);
+                    g_lo = g_hi;
+                }
+            }
+        };
+
+        // ---- parse of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
+        // kind: 0 nothing to do, 1 gap-free (record made), 2 for the general kernel, 3 one short indel
+        auto parse_read = [&](bool live, int64_t r, int &kind, int &rstrand, uint32_t &columns, PlaneRecord &rec) {
+            kind = 0;
+            rstrand = 0;
+            columns = 0;
+            if (!live) return;
+            const uint32_t flag = b.flag[r];
+            const uint32_t lib = b.lib[r];
+            const int32_t tid_ref = b.tid[r];
+            const int64_t pos = b.pos[r];
+            const uint32_t l_seq = b.l_seq[r], boff = b.base_off[r], c0 = b.cigar_off[r], c1 = b.cigar_off[r + 1];
+            const uint32_t cig0 = c1 > c0 ? __ldg(b.cigar + c0) : 0;
+            if (flag & FILTERED_FLAGS) return;
+            if (lib >= (uint32_t)p.n_lib) {
+                atomicCAS(t.error_flag, 0, DATA_ERR_LIB);
+                return;
+            }
+            if (subset && lib != (uint32_t)sub.lib) return;  // cannot happen: the list is grouped by library
+            if (tid_ref < 0 || tid_ref >= ref.n_contigs) {
+                atomicCAS(t.error_flag, 0, DATA_ERR_TID);
+                return;
+            }
+            rstrand = (flag >> 4) & 1;
+            uint32_t lead = 0, trail = 0, cols = 0, gap_len = 0, gap_del = 0;
+            int state = 0, n_lead = 0, n_trail = 0;
+            bool simple = c1 > c0;
+            if (c1 - c0 == 1 && ((0x181u >> (cig0 & 0xF)) & 1u)) {
+                cols = cig0 >> 4;  // one match block (M, = or X): nearly every read of an untrimmed library
+                state = 1;
+            } else
+            for (uint32_t k = c0; k < c1 && simple; ++k) {
+                const uint32_t w = k == c0 ? cig0 : __ldg(b.cigar + k), op = w & 0xF, len = w >> 4;
+                const bool match = op == OP_M || op == OP_EQ || op == OP_X;
+                if (state == 0) {
+                    if (op == OP_H) simple = n_lead == 0;
+                    else if (op == OP_S) { lead += len; ++n_lead; }
+                    else if (match) { cols += len; state = 1; }
+                    else simple = false;
+                } else if (state == 1) {
+                    if (match) cols += len;
+                    else if (op == OP_S) { trail += len; ++n_trail; state = 2; }
+                    else if (op == OP_H) state = 3;
+                    else if ((op == OP_I || op == OP_D) && !gap_len && len >= 1 && len <= 7 && cols >= 1) {
+                        gap_len = len; gap_del = op == OP_D;
+                        cols += len;
+                        state = 4;
+                    } else simple = false;
+                } else if (state == 2) {
+                    if (op == OP_S) { trail += len; ++n_trail; }
+                    else if (op == OP_H) state = 3;
+                    else simple = false;
+                } else if (state == 4) {  // the match block after the indel
+                    if (match && len >= 1) { cols += len; state = 1; }
+                    else simple = false;
+                } else {
+                    simple = op == OP_H;
+                }
+            }
+            simple = simple && state != 4;
+            const uint32_t n_query = cols - (gap_del ? gap_len : 0), ref_span = cols - (gap_len && !gap_del ? gap_len : 0);
+            const int64_t contig_len = ref.contig_len[tid_ref];
+            const uint64_t ref0 = ref.contig_off[tid_ref] + (uint64_t)(pos > 0 ? pos : 0);
+            simple = simple && state >= 1 && cols > 0 && cols < 32768 && n_lead <= 1 && n_trail <= 1 &&
+                     (uint64_t)lead + n_query + trail == l_seq && pos >= 0 && pos + (int64_t)ref_span <= contig_len &&
+                     ref0 < (1ull << 33);
+            if (!simple) {
+                kind = 2;
+                return;
+            }
+            if (gap_len) {
+                kind = 3;  // count_staged_kernel's indel variant parses this read again and does all of its bookkeeping
+                return;
+            }
+            kind = 1;
+            columns = cols;
+            const int64_t aend = pos + ref_span;
+            const uint32_t lf = (uint32_t)min((int64_t)A, pos);
+            const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
+            rec.q0 = (uint32_t)((uint64_t)boff + lead);
+            rec.rg = (uint32_t)(ref0 >> 5);
+            rec.cols = cols | (lf << 16) | (rf << 24);
+            rec.misc = min(cols, (uint32_t)L) | (uint32_t)(ref0 & 31) << 16;
+            // FragmentLengths.update, statistics.py:117-126
+            int64_t length = -1;
+            int lkind = 0;
+            if (flag & 0x1) {
+                if ((flag & 0x40) && (flag & 0x2)) {
+                    const int64_t tl = b.tlen[r];
+                    length = tl < 0 ? -tl : tl;
+                }
+            } else {
+                lkind = 1;
+                length = ref_span;
+            }
+            if (length >= 0) {
+                if (length < MDG_LG_SMEM_BINS && length < p.lg_bins) {
+                    atomicAdd(s_lg + (lkind * 2 + rstrand) * MDG_LG_SMEM_BINS + length, 1u);
+                } else if (length < p.lg_bins) {
+                    atomicAdd(t.lghist + (size_t)(lkind * 2 + rstrand) * p.lg_bins + length, 1ull);
+                } else {
+                    const unsigned long long at = atomicAdd(t.lg_overflow_count, 1ull);
+                    if ((int64_t)at < t.lg_overflow_cap) {
+                        int32_t *row = t.lg_overflow_rows + at * 4;
+                        row[0] = sub.list ? sub.lib : 0; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
+                    }
+                }
+            }
+            // update_soft_clipping, statistics.py:37-51
+            if (lead) {
+                const int end = rstrand ? 1 : 0, lim = (int)min(lead, (uint32_t)L);
+                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
+            }
+            if (trail) {
+                const int end = rstrand ? 0 : 1, lim = (int)min(trail, (uint32_t)L);
+                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
+            }
+        };
+
+        // L2 prefetch of the record arrays of a tile this team will parse later
+        auto prefetch_headers = [&](int64_t tile_index) {
+            const int64_t r4 = tile_index * T + (int64_t)ptid * 32;
+            if (subset) {
+                const int64_t at = tile_index * T + ptid;
+                if (at < n_todo) {
+                    const uint32_t r = subset[at];
+                    prefetch_l2(b.flag + r);
+                    prefetch_l2(b.tid + r);
+                    prefetch_l2(b.pos + r);
+                    prefetch_l2(b.l_seq + r);
+                    prefetch_l2(b.base_off + r);
+                    prefetch_l2(b.cigar_off + r);
+                }
+            } else if (ptid * 32 < T && r4 < b.n_reads) {
+                prefetch_l2(b.tid + r4);
+                prefetch_l2(b.pos + r4);
+                prefetch_l2(b.l_seq + r4);
+                prefetch_l2(b.tlen + r4);
+                prefetch_l2(b.base_off + r4);
+                prefetch_l2(b.cigar_off + r4);
+                prefetch_l2(b.cigar + r4);  // one op per read: the same place; otherwise a guess
+                if (!(ptid & 1)) {
+                    prefetch_l2(b.flag + r4);
+                    prefetch_l2(b.lib + r4);
+                }
+            }
+        };
+        // one thread: the stretch of seq4 the reads of a tile occupy (reads are laid out in order; a stage thread checks
+        // that its read really lies inside), 32 bytes more in front and 48 behind for the windows' flanks, as one bulk copy
+        auto issue_slab = [&](int64_t tile_index) {
+            s_slab[team][1] = 0;
+            if (subset || g.seq_words <= 0 || tile_index >= n_tiles) return;
+            const int64_t r0 = tile_index * T, r1 = min(n_todo, r0 + (int64_t)T) - 1;
+            const uint64_t first = b.base_off[r0], last = (uint64_t)b.base_off[r1] + b.l_seq[r1];
+            const int64_t lo = ((int64_t)(first >> 1) - 32) & ~15ll, hi = ((int64_t)((last + 1) >> 1) + 48 + 15) & ~15ll;
+            const int64_t bytes = hi - lo;
+            if (bytes <= 0 || bytes > 4ll * g.seq_words) return;
+            s_slab[team][0] = (int32_t)(lo >> 2);
+            s_slab[team][1] = (int32_t)(bytes >> 2);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_seq);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(slab_addr), "r"((uint32_t)bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"((const char *)b.seq4 + lo), "r"((uint32_t)bytes), "r"(slab_addr)
+                         : "memory");
+        };
+
+        prefetch_headers(tile_of(0, team));
+        prefetch_headers(tile_of(1, team));
+        if (ptid == 0) issue_slab(tile_of(0, team));
+        named_barrier<T>(1 + team);  // s_slab of the first tile
+        for (int64_t k = 0;; ++k) {
+            const int64_t tile = tile_of(k, team);
+            if (tile >= n_tiles) break;
+            uint32_t *const s_ctl = s_ctl_base + WS_CTL * (int)(k % 3);
+            uint32_t *const s_ctl_next = s_ctl_base + WS_CTL * (int)((k + 1) % 3);
+
+            // ---- parse: one read per thread ----
+            {
+                const int64_t at = tile * T + ptid;
+                const bool live = at < n_todo;
+                const int64_t r = !live ? 0 : subset ? (int64_t)subset[at] : at;
+                int kind, rstrand;
+                uint32_t columns;
+                PlaneRecord rec{};
+                parse_read(live, r, kind, rstrand, columns, rec);
+                if (g.uniform) {
+                    const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
+                    const uint32_t hi = __reduce_max_sync(0xffffffffu, kind == 1 ? columns : 0u);
+                    if (lane == 0 && hi) {
+                        atomicMin(s_ctl + 3, lo);
+                        atomicMax(s_ctl + 4, hi);
+                    }
+                }
+                // warp-aggregated appends to the four lists
+                const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int which = 0; which < 4; ++which) {
+                    const bool mine = which == 2 ? kind == 2 : which == 3 ? kind == 3 : (kind == 1 && rstrand == which);
+                    const uint32_t m = __ballot_sync(0xffffffffu, mine);
+                    if (m) {
+                        uint32_t base = 0;
+                        if (lane == __ffs(m) - 1) base = atomicAdd(s_ctl + (which == 3 ? 5 : which), (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                        if (mine) {
+                            const uint32_t slot = base + __popc(m & lt);
+                            if (which == 2) s_cx[slot] = (uint32_t)r;
+                            else if (which == 3) s_ix[slot] = (uint32_t)r;
+                            else s_rec[which == 0 ? slot : T - 1 - slot] = rec;
+                        }
+                    }
+                }
+            }
+            named_barrier<T>(1 + team);
+
+            // ---- reads this kernel does not count go to the two work lists ----
+            if (pwarp == 0 && s_ctl[2]) {
+                const uint32_t n_cx = s_ctl[2];
+                unsigned long long base = 0;
+                uint32_t *const wl = sub.list ? worklist + sub.offsets[sub.lib] : worklist;
+                if (lane == 0) base = atomicAdd(work_count + (sub.list ? sub.lib : 0), (unsigned long long)n_cx);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (uint32_t i = lane; i < n_cx; i += 32) wl[base + i] = s_cx[i];
+            }
+            if (pwarp == 1 && s_ctl[5]) {
+                const uint32_t n_ix = s_ctl[5];
+                unsigned long long base = 0;
+                uint32_t *const il = sub.list ? indel_list + sub.offsets[sub.lib] : indel_list;
+                if (lane == 0) {
+                    base = atomicAdd(indel_count + (sub.list ? sub.lib : 0), (unsigned long long)n_ix);
+                    if (g.indel_seen) atomicAdd(g.indel_seen, (unsigned long long)n_ix);
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (uint32_t i = lane; i < n_ix; i += 32) il[base + i] = s_ix[i];
+            }
+            // the control block of the tile after this one (last read by the consumers two tiles ago)
+            if (ptid < WS_CTL) s_ctl_next[ptid] = ptid == 3 ? 0xffffffffu : 0u;
+
+            // ---- one window per read when every gap-free read of the tile has the same length ----
+            {
+                int want = 0;
+                const uint32_t lo = s_ctl[3], hi = s_ctl[4];
+                if (g.uniform && lo == hi && hi > 0) {
+                    const int words = ((int)hi + 2 * A + 31) / 32;
+                    if (words < WPR_MAX && PAIRS / words >= 2) want = (int)hi;
+                }
+                if (ptid == 0) s_ctl[6] = (uint32_t)want;
+                if (want != mode) {
+                    mode = want;
+                    fill_masks(want);
+                    named_barrier<T>(1 + team);
+                }
+            }
+            prefetch_headers(tile_of(k + 2, team));
+
+            // ---- stage: one thread per (read, window), once the consumers are done with the tile before ----
+            const int n_fwd = (int)s_ctl[0], n_rev = (int)s_ctl[1];
+            if (k > 0) mbar_wait(empty_addr, (uint32_t)((k - 1) & 1));
+            const int slab_w0 = s_slab[team][0], slab_words = s_slab[team][1];
+            if (slab_words) {
+                mbar_wait(slab_addr, slab_phase & 1u);
+                ++slab_phase;
+            }
+            {
+                const int n_windows = mode ? 1 : 2, n_items = (n_fwd + n_rev) * n_windows;
+                const int wpr = words_of(mode);
+                for (int item = ptid; item < n_items; item += T) {
+                    const int li = mode ? item : item >> 1, side = mode ? 0 : item & 1;
+                    const int row = li < n_fwd ? li : T - 1 - (li - n_fwd);
+                    const PlaneRecord rec = s_rec[row];
+                    uint32_t *const row_at = s_stage + (size_t)row * ROW;
+                    const int n_words = mode ? wpr : NWA, first_word = side ? NWA : 0;
+                    const int c_start = side ? (int)(rec.cols & 0x7FFF) + A - 32 * NWA : -A;
+                    if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, li >= n_fwd);
+                    else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, li >= n_fwd);
+                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, li >= n_fwd);
+                }
+            }
+            mbar_arrive(full_addr);  // release: this thread's words of the buffer (and the control block) are visible to the consumers
+            named_barrier<T>(1 + team);
+            if (ptid == 0) issue_slab(tile_of(k + 1, team));  // lands while the next tile is parsed
+            // (the next parse does not read s_slab; the barrier after it orders this write before the stage)
+        }
+    } else {
+        // =============================================== consumers ===============================================
+        const int ctid = tid - PRODUCERS, cwarp = ctid >> 5;
+        const int group = cwarp & 3;                 // reference base of this thread's classes
+        const int pair = (cwarp >> 2) * 32 + lane;   // index among the (slot, word) pairs of its group
+        int mode = 0, ws = 0, slot = 0, strand = 0, mode_slots = 2;
+        bool active = false;
+        auto set_mode = [&](int columns) {
+            mode = columns;
+            const int wpr = words_of(columns);
+            mode_slots = (PAIRS / wpr) & ~1;
+            active = pair < wpr * mode_slots;
+            ws = pair % wpr;
+            slot = pair / wpr;
+            strand = slot & 1;
+        };
+        set_mode(0);
+        uint32_t cnt[PL_CLASSES][PL_REG];
+#pragma unroll
+        for (int c = 0; c < PL_CLASSES; ++c)
+#pragma unroll
+            for (int k = 0; k < PL_REG; ++k) cnt[c][k] = 0;
+        int n_iter = 0;  // eight-read iterations since planes 4 .. 7 were moved up
+        uint32_t *const my_wide = s_wide + ctid;  // plane k of class c at my_wide[(k * PL_CLASSES + c) * CT]
+
+        // planes 4 .. 7 of the register counters -> the wide counters in shared memory (a ripple-carry add, plane by plane)
+        auto spill = [&]() {
+#pragma unroll
+            for (int c = 0; c < PL_CLASSES; ++c) {
+                uint32_t *w = my_wide + c * CT;
+                uint32_t carry = 0;
+#pragma unroll
+                for (int k = 0; k < PL_REG - 4; ++k) {
+                    const uint32_t wk = w[k * PL_CLASSES * CT], v = cnt[c][4 + k];
+                    w[k * PL_CLASSES * CT] = wk ^ v ^ carry;
+                    carry = (wk & v) | ((wk ^ v) & carry);
+                    cnt[c][4 + k] = 0;
+                }
+                for (int k = PL_REG - 4; carry && k < PL_WIDE; ++k) {
+                    const uint32_t wk = w[k * PL_CLASSES * CT];
+                    w[k * PL_CLASSES * CT] = wk ^ carry;
+                    carry &= wk;
+                }
+            }
+            n_iter = 0;
+        };
+        auto add_cell = [&](int canchor, int cstrand, int cls, int pos, unsigned long long sum) {
+            // window position `pos` of an anchor -> table cell; classes are complemented on the reverse strand
+            const int es = (canchor ^ cstrand) * 2 + cstrand;
+            if (pos >= 0) {
+                if (cls < 4) {
+                    const int gb = cstrand ? 3 - cls : cls;
+                    atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + gb) * L + pos, sum);
+                } else {
+                    const int rb = cstrand ? 3 - (cls - 4) : cls - 4;
+                    atomicAdd(t.dnacomp + ((size_t)es * 4 + rb) * LA + pos, sum);
+                }
+            } else if (cls < 4) {
+                const int gb = cstrand ? 3 - cls : cls;
+                atomicAdd(t.dnacomp + ((size_t)es * 4 + gb) * LA + L - pos - 1, sum);
+            }
+        };
+        // reduces the consumers' counters into the 64-bit tables (end of the kernel, on layout changes, and before a
+        // 12-bit counter could overflow)
+        auto flush = [&]() {
+            spill();
+            const int wpr = words_of(mode), bits = 32 * wpr;
+            for (int i = ctid; i < 2 * 8 * bits; i += CT) s_red[i] = 0;
+            named_barrier<CT>(1 + kTeams);
+            if (active) {
+#pragma unroll
+                for (int c = 0; c < PL_CLASSES; ++c) {
+                    const int cls = c == 0 ? group : 4 + group;  // class of the tables: R_g, H_g
+                    uint32_t pl[4 + PL_WIDE];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pl[k] = cnt[c][k];
+#pragma unroll
+                    for (int k = 0; k < PL_WIDE; ++k) {
+                        pl[4 + k] = my_wide[(k * PL_CLASSES + c) * CT];
+                        my_wide[(k * PL_CLASSES + c) * CT] = 0;
+                    }
+                    uint32_t any = 0;
+#pragma unroll
+                    for (int k = 0; k < 4 + PL_WIDE; ++k) any |= pl[k];
+                    uint32_t *const to = s_red + ((size_t)strand * 8 + cls) * bits + 32 * ws;
+                    while (any) {
+                        const int j = __ffs(any) - 1;
+                        any &= any - 1;
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int k = 0; k < 4 + PL_WIDE; ++k) v |= ((pl[k] >> j) & 1u) << k;
+                        atomicAdd(to + j, v);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < PL_CLASSES; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cnt[c][k] = 0;
+            named_barrier<CT>(1 + kTeams);
+            for (int cell = ctid; cell < 2 * 8 * bits; cell += CT) {
+                const int bit = cell % bits, cls = (cell / bits) % 8, cstrand = cell / (8 * bits);
+                const unsigned long long sum = s_red[cell];
+                if (!sum) continue;
+                if (mode) {
+                    const int pos = bit - A;  // column
+                    if (pos < 0) add_cell(0, cstrand, cls, pos, sum);                          // left flank
+                    else if (pos >= mode) add_cell(1, cstrand, cls, mode - 1 - pos, sum);      // right flank at distance pos - C + 1
+                    else {
+                        if (pos < L) add_cell(0, cstrand, cls, pos, sum);
+                        if (mode - 1 - pos < L) add_cell(1, cstrand, cls, mode - 1 - pos, sum);
+                    }
+                } else if (bit < 32 * NWA) {
+                    const int pos = bit - A;
+                    if (pos < L) add_cell(0, cstrand, cls, pos, sum);
+                } else {
+                    const int pos = 32 * NWA - A - 1 - (bit - 32 * NWA);  // columns from the right end; negative: flank
+                    if (pos < L) add_cell(1, cstrand, cls, pos, sum);
+                }
+            }
+            named_barrier<CT>(1 + kTeams);
+        };
+
+        int since_flush = 0, tiles_since_flush = 0;  // reads a counter may have seen / tiles since the last reduction
+        bool dirty = false, more = true;
+        for (int64_t k = 0; more; ++k) {
+            for (int team = 0; team < kTeams; ++team) {
+                if (tile_of(k, team) >= n_tiles) {
+                    more = false;
+                    break;
+                }
+                const uint32_t *const s_stage = s_teams + (size_t)team * team_words;
+                const uint32_t *const s_ctl = s_stage + T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
+                mbar_wait((uint32_t)__cvta_generic_to_shared(&s_full[team]), (uint32_t)(k & 1));
+                const int n_fwd = (int)s_ctl[0], n_rev = (int)s_ctl[1], want = (int)s_ctl[6];
+                if (want != mode) {
+                    if (dirty) flush();
+                    set_mode(want);
+                    dirty = false;
+                    since_flush = 0;
+                    tiles_since_flush = 0;
+                }
+                const int stride = mode_slots >> 1;
+                const int bound = ((max(n_fwd, n_rev) + stride - 1) / stride + 7) & ~7;  // reads a thread adds at most, whole iterations
+                if (since_flush + bound > WS_CAPACITY) {
+                    flush();
+                    since_flush = 0;
+                    tiles_since_flush = 0;
+                }
+                since_flush += bound;
+                dirty = dirty || n_fwd + n_rev > 0;
+                // ---- count: this thread's window word and reference base, every stride-th read of its strand ----
+                if (active) {
+                    const int n_mine = strand ? n_rev : n_fwd;
+                    const int row_step = (strand ? -stride : stride) * ROW;
+                    const uint32_t *at0 = s_stage + (size_t)(strand ? T - 1 - (slot >> 1) : (slot >> 1)) * ROW + 8 * ws;
+                    auto count_tile = [&](auto gtag) {
+                        constexpr int G = decltype(gtag)::value;
+                        const uint32_t *at = at0;
+                        for (int i = slot >> 1; i < n_mine; i += 8 * stride) {
+                            uint32_t xg[8], y[8];
+                            if (i + 7 * stride < n_mine) {  // eight reads in hand: no tests
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    xg[u] = at[u * row_step + G];
+                                    y[u] = at[u * row_step + 4 + G];
+                                }
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    const bool live = i + u * stride < n_mine;
+                                    xg[u] = live ? at[u * row_step + G] : 0u;
+                                    y[u] = live ? at[u * row_step + 4 + G] : 0u;
+                                }
+                            }
+                            at += 8 * row_step;
+                            MDG_ADD8(cnt[0], y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7])  // R_g
+                            MDG_ADD8(cnt[1], xg[0], xg[1], xg[2], xg[3], xg[4], xg[5], xg[6], xg[7])  // H_g
+                            if (++n_iter == 30) spill();  // planes 0-3 hold at most 15, thirty more iterations add 240: 255 fits eight planes
+                        }
+                    };
+                    switch (group) {
+                    case 0: count_tile(std::integral_constant<int, 0>{}); break;
+                    case 1: count_tile(std::integral_constant<int, 1>{}); break;
+                    case 2: count_tile(std::integral_constant<int, 2>{}); break;
+                    default: count_tile(std::integral_constant<int, 3>{}); break;
+                    }
+                }
+                mbar_arrive((uint32_t)__cvta_generic_to_shared(&s_empty[team]));  // the buffer may be staged again
+                if (g.flush_tiles > 0 && ++tiles_since_flush >= g.flush_tiles) {
+                    flush();
+                    since_flush = 0;
+                    tiles_since_flush = 0;
+                    dirty = false;
+                }
+            }
+        }
+        flush();
+    }
+
+    // ---- everybody: the block's event tables into the 64-bit tables ----
+    __syncthreads();
+    for (int cell = tid; cell < 4 * 12 * L; cell += NTHREADS) {
+        const uint32_t v = s_sub[cell];
+        if (!v) continue;
+        const int pos = cell % L, cls = (cell / L) % 12, cstrand = (cell / (12 * L)) & 1, canchor = cell / (24 * L);
+        int gb = cls / 3, rb = cls % 3;
+        rb += rb >= gb ? 1 : 0;
+        if (cstrand) { gb = 3 - gb; rb = 3 - rb; }
+        const int es = (canchor ^ cstrand) * 2 + cstrand;
+        atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + 4 + 5 * gb + rb) * L + pos, (unsigned long long)v);
+    }
+    for (int i = tid; i < 4 * MDG_LG_SMEM_BINS; i += NTHREADS) {
+        const uint32_t v = s_lg[i];
+        if (v) atomicAdd(t.lghist + (size_t)(i / MDG_LG_SMEM_BINS) * p.lg_bins + i % MDG_LG_SMEM_BINS, (unsigned long long)v);
+    }
+    for (int i = tid; i < 4 * L; i += NTHREADS) {
+        const uint32_t v = s_clip[i];
+        if (v) atomicAdd(t.misincorp + ((size_t)(i / L) * MDG_N_CLASSES + MDG_CLASS_SOFTCLIP) * L + i % L, (unsigned long long)v);
+    }
+}
+
+// dynamic shared memory of count_planes_ws_kernel<kTeams, kTeamWarps, kConsWarps> (bytes)
+inline size_t planes_ws_smem(int teams, int team_warps, int cons_warps, int L, int nw_anchor, int row_words, int seq_words)
+{
+    const size_t T = (size_t)team_warps * 32, CT = (size_t)cons_warps * 32, wpr_max = 2 * (size_t)nw_anchor;
+    const size_t shared = PL_WIDE * PL_CLASSES * CT + 2 * 8 * 32 * wpr_max + 4 * 12 * (size_t)L + 4 * MDG_LG_SMEM_BINS + 4 * (size_t)L + 4;
+    const size_t team = T * row_words + 4 * T + 2 * T + ((2 * wpr_max + 3) & ~(size_t)3) + 4 * WS_CTL + (((size_t)seq_words + 3) & ~(size_t)3);
+    return (shared + teams * team) * 4;
+}
+
+}  // namespace mdg

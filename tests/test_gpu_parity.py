@@ -295,7 +295,11 @@ def test_optional_arrays_default_on_device(name):
                                  {"MDG_STAGE_TILE": "96"}, {"MDG_STAGE_INDELS": "1"}, {"MDG_STAGE_INDELS": "0"}, {"MDG_KERNEL": "swar"},
                                  {"MDG_KERNEL": "staged"}, {"MDG_KERNEL": "staged", "MDG_SWAR_FLUSH_TILES": "3"},
                                  {"MDG_PLANES_TILE": "224", "MDG_SWAR_FLUSH_TILES": "2"}, {"MDG_PLANES_SLAB": "0"},
-                                 {"MDG_KERNEL": "swar", "MDG_SWAR_VARIANT": "512,1", "MDG_SWAR_FLUSH_TILES": "2"}])
+                                 {"MDG_KERNEL": "swar", "MDG_SWAR_VARIANT": "512,1", "MDG_SWAR_FLUSH_TILES": "2"},
+                                 {"MDG_PLANES_WS": "0"}, {"MDG_PLANES_WS": "2x8+8"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_FLUSH_TILES": "3"},
+                                 {"MDG_PLANES_WS": "2x8+8", "MDG_PLANES_SLAB": "0"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_UNIFORM": "0"},
+                                 {"MDG_PLANES_WS": "3x6+8"}, {"MDG_PLANES_WS": "4x4+8", "MDG_SWAR_FLUSH_TILES": "5"},
+                                 {"MDG_PLANES_WS": "2x8+4"}, {"MDG_PLANES_THREADS": "256"}])
 @pytest.mark.parametrize("min_qual", [0, 25])
 def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
     """1.3 M reads laid out so that every block of the bit-sliced kernel alternates between equal-length tiles
@@ -328,6 +332,48 @@ def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
     for name, a, b, c in zip(("misincorp", "dnacomp", "lghist"), got, want, twice):
         assert np.array_equal(a, b), name
         assert np.array_equal(2 * a, c), name
+
+
+@pytest.mark.parametrize("env", [{}, {"MDG_PLANES_WS": "0"}, {"MDG_PLANES_WS": "2x8+8"}, {"MDG_KERNEL": "staged"}])
+@pytest.mark.parametrize("length", [(100, 100), (60, 140)])
+def test_identical_reads_do_not_overflow_the_block_counters(env, length, monkeypatch):
+    """12 M forward reads of ONE place of the genome (an amplicon, a tower of PCR duplicates): every read adds to the same
+    table cells, so a block's private counters (12-bit vertical counters, 16-bit nibble counters) reach their capacity
+    as fast as they ever can and must be reduced into the 64-bit tables in time."""
+    from mapdamage_b200.batch import ReadBatch
+
+    for key, value in env.items():
+        monkeypatch.setenv(key, value)
+    reference = synth.make_reference([50_000], seed=9)
+    n = 12_000_000
+    lo, hi = length
+    lens = np.full(n, lo, dtype=np.int64) if lo == hi else lo + (np.arange(n, dtype=np.int64) * 7) % (hi - lo + 1)
+    template = synth.simulate_reads(reference, 1, seed=3, length=(hi, hi))  # one read of the longest length, as packed bases
+    row = np.zeros((hi + 1) // 2, dtype=np.uint8)
+    row[:] = template.seq4[:row.shape[0]]
+    padded = (lens + 1) & ~1
+    base_off = np.zeros(n, dtype=np.int64)
+    np.cumsum(padded[:-1], out=base_off[1:])
+    if lo == hi:
+        seq4 = np.tile(row[:(lo + 1) // 2], n)
+    else:
+        seq4 = np.zeros(int(base_off[-1] + padded[-1]) // 2, dtype=np.uint8)
+        for ln in range(lo, hi + 1):
+            idx = np.nonzero(lens == ln)[0]
+            if idx.size:
+                at = (base_off[idx] // 2)[:, None] + np.arange((ln + 1) // 2)[None, :]
+                seq4[at] = row[:(ln + 1) // 2][None, :]
+    batch = ReadBatch(flag=np.zeros(n, np.uint16), tid=np.zeros(n, np.int32), pos=np.full(n, int(template.pos[0]), np.int32),
+                      l_seq=lens, base_off=base_off, cigar_off=np.arange(n + 1), cigar=(lens << 4).astype(np.uint32), seq4=seq4)
+    want = oracle.count(batch, reference, lg_bins=8192, threads=8)
+    with DamageEngine(max_reads=0) as engine:
+        engine.set_reference(reference)
+        dev = engine.upload(batch)
+        engine.count_resident(dev)
+        got = engine.tables()
+        dev.free()
+    for name, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
+        assert np.array_equal(a, b), name
 
 
 @pytest.mark.parametrize("name", ["pe_mixed", "short", "long"])
