@@ -143,7 +143,7 @@ count_planes_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneG
     // the tile's stretch of seq4, brought in by one bulk asynchronous copy (cp.async.bulk, completion on an mbarrier)
     // while the tile before is counted
     uint32_t *const s_sub = s_ctl_base + 16;                                    // [strand][12 substitution classes][32 * WPR_MAX window bits]
-    uint32_t *const s_seq = (uint32_t *)(((uintptr_t)(s_sub + 2 * 12 * 32 * WPR_MAX) + 15) & ~(uintptr_t)15);
+    uint32_t *const s_seq = s_sub + 2 * 12 * 32 * WPR_MAX;  // every piece above is a multiple of four words: 16-byte aligned (a cast through an integer would make every load from it a generic load)
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int32_t s_slab[2];  // first seq4 word held in s_seq (may be negative: the words in front of the array), words (0: no copy)
 

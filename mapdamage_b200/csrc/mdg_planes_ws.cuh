@@ -34,13 +34,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t addr)
 }
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
 {
+    // the hardware parks the warp until the phase completes (or the hint, in ns, runs out): a waiting warp takes no issue slots
     uint32_t done;
     do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done)
-                     : "r"(addr), "r"(parity)
+                     : "r"(addr), "r"(parity), "r"(1000000u)
                      : "memory");
     } while (!done);
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");  // ordered after the mbarrier wait it follows
+    return v;
 }
 template <int kCount>
 __device__ __forceinline__ void named_barrier(int id)
@@ -78,7 +85,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     uint32_t *const s_sub = s_red + 2 * 8 * 32 * WPR_MAX;             // [anchor][strand][12][L] substitution events
     uint32_t *const s_lg = s_sub + 4 * 12 * L;                        // [kind][strand][MDG_LG_SMEM_BINS]
     uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;             // [end][strand][L]
-    uint32_t *const s_teams = (uint32_t *)(((uintptr_t)(s_clip + 4 * L) + 15) & ~(uintptr_t)15);
+    uint32_t *const s_teams = s_clip + 4 * L;  // every piece above is a multiple of four words: 16-byte aligned, and still a shared-memory pointer
     // per team: stage rows [T][ROW], records [T], two index lists [T], masks [WPR_MAX][2], three control blocks, seq4 stretch
     const int seq_words = (g.seq_words + 3) & ~3;
     const int team_words = T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + seq_words;
@@ -160,8 +167,17 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             const int qs = (int)(qn & 7);
             const int64_t qw = qn >> 3, in_slab = qw - slab_w0;
             const bool from_smem = slab_words > 0 && in_slab >= 0 && in_slab + 4 * (kNW > 0 ? kNW : n_words) + 1 <= slab_words;
-            const uint32_t *const qs_ptr = s_seq + (from_smem ? in_slab : 0), *const qg_ptr = seq32 + qw;
-            auto seq_word = [&](int m) { return from_smem ? qs_ptr[m] : __ldg(qg_ptr + m); };
+            // (two loads in two address spaces: written as a value select the compiler makes it ONE generic load)
+            const uint32_t qs_addr = (uint32_t)__cvta_generic_to_shared(s_seq) + 4u * (uint32_t)(from_smem ? in_slab : 0);
+            const uint32_t *const qg_ptr = seq32 + qw;
+            auto seq_words4 = [&](int m, uint32_t &w1, uint32_t &w2, uint32_t &w3, uint32_t &w4) {
+                if (from_smem) {
+                    w1 = lds_u32(qs_addr + 4 * m); w2 = lds_u32(qs_addr + 4 * m + 4); w3 = lds_u32(qs_addr + 4 * m + 8); w4 = lds_u32(qs_addr + 4 * m + 12);
+                } else {
+                    w1 = __ldg(qg_ptr + m); w2 = __ldg(qg_ptr + m + 1); w3 = __ldg(qg_ptr + m + 2); w4 = __ldg(qg_ptr + m + 3);
+                }
+            };
+            auto seq_word = [&](int m) { return from_smem ? lds_u32(qs_addr + 4 * m) : __ldg(qg_ptr + m); };
             const int64_t rn = ((int64_t)rec.rg << 5) + (int)((rec.misc >> 16) & 31) + c_start;
             const uint4 *rp = planes + (rn >> 5);
             const int rs = (int)(rn & 31);
@@ -240,7 +256,8 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 }
 #pragma unroll
                 for (int k = 0; k < kNW; ++k) {
-                    const uint32_t w1 = seq_word(4 * k + 1), w2 = seq_word(4 * k + 2), w3 = seq_word(4 * k + 3), w4 = seq_word(4 * k + 4);
+                    uint32_t w1, w2, w3, w4;
+                    seq_words4(4 * k + 1, w1, w2, w3, w4);
                     emit(k, q0, w1, w2, w3, w4, gw[k], gw[k + 1]);
                 }
             } else {
@@ -252,7 +269,8 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 }
                 uint4 g_lo = __ldg(rp);
                 for (int k = 0; k < n_words; ++k) {
-                    const uint32_t w1 = seq_word(4 * k + 1), w2 = seq_word(4 * k + 2), w3 = seq_word(4 * k + 3), w4 = seq_word(4 * k + 4);
+                    uint32_t w1, w2, w3, w4;
+                    seq_words4(4 * k + 1, w1, w2, w3, w4);
                     const uint4 g_hi = __ldg(rp + k + 1);
                     emit(k, q0, w1, w2, w3, w4, g_lo, g_hi);
                     g_lo = g_hi;
@@ -646,100 +664,90 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 const int bit = cell % bits, cls = (cell / bits) % 8, cstrand = cell / (8 * bits);
                 const unsigned long long sum = s_red[cell];
                 if (!sum) continue;
+                // a window bit feeds the table of the left end (anchor 0), of the right end (anchor 1), or both
+                int pos0 = L, pos1 = L;  // L: no cell
                 if (mode) {
-                    const int pos = bit - A;  // column
-                    if (pos < 0) add_cell(0, cstrand, cls, pos, sum);                          // left flank
-                    else if (pos >= mode) add_cell(1, cstrand, cls, mode - 1 - pos, sum);      // right flank at distance pos - C + 1
+                    const int col = bit - A;
+                    if (col < 0) pos0 = col;                      // left flank
+                    else if (col >= mode) pos1 = mode - 1 - col;  // right flank at distance col - C + 1
                     else {
-                        if (pos < L) add_cell(0, cstrand, cls, pos, sum);
-                        if (mode - 1 - pos < L) add_cell(1, cstrand, cls, mode - 1 - pos, sum);
+                        pos0 = col;
+                        pos1 = mode - 1 - col;
                     }
                 } else if (bit < 32 * NWA) {
-                    const int pos = bit - A;
-                    if (pos < L) add_cell(0, cstrand, cls, pos, sum);
+                    pos0 = bit - A;
                 } else {
-                    const int pos = 32 * NWA - A - 1 - (bit - 32 * NWA);  // columns from the right end; negative: flank
-                    if (pos < L) add_cell(1, cstrand, cls, pos, sum);
+                    pos1 = 32 * NWA - A - 1 - (bit - 32 * NWA);  // columns from the right end; negative: flank
+                }
+#pragma unroll 1
+                for (int canchor = 0; canchor < 2; ++canchor) {
+                    const int pos = canchor ? pos1 : pos0;
+                    if (pos < L) add_cell(canchor, cstrand, cls, pos, sum);
                 }
             }
             named_barrier<CT>(1 + kTeams);
         };
 
         int since_flush = 0, tiles_since_flush = 0;  // reads a counter may have seen / tiles since the last reduction
-        bool dirty = false, more = true;
-        for (int64_t k = 0; more; ++k) {
-            for (int team = 0; team < kTeams; ++team) {
-                if (tile_of(k, team) >= n_tiles) {
-                    more = false;
-                    break;
-                }
-                const uint32_t *const s_stage = s_teams + (size_t)team * team_words;
-                const uint32_t *const s_ctl = s_stage + T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
+        bool dirty = false;
+        for (int64_t k = 0, team = 0;; ++team) {
+            if (team == kTeams) {
+                team = 0;
+                ++k;
+            }
+            const bool last = tile_of(k, (int)team) >= n_tiles;  // tiles grow with (k, team): nothing behind this one either
+            const uint32_t *const s_stage = s_teams + (size_t)team * team_words;
+            const uint32_t *const s_ctl = s_stage + T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
+            int n_fwd = 0, n_rev = 0, want = mode;
+            if (!last) {
                 mbar_wait((uint32_t)__cvta_generic_to_shared(&s_full[team]), (uint32_t)(k & 1));
-                const int n_fwd = (int)s_ctl[0], n_rev = (int)s_ctl[1], want = (int)s_ctl[6];
-                if (want != mode) {
-                    if (dirty) flush();
-                    set_mode(want);
-                    dirty = false;
-                    since_flush = 0;
-                    tiles_since_flush = 0;
-                }
+                n_fwd = (int)s_ctl[0];
+                n_rev = (int)s_ctl[1];
+                want = (int)s_ctl[6];
+            }
+            const int want_stride = ((PAIRS / words_of(want)) & ~1) >> 1;
+            const int bound = ((max(n_fwd, n_rev) + want_stride - 1) / want_stride + 7) & ~7;  // reads a thread adds at most, whole iterations
+            if (last || (want != mode && dirty) || since_flush + bound > WS_CAPACITY || (g.flush_tiles > 0 && tiles_since_flush >= g.flush_tiles)) {
+                flush();
+                since_flush = 0;
+                tiles_since_flush = 0;
+                dirty = false;
+            }
+            if (last) break;
+            if (want != mode) set_mode(want);
+            since_flush += bound;
+            ++tiles_since_flush;
+            dirty = dirty || n_fwd + n_rev > 0;
+            // ---- count: this thread's window word and reference base, every stride-th read of its strand ----
+            if (active) {
                 const int stride = mode_slots >> 1;
-                const int bound = ((max(n_fwd, n_rev) + stride - 1) / stride + 7) & ~7;  // reads a thread adds at most, whole iterations
-                if (since_flush + bound > WS_CAPACITY) {
-                    flush();
-                    since_flush = 0;
-                    tiles_since_flush = 0;
-                }
-                since_flush += bound;
-                dirty = dirty || n_fwd + n_rev > 0;
-                // ---- count: this thread's window word and reference base, every stride-th read of its strand ----
-                if (active) {
-                    const int n_mine = strand ? n_rev : n_fwd;
-                    const int row_step = (strand ? -stride : stride) * ROW;
-                    const uint32_t *at0 = s_stage + (size_t)(strand ? T - 1 - (slot >> 1) : (slot >> 1)) * ROW + 8 * ws;
-                    auto count_tile = [&](auto gtag) {
-                        constexpr int G = decltype(gtag)::value;
-                        const uint32_t *at = at0;
-                        for (int i = slot >> 1; i < n_mine; i += 8 * stride) {
-                            uint32_t xg[8], y[8];
-                            if (i + 7 * stride < n_mine) {  // eight reads in hand: no tests
+                const int n_mine = strand ? n_rev : n_fwd;
+                const int row_step = (strand ? -stride : stride) * ROW;
+                const uint32_t *at = s_stage + (size_t)(strand ? T - 1 - (slot >> 1) : (slot >> 1)) * ROW + 8 * ws + group;
+                for (int i = slot >> 1; i < n_mine; i += 8 * stride) {
+                    uint32_t xg[8], y[8];
+                    if (i + 7 * stride < n_mine) {  // eight reads in hand: no tests
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    xg[u] = at[u * row_step + G];
-                                    y[u] = at[u * row_step + 4 + G];
-                                }
-                            } else {
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    const bool live = i + u * stride < n_mine;
-                                    xg[u] = live ? at[u * row_step + G] : 0u;
-                                    y[u] = live ? at[u * row_step + 4 + G] : 0u;
-                                }
-                            }
-                            at += 8 * row_step;
-                            MDG_ADD8(cnt[0], y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7])  // R_g
-                            MDG_ADD8(cnt[1], xg[0], xg[1], xg[2], xg[3], xg[4], xg[5], xg[6], xg[7])  // H_g
-                            if (++n_iter == 30) spill();  // planes 0-3 hold at most 15, thirty more iterations add 240: 255 fits eight planes
+                        for (int u = 0; u < 8; ++u) {
+                            xg[u] = at[u * row_step];
+                            y[u] = at[u * row_step + 4];
                         }
-                    };
-                    switch (group) {
-                    case 0: count_tile(std::integral_constant<int, 0>{}); break;
-                    case 1: count_tile(std::integral_constant<int, 1>{}); break;
-                    case 2: count_tile(std::integral_constant<int, 2>{}); break;
-                    default: count_tile(std::integral_constant<int, 3>{}); break;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const bool live = i + u * stride < n_mine;
+                            xg[u] = live ? at[u * row_step] : 0u;
+                            y[u] = live ? at[u * row_step + 4] : 0u;
+                        }
                     }
-                }
-                mbar_arrive((uint32_t)__cvta_generic_to_shared(&s_empty[team]));  // the buffer may be staged again
-                if (g.flush_tiles > 0 && ++tiles_since_flush >= g.flush_tiles) {
-                    flush();
-                    since_flush = 0;
-                    tiles_since_flush = 0;
-                    dirty = false;
+                    at += 8 * row_step;
+                    MDG_ADD8(cnt[0], y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7])  // R_g
+                    MDG_ADD8(cnt[1], xg[0], xg[1], xg[2], xg[3], xg[4], xg[5], xg[6], xg[7])  // H_g
+                    if (++n_iter == 30) spill();  // planes 0-3 hold at most 15, thirty more iterations add 240: 255 fits eight planes
                 }
             }
+            mbar_arrive((uint32_t)__cvta_generic_to_shared(&s_empty[team]));  // the buffer may be staged again
         }
-        flush();
     }
 
     // ---- everybody: the block's event tables into the 64-bit tables ----
