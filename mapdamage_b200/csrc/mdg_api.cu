@@ -420,14 +420,14 @@ using WsKernel = void (*)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::Cou
                           uint32_t *, unsigned long long *, mdg::SwarSubset);
 struct WsVariant {
     const char *name;
-    int teams, team_warps, cons_warps;
+    int teams, team_warps, cons_warps, nw_anchor;  // nw_anchor = ceil((L + A) / 32) is compiled in
     WsKernel kernel;
 };
 const WsVariant WS_VARIANTS[] = {
-    {"2x8+8", 2, 8, 8, mdg::count_planes_ws_kernel<2, 8, 8>},
-    {"2x8+4", 2, 8, 4, mdg::count_planes_ws_kernel<2, 8, 4>},
-    {"3x6+8", 3, 6, 8, mdg::count_planes_ws_kernel<3, 6, 8>},
-    {"4x4+8", 4, 4, 8, mdg::count_planes_ws_kernel<4, 4, 8>},
+    {"2x8+8", 2, 8, 8, 3, mdg::count_planes_ws_kernel<2, 8, 8, 3>},
+    {"2x8+8", 2, 8, 8, 2, mdg::count_planes_ws_kernel<2, 8, 8, 2>},
+    {"2x8+4", 2, 8, 4, 3, mdg::count_planes_ws_kernel<2, 8, 4, 3>},
+    {"3x6+8", 3, 6, 8, 3, mdg::count_planes_ws_kernel<3, 6, 8, 3>},
 };
 
 // The counting kernels over one device batch.
@@ -841,13 +841,13 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             const char *want = ws_env ? ws_env : "0";
             for (int i = 0; i < (int)(sizeof(WS_VARIANTS) / sizeof(WS_VARIANTS[0])); ++i) {
                 const WsVariant &v = WS_VARIANTS[i];
-                if (strcmp(want, v.name)) continue;
+                if (strcmp(want, v.name) || v.nw_anchor != ctx->planes.nw_anchor) continue;
                 mdg::PlaneGeom wg = ctx->planes;
                 wg.threads = (v.teams * v.team_warps + v.cons_warps) * 32;
                 wg.tile = v.team_warps * 32;
                 const char *slab_env = getenv("MDG_PLANES_SLAB");
                 wg.seq_words = slab_env && slab_env[0] == '0' ? 0 : wg.tile * 56 / 4;
-                const size_t bytes = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, wg.row_words, wg.seq_words);
+                const size_t bytes = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor);
                 const int pairs = (v.cons_warps * 32 >> 7) * 32;
                 if (bytes <= ctx->smem_optin && 2 * wg.nw_anchor * 2 <= pairs) {
                     MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

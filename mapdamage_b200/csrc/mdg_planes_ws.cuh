@@ -55,17 +55,24 @@ __device__ __forceinline__ void named_barrier(int id)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kCount) : "memory");
 }
 
-// the plane's eight bits of a seq4 word (as BAM stores it) in bits 24..31 -- see count_planes_kernel::plane_byte
-__device__ __forceinline__ uint32_t ws_plane_byte(uint32_t w, int pl)
+// Planes p and p + 2 (p = 0, 1) of the eight bases of a seq4 word, each as eight bits in bits 24..31 of a word.
+// BAM's nibble IS one-hot (A, C, G, T = 1, 2, 4, 8), so plane p of base j is bit p of nibble j: keep bits p and p + 2 of
+// every nibble (one AND), put the two nibbles of a byte side by side in base order -- BAM stores the first base of a byte
+// in the HIGH nibble -- (two shifts, one OR-AND: the byte then holds {base 2b, base 2b+1} of plane p in bits 0-1 and of
+// plane p + 2 in bits 2-3), and gather the four bytes' bit pairs into the top byte with one multiplication per plane (the
+// sixteen partial products land on distinct bits: no carries).  The shifts and multiplications issue on the FMA pipe.
+__device__ __forceinline__ void ws_plane_bytes(uint32_t w, int p, uint32_t &lo_plane, uint32_t &hi_plane)
 {
-    const uint32_t y = (pl ? shr_fma(w, pl) : w) & 0x11111111u;
-    return ((shr_fma(y, 4) | shl_fma(y, 1)) & 0x03030303u) * 0x01041040u;
+    const uint32_t y = (p ? shr_fma(w, p) : w) & 0x55555555u;
+    const uint32_t t = shr_fma(y, 4) | shl_fma(y, 1);
+    lo_plane = (t & 0x03030303u) * 0x01041040u;
+    hi_plane = (t & 0x0C0C0C0Cu) * 0x00410410u;
 }
 
 constexpr int WS_CTL = 8;        // words per tile control block: n_fwd, n_rev, n_cx, min cols, max cols, n_ix, mode, -
 constexpr int WS_CAPACITY = 4000;  // reads a counter may see between two reductions (12 bits: planes 0-3 + wide 4-11)
 
-template <int kTeams, int kTeamWarps, int kConsWarps>
+template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA>
 __global__ void __launch_bounds__((kTeams * kTeamWarps + kConsWarps) * 32, 1)
 count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneGeom g, uint32_t *__restrict__ worklist,
                        unsigned long long *__restrict__ work_count, uint32_t *__restrict__ indel_list,
@@ -78,7 +85,9 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     static_assert(kConsWarps % 4 == 0, "consumer warps come in fours: one per reference base");
     extern __shared__ __align__(16) uint32_t smem[];
     const int L = p.L, A = p.A, LA = L + A;
-    const int NWA = g.nw_anchor, WPR_MAX = 2 * NWA, ROW = g.row_words;
+    // words per anchor window ceil((L + A) / 32), per read, and per staged row (rows land on different banks): compile-time,
+    // so that the address arithmetic folds
+    constexpr int NWA = kNWA, WPR_MAX = 2 * NWA, ROW = 16 * NWA + 4;
     // ---- shared memory ----
     uint32_t *const s_wide = smem;                                    // [PL_WIDE][PL_CLASSES][CT]
     uint32_t *const s_red = s_wide + PL_WIDE * PL_CLASSES * CT;       // [strand][8 classes][32 WPR_MAX]: a reduction's sums
@@ -87,9 +96,11 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;             // [end][strand][L]
     uint32_t *const s_teams = s_clip + 4 * L;  // every piece above is a multiple of four words: 16-byte aligned, and still a shared-memory pointer
     // per team: stage rows [T][ROW], records [T], two index lists [T], masks [WPR_MAX][2], three control blocks, seq4 stretch
-    const int seq_words = (g.seq_words + 3) & ~3;
-    const int team_words = T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + seq_words;
-    __shared__ __align__(8) unsigned long long s_full[kTeams], s_empty[kTeams], s_slab_bar[kTeams];
+    constexpr int SEQ_WORDS = T * 14;  // 56 bytes of seq4 per read: reads of up to about 110 bases on average
+    // the record arrays of a tile (flag, lib: 16 bit; tid, pos, l_seq, base_off, cigar_off[T + 1]), bulk-copied a tile ahead
+    constexpr int HDR_WORDS = T / 2 + T / 2 + 4 * T + (T + 4);
+    constexpr int team_words = T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + SEQ_WORDS + HDR_WORDS;
+    __shared__ __align__(8) unsigned long long s_full[kTeams], s_empty[kTeams], s_slab_bar[kTeams], s_hdr_bar[kTeams];
     __shared__ int32_t s_slab[kTeams][2];  // first seq4 word held in the team's copy (may be negative), words (0: no copy)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,6 +110,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         mbar_init((uint32_t)__cvta_generic_to_shared(&s_full[tid]), T);
         mbar_init((uint32_t)__cvta_generic_to_shared(&s_empty[tid]), CT);
         mbar_init((uint32_t)__cvta_generic_to_shared(&s_slab_bar[tid]), 1);
+        mbar_init((uint32_t)__cvta_generic_to_shared(&s_hdr_bar[tid]), 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         s_slab[tid][0] = 0;
         s_slab[tid][1] = 0;
@@ -127,9 +139,15 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         uint32_t *const s_mask = s_ix + T;                              // [WPR_MAX][2] aligned / flank masks of a typical read
         uint32_t *const s_ctl_base = s_mask + ((2 * WPR_MAX + 3) & ~3);
         uint32_t *const s_seq = s_ctl_base + 4 * WS_CTL;
+        const uint16_t *const s_hflag = (const uint16_t *)(s_seq + SEQ_WORDS), *const s_hlib = s_hflag + T;
+        const int32_t *const s_htid = (const int32_t *)(s_hlib + T), *const s_hpos = s_htid + T;
+        const uint32_t *const s_hlseq = (const uint32_t *)(s_hpos + T), *const s_hboff = s_hlseq + T, *const s_hcoff = s_hboff + T;
+        const uint32_t hdr_addr = (uint32_t)__cvta_generic_to_shared(&s_hdr_bar[team]);
+        uint32_t hdr_phase = 0;
         const uint32_t full_addr = (uint32_t)__cvta_generic_to_shared(&s_full[team]);
         const uint32_t empty_addr = (uint32_t)__cvta_generic_to_shared(&s_empty[team]);
         const uint32_t slab_addr = (uint32_t)__cvta_generic_to_shared(&s_slab_bar[team]);
+        const bool staged_headers = !subset;  // tiles of an index list read their records from global memory
         const uint32_t *__restrict__ seq32 = (const uint32_t *)b.seq4;
         const uint4 *__restrict__ planes = ref.planes;
         uint32_t slab_phase = 0;
@@ -185,11 +203,19 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             auto emit = [&](int k, uint32_t (&q0)[4], uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, const uint4 &g_lo, const uint4 &g_hi) {
                 uint32_t xp[4];
 #pragma unroll
-                for (int pl = 0; pl < 4; ++pl) {
-                    const uint32_t q1 = ws_plane_byte(w1, pl), q2 = ws_plane_byte(w2, pl), q3 = ws_plane_byte(w3, pl), q4 = ws_plane_byte(w4, pl);
-                    const uint32_t lo = __byte_perm(__byte_perm(q0[pl], q1, 0x0073), __byte_perm(q2, q3, 0x0073), 0x5410);
-                    xp[pl] = __funnelshift_r(lo, q4 >> 24, qs);
-                    q0[pl] = q4;
+                for (int pp = 0; pp < 2; ++pp) {
+                    uint32_t q1[2], q2[2], q3[2], q4[2];
+                    ws_plane_bytes(w1, pp, q1[0], q1[1]);
+                    ws_plane_bytes(w2, pp, q2[0], q2[1]);
+                    ws_plane_bytes(w3, pp, q3[0], q3[1]);
+                    ws_plane_bytes(w4, pp, q4[0], q4[1]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int pl = pp + 2 * h;
+                        const uint32_t lo = __byte_perm(__byte_perm(q0[pl], q1[h], 0x0073), __byte_perm(q2[h], q3[h], 0x0073), 0x5410);
+                        xp[pl] = __funnelshift_r(lo, q4[h] >> 24, qs);
+                        q0[pl] = q4[h];
+                    }
                 }
                 const uint32_t xa = xp[0], xc = xp[1], xg = xp[2], xt = xp[3];
                 const uint32_t ya = __funnelshift_r(g_lo.x, g_hi.x, rs), yc = __funnelshift_r(g_lo.y, g_hi.y, rs);
@@ -251,8 +277,8 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 uint32_t q0[4];
                 {
                     const uint32_t w0 = seq_word(0);
-#pragma unroll
-                    for (int pl = 0; pl < 4; ++pl) q0[pl] = ws_plane_byte(w0, pl);
+                    ws_plane_bytes(w0, 0, q0[0], q0[2]);
+                    ws_plane_bytes(w0, 1, q0[1], q0[3]);
                 }
 #pragma unroll
                 for (int k = 0; k < kNW; ++k) {
@@ -264,8 +290,8 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 uint32_t q0[4];
                 {
                     const uint32_t w0 = seq_word(0);
-#pragma unroll
-                    for (int pl = 0; pl < 4; ++pl) q0[pl] = ws_plane_byte(w0, pl);
+                    ws_plane_bytes(w0, 0, q0[0], q0[2]);
+                    ws_plane_bytes(w0, 1, q0[1], q0[3]);
                 }
                 uint4 g_lo = __ldg(rp);
                 for (int k = 0; k < n_words; ++k) {
@@ -280,16 +306,21 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
 
         // ---- parse of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
         // kind: 0 nothing to do, 1 gap-free (record made), 2 for the general kernel, 3 one short indel
-        auto parse_read = [&](bool live, int64_t r, int &kind, int &rstrand, uint32_t &columns, PlaneRecord &rec) {
+        auto parse_read = [&](bool live, int64_t r, int q, int &kind, int &rstrand, uint32_t &columns, PlaneRecord &rec) {
             kind = 0;
             rstrand = 0;
             columns = 0;
             if (!live) return;
-            const uint32_t flag = b.flag[r];
-            const uint32_t lib = b.lib[r];
-            const int32_t tid_ref = b.tid[r];
-            const int64_t pos = b.pos[r];
-            const uint32_t l_seq = b.l_seq[r], boff = b.base_off[r], c0 = b.cigar_off[r], c1 = b.cigar_off[r + 1];
+            uint32_t flag, lib, l_seq, boff, c0, c1;
+            int32_t tid_ref;
+            int64_t pos;
+            if (staged_headers) {  // read q of the tile, from the team's copy
+                flag = s_hflag[q]; lib = s_hlib[q]; tid_ref = s_htid[q]; pos = s_hpos[q];
+                l_seq = s_hlseq[q]; boff = s_hboff[q]; c0 = s_hcoff[q]; c1 = s_hcoff[q + 1];
+            } else {
+                flag = b.flag[r]; lib = b.lib[r]; tid_ref = b.tid[r]; pos = b.pos[r];
+                l_seq = b.l_seq[r]; boff = b.base_off[r]; c0 = b.cigar_off[r]; c1 = b.cigar_off[r + 1];
+            }
             const uint32_t cig0 = c1 > c0 ? __ldg(b.cigar + c0) : 0;
             if (flag & FILTERED_FLAGS) return;
             if (lib >= (uint32_t)p.n_lib) {
@@ -412,29 +443,47 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     prefetch_l2(b.cigar_off + r);
                 }
             } else if (ptid * 32 < T && r4 < b.n_reads) {
-                prefetch_l2(b.tid + r4);
-                prefetch_l2(b.pos + r4);
-                prefetch_l2(b.l_seq + r4);
+                // the record arrays come by bulk copy; what parse still reads from global memory: the first CIGAR word
+                // (one op per read: this place exactly; otherwise a guess) and, for pairs, the template length
+                prefetch_l2(b.cigar + r4);
                 prefetch_l2(b.tlen + r4);
-                prefetch_l2(b.base_off + r4);
-                prefetch_l2(b.cigar_off + r4);
-                prefetch_l2(b.cigar + r4);  // one op per read: the same place; otherwise a guess
-                if (!(ptid & 1)) {
-                    prefetch_l2(b.flag + r4);
-                    prefetch_l2(b.lib + r4);
-                }
             }
         };
-        // one thread: the stretch of seq4 the reads of a tile occupy (reads are laid out in order; a stage thread checks
-        // that its read really lies inside), 32 bytes more in front and 48 behind for the windows' flanks, as one bulk copy
+        // one thread: the record arrays of a tile as seven bulk copies on one mbarrier (sizes rounded up to 16 bytes: the
+        // batch's arrays are 256-byte aligned with slack behind them, and a tile starts on a multiple of T records)
+        auto issue_headers = [&](int64_t tile_index) {
+            if (!staged_headers || tile_index >= n_tiles) return;
+            const int64_t r0 = tile_index * T;
+            const uint32_t n = (uint32_t)min((int64_t)T, n_todo - r0);
+            const uint32_t b16 = (2 * n + 15) & ~15u, b32 = (4 * n + 15) & ~15u, b32p = (4 * (n + 1) + 15) & ~15u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hdr_addr), "r"(2 * b16 + 4 * b32 + b32p) : "memory");
+            auto copy = [&](const void *to, const void *from, uint32_t bytes) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(to)),
+                             "l"(from), "r"(bytes), "r"(hdr_addr)
+                             : "memory");
+            };
+            copy(s_hflag, b.flag + r0, b16);
+            copy(s_hlib, b.lib + r0, b16);
+            copy(s_htid, b.tid + r0, b32);
+            copy(s_hpos, b.pos + r0, b32);
+            copy(s_hlseq, b.l_seq + r0, b32);
+            copy(s_hboff, b.base_off + r0, b32);
+            copy(s_hcoff, b.cigar_off + r0, b32p);
+        };
+        // one thread, once the tile's records have landed: the stretch of seq4 its reads occupy (reads are laid out in order;
+        // a stage thread checks that its read really lies inside), 32 bytes more in front and 48 behind for the windows'
+        // flanks, as one bulk copy
         auto issue_slab = [&](int64_t tile_index) {
             s_slab[team][1] = 0;
-            if (subset || g.seq_words <= 0 || tile_index >= n_tiles) return;
-            const int64_t r0 = tile_index * T, r1 = min(n_todo, r0 + (int64_t)T) - 1;
-            const uint64_t first = b.base_off[r0], last = (uint64_t)b.base_off[r1] + b.l_seq[r1];
+            if (subset || tile_index >= n_tiles) return;
+            mbar_wait(hdr_addr, hdr_phase & 1u);  // (every thread waits for the same phase again before it parses)
+            if (g.seq_words <= 0) return;  // bases from global memory (tests)
+            const int n = (int)min((int64_t)T, n_todo - tile_index * T);
+            const uint64_t first = s_hboff[0], last = (uint64_t)s_hboff[n - 1] + s_hlseq[n - 1];
             const int64_t lo = ((int64_t)(first >> 1) - 32) & ~15ll, hi = ((int64_t)((last + 1) >> 1) + 48 + 15) & ~15ll;
             const int64_t bytes = hi - lo;
-            if (bytes <= 0 || bytes > 4ll * g.seq_words) return;
+            if (bytes <= 0 || bytes > 4ll * SEQ_WORDS) return;
             s_slab[team][0] = (int32_t)(lo >> 2);
             s_slab[team][1] = (int32_t)(bytes >> 2);
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_seq);
@@ -446,7 +495,10 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
 
         prefetch_headers(tile_of(0, team));
         prefetch_headers(tile_of(1, team));
-        if (ptid == 0) issue_slab(tile_of(0, team));
+        if (ptid == 0) {
+            issue_headers(tile_of(0, team));
+            issue_slab(tile_of(0, team));
+        }
         named_barrier<T>(1 + team);  // s_slab of the first tile
         for (int64_t k = 0;; ++k) {
             const int64_t tile = tile_of(k, team);
@@ -455,6 +507,10 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             uint32_t *const s_ctl_next = s_ctl_base + WS_CTL * (int)((k + 1) % 3);
 
             // ---- parse: one read per thread ----
+            if (staged_headers) {
+                mbar_wait(hdr_addr, hdr_phase & 1u);
+                ++hdr_phase;
+            }
             {
                 const int64_t at = tile * T + ptid;
                 const bool live = at < n_todo;
@@ -462,7 +518,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 int kind, rstrand;
                 uint32_t columns;
                 PlaneRecord rec{};
-                parse_read(live, r, kind, rstrand, columns, rec);
+                parse_read(live, r, ptid, kind, rstrand, columns, rec);
                 if (g.uniform) {
                     const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
                     const uint32_t hi = __reduce_max_sync(0xffffffffu, kind == 1 ? columns : 0u);
@@ -514,6 +570,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
             // the control block of the tile after this one (last read by the consumers two tiles ago)
             if (ptid < WS_CTL) s_ctl_next[ptid] = ptid == 3 ? 0xffffffffu : 0u;
+            if (ptid == 32) issue_headers(tile_of(k + 1, team));  // everyone is done with this tile's records: the next tile's land while this one is staged
 
             // ---- one window per read when every gap-free read of the tile has the same length ----
             {
@@ -772,12 +829,12 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     }
 }
 
-// dynamic shared memory of count_planes_ws_kernel<kTeams, kTeamWarps, kConsWarps> (bytes)
-inline size_t planes_ws_smem(int teams, int team_warps, int cons_warps, int L, int nw_anchor, int row_words, int seq_words)
+// dynamic shared memory of count_planes_ws_kernel<kTeams, kTeamWarps, kConsWarps, kNWA> (bytes)
+inline size_t planes_ws_smem(int teams, int team_warps, int cons_warps, int L, int nw_anchor)
 {
-    const size_t T = (size_t)team_warps * 32, CT = (size_t)cons_warps * 32, wpr_max = 2 * (size_t)nw_anchor;
-    const size_t shared = PL_WIDE * PL_CLASSES * CT + 2 * 8 * 32 * wpr_max + 4 * 12 * (size_t)L + 4 * MDG_LG_SMEM_BINS + 4 * (size_t)L + 4;
-    const size_t team = T * row_words + 4 * T + 2 * T + ((2 * wpr_max + 3) & ~(size_t)3) + 4 * WS_CTL + (((size_t)seq_words + 3) & ~(size_t)3);
+    const size_t T = (size_t)team_warps * 32, CT = (size_t)cons_warps * 32, wpr_max = 2 * (size_t)nw_anchor, row = 16 * (size_t)nw_anchor + 4;
+    const size_t shared = PL_WIDE * PL_CLASSES * CT + 2 * 8 * 32 * wpr_max + 4 * 12 * (size_t)L + 4 * MDG_LG_SMEM_BINS + 4 * (size_t)L;
+    const size_t team = T * row + 4 * T + 2 * T + ((2 * wpr_max + 3) & ~(size_t)3) + 4 * WS_CTL + T * 14 + 6 * T + 4;
     return (shared + teams * team) * 4;
 }
 
