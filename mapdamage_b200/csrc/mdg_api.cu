@@ -838,7 +838,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
         // warp-specialised bit-plane kernel: MDG_PLANES_WS=<variant name> (or 0: off)
         if (ctx->planes_enabled) {
             const char *ws_env = getenv("MDG_PLANES_WS");
-            const char *want = ws_env ? ws_env : "0";
+            const char *want = ws_env ? ws_env : "2x8+8";  // the default; MDG_PLANES_WS=0: the one-role kernel (count_planes_kernel)
             for (int i = 0; i < (int)(sizeof(WS_VARIANTS) / sizeof(WS_VARIANTS[0])); ++i) {
                 const WsVariant &v = WS_VARIANTS[i];
                 if (strcmp(want, v.name) || v.nw_anchor != ctx->planes.nw_anchor) continue;
