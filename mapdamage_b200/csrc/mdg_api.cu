@@ -167,6 +167,7 @@ struct mdg_ctx {
     mdg::PlaneGeom ws{};
     size_t ws_smem = 0;
     void *planes_block = nullptr;  // genome as bit planes
+    size_t ref_words_bytes = 0;    // size of one genome image
     std::vector<WorkList> worklists;
     // measurement
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -466,6 +467,8 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             if (use_planes && ctx->ws_variant >= 0) {
                 mdg::PlaneGeom pg = ctx->ws;
                 pg.indel_seen = ctx->indel_seen_dev;
+                // genome image larger than what stays in L2: prefetch each read's genome entries while it is parsed
+                if (!getenv("MDG_PLANES_PREFETCH") && ctx->ref_words_bytes > ((size_t)48 << 20)) pg.prefetch_bases |= 2;
                 const WsVariant &v = WS_VARIANTS[ctx->ws_variant];
                 const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
                 const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, (tiles + v.teams - 1) / v.teams);
@@ -802,7 +805,7 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
             pg.threads = pt_env && atoi(pt_env) == 256 ? 256 : 512;
             const size_t smem_budget = pg.threads == 256 ? (ctx->smem_optin + 1024) / 2 - 1024 : ctx->smem_optin;
             const char *pf_env = getenv("MDG_PLANES_PREFETCH");
-            pg.prefetch_bases = !(pf_env && pf_env[0] == '0');
+            pg.prefetch_bases = pf_env ? atoi(pf_env) : 1;  // bit 0: bases of the tile after next (one-role kernel); bits 1, 2: A/B switches of the warp-specialised kernel
             pg.uniform = g.uniform;
             pg.flush_tiles = g.flush_tiles;
             pg.nw_anchor = (cfg->length + cfg->around + 31) / 32;
@@ -937,6 +940,7 @@ int mdg_set_reference(mdg_ctx *ctx, const uint8_t *packed, int64_t n_bytes, cons
     // 4 KB of "not a base" on both sides: the kernels read whole words around an alignment (up to L + A bases away)
     const size_t pad = 4096;
     size_t words_bytes = align_up((size_t)n_bytes + pad);
+    ctx->ref_words_bytes = words_bytes;
     size_t off_bytes = align_up((size_t)n_contigs * 8);
     size_t len_bytes = align_up((size_t)n_contigs * 4);
     MDG_CUDA(ctx, cudaMalloc(&ctx->ref_block, pad + words_bytes + off_bytes + len_bytes));
@@ -995,6 +999,7 @@ int mdg_synth_reference(mdg_ctx *ctx, const uint32_t *contig_len, int32_t n_cont
     ctx->ref = mdg::DevRef{};
     const size_t pad = 4096;
     const size_t words_bytes = align_up((size_t)n_bytes + pad), off_bytes = align_up((size_t)n_contigs * 8), len_bytes = align_up((size_t)n_contigs * 4);
+    ctx->ref_words_bytes = words_bytes;
     MDG_CUDA(ctx, cudaMalloc(&ctx->ref_block, pad + words_bytes + off_bytes + len_bytes));
     MDG_CUDA(ctx, cudaMalloc(&ctx->planes_block, pad + words_bytes));
     char *p = (char *)ctx->ref_block + pad;

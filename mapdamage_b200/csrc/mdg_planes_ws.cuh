@@ -99,7 +99,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     constexpr int SEQ_WORDS = T * 14;  // 56 bytes of seq4 per read: reads of up to about 110 bases on average
     // the record arrays of a tile (flag, lib: 16 bit; tid, pos, l_seq, base_off, cigar_off[T + 1]), bulk-copied a tile ahead
     constexpr int HDR_WORDS = T / 2 + T / 2 + 4 * T + (T + 4);
-    constexpr int team_words = T * ROW + 2 * 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + SEQ_WORDS + HDR_WORDS;
+    constexpr int team_words = T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + SEQ_WORDS + HDR_WORDS;
     __shared__ __align__(8) unsigned long long s_full[kTeams], s_empty[kTeams], s_slab_bar[kTeams], s_hdr_bar[kTeams];
     __shared__ int32_t s_slab[kTeams][2];  // first seq4 word held in the team's copy (may be negative), words (0: no copy)
 
@@ -117,7 +117,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     }
     for (int i = tid; i < kTeams * 3 * WS_CTL; i += NTHREADS) {
         const int team = i / (3 * WS_CTL), w = i % (3 * WS_CTL);
-        (s_teams + (size_t)team * team_words + T * ROW + 2 * 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3))[w] = (w % WS_CTL) == 3 ? 0xffffffffu : 0u;
+        (s_teams + (size_t)team * team_words + T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3))[w] = (w % WS_CTL) == 3 ? 0xffffffffu : 0u;
     }
     __syncthreads();
 
@@ -129,20 +129,12 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     // tile `k` of team `team` of this block
     auto tile_of = [&](int64_t k, int team) { return (k * gridDim.x + blockIdx.x) * kTeams + team; };
 
-    // Registers follow the roles (setmaxnreg, whole warpgroups): the launch gives every thread the same share of the register
-    // file; the consumers hand back what they do not need and the producers' transposition gets it.
-    constexpr int REGS_EVEN = (65536 / NTHREADS) / 8 * 8;
-    constexpr bool kRebalance = kTeamWarps % 4 == 0 && kConsWarps % 4 == 0 && REGS_EVEN >= 72;
-    constexpr int REGS_CONS = 64, REGS_PROD = kRebalance ? ((65536 / 32 - kConsWarps * REGS_CONS) / (kTeams * kTeamWarps)) / 8 * 8 : REGS_EVEN;
     if (warp < kTeams * kTeamWarps) {
         // =========================================== producer team ===========================================
-        if constexpr (kRebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
         const int team = warp / kTeamWarps, ptid = tid - team * T, pwarp = ptid >> 5;
         uint32_t *const s_stage = s_teams + (size_t)team * team_words;
-        // records of the tile in hand and of the next one (the warps that are done staging go on parsing): forward reads
-        // from the front, reverse from the back
-        PlaneRecord *const s_rec2 = (PlaneRecord *)(s_stage + T * ROW);
-        uint32_t *const s_cx = (uint32_t *)(s_rec2 + 2 * T);            // reads for the general kernel
+        PlaneRecord *const s_rec = (PlaneRecord *)(s_stage + T * ROW);  // forward reads from the front, reverse from the back
+        uint32_t *const s_cx = (uint32_t *)(s_rec + T);                 // reads for the general kernel
         uint32_t *const s_ix = s_cx + T;                                // one-indel reads
         uint32_t *const s_mask = s_ix + T;                              // [WPR_MAX][2] aligned / flank masks of a typical read
         uint32_t *const s_ctl_base = s_mask + ((2 * WPR_MAX + 3) & ~3);
@@ -398,6 +390,14 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
             rec.q0 = (uint32_t)((uint64_t)boff + lead);
             rec.rg = (uint32_t)(ref0 >> 5);
+            if (g.prefetch_bases & 2) {
+                // a genome that does not fit L2: the entries this read's window(s) will gather, pulled towards L2 now -- the
+                // stage comes a barrier and a buffer hand-over later.  Measured on 3.1 Gbp: reads in coordinate order (what
+                // a sorted BAM holds) 0.546 -> 0.487 ms per 4.17 M reads, reads in random order 0.591 -> 0.611.
+                const char *const first = (const char *)(planes + ((int64_t)(ref0 >> 5) - 1));
+                prefetch_l2(first);
+                prefetch_l2(first + 16 * (((ref0 & 31) + cols + 2 * A + 63) >> 5));
+            }
             rec.cols = cols | (lf << 16) | (rf << 24);
             rec.misc = min(cols, (uint32_t)L) | (uint32_t)(ref0 & 31) << 16;
             // FragmentLengths.update, statistics.py:117-126
@@ -513,7 +513,6 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             if (tile >= n_tiles) break;
             uint32_t *const s_ctl = s_ctl_base + WS_CTL * (int)(k % 3);
             uint32_t *const s_ctl_next = s_ctl_base + WS_CTL * (int)((k + 1) % 3);
-            PlaneRecord *const s_rec = s_rec2 + T * (int)(k & 1);
 
             // ---- parse: one read per thread ----
             if (staged_headers) {
@@ -622,19 +621,12 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 }
             }
             mbar_arrive(full_addr);  // release: this thread's words of the buffer (and the control block) are visible to the consumers
-            // Only the first warp waits until every thread is done with the tile's seq4 stretch (to order the next bulk copy
-            // into it); the others arrive and go straight on to parse the next tile, whose records have their own buffer.
-            if (pwarp == 0) {
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + kTeams + 1 + team), "n"(T) : "memory");
-                if (ptid == 0) issue_slab(tile_of(k + 1, team));  // lands while the next tile is parsed
-            } else {
-                asm volatile("bar.arrive %0, %1;" ::"r"(1 + kTeams + 1 + team), "n"(T) : "memory");
-            }
+            named_barrier<T>(1 + team);
+            if (ptid == 0) issue_slab(tile_of(k + 1, team));  // lands while the next tile is parsed
             // (the next parse does not read s_slab; the barrier after it orders this write before the stage)
         }
     } else {
         // =============================================== consumers ===============================================
-        if constexpr (kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONS));
         const int ctid = tid - PRODUCERS, cwarp = ctid >> 5;
         const int group = cwarp & 3;                 // reference base of this thread's classes
         const int pair = (cwarp >> 2) * 32 + lane;   // index among the (slot, word) pairs of its group
@@ -770,7 +762,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
             const bool last = tile_of(k, (int)team) >= n_tiles;  // tiles grow with (k, team): nothing behind this one either
             const uint32_t *const s_stage = s_teams + (size_t)team * team_words;
-            const uint32_t *const s_ctl = s_stage + T * ROW + 2 * 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
+            const uint32_t *const s_ctl = s_stage + T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
             int n_fwd = 0, n_rev = 0, want = mode;
             if (!last) {
                 mbar_wait((uint32_t)__cvta_generic_to_shared(&s_full[team]), (uint32_t)(k & 1));
@@ -850,7 +842,7 @@ inline size_t planes_ws_smem(int teams, int team_warps, int cons_warps, int L, i
 {
     const size_t T = (size_t)team_warps * 32, CT = (size_t)cons_warps * 32, wpr_max = 2 * (size_t)nw_anchor, row = 16 * (size_t)nw_anchor + 4;
     const size_t shared = PL_WIDE * PL_CLASSES * CT + 2 * 8 * 32 * wpr_max + 4 * 12 * (size_t)L + 4 * MDG_LG_SMEM_BINS + 4 * (size_t)L;
-    const size_t team = T * row + 2 * 4 * T + 2 * T + ((2 * wpr_max + 3) & ~(size_t)3) + 4 * WS_CTL + T * 14 + 6 * T + 4;
+    const size_t team = T * row + 4 * T + 2 * T + ((2 * wpr_max + 3) & ~(size_t)3) + 4 * WS_CTL + T * 14 + 6 * T + 4;
     return (shared + teams * team) * 4;
 }
 
