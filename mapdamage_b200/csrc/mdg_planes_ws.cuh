@@ -95,11 +95,12 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     uint32_t *const s_lg = s_sub + 4 * 12 * L;                        // [kind][strand][MDG_LG_SMEM_BINS]
     uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;             // [end][strand][L]
     uint32_t *const s_teams = s_clip + 4 * L;  // every piece above is a multiple of four words: 16-byte aligned, and still a shared-memory pointer
-    // per team: stage rows [T][ROW], records [T], two index lists [T], masks [WPR_MAX][2], three control blocks, seq4 stretch
+    // per team: stage rows [T][ROW] (forward reads from the front, reverse from the back), two index lists [T], masks
+    // [WPR_MAX][2], three control blocks, seq4 stretch, record arrays
     constexpr int SEQ_WORDS = T * 14;  // 56 bytes of seq4 per read: reads of up to about 110 bases on average
     // the record arrays of a tile (flag, lib: 16 bit; tid, pos, l_seq, base_off, cigar_off[T + 1]), bulk-copied a tile ahead
     constexpr int HDR_WORDS = T / 2 + T / 2 + 4 * T + (T + 4);
-    constexpr int team_words = T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + SEQ_WORDS + HDR_WORDS;
+    constexpr int team_words = T * ROW + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + SEQ_WORDS + HDR_WORDS;
     __shared__ __align__(8) unsigned long long s_full[kTeams], s_empty[kTeams], s_slab_bar[kTeams], s_hdr_bar[kTeams];
     __shared__ int32_t s_slab[kTeams][2];  // first seq4 word held in the team's copy (may be negative), words (0: no copy)
 
@@ -117,7 +118,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     }
     for (int i = tid; i < kTeams * 3 * WS_CTL; i += NTHREADS) {
         const int team = i / (3 * WS_CTL), w = i % (3 * WS_CTL);
-        (s_teams + (size_t)team * team_words + T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3))[w] = (w % WS_CTL) == 3 ? 0xffffffffu : 0u;
+        (s_teams + (size_t)team * team_words + T * ROW + 2 * T + ((2 * WPR_MAX + 3) & ~3))[w] = (w % WS_CTL) == 3 ? 0xffffffffu : 0u;
     }
     __syncthreads();
 
@@ -133,8 +134,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         // =========================================== producer team ===========================================
         const int team = warp / kTeamWarps, ptid = tid - team * T, pwarp = ptid >> 5;
         uint32_t *const s_stage = s_teams + (size_t)team * team_words;
-        PlaneRecord *const s_rec = (PlaneRecord *)(s_stage + T * ROW);  // forward reads from the front, reverse from the back
-        uint32_t *const s_cx = (uint32_t *)(s_rec + T);                 // reads for the general kernel
+        uint32_t *const s_cx = s_stage + T * ROW;                       // reads for the general kernel
         uint32_t *const s_ix = s_cx + T;                                // one-indel reads
         uint32_t *const s_mask = s_ix + T;                              // [WPR_MAX][2] aligned / flank masks of a typical read
         uint32_t *const s_ctl_base = s_mask + ((2 * WPR_MAX + 3) & ~3);
@@ -519,13 +519,15 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 mbar_wait(hdr_addr, hdr_phase & 1u);
                 ++hdr_phase;
             }
+            // the thread that parses a read also stages it: the record stays in its registers
+            int kind, rstrand;
+            uint32_t rank = 0;  // of a gap-free read: index in its strand's list = its row from the front (forward) or the back (reverse)
+            PlaneRecord rec{};
             {
                 const int64_t at = tile * T + ptid;
                 const bool live = at < n_todo;
                 const int64_t r = !live ? 0 : subset ? (int64_t)subset[at] : at;
-                int kind, rstrand;
                 uint32_t columns;
-                PlaneRecord rec{};
                 parse_read(live, r, ptid, kind, rstrand, columns, rec);
                 if (g.uniform) {
                     const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
@@ -549,7 +551,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                             const uint32_t slot = base + __popc(m & lt);
                             if (which == 2) s_cx[slot] = (uint32_t)r;
                             else if (which == 3) s_ix[slot] = (uint32_t)r;
-                            else s_rec[which == 0 ? slot : T - 1 - slot] = rec;
+                            else rank = slot;
                         }
                     }
                 }
@@ -598,26 +600,22 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             prefetch_headers(tile_of(k + 2, team));
 
             // ---- stage: one thread per (read, window), once the consumers are done with the tile before ----
-            const int n_fwd = (int)s_ctl[0], n_rev = (int)s_ctl[1];
             if (k > 0) mbar_wait(empty_addr, (uint32_t)((k - 1) & 1));
             const int slab_w0 = s_slab[team][0], slab_words = s_slab[team][1];
             if (slab_words) {
                 mbar_wait(slab_addr, slab_phase & 1u);
                 ++slab_phase;
             }
-            {
-                const int n_windows = mode ? 1 : 2, n_items = (n_fwd + n_rev) * n_windows;
-                const int wpr = words_of(mode);
-                for (int item = ptid; item < n_items; item += T) {
-                    const int li = mode ? item : item >> 1, side = mode ? 0 : item & 1;
-                    const int row = li < n_fwd ? li : T - 1 - (li - n_fwd);
-                    const PlaneRecord rec = s_rec[row];
-                    uint32_t *const row_at = s_stage + (size_t)row * ROW;
-                    const int n_words = mode ? wpr : NWA, first_word = side ? NWA : 0;
+            if (kind == 1) {
+                const int row = rstrand ? T - 1 - (int)rank : (int)rank;
+                uint32_t *const row_at = s_stage + (size_t)row * ROW;
+                const int n_words = mode ? words_of(mode) : NWA;
+                for (int side = 0; side < (mode ? 1 : 2); ++side) {
+                    const int first_word = side ? NWA : 0;
                     const int c_start = side ? (int)(rec.cols & 0x7FFF) + A - 32 * NWA : -A;
-                    if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, li >= n_fwd);
-                    else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, li >= n_fwd);
-                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, li >= n_fwd);
+                    if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, rstrand);
+                    else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, rstrand);
+                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand);
                 }
             }
             mbar_arrive(full_addr);  // release: this thread's words of the buffer (and the control block) are visible to the consumers
@@ -762,7 +760,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
             const bool last = tile_of(k, (int)team) >= n_tiles;  // tiles grow with (k, team): nothing behind this one either
             const uint32_t *const s_stage = s_teams + (size_t)team * team_words;
-            const uint32_t *const s_ctl = s_stage + T * ROW + 4 * T + 2 * T + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
+            const uint32_t *const s_ctl = s_stage + T * ROW + 2 * T + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
             int n_fwd = 0, n_rev = 0, want = mode;
             if (!last) {
                 mbar_wait((uint32_t)__cvta_generic_to_shared(&s_full[team]), (uint32_t)(k & 1));
@@ -842,7 +840,7 @@ inline size_t planes_ws_smem(int teams, int team_warps, int cons_warps, int L, i
 {
     const size_t T = (size_t)team_warps * 32, CT = (size_t)cons_warps * 32, wpr_max = 2 * (size_t)nw_anchor, row = 16 * (size_t)nw_anchor + 4;
     const size_t shared = PL_WIDE * PL_CLASSES * CT + 2 * 8 * 32 * wpr_max + 4 * 12 * (size_t)L + 4 * MDG_LG_SMEM_BINS + 4 * (size_t)L;
-    const size_t team = T * row + 4 * T + 2 * T + ((2 * wpr_max + 3) & ~(size_t)3) + 4 * WS_CTL + T * 14 + 6 * T + 4;
+    const size_t team = T * row + 2 * T + ((2 * wpr_max + 3) & ~(size_t)3) + 4 * WS_CTL + T * 14 + 6 * T + 4;
     return (shared + teams * team) * 4;
 }
 
