@@ -166,6 +166,8 @@ struct mdg_ctx {
     int ws_variant = -1;  // index into WS_VARIANTS, -1: off
     mdg::PlaneGeom ws{};
     size_t ws_smem = 0;
+    bool ws_libraries = false;  // it counts every library in one launch (two of them: mdg::WS_MAX_LIB)
+    size_t ws_smem_libraries = 0;
     void *planes_block = nullptr;  // genome as bit planes
     size_t ref_words_bytes = 0;    // size of one genome image
     std::vector<WorkList> worklists;
@@ -422,13 +424,13 @@ using WsKernel = void (*)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::Cou
 struct WsVariant {
     const char *name;
     int teams, team_warps, cons_warps, nw_anchor;  // nw_anchor = ceil((L + A) / 32) is compiled in
-    WsKernel kernel;
+    WsKernel kernel, kernel_two_libraries;  // one library per launch; every read's own of two libraries
 };
 const WsVariant WS_VARIANTS[] = {
-    {"2x8+8", 2, 8, 8, 3, mdg::count_planes_ws_kernel<2, 8, 8, 3>},
-    {"2x8+8", 2, 8, 8, 2, mdg::count_planes_ws_kernel<2, 8, 8, 2>},
-    {"2x8+4", 2, 8, 4, 3, mdg::count_planes_ws_kernel<2, 8, 4, 3>},
-    {"3x6+8", 3, 6, 8, 3, mdg::count_planes_ws_kernel<3, 6, 8, 3>},
+    {"2x8+8", 2, 8, 8, 3, mdg::count_planes_ws_kernel<2, 8, 8, 3, 1>, mdg::count_planes_ws_kernel<2, 8, 8, 3, 2>},
+    {"2x8+8", 2, 8, 8, 2, mdg::count_planes_ws_kernel<2, 8, 8, 2, 1>, mdg::count_planes_ws_kernel<2, 8, 8, 2, 2>},
+    {"2x8+4", 2, 8, 4, 3, mdg::count_planes_ws_kernel<2, 8, 4, 3, 1>, nullptr},
+    {"3x6+8", 3, 6, 8, 3, mdg::count_planes_ws_kernel<3, 6, 8, 3, 1>, nullptr},
 };
 
 // The counting kernels over one device batch.
@@ -472,8 +474,9 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
                 const WsVariant &v = WS_VARIANTS[ctx->ws_variant];
                 const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
                 const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, (tiles + v.teams - 1) / v.teams);
-                v.kernel<<<pgrid, pg.threads, ctx->ws_smem, stream>>>(b, ctx->ref, p, tl, pg, wl->reads, wl->count, wl->indel_reads,
-                                                                     wl->indel_count, subset);
+                const bool together = !subset.list && subset.offsets;
+                (together ? v.kernel_two_libraries : v.kernel)<<<pgrid, pg.threads, together ? ctx->ws_smem_libraries : ctx->ws_smem, stream>>>(
+                    b, ctx->ref, p, tl, pg, wl->reads, wl->count, wl->indel_reads, wl->indel_count, subset);
             } else if (use_planes) {
                 mdg::PlaneGeom pg = ctx->planes;
                 pg.indel_seen = ctx->indel_seen_dev;
@@ -510,11 +513,19 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             const int pgrid = (int)std::min<int64_t>((b.n_reads + 1023) / 1024, (int64_t)ctx->sm_count * 8);
             mdg::library_count_kernel<<<pgrid, 256, (size_t)nl * 4, stream>>>(b, nl, counts, ctx->count_tables.error_flag);
             mdg::library_offsets_kernel<<<1, 256, 0, stream>>>(counts, nl, offsets, cursors);
-            mdg::library_scatter_kernel<<<(unsigned)((b.n_reads + 1023) / 1024), 256, (size_t)nl * 8, stream>>>(b, nl, cursors,
-                                                                                                                wl->by_library);
-            MDG_CUDA(ctx, cudaGetLastError());
-            for (int lib = 0; lib < nl; ++lib) launch_bitsliced(lib_tables(ctx, lib), mdg::SwarSubset{wl->by_library, offsets, lib});
-            ctx->launches += 3 + nl;
+            if (use_planes && ctx->ws_variant >= 0 && ctx->ws_libraries) {
+                // one launch: a read's library picks its counters and tables; the offsets place the per-library lists of
+                // the reads left to the other kernels
+                MDG_CUDA(ctx, cudaGetLastError());
+                launch_bitsliced(ctx->count_tables, mdg::SwarSubset{nullptr, offsets, 0});
+                ctx->launches += 3;
+            } else {
+                mdg::library_scatter_kernel<<<(unsigned)((b.n_reads + 1023) / 1024), 256, (size_t)nl * 8, stream>>>(b, nl, cursors,
+                                                                                                                    wl->by_library);
+                MDG_CUDA(ctx, cudaGetLastError());
+                for (int lib = 0; lib < nl; ++lib) launch_bitsliced(lib_tables(ctx, lib), mdg::SwarSubset{wl->by_library, offsets, lib});
+                ctx->launches += 3 + nl;
+            }
         }
         MDG_CUDA(ctx, cudaGetLastError());
         if (use_planes) {
@@ -850,9 +861,19 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 wg.tile = v.team_warps * 32;
                 const char *slab_env = getenv("MDG_PLANES_SLAB");
                 wg.seq_words = slab_env && slab_env[0] == '0' ? 0 : wg.tile * 56 / 4;
-                const size_t bytes = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor);
                 const int pairs = (v.cons_warps * 32 >> 7) * 32;
+                // every library in one launch when their event tables fit next to the stage buffers and every group
+                // (library, strand) gets a read slot in the two-window layout
+                const char *lib_env = getenv("MDG_PLANES_WS_LIBS");
+                const size_t bytes_together = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 2);
+                const bool together = nl == 2 && v.kernel_two_libraries && 2 * wg.nw_anchor * 2 * 2 <= pairs && !(lib_env && lib_env[0] == '0') &&
+                                      bytes_together <= ctx->smem_optin;
+                const size_t bytes = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 1);
                 if (bytes <= ctx->smem_optin && 2 * wg.nw_anchor * 2 <= pairs) {
+                    ctx->ws_libraries = together;
+                    ctx->ws_smem_libraries = bytes_together;
+                    if (together)
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_together));
                     MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                     ctx->ws = wg;
                     ctx->ws_smem = bytes;

@@ -69,10 +69,16 @@ __device__ __forceinline__ void ws_plane_bytes(uint32_t w, int p, uint32_t &lo_p
     hi_plane = (t & 0x0C0C0C0Cu) * 0x00410410u;
 }
 
-constexpr int WS_CTL = 8;        // words per tile control block: n_fwd, n_rev, n_cx, min cols, max cols, n_ix, mode, -
+// Words of a tile's control block.  Reads are grouped by (library, strand): group = strand + 2 * library.
+constexpr int WS_CTL = 16;
+constexpr int WS_MAX_LIB = 2;     // libraries counted in one launch (more: one launch per library over an index list)
+constexpr int CTL_GROUP = 0;      // [4] gap-free reads of the tile per group
+constexpr int CTL_MIN = 4, CTL_MAX = 5, CTL_MODE = 6;  // columns of the gap-free reads, window layout chosen
+constexpr int CTL_CX = 8;         // [2] reads for the general kernel, per library
+constexpr int CTL_IX = 10;        // [2] one-indel reads, per library
 constexpr int WS_CAPACITY = 4000;  // reads a counter may see between two reductions (12 bits: planes 0-3 + wide 4-11)
 
-template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA>
+template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA, int kNL>
 __global__ void __launch_bounds__((kTeams * kTeamWarps + kConsWarps) * 32, 1)
 count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneGeom g, uint32_t *__restrict__ worklist,
                        unsigned long long *__restrict__ work_count, uint32_t *__restrict__ indel_list,
@@ -91,22 +97,28 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     // ---- shared memory ----
     uint32_t *const s_wide = smem;                                    // [PL_WIDE][PL_CLASSES][CT]
     uint32_t *const s_red = s_wide + PL_WIDE * PL_CLASSES * CT;       // [strand][8 classes][32 WPR_MAX]: a reduction's sums
-    uint32_t *const s_sub = s_red + 2 * 8 * 32 * WPR_MAX;             // [anchor][strand][12][L] substitution events
-    uint32_t *const s_lg = s_sub + 4 * 12 * L;                        // [kind][strand][MDG_LG_SMEM_BINS]
-    uint32_t *const s_clip = s_lg + 4 * MDG_LG_SMEM_BINS;             // [end][strand][L]
-    uint32_t *const s_teams = s_clip + 4 * L;  // every piece above is a multiple of four words: 16-byte aligned, and still a shared-memory pointer
+    // libraries counted by this launch: every read's own (sub.offsets without a list: the lists of left-over reads are kept
+    // per library at those offsets), or one (the tables passed are that library's)
+    // (kNL > 1 is launched like that only: without a list, with the offsets, p.n_lib == kNL)
+    constexpr int NL = kNL, n_groups = 2 * NL;
+    static_assert(kNL >= 1 && kNL <= WS_MAX_LIB, "libraries per launch");
+    uint32_t *const s_sub = s_red + 2 * 8 * 32 * WPR_MAX;             // [lib][anchor][strand][12][L] substitution events
+    uint32_t *const s_lg = s_sub + NL * 4 * 12 * L;                   // [lib][kind][strand][MDG_LG_SMEM_BINS]
+    uint32_t *const s_clip = s_lg + NL * 4 * MDG_LG_SMEM_BINS;        // [lib][end][strand][L]
+    uint32_t *const s_teams = s_clip + NL * 4 * L;  // every piece above is a multiple of four words: 16-byte aligned, and still a shared-memory pointer
     // per team: stage rows [T][ROW] (forward reads from the front, reverse from the back), two index lists [T], masks
     // [WPR_MAX][2], three control blocks, seq4 stretch, record arrays
     constexpr int SEQ_WORDS = T * 14;  // 56 bytes of seq4 per read: reads of up to about 110 bases on average
     // the record arrays of a tile (flag, lib: 16 bit; tid, pos, l_seq, base_off, cigar_off[T + 1]), bulk-copied a tile ahead
     constexpr int HDR_WORDS = T / 2 + T / 2 + 4 * T + (T + 4);
-    constexpr int team_words = T * ROW + 2 * T + ((2 * WPR_MAX + 3) & ~3) + 4 * WS_CTL + SEQ_WORDS + HDR_WORDS;
+    constexpr int LISTS = 2 * WS_MAX_LIB * T;  // reads this kernel leaves to others: [general | one indel][lib][T]
+    constexpr int team_words = T * ROW + LISTS + ((2 * WPR_MAX + 3) & ~3) + 3 * WS_CTL + SEQ_WORDS + HDR_WORDS;
     __shared__ __align__(8) unsigned long long s_full[kTeams], s_empty[kTeams], s_slab_bar[kTeams], s_hdr_bar[kTeams];
     __shared__ int32_t s_slab[kTeams][2];  // first seq4 word held in the team's copy (may be negative), words (0: no copy)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < PL_WIDE * PL_CLASSES * CT; i += NTHREADS) s_wide[i] = 0;
-    for (int i = tid; i < 4 * 12 * L + 4 * MDG_LG_SMEM_BINS + 4 * L; i += NTHREADS) s_sub[i] = 0;
+    for (int i = tid; i < NL * (4 * 12 * L + 4 * MDG_LG_SMEM_BINS + 4 * L); i += NTHREADS) s_sub[i] = 0;
     if (tid < kTeams) {
         mbar_init((uint32_t)__cvta_generic_to_shared(&s_full[tid]), T);
         mbar_init((uint32_t)__cvta_generic_to_shared(&s_empty[tid]), CT);
@@ -118,7 +130,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     }
     for (int i = tid; i < kTeams * 3 * WS_CTL; i += NTHREADS) {
         const int team = i / (3 * WS_CTL), w = i % (3 * WS_CTL);
-        (s_teams + (size_t)team * team_words + T * ROW + 2 * T + ((2 * WPR_MAX + 3) & ~3))[w] = (w % WS_CTL) == 3 ? 0xffffffffu : 0u;
+        (s_teams + (size_t)team * team_words + T * ROW + LISTS + ((2 * WPR_MAX + 3) & ~3))[w] = (w % WS_CTL) == CTL_MIN ? 0xffffffffu : 0u;
     }
     __syncthreads();
 
@@ -134,11 +146,11 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         // =========================================== producer team ===========================================
         const int team = warp / kTeamWarps, ptid = tid - team * T, pwarp = ptid >> 5;
         uint32_t *const s_stage = s_teams + (size_t)team * team_words;
-        uint32_t *const s_cx = s_stage + T * ROW;                       // reads for the general kernel
-        uint32_t *const s_ix = s_cx + T;                                // one-indel reads
-        uint32_t *const s_mask = s_ix + T;                              // [WPR_MAX][2] aligned / flank masks of a typical read
+        uint32_t *const s_cx = s_stage + T * ROW;                       // [lib][T] reads for the general kernel
+        uint32_t *const s_ix = s_cx + WS_MAX_LIB * T;                   // [lib][T] one-indel reads
+        uint32_t *const s_mask = s_ix + WS_MAX_LIB * T;                 // [WPR_MAX][2] aligned / flank masks of a typical read
         uint32_t *const s_ctl_base = s_mask + ((2 * WPR_MAX + 3) & ~3);
-        uint32_t *const s_seq = s_ctl_base + 4 * WS_CTL;
+        uint32_t *const s_seq = s_ctl_base + 3 * WS_CTL;
         const uint16_t *const s_hflag = (const uint16_t *)(s_seq + SEQ_WORDS), *const s_hlib = s_hflag + T;
         const int32_t *const s_htid = (const int32_t *)(s_hlib + T), *const s_hpos = s_htid + T;
         const uint32_t *const s_hlseq = (const uint32_t *)(s_hpos + T), *const s_hboff = s_hlseq + T, *const s_hcoff = s_hboff + T;
@@ -175,7 +187,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
 
         // ---- stage: the plane words of one window of one read (see count_planes_kernel::stage_window) ----
         auto stage_window = [&](auto nw_tag, const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
-                                int slab_w0, int slab_words, int rstrand) {
+                                int slab_w0, int slab_words, int rstrand, int libx) {
             constexpr int kNW = decltype(nw_tag)::value;
             const int cols = (int)(rec.cols & 0x7FFF);
             const int v = (int)(rec.misc & 0xFFFF);
@@ -199,7 +211,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             const int64_t rn = ((int64_t)rec.rg << 5) + (int)((rec.misc >> 16) & 31) + c_start;
             const uint4 *rp = planes + (rn >> 5);
             const int rs = (int)(rn & 31);
-            uint32_t *const sub_at = s_sub + (size_t)rstrand * 12 * L;
+            uint32_t *const sub_at = s_sub + ((size_t)libx * 4 + rstrand) * 12 * L;
             auto emit = [&](int k, uint32_t (&q0)[4], uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, const uint4 &g_lo, const uint4 &g_hi) {
                 uint32_t xp[4];
 #pragma unroll
@@ -306,9 +318,10 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
 
         // ---- parse of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
         // kind: 0 nothing to do, 1 gap-free (record made), 2 for the general kernel, 3 one short indel
-        auto parse_read = [&](bool live, int64_t r, int q, int &kind, int &rstrand, uint32_t &columns, PlaneRecord &rec) {
+        auto parse_read = [&](bool live, int64_t r, int q, int &kind, int &rstrand, int &libx, uint32_t &columns, PlaneRecord &rec) {
             kind = 0;
             rstrand = 0;
+            libx = 0;
             columns = 0;
             if (!live) return;
             uint32_t flag, lib, l_seq, boff, c0, c1;
@@ -328,6 +341,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 return;
             }
             if (subset && lib != (uint32_t)sub.lib) return;  // cannot happen: the list is grouped by library
+            libx = NL > 1 ? (int)lib : 0;  // which of this launch's table sets and lists the read belongs to
             if (tid_ref < 0 || tid_ref >= ref.n_contigs) {
                 atomicCAS(t.error_flag, 0, DATA_ERR_TID);
                 return;
@@ -414,25 +428,25 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
             if (length >= 0) {
                 if (length < MDG_LG_SMEM_BINS && length < p.lg_bins) {
-                    atomicAdd(s_lg + (lkind * 2 + rstrand) * MDG_LG_SMEM_BINS + length, 1u);
+                    atomicAdd(s_lg + ((libx * 2 + lkind) * 2 + rstrand) * MDG_LG_SMEM_BINS + length, 1u);
                 } else if (length < p.lg_bins) {
-                    atomicAdd(t.lghist + (size_t)(lkind * 2 + rstrand) * p.lg_bins + length, 1ull);
+                    atomicAdd(t.lghist + (size_t)((libx * 2 + lkind) * 2 + rstrand) * p.lg_bins + length, 1ull);
                 } else {
                     const unsigned long long at = atomicAdd(t.lg_overflow_count, 1ull);
                     if ((int64_t)at < t.lg_overflow_cap) {
                         int32_t *row = t.lg_overflow_rows + at * 4;
-                        row[0] = sub.list ? sub.lib : 0; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
+                        row[0] = sub.list ? sub.lib : libx; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
                     }
                 }
             }
             // update_soft_clipping, statistics.py:37-51
             if (lead) {
                 const int end = rstrand ? 1 : 0, lim = (int)min(lead, (uint32_t)L);
-                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
+                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + ((libx * 2 + end) * 2 + rstrand) * L + i, 1u);
             }
             if (trail) {
                 const int end = rstrand ? 0 : 1, lim = (int)min(trail, (uint32_t)L);
-                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + (end * 2 + rstrand) * L + i, 1u);
+                for (int i = 0; i < lim; ++i) atomicAdd(s_clip + ((libx * 2 + end) * 2 + rstrand) * L + i, 1u);
             }
         };
 
@@ -520,77 +534,84 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 ++hdr_phase;
             }
             // the thread that parses a read also stages it: the record stays in its registers
-            int kind, rstrand;
-            uint32_t rank = 0;  // of a gap-free read: index in its strand's list = its row from the front (forward) or the back (reverse)
+            int kind, rstrand, libx;
+            uint32_t rank = 0;  // of a gap-free read: its index among the tile's reads of its group (library, strand)
+            int key;            // group of a gap-free read; CTL_CX / CTL_IX + library of a read left to another kernel; -1: nothing
             PlaneRecord rec{};
             {
                 const int64_t at = tile * T + ptid;
                 const bool live = at < n_todo;
                 const int64_t r = !live ? 0 : subset ? (int64_t)subset[at] : at;
                 uint32_t columns;
-                parse_read(live, r, ptid, kind, rstrand, columns, rec);
+                parse_read(live, r, ptid, kind, rstrand, libx, columns, rec);
                 if (g.uniform) {
                     const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
                     const uint32_t hi = __reduce_max_sync(0xffffffffu, kind == 1 ? columns : 0u);
                     if (lane == 0 && hi) {
-                        atomicMin(s_ctl + 3, lo);
-                        atomicMax(s_ctl + 4, hi);
+                        atomicMin(s_ctl + CTL_MIN, lo);
+                        atomicMax(s_ctl + CTL_MAX, hi);
                     }
                 }
-                // warp-aggregated appends to the four lists
-                const uint32_t lt = (1u << lane) - 1u;
+                // warp-aggregated appends: the lanes with the same key take consecutive places behind one atomic
+                key = kind == 1 ? CTL_GROUP + rstrand + 2 * libx : kind == 2 ? CTL_CX + libx : kind == 3 ? CTL_IX + libx : -1;
+                if constexpr (kNL == 1) {
+                    // four keys: one vote each (cheaper than a match)
+                    const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-                for (int which = 0; which < 4; ++which) {
-                    const bool mine = which == 2 ? kind == 2 : which == 3 ? kind == 3 : (kind == 1 && rstrand == which);
-                    const uint32_t m = __ballot_sync(0xffffffffu, mine);
-                    if (m) {
-                        uint32_t base = 0;
-                        if (lane == __ffs(m) - 1) base = atomicAdd(s_ctl + (which == 3 ? 5 : which), (uint32_t)__popc(m));
-                        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                        if (mine) {
-                            const uint32_t slot = base + __popc(m & lt);
-                            if (which == 2) s_cx[slot] = (uint32_t)r;
-                            else if (which == 3) s_ix[slot] = (uint32_t)r;
-                            else rank = slot;
+                    for (int which = 0; which < 4; ++which) {
+                        const int this_key = which == 2 ? CTL_CX : which == 3 ? CTL_IX : CTL_GROUP + which;
+                        const uint32_t m = __ballot_sync(0xffffffffu, key == this_key);
+                        if (m) {
+                            uint32_t base = 0;
+                            if (lane == __ffs(m) - 1) base = atomicAdd(s_ctl + this_key, (uint32_t)__popc(m));
+                            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                            if (key == this_key) rank = base + __popc(m & lt);
                         }
                     }
+                } else {
+                    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                    if (key >= 0) {
+                        const int leader = __ffs(peers) - 1;
+                        uint32_t base = 0;
+                        if (lane == leader) base = atomicAdd(s_ctl + key, (uint32_t)__popc(peers));
+                        rank = __shfl_sync(peers, base, leader) + __popc(peers & ((1u << lane) - 1u));
+                    }
                 }
+                if (kind == 2) s_cx[libx * T + rank] = (uint32_t)r;
+                else if (kind == 3) s_ix[libx * T + rank] = (uint32_t)r;
             }
             named_barrier<T>(1 + team);
 
             // ---- reads this kernel does not count go to the two work lists ----
-            if (pwarp == 0 && s_ctl[2]) {
-                const uint32_t n_cx = s_ctl[2];
-                unsigned long long base = 0;
-                uint32_t *const wl = sub.list ? worklist + sub.offsets[sub.lib] : worklist;
-                if (lane == 0) base = atomicAdd(work_count + (sub.list ? sub.lib : 0), (unsigned long long)n_cx);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                for (uint32_t i = lane; i < n_cx; i += 32) wl[base + i] = s_cx[i];
-            }
-            if (pwarp == 1 && s_ctl[5]) {
-                const uint32_t n_ix = s_ctl[5];
-                unsigned long long base = 0;
-                uint32_t *const il = sub.list ? indel_list + sub.offsets[sub.lib] : indel_list;
-                if (lane == 0) {
-                    base = atomicAdd(indel_count + (sub.list ? sub.lib : 0), (unsigned long long)n_ix);
-                    if (g.indel_seen) atomicAdd(g.indel_seen, (unsigned long long)n_ix);
+            if (pwarp < 2) {  // warp 0: reads for the general kernel, warp 1: one-indel reads; per library
+                for (int lib = 0; lib < NL; ++lib) {
+                    const uint32_t n = s_ctl[(pwarp ? CTL_IX : CTL_CX) + lib];
+                    if (!n) continue;
+                    const int at_lib = sub.list ? sub.lib : lib;  // the global lists are kept per library
+                    const uint32_t *const from = (pwarp ? s_ix : s_cx) + lib * T;
+                    uint32_t *const to = (pwarp ? indel_list : worklist) + (sub.offsets ? sub.offsets[at_lib] : 0);
+                    unsigned long long base = 0;
+                    if (lane == 0) {
+                        base = atomicAdd((pwarp ? indel_count : work_count) + at_lib, (unsigned long long)n);
+                        if (pwarp && g.indel_seen) atomicAdd(g.indel_seen, (unsigned long long)n);
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    for (uint32_t i = lane; i < n; i += 32) to[base + i] = from[i];
                 }
-                base = __shfl_sync(0xffffffffu, base, 0);
-                for (uint32_t i = lane; i < n_ix; i += 32) il[base + i] = s_ix[i];
             }
             // the control block of the tile after this one (last read by the consumers two tiles ago)
-            if (ptid < WS_CTL) s_ctl_next[ptid] = ptid == 3 ? 0xffffffffu : 0u;
+            if (ptid < WS_CTL) s_ctl_next[ptid] = ptid == CTL_MIN ? 0xffffffffu : 0u;
             if (ptid == 32) issue_headers(tile_of(k + 1, team));  // everyone is done with this tile's records: the next tile's land while this one is staged
 
             // ---- one window per read when every gap-free read of the tile has the same length ----
             {
                 int want = 0;
-                const uint32_t lo = s_ctl[3], hi = s_ctl[4];
+                const uint32_t lo = s_ctl[CTL_MIN], hi = s_ctl[CTL_MAX];
                 if (g.uniform && lo == hi && hi > 0) {
                     const int words = ((int)hi + 2 * A + 31) / 32;
-                    if (words < WPR_MAX && PAIRS / words >= 2) want = (int)hi;
+                    if (words < WPR_MAX && PAIRS / words >= n_groups) want = (int)hi;
                 }
-                if (ptid == 0) s_ctl[6] = (uint32_t)want;
+                if (ptid == 0) s_ctl[CTL_MODE] = (uint32_t)want;
                 if (want != mode) {
                     mode = want;
                     fill_masks(want);
@@ -607,15 +628,18 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 ++slab_phase;
             }
             if (kind == 1) {
-                const int row = rstrand ? T - 1 - (int)rank : (int)rank;
+                int row = (int)rank;  // the groups' rows follow each other
+#pragma unroll
+                for (int lower = 0; lower < n_groups - 1; ++lower)
+                    if (lower < key) row += (int)s_ctl[CTL_GROUP + lower];
                 uint32_t *const row_at = s_stage + (size_t)row * ROW;
                 const int n_words = mode ? words_of(mode) : NWA;
                 for (int side = 0; side < (mode ? 1 : 2); ++side) {
                     const int first_word = side ? NWA : 0;
                     const int c_start = side ? (int)(rec.cols & 0x7FFF) + A - 32 * NWA : -A;
-                    if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, rstrand);
-                    else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, rstrand);
-                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand);
+                    if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, rstrand, libx);
+                    else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, rstrand, libx);
+                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand, libx);
                 }
             }
             mbar_arrive(full_addr);  // release: this thread's words of the buffer (and the control block) are visible to the consumers
@@ -628,16 +652,20 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         const int ctid = tid - PRODUCERS, cwarp = ctid >> 5;
         const int group = cwarp & 3;                 // reference base of this thread's classes
         const int pair = (cwarp >> 2) * 32 + lane;   // index among the (slot, word) pairs of its group
-        int mode = 0, ws = 0, slot = 0, strand = 0, mode_slots = 2;
+        // a read slot belongs to one group (library, strand) and takes every spg-th read of it
+        int mode = 0, ws = 0, grp = 0, idx = 0, strand = 0, mylib = 0, spg = 1;
         bool active = false;
         auto set_mode = [&](int columns) {
             mode = columns;
             const int wpr = words_of(columns);
-            mode_slots = (PAIRS / wpr) & ~1;
-            active = pair < wpr * mode_slots;
+            spg = (PAIRS / wpr) / n_groups;  // slots per group (at least one: the host and the producers see to it)
+            active = pair < wpr * spg * n_groups;
             ws = pair % wpr;
-            slot = pair / wpr;
-            strand = slot & 1;
+            const int slot = pair / wpr;
+            grp = slot % n_groups;
+            idx = slot / n_groups;
+            strand = grp & 1;
+            mylib = grp >> 1;
         };
         set_mode(0);
         uint32_t cnt[PL_CLASSES][PL_REG];
@@ -669,9 +697,9 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
             n_iter = 0;
         };
-        auto add_cell = [&](int canchor, int cstrand, int cls, int pos, unsigned long long sum) {
-            // window position `pos` of an anchor -> table cell; classes are complemented on the reverse strand
-            const int es = (canchor ^ cstrand) * 2 + cstrand;
+        auto add_cell = [&](int lib, int canchor, int cstrand, int cls, int pos, unsigned long long sum) {
+            // window position `pos` of an anchor -> table cell of the library; classes are complemented on the reverse strand
+            const int es = lib * 4 + (canchor ^ cstrand) * 2 + cstrand;
             if (pos >= 0) {
                 if (cls < 4) {
                     const int gb = cstrand ? 3 - cls : cls;
@@ -690,68 +718,70 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         auto flush = [&]() {
             spill();
             const int wpr = words_of(mode), bits = 32 * wpr;
-            for (int i = ctid; i < 2 * 8 * bits; i += CT) s_red[i] = 0;
-            named_barrier<CT>(1 + kTeams);
-            if (active) {
+            for (int lib = 0; lib < NL; ++lib) {  // one library at a time through the reduction area
+                for (int i = ctid; i < 2 * 8 * bits; i += CT) s_red[i] = 0;
+                named_barrier<CT>(1 + kTeams);
+                if (active && mylib == lib) {
 #pragma unroll
-                for (int c = 0; c < PL_CLASSES; ++c) {
-                    const int cls = c == 0 ? group : 4 + group;  // class of the tables: R_g, H_g
-                    uint32_t pl[4 + PL_WIDE];
+                    for (int c = 0; c < PL_CLASSES; ++c) {
+                        const int cls = c == 0 ? group : 4 + group;  // class of the tables: R_g, H_g
+                        uint32_t pl[4 + PL_WIDE];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) pl[k] = cnt[c][k];
+                        for (int k = 0; k < 4; ++k) {
+                            pl[k] = cnt[c][k];
+                            cnt[c][k] = 0;
+                        }
 #pragma unroll
-                    for (int k = 0; k < PL_WIDE; ++k) {
-                        pl[4 + k] = my_wide[(k * PL_CLASSES + c) * CT];
-                        my_wide[(k * PL_CLASSES + c) * CT] = 0;
-                    }
-                    uint32_t any = 0;
+                        for (int k = 0; k < PL_WIDE; ++k) {
+                            pl[4 + k] = my_wide[(k * PL_CLASSES + c) * CT];
+                            my_wide[(k * PL_CLASSES + c) * CT] = 0;
+                        }
+                        uint32_t any = 0;
 #pragma unroll
-                    for (int k = 0; k < 4 + PL_WIDE; ++k) any |= pl[k];
-                    uint32_t *const to = s_red + ((size_t)strand * 8 + cls) * bits + 32 * ws;
-                    while (any) {
-                        const int j = __ffs(any) - 1;
-                        any &= any - 1;
-                        uint32_t v = 0;
+                        for (int k = 0; k < 4 + PL_WIDE; ++k) any |= pl[k];
+                        uint32_t *const to = s_red + ((size_t)strand * 8 + cls) * bits + 32 * ws;
+                        while (any) {
+                            const int j = __ffs(any) - 1;
+                            any &= any - 1;
+                            uint32_t v = 0;
 #pragma unroll
-                        for (int k = 0; k < 4 + PL_WIDE; ++k) v |= ((pl[k] >> j) & 1u) << k;
-                        atomicAdd(to + j, v);
+                            for (int k = 0; k < 4 + PL_WIDE; ++k) v |= ((pl[k] >> j) & 1u) << k;
+                            atomicAdd(to + j, v);
+                        }
                     }
                 }
-            }
-#pragma unroll
-            for (int c = 0; c < PL_CLASSES; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) cnt[c][k] = 0;
-            named_barrier<CT>(1 + kTeams);
-            for (int cell = ctid; cell < 2 * 8 * bits; cell += CT) {
-                const int bit = cell % bits, cls = (cell / bits) % 8, cstrand = cell / (8 * bits);
-                const unsigned long long sum = s_red[cell];
-                if (!sum) continue;
-                // a window bit feeds the table of the left end (anchor 0), of the right end (anchor 1), or both
-                int pos0 = L, pos1 = L;  // L: no cell
-                if (mode) {
-                    const int col = bit - A;
-                    if (col < 0) pos0 = col;                      // left flank
-                    else if (col >= mode) pos1 = mode - 1 - col;  // right flank at distance col - C + 1
-                    else {
-                        pos0 = col;
-                        pos1 = mode - 1 - col;
+                named_barrier<CT>(1 + kTeams);
+                for (int cell = ctid; cell < 2 * 8 * bits; cell += CT) {
+                    const int bit = cell % bits, cls = (cell / bits) % 8, cstrand = cell / (8 * bits);
+                    const unsigned long long sum = s_red[cell];
+                    if (!sum) continue;
+                    // a window bit feeds the table of the left end (anchor 0), of the right end (anchor 1), or both
+                    int pos0 = L, pos1 = L;  // L: no cell
+                    if (mode) {
+                        const int col = bit - A;
+                        if (col < 0) pos0 = col;                      // left flank
+                        else if (col >= mode) pos1 = mode - 1 - col;  // right flank at distance col - C + 1
+                        else {
+                            pos0 = col;
+                            pos1 = mode - 1 - col;
+                        }
+                    } else if (bit < 32 * NWA) {
+                        pos0 = bit - A;
+                    } else {
+                        pos1 = 32 * NWA - A - 1 - (bit - 32 * NWA);  // columns from the right end; negative: flank
                     }
-                } else if (bit < 32 * NWA) {
-                    pos0 = bit - A;
-                } else {
-                    pos1 = 32 * NWA - A - 1 - (bit - 32 * NWA);  // columns from the right end; negative: flank
-                }
 #pragma unroll 1
-                for (int canchor = 0; canchor < 2; ++canchor) {
-                    const int pos = canchor ? pos1 : pos0;
-                    if (pos < L) add_cell(canchor, cstrand, cls, pos, sum);
+                    for (int canchor = 0; canchor < 2; ++canchor) {
+                        const int pos = canchor ? pos1 : pos0;
+                        if (pos < L) add_cell(lib, canchor, cstrand, cls, pos, sum);
+                    }
                 }
+                named_barrier<CT>(1 + kTeams);
             }
-            named_barrier<CT>(1 + kTeams);
         };
 
         int since_flush = 0, tiles_since_flush = 0;  // reads a counter may have seen / tiles since the last reduction
+        int mode_counted = 0;                        // window layout the counters hold
         bool dirty = false;
         for (int64_t k = 0, team = 0;; ++team) {
             if (team == kTeams) {
@@ -760,36 +790,44 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
             const bool last = tile_of(k, (int)team) >= n_tiles;  // tiles grow with (k, team): nothing behind this one either
             const uint32_t *const s_stage = s_teams + (size_t)team * team_words;
-            const uint32_t *const s_ctl = s_stage + T * ROW + 2 * T + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
-            int n_fwd = 0, n_rev = 0, want = mode;
+            const uint32_t *const s_ctl = s_stage + T * ROW + LISTS + ((2 * WPR_MAX + 3) & ~3) + WS_CTL * (int)(k % 3);
+            int n_most = 0, n_all = 0, n_mine = 0, my_row = 0, want = mode;
             if (!last) {
                 mbar_wait((uint32_t)__cvta_generic_to_shared(&s_full[team]), (uint32_t)(k & 1));
-                n_fwd = (int)s_ctl[0];
-                n_rev = (int)s_ctl[1];
-                want = (int)s_ctl[6];
+                want = (int)s_ctl[CTL_MODE];
+                if (want != mode) set_mode(want);  // (the counters are reduced below before they are used in the new layout)
+                for (int other = 0; other < n_groups; ++other) {
+                    const int n = (int)s_ctl[CTL_GROUP + other];
+                    n_most = max(n_most, n);
+                    n_all += n;
+                    if (other < grp) my_row += n;  // the groups' rows follow each other
+                    if (other == grp) n_mine = n;
+                }
             }
-            const int want_stride = ((PAIRS / words_of(want)) & ~1) >> 1;
-            const int bound = ((max(n_fwd, n_rev) + want_stride - 1) / want_stride + 7) & ~7;  // reads a thread adds at most, whole iterations
-            if (last || (want != mode && dirty) || since_flush + bound > WS_CAPACITY || (g.flush_tiles > 0 && tiles_since_flush >= g.flush_tiles)) {
+            const int bound = ((n_most + spg - 1) / spg + 7) & ~7;  // reads a thread adds at most, whole iterations
+            if (last || (want != mode_counted && dirty) || since_flush + bound > WS_CAPACITY ||
+                (g.flush_tiles > 0 && tiles_since_flush >= g.flush_tiles)) {
+                // (reduce in the layout the counters were filled in)
+                const int now = mode;
+                if (now != mode_counted) set_mode(mode_counted);
                 flush();
+                if (now != mode_counted) set_mode(now);
                 since_flush = 0;
                 tiles_since_flush = 0;
                 dirty = false;
             }
             if (last) break;
-            if (want != mode) set_mode(want);
+            mode_counted = mode;
             since_flush += bound;
             ++tiles_since_flush;
-            dirty = dirty || n_fwd + n_rev > 0;
-            // ---- count: this thread's window word and reference base, every stride-th read of its strand ----
+            dirty = dirty || n_all > 0;
+            // ---- count: this thread's window word and reference base, every spg-th read of its group ----
             if (active) {
-                const int stride = mode_slots >> 1;
-                const int n_mine = strand ? n_rev : n_fwd;
-                const int row_step = (strand ? -stride : stride) * ROW;
-                const uint32_t *at = s_stage + (size_t)(strand ? T - 1 - (slot >> 1) : (slot >> 1)) * ROW + 8 * ws + group;
-                for (int i = slot >> 1; i < n_mine; i += 8 * stride) {
+                const int row_step = spg * ROW;
+                const uint32_t *at = s_stage + (size_t)(my_row + idx) * ROW + 8 * ws + group;
+                for (int i = idx; i < n_mine; i += 8 * spg) {
                     uint32_t xg[8], y[8];
-                    if (i + 7 * stride < n_mine) {  // eight reads in hand: no tests
+                    if (i + 7 * spg < n_mine) {  // eight reads in hand: no tests
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             xg[u] = at[u * row_step];
@@ -798,7 +836,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     } else {
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const bool live = i + u * stride < n_mine;
+                            const bool live = i + u * spg < n_mine;
                             xg[u] = live ? at[u * row_step] : 0u;
                             y[u] = live ? at[u * row_step + 4] : 0u;
                         }
@@ -815,32 +853,32 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
 
     // ---- everybody: the block's event tables into the 64-bit tables ----
     __syncthreads();
-    for (int cell = tid; cell < 4 * 12 * L; cell += NTHREADS) {
+    for (int cell = tid; cell < NL * 4 * 12 * L; cell += NTHREADS) {
         const uint32_t v = s_sub[cell];
         if (!v) continue;
-        const int pos = cell % L, cls = (cell / L) % 12, cstrand = (cell / (12 * L)) & 1, canchor = cell / (24 * L);
+        const int pos = cell % L, cls = (cell / L) % 12, cstrand = (cell / (12 * L)) & 1, canchor = (cell / (24 * L)) & 1, lib = cell / (48 * L);
         int gb = cls / 3, rb = cls % 3;
         rb += rb >= gb ? 1 : 0;
         if (cstrand) { gb = 3 - gb; rb = 3 - rb; }
-        const int es = (canchor ^ cstrand) * 2 + cstrand;
+        const int es = lib * 4 + (canchor ^ cstrand) * 2 + cstrand;
         atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + 4 + 5 * gb + rb) * L + pos, (unsigned long long)v);
     }
-    for (int i = tid; i < 4 * MDG_LG_SMEM_BINS; i += NTHREADS) {
+    for (int i = tid; i < NL * 4 * MDG_LG_SMEM_BINS; i += NTHREADS) {  // [lib][kind][strand][bin]: the tables' own order
         const uint32_t v = s_lg[i];
         if (v) atomicAdd(t.lghist + (size_t)(i / MDG_LG_SMEM_BINS) * p.lg_bins + i % MDG_LG_SMEM_BINS, (unsigned long long)v);
     }
-    for (int i = tid; i < 4 * L; i += NTHREADS) {
+    for (int i = tid; i < NL * 4 * L; i += NTHREADS) {  // [lib][end][strand][position]
         const uint32_t v = s_clip[i];
         if (v) atomicAdd(t.misincorp + ((size_t)(i / L) * MDG_N_CLASSES + MDG_CLASS_SOFTCLIP) * L + i % L, (unsigned long long)v);
     }
 }
 
 // dynamic shared memory of count_planes_ws_kernel<kTeams, kTeamWarps, kConsWarps, kNWA> (bytes)
-inline size_t planes_ws_smem(int teams, int team_warps, int cons_warps, int L, int nw_anchor)
+inline size_t planes_ws_smem(int teams, int team_warps, int cons_warps, int L, int nw_anchor, int n_lib)
 {
     const size_t T = (size_t)team_warps * 32, CT = (size_t)cons_warps * 32, wpr_max = 2 * (size_t)nw_anchor, row = 16 * (size_t)nw_anchor + 4;
-    const size_t shared = PL_WIDE * PL_CLASSES * CT + 2 * 8 * 32 * wpr_max + 4 * 12 * (size_t)L + 4 * MDG_LG_SMEM_BINS + 4 * (size_t)L;
-    const size_t team = T * row + 2 * T + ((2 * wpr_max + 3) & ~(size_t)3) + 4 * WS_CTL + T * 14 + 6 * T + 4;
+    const size_t shared = PL_WIDE * PL_CLASSES * CT + 2 * 8 * 32 * wpr_max + n_lib * (4 * 12 * (size_t)L + 4 * MDG_LG_SMEM_BINS + 4 * (size_t)L);
+    const size_t team = T * row + 2 * WS_MAX_LIB * T + ((2 * wpr_max + 3) & ~(size_t)3) + 3 * WS_CTL + T * 14 + 6 * T + 4;
     return (shared + teams * team) * 4;
 }
 
