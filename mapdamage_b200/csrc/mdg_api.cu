@@ -166,7 +166,9 @@ struct mdg_ctx {
     int ws_variant = -1;  // index into WS_VARIANTS, -1: off
     mdg::PlaneGeom ws{};
     size_t ws_smem = 0;
-    bool ws_libraries = false;  // it counts every library in one launch (two of them: mdg::WS_MAX_LIB)
+    // its two-library form (a read's library picks counters and tables; smaller tiles: two sets of event tables)
+    int ws_variant_libraries = -1;
+    mdg::PlaneGeom ws_libraries_geom{};
     size_t ws_smem_libraries = 0;
     void *planes_block = nullptr;  // genome as bit planes
     size_t ref_words_bytes = 0;    // size of one genome image
@@ -427,7 +429,9 @@ struct WsVariant {
     WsKernel kernel, kernel_two_libraries;  // one library per launch; every read's own of two libraries
 };
 const WsVariant WS_VARIANTS[] = {
-    {"2x8+8", 2, 8, 8, 3, mdg::count_planes_ws_kernel<2, 8, 8, 3, 1>, mdg::count_planes_ws_kernel<2, 8, 8, 3, 2>},
+    {"2x9+8", 2, 9, 8, 3, mdg::count_planes_ws_kernel<2, 9, 8, 3, 1>, nullptr},  // the default: 0.413 ms per 4 M 100 bp reads
+    {"2x9+8", 2, 9, 8, 2, mdg::count_planes_ws_kernel<2, 9, 8, 2, 1>, nullptr},
+    {"2x8+8", 2, 8, 8, 3, mdg::count_planes_ws_kernel<2, 8, 8, 3, 1>, mdg::count_planes_ws_kernel<2, 8, 8, 3, 2>},  // 0.428
     {"2x8+8", 2, 8, 8, 2, mdg::count_planes_ws_kernel<2, 8, 8, 2, 1>, mdg::count_planes_ws_kernel<2, 8, 8, 2, 2>},
     {"2x8+4", 2, 8, 4, 3, mdg::count_planes_ws_kernel<2, 8, 4, 3, 1>, nullptr},
     {"3x6+8", 3, 6, 8, 3, mdg::count_planes_ws_kernel<3, 6, 8, 3, 1>, nullptr},
@@ -467,14 +471,14 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         // one launch of the bit-sliced kernel over a library's reads (or all reads) into the tables `tl`
         auto launch_bitsliced = [&](const mdg::CountTables &tl, const mdg::SwarSubset &subset) {
             if (use_planes && ctx->ws_variant >= 0) {
-                mdg::PlaneGeom pg = ctx->ws;
+                const bool together = !subset.list && subset.offsets;  // every library in this launch
+                mdg::PlaneGeom pg = together ? ctx->ws_libraries_geom : ctx->ws;
                 pg.indel_seen = ctx->indel_seen_dev;
                 // genome image larger than what stays in L2: prefetch each read's genome entries while it is parsed
                 if (!getenv("MDG_PLANES_PREFETCH") && ctx->ref_words_bytes > ((size_t)48 << 20)) pg.prefetch_bases |= 2;
-                const WsVariant &v = WS_VARIANTS[ctx->ws_variant];
+                const WsVariant &v = WS_VARIANTS[together ? ctx->ws_variant_libraries : ctx->ws_variant];
                 const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
                 const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, (tiles + v.teams - 1) / v.teams);
-                const bool together = !subset.list && subset.offsets;
                 (together ? v.kernel_two_libraries : v.kernel)<<<pgrid, pg.threads, together ? ctx->ws_smem_libraries : ctx->ws_smem, stream>>>(
                     b, ctx->ref, p, tl, pg, wl->reads, wl->count, wl->indel_reads, wl->indel_count, subset);
             } else if (use_planes) {
@@ -513,7 +517,7 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             const int pgrid = (int)std::min<int64_t>((b.n_reads + 1023) / 1024, (int64_t)ctx->sm_count * 8);
             mdg::library_count_kernel<<<pgrid, 256, (size_t)nl * 4, stream>>>(b, nl, counts, ctx->count_tables.error_flag);
             mdg::library_offsets_kernel<<<1, 256, 0, stream>>>(counts, nl, offsets, cursors);
-            if (use_planes && ctx->ws_variant >= 0 && ctx->ws_libraries) {
+            if (use_planes && ctx->ws_variant >= 0 && ctx->ws_variant_libraries >= 0) {
                 // one launch: a read's library picks its counters and tables; the offsets place the per-library lists of
                 // the reads left to the other kernels
                 MDG_CUDA(ctx, cudaGetLastError());
@@ -852,34 +856,36 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
         // warp-specialised bit-plane kernel: MDG_PLANES_WS=<variant name> (or 0: off)
         if (ctx->planes_enabled) {
             const char *ws_env = getenv("MDG_PLANES_WS");
-            const char *want = ws_env ? ws_env : "2x8+8";  // the default; MDG_PLANES_WS=0: the one-role kernel (count_planes_kernel)
+            const char *want = ws_env ? ws_env : "2x9+8";  // the default; MDG_PLANES_WS=0: the one-role kernel (count_planes_kernel)
+            const char *lib_env = getenv("MDG_PLANES_WS_LIBS");  // 0: two libraries as two launches over index lists (A/B, tests)
+            const char *slab_env = getenv("MDG_PLANES_SLAB");
             for (int i = 0; i < (int)(sizeof(WS_VARIANTS) / sizeof(WS_VARIANTS[0])); ++i) {
                 const WsVariant &v = WS_VARIANTS[i];
-                if (strcmp(want, v.name) || v.nw_anchor != ctx->planes.nw_anchor) continue;
+                if (v.nw_anchor != ctx->planes.nw_anchor) continue;
                 mdg::PlaneGeom wg = ctx->planes;
                 wg.threads = (v.teams * v.team_warps + v.cons_warps) * 32;
                 wg.tile = v.team_warps * 32;
-                const char *slab_env = getenv("MDG_PLANES_SLAB");
                 wg.seq_words = slab_env && slab_env[0] == '0' ? 0 : wg.tile * 56 / 4;
                 const int pairs = (v.cons_warps * 32 >> 7) * 32;
-                // every library in one launch when their event tables fit next to the stage buffers and every group
-                // (library, strand) gets a read slot in the two-window layout
-                const char *lib_env = getenv("MDG_PLANES_WS_LIBS");
-                const size_t bytes_together = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 2);
-                const bool together = nl == 2 && v.kernel_two_libraries && 2 * wg.nw_anchor * 2 * 2 <= pairs && !(lib_env && lib_env[0] == '0') &&
-                                      bytes_together <= ctx->smem_optin;
                 const size_t bytes = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 1);
-                if (bytes <= ctx->smem_optin && 2 * wg.nw_anchor * 2 <= pairs) {
-                    ctx->ws_libraries = together;
-                    ctx->ws_smem_libraries = bytes_together;
-                    if (together)
-                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_together));
+                if (ctx->ws_variant < 0 && !strcmp(want, v.name) && bytes <= ctx->smem_optin && 2 * wg.nw_anchor * 2 <= pairs) {
                     MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                     ctx->ws = wg;
                     ctx->ws_smem = bytes;
                     ctx->ws_variant = i;
                 }
+                // two libraries in one launch: the first shape whose two sets of event tables fit next to the stage buffers
+                // and that gives every group (library, strand) a read slot in the two-window layout
+                const size_t bytes_two = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 2);
+                if (ctx->ws_variant_libraries < 0 && nl == 2 && v.kernel_two_libraries && strcmp(want, "0") && !(lib_env && lib_env[0] == '0') &&
+                    bytes_two <= ctx->smem_optin && 2 * wg.nw_anchor * 2 * 2 <= pairs) {
+                    MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_two));
+                    ctx->ws_libraries_geom = wg;
+                    ctx->ws_smem_libraries = bytes_two;
+                    ctx->ws_variant_libraries = i;
+                }
             }
+            if (ctx->ws_variant < 0) ctx->ws_variant_libraries = -1;
         }
         const char *env = getenv("MDG_FORCE_GENERAL");
         ctx->force_general = env && env[0] == '1';

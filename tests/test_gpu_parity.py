@@ -298,7 +298,7 @@ def test_optional_arrays_default_on_device(name):
                                  {"MDG_KERNEL": "swar", "MDG_SWAR_VARIANT": "512,1", "MDG_SWAR_FLUSH_TILES": "2"},
                                  {"MDG_PLANES_WS": "0"}, {"MDG_PLANES_WS": "2x8+8"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_FLUSH_TILES": "3"},
                                  {"MDG_PLANES_WS": "2x8+8", "MDG_PLANES_SLAB": "0"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_UNIFORM": "0"},
-                                 {"MDG_PLANES_WS": "3x6+8"}, {"MDG_PLANES_WS": "4x4+8", "MDG_SWAR_FLUSH_TILES": "5"},
+                                 {"MDG_PLANES_WS": "2x9+8", "MDG_SWAR_FLUSH_TILES": "5"},
                                  {"MDG_PLANES_WS": "2x8+4"}, {"MDG_PLANES_THREADS": "256"}])
 @pytest.mark.parametrize("min_qual", [0, 25])
 def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
@@ -332,6 +332,39 @@ def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
     for name, a, b, c in zip(("misincorp", "dnacomp", "lghist"), got, want, twice):
         assert np.array_equal(a, b), name
         assert np.array_equal(2 * a, c), name
+
+
+@pytest.mark.parametrize("env", [{}, {"MDG_PLANES_WS_LIBS": "0"}, {"MDG_PLANES_WS": "0"}, {"MDG_SWAR_FLUSH_TILES": "4"},
+                                 {"MDG_SWAR_UNIFORM": "0"}])
+@pytest.mark.parametrize("n_libs", [2, 3])
+def test_libraries_in_one_launch(env, n_libs, monkeypatch):
+    """Two libraries are counted by ONE launch of the warp-specialised kernel (a read's library picks its counters, event
+    tables and the lists of left-over reads); three fall back to a launch per library over index lists.  Equal-length and
+    mixed stretches, indels, clips, filtered flags: the tables of every library equal the oracle's."""
+    from mapdamage_b200.batch import concatenate
+
+    for key, value in env.items():
+        monkeypatch.setenv(key, value)
+    reference = synth.make_reference([300_000, 70_000], seed=8, other_rate=0.001)
+    with DamageEngine(n_libraries=n_libs, max_reads=1024) as engine:
+        engine.set_reference(reference)
+        parts = []
+        for k, kw in enumerate((dict(length=(100, 100)), dict(length=(35, 140), mix=(6, 1, 1, 2), read_n_rate=0.01, paired=True),
+                                dict(length=(100, 100), filtered_rate=0.2))):
+            dev = engine.synth_batch(250_000, seed=70 + k, n_libs=n_libs, **kw)
+            parts.append(engine.download(dev))
+            dev.free()
+    batch = concatenate(parts)
+    assert len(np.unique(batch.lib)) == n_libs
+    want = oracle.count(batch, reference, n_lib=n_libs, lg_bins=8192, threads=8)
+    with DamageEngine(n_libraries=n_libs, max_reads=0) as engine:
+        engine.set_reference(reference)
+        dev = engine.upload(batch)
+        engine.count_resident(dev)
+        got = engine.tables()
+        dev.free()
+    for name, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
+        assert np.array_equal(a, b), name
 
 
 @pytest.mark.parametrize("env", [{}, {"MDG_PLANES_WS": "0"}, {"MDG_PLANES_WS": "2x8+8"}, {"MDG_KERNEL": "staged"}])
