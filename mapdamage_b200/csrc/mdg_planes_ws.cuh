@@ -186,9 +186,8 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         };
 
         // ---- stage: the plane words of one window of one read (see count_planes_kernel::stage_window) ----
-        auto stage_window = [&](auto nw_tag, const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
+        auto stage_window = [&](const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
                                 int slab_w0, int slab_words, int rstrand, int libx) {
-            constexpr int kNW = decltype(nw_tag)::value;
             const int cols = (int)(rec.cols & 0x7FFF);
             const int v = (int)(rec.misc & 0xFFFF);
             const int lf = (int)((rec.cols >> 16) & 0xFF), rf = (int)(rec.cols >> 24);
@@ -196,7 +195,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             const int64_t qn = (int64_t)rec.q0 + c_start;
             const int qs = (int)(qn & 7);
             const int64_t qw = qn >> 3, in_slab = qw - slab_w0;
-            const bool from_smem = slab_words > 0 && in_slab >= 0 && in_slab + 4 * (kNW > 0 ? kNW : n_words) + 1 <= slab_words;
+            const bool from_smem = slab_words > 0 && in_slab >= 0 && in_slab + 4 * n_words + 1 <= slab_words;
             // (two loads in two address spaces: written as a value select the compiler makes it ONE generic load)
             const uint32_t qs_addr = (uint32_t)__cvta_generic_to_shared(s_seq) + 4u * (uint32_t)(from_smem ? in_slab : 0);
             const uint32_t *const qg_ptr = seq32 + qw;
@@ -282,36 +281,25 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     } while (ev);
                 }
             };
-            if constexpr (kNW > 0) {
-                uint4 gw[kNW + 1];
-#pragma unroll
-                for (int k = 0; k <= kNW; ++k) gw[k] = __ldg(rp + k);
+            {
                 uint32_t q0[4];
                 {
                     const uint32_t w0 = seq_word(0);
                     ws_plane_bytes(w0, 0, q0[0], q0[2]);
                     ws_plane_bytes(w0, 1, q0[1], q0[3]);
                 }
-#pragma unroll
-                for (int k = 0; k < kNW; ++k) {
-                    uint32_t w1, w2, w3, w4;
-                    seq_words4(4 * k + 1, w1, w2, w3, w4);
-                    emit(k, q0, w1, w2, w3, w4, gw[k], gw[k + 1]);
-                }
-            } else {
-                uint32_t q0[4];
-                {
-                    const uint32_t w0 = seq_word(0);
-                    ws_plane_bytes(w0, 0, q0[0], q0[2]);
-                    ws_plane_bytes(w0, 1, q0[1], q0[3]);
-                }
-                uint4 g_lo = __ldg(rp);
+                // ONE copy of the word's code (unrolled per window length it was 7 % slower: the two roles and two teams of an
+                // SM run different code at the same time and miss the instruction cache); the genome entry after next is in
+                // flight while a word is made
+                uint4 g_lo = __ldg(rp), g_hi = __ldg(rp + 1);
+#pragma unroll 1
                 for (int k = 0; k < n_words; ++k) {
                     uint32_t w1, w2, w3, w4;
                     seq_words4(4 * k + 1, w1, w2, w3, w4);
-                    const uint4 g_hi = __ldg(rp + k + 1);
+                    const uint4 g_next = __ldg(rp + min(k + 2, n_words));
                     emit(k, q0, w1, w2, w3, w4, g_lo, g_hi);
                     g_lo = g_hi;
+                    g_hi = g_next;
                 }
             }
         };
@@ -634,12 +622,11 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     if (lower < key) row += (int)s_ctl[CTL_GROUP + lower];
                 uint32_t *const row_at = s_stage + (size_t)row * ROW;
                 const int n_words = mode ? words_of(mode) : NWA;
+#pragma unroll 1
                 for (int side = 0; side < (mode ? 1 : 2); ++side) {
                     const int first_word = side ? NWA : 0;
                     const int c_start = side ? (int)(rec.cols & 0x7FFF) + A - 32 * NWA : -A;
-                    if (n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, rstrand, libx);
-                    else if (n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, rstrand, libx);
-                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand, libx);
+                    stage_window(rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand, libx);
                 }
             }
             mbar_arrive(full_addr);  // release: this thread's words of the buffer (and the control block) are visible to the consumers

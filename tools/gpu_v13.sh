@@ -1,0 +1,4 @@
+#!/bin/bash
+for v in 1 9; do
+echo "== MDG_PLANES_PREFETCH=$v"; MDG_PLANES_PREFETCH=$v timeout 120 python tools/bench_shapes.py se100 se50-150 "c3 1 lib" "se100 2 libs" 2>&1 | tail -4
+done
