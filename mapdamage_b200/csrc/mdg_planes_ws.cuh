@@ -814,19 +814,12 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 const uint32_t *at = s_stage + (size_t)(my_row + idx) * ROW + 8 * ws + group;
                 for (int i = idx; i < n_mine; i += 8 * spg) {
                     uint32_t xg[8], y[8];
-                    if (i + 7 * spg < n_mine) {  // eight reads in hand: no tests
+                    // (one path with tests: a copy without them for full iterations measured the same and is more code)
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            xg[u] = at[u * row_step];
-                            y[u] = at[u * row_step + 4];
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const bool live = i + u * spg < n_mine;
-                            xg[u] = live ? at[u * row_step] : 0u;
-                            y[u] = live ? at[u * row_step + 4] : 0u;
-                        }
+                    for (int u = 0; u < 8; ++u) {
+                        const bool live = i + u * spg < n_mine;
+                        xg[u] = live ? at[u * row_step] : 0u;
+                        y[u] = live ? at[u * row_step + 4] : 0u;
                     }
                     at += 8 * row_step;
                     MDG_ADD8(cnt[0], y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7])  // R_g
