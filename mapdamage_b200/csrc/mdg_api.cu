@@ -426,15 +426,18 @@ using WsKernel = void (*)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::Cou
 struct WsVariant {
     const char *name;
     int teams, team_warps, cons_warps, nw_anchor;  // nw_anchor = ceil((L + A) / 32) is compiled in
-    WsKernel kernel, kernel_two_libraries;  // one library per launch; every read's own of two libraries
+    // one library per launch; every read's own of two libraries.  [0]: genome in L2 (one rolled stage loop), [1]: a genome
+    // that does not fit (all of a window's gathers in flight before its first word)
+    WsKernel kernel[2], kernel_two_libraries[2];
 };
 const WsVariant WS_VARIANTS[] = {
-    {"2x9+8", 2, 9, 8, 3, mdg::count_planes_ws_kernel<2, 9, 8, 3, 1>, nullptr},  // the default: 0.413 ms per 4 M 100 bp reads
-    {"2x9+8", 2, 9, 8, 2, mdg::count_planes_ws_kernel<2, 9, 8, 2, 1>, nullptr},
-    {"2x8+8", 2, 8, 8, 3, mdg::count_planes_ws_kernel<2, 8, 8, 3, 1>, mdg::count_planes_ws_kernel<2, 8, 8, 3, 2>},  // 0.428
-    {"2x8+8", 2, 8, 8, 2, mdg::count_planes_ws_kernel<2, 8, 8, 2, 1>, mdg::count_planes_ws_kernel<2, 8, 8, 2, 2>},
-    {"2x8+4", 2, 8, 4, 3, mdg::count_planes_ws_kernel<2, 8, 4, 3, 1>, nullptr},
-    {"3x6+8", 3, 6, 8, 3, mdg::count_planes_ws_kernel<3, 6, 8, 3, 1>, nullptr},
+#define MDG_WS(teams, warps, cons, nwa, libs) {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true>}
+    {"2x9+8", 2, 9, 8, 3, MDG_WS(2, 9, 8, 3, 1), {nullptr, nullptr}},  // the default: 0.39 ms per 4 M 100 bp reads
+    {"2x9+8", 2, 9, 8, 2, MDG_WS(2, 9, 8, 2, 1), {nullptr, nullptr}},
+    {"2x8+8", 2, 8, 8, 3, MDG_WS(2, 8, 8, 3, 1), MDG_WS(2, 8, 8, 3, 2)},
+    {"2x8+8", 2, 8, 8, 2, MDG_WS(2, 8, 8, 2, 1), MDG_WS(2, 8, 8, 2, 2)},
+    {"2x8+4", 2, 8, 4, 3, MDG_WS(2, 8, 4, 3, 1), {nullptr, nullptr}},
+#undef MDG_WS
 };
 
 // The counting kernels over one device batch.
@@ -474,12 +477,16 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
                 const bool together = !subset.list && subset.offsets;  // every library in this launch
                 mdg::PlaneGeom pg = together ? ctx->ws_libraries_geom : ctx->ws;
                 pg.indel_seen = ctx->indel_seen_dev;
-                // genome image larger than what stays in L2: prefetch each read's genome entries while it is parsed
-                if (!getenv("MDG_PLANES_PREFETCH") && ctx->ref_words_bytes > ((size_t)48 << 20)) pg.prefetch_bases |= 2;
+                // genome image larger than what stays in L2: prefetch each read's genome entries while it is parsed, and the
+                // stage that has all of a window's gathers in flight at once
+                const bool big = ctx->ref_words_bytes > ((size_t)48 << 20);
+                if (!getenv("MDG_PLANES_PREFETCH") && big) pg.prefetch_bases |= 2;
+                const char *gather_env = getenv("MDG_PLANES_GATHER");
+                const int gather = gather_env ? atoi(gather_env) != 0 : big;
                 const WsVariant &v = WS_VARIANTS[together ? ctx->ws_variant_libraries : ctx->ws_variant];
                 const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
                 const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, (tiles + v.teams - 1) / v.teams);
-                (together ? v.kernel_two_libraries : v.kernel)<<<pgrid, pg.threads, together ? ctx->ws_smem_libraries : ctx->ws_smem, stream>>>(
+                (together ? v.kernel_two_libraries : v.kernel)[gather]<<<pgrid, pg.threads, together ? ctx->ws_smem_libraries : ctx->ws_smem, stream>>>(
                     b, ctx->ref, p, tl, pg, wl->reads, wl->count, wl->indel_reads, wl->indel_count, subset);
             } else if (use_planes) {
                 mdg::PlaneGeom pg = ctx->planes;
@@ -869,7 +876,8 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 const int pairs = (v.cons_warps * 32 >> 7) * 32;
                 const size_t bytes = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 1);
                 if (ctx->ws_variant < 0 && !strcmp(want, v.name) && bytes <= ctx->smem_optin && 2 * wg.nw_anchor * 2 <= pairs) {
-                    MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                    for (int gather = 0; gather < 2; ++gather)
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel[gather], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                     ctx->ws = wg;
                     ctx->ws_smem = bytes;
                     ctx->ws_variant = i;
@@ -877,9 +885,10 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 // two libraries in one launch: the first shape whose two sets of event tables fit next to the stage buffers
                 // and that gives every group (library, strand) a read slot in the two-window layout
                 const size_t bytes_two = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 2);
-                if (ctx->ws_variant_libraries < 0 && nl == 2 && v.kernel_two_libraries && strcmp(want, "0") && !(lib_env && lib_env[0] == '0') &&
+                if (ctx->ws_variant_libraries < 0 && nl == 2 && v.kernel_two_libraries[0] && strcmp(want, "0") && !(lib_env && lib_env[0] == '0') &&
                     bytes_two <= ctx->smem_optin && 2 * wg.nw_anchor * 2 * 2 <= pairs) {
-                    MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_two));
+                    for (int gather = 0; gather < 2; ++gather)
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries[gather], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_two));
                     ctx->ws_libraries_geom = wg;
                     ctx->ws_smem_libraries = bytes_two;
                     ctx->ws_variant_libraries = i;

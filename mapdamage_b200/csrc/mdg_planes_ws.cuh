@@ -78,7 +78,9 @@ constexpr int CTL_CX = 8;         // [2] reads for the general kernel, per libra
 constexpr int CTL_IX = 10;        // [2] one-indel reads, per library
 constexpr int WS_CAPACITY = 4000;  // reads a counter may see between two reductions (12 bits: planes 0-3 + wide 4-11)
 
-template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA, int kNL>
+// kGather: the stage issues all of a window's genome loads before it makes the first word (a copy of the word's code per
+// window length) -- for genomes that do not fit L2, where the gathers are DRAM accesses; otherwise one rolled loop.
+template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA, int kNL, bool kGather>
 __global__ void __launch_bounds__((kTeams * kTeamWarps + kConsWarps) * 32, 1)
 count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneGeom g, uint32_t *__restrict__ worklist,
                        unsigned long long *__restrict__ work_count, uint32_t *__restrict__ indel_list,
@@ -186,8 +188,9 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         };
 
         // ---- stage: the plane words of one window of one read (see count_planes_kernel::stage_window) ----
-        auto stage_window = [&](const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
+        auto stage_window = [&](auto nw_tag, const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
                                 int slab_w0, int slab_words, int rstrand, int libx) {
+            constexpr int kNW = decltype(nw_tag)::value;  // > 0: words of the window, known at compile time (kGather)
             const int cols = (int)(rec.cols & 0x7FFF);
             const int v = (int)(rec.misc & 0xFFFF);
             const int lf = (int)((rec.cols >> 16) & 0xFF), rf = (int)(rec.cols >> 24);
@@ -281,16 +284,32 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     } while (ev);
                 }
             };
-            {
+            if constexpr (kNW > 0) {
+                uint4 gw[kNW + 1];
+#pragma unroll
+                for (int k = 0; k <= kNW; ++k) gw[k] = __ldg(rp + k);
                 uint32_t q0[4];
                 {
                     const uint32_t w0 = seq_word(0);
                     ws_plane_bytes(w0, 0, q0[0], q0[2]);
                     ws_plane_bytes(w0, 1, q0[1], q0[3]);
                 }
-                // ONE copy of the word's code (unrolled per window length it was 7 % slower: the two roles and two teams of an
-                // SM run different code at the same time and miss the instruction cache); the genome entry after next is in
-                // flight while a word is made
+#pragma unroll
+                for (int k = 0; k < kNW; ++k) {
+                    uint32_t w1, w2, w3, w4;
+                    seq_words4(4 * k + 1, w1, w2, w3, w4);
+                    emit(k, q0, w1, w2, w3, w4, gw[k], gw[k + 1]);
+                }
+            } else {
+                uint32_t q0[4];
+                {
+                    const uint32_t w0 = seq_word(0);
+                    ws_plane_bytes(w0, 0, q0[0], q0[2]);
+                    ws_plane_bytes(w0, 1, q0[1], q0[3]);
+                }
+                // ONE copy of the word's code (unrolled per window length it is 7 % slower on a genome that sits in L2: the
+                // two roles and two teams of an SM run different code at the same time and miss the instruction cache); the
+                // genome entry after next is in flight while a word is made
                 uint4 g_lo = __ldg(rp), g_hi = __ldg(rp + 1);
 #pragma unroll 1
                 for (int k = 0; k < n_words; ++k) {
@@ -626,7 +645,9 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 for (int side = 0; side < (mode ? 1 : 2); ++side) {
                     const int first_word = side ? NWA : 0;
                     const int c_start = side ? (int)(rec.cols & 0x7FFF) + A - 32 * NWA : -A;
-                    stage_window(rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand, libx);
+                    if (kGather && n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, rstrand, libx);
+                    else if (kGather && n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, rstrand, libx);
+                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand, libx);
                 }
             }
             mbar_arrive(full_addr);  // release: this thread's words of the buffer (and the control block) are visible to the consumers

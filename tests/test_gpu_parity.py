@@ -299,7 +299,8 @@ def test_optional_arrays_default_on_device(name):
                                  {"MDG_PLANES_WS": "0"}, {"MDG_PLANES_WS": "2x8+8"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_FLUSH_TILES": "3"},
                                  {"MDG_PLANES_WS": "2x8+8", "MDG_PLANES_SLAB": "0"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_UNIFORM": "0"},
                                  {"MDG_PLANES_WS": "2x9+8", "MDG_SWAR_FLUSH_TILES": "5"},
-                                 {"MDG_PLANES_WS": "2x8+4"}, {"MDG_PLANES_THREADS": "256"}])
+                                 {"MDG_PLANES_WS": "2x8+4"}, {"MDG_PLANES_THREADS": "256"},
+                                 {"MDG_PLANES_GATHER": "1", "MDG_PLANES_PREFETCH": "3"}, {"MDG_PLANES_GATHER": "1", "MDG_PLANES_WS": "2x8+8"}])
 @pytest.mark.parametrize("min_qual", [0, 25])
 def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
     """1.3 M reads laid out so that every block of the bit-sliced kernel alternates between equal-length tiles
@@ -335,7 +336,7 @@ def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{}, {"MDG_PLANES_WS_LIBS": "0"}, {"MDG_PLANES_WS": "0"}, {"MDG_SWAR_FLUSH_TILES": "4"},
-                                 {"MDG_SWAR_UNIFORM": "0"}])
+                                 {"MDG_SWAR_UNIFORM": "0"}, {"MDG_PLANES_GATHER": "1", "MDG_PLANES_PREFETCH": "3"}])
 @pytest.mark.parametrize("n_libs", [2, 3])
 def test_libraries_in_one_launch(env, n_libs, monkeypatch):
     """Two libraries are counted by ONE launch of the warp-specialised kernel (a read's library picks its counters, event
