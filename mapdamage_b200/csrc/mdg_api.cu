@@ -426,18 +426,25 @@ using WsKernel = void (*)(mdg::DevBatch, mdg::DevRef, mdg::CountParams, mdg::Cou
 struct WsVariant {
     const char *name;
     int teams, team_warps, cons_warps, nw_anchor;  // nw_anchor = ceil((L + A) / 32) is compiled in
-    // one library per launch; every read's own of two libraries.  [0]: genome in L2 (one rolled stage loop), [1]: a genome
-    // that does not fit (all of a window's gathers in flight before its first word)
-    WsKernel kernel[2], kernel_two_libraries[2];
+    // one library per launch; every read's own of two libraries.  First index: 0 genome in L2 (one rolled stage loop), 1 a
+    // genome that does not fit (all of a window's gathers in flight before its first word); second index: 1 stages reads
+    // with one insertion / deletion itself
+    WsKernel kernel[2][2], kernel_two_libraries[2][2];
 };
 const WsVariant WS_VARIANTS[] = {
-#define MDG_WS(teams, warps, cons, nwa, libs) {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true>}
-    {"2x9+8", 2, 9, 8, 3, MDG_WS(2, 9, 8, 3, 1), {nullptr, nullptr}},  // the default: 0.39 ms per 4 M 100 bp reads
-    {"2x9+8", 2, 9, 8, 2, MDG_WS(2, 9, 8, 2, 1), {nullptr, nullptr}},
+#define MDG_WS(teams, warps, cons, nwa, libs)                                                                                         \
+    {                                                                                                                                \
+        {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false, false>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false, true>}, \
+        {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true, false>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true, true>}    \
+    }
+#define MDG_WS_NONE {{nullptr, nullptr}, {nullptr, nullptr}}
+    {"2x9+8", 2, 9, 8, 3, MDG_WS(2, 9, 8, 3, 1), MDG_WS_NONE},  // the default: 0.39 ms per 4 M 100 bp reads
+    {"2x9+8", 2, 9, 8, 2, MDG_WS(2, 9, 8, 2, 1), MDG_WS_NONE},
     {"2x8+8", 2, 8, 8, 3, MDG_WS(2, 8, 8, 3, 1), MDG_WS(2, 8, 8, 3, 2)},
     {"2x8+8", 2, 8, 8, 2, MDG_WS(2, 8, 8, 2, 1), MDG_WS(2, 8, 8, 2, 2)},
-    {"2x8+4", 2, 8, 4, 3, MDG_WS(2, 8, 4, 3, 1), {nullptr, nullptr}},
+    {"2x8+4", 2, 8, 4, 3, MDG_WS(2, 8, 4, 3, 1), MDG_WS_NONE},
 #undef MDG_WS
+#undef MDG_WS_NONE
 };
 
 // The counting kernels over one device batch.
@@ -481,12 +488,16 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
                 // stage that has all of a window's gathers in flight at once
                 const bool big = ctx->ref_words_bytes > ((size_t)48 << 20);
                 if (!getenv("MDG_PLANES_PREFETCH") && big) pg.prefetch_bases |= 2;
+                // reads with one insertion / deletion staged by this kernel once the data have shown such reads
+                // (MDG_PLANES_INDELS=0 / 1 pins it: A/B, tests)
+                const char *indel_env = getenv("MDG_PLANES_INDELS");
+                const int indels = indel_env ? atoi(indel_env) != 0 : ctx->staged_indels;
                 const char *gather_env = getenv("MDG_PLANES_GATHER");
                 const int gather = gather_env ? atoi(gather_env) != 0 : big;
                 const WsVariant &v = WS_VARIANTS[together ? ctx->ws_variant_libraries : ctx->ws_variant];
                 const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
                 const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, (tiles + v.teams - 1) / v.teams);
-                (together ? v.kernel_two_libraries : v.kernel)[gather]<<<pgrid, pg.threads, together ? ctx->ws_smem_libraries : ctx->ws_smem, stream>>>(
+                (together ? v.kernel_two_libraries : v.kernel)[gather][indels]<<<pgrid, pg.threads, together ? ctx->ws_smem_libraries : ctx->ws_smem, stream>>>(
                     b, ctx->ref, p, tl, pg, wl->reads, wl->count, wl->indel_reads, wl->indel_count, subset);
             } else if (use_planes) {
                 mdg::PlaneGeom pg = ctx->planes;
@@ -876,8 +887,8 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 const int pairs = (v.cons_warps * 32 >> 7) * 32;
                 const size_t bytes = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 1);
                 if (ctx->ws_variant < 0 && !strcmp(want, v.name) && bytes <= ctx->smem_optin && 2 * wg.nw_anchor * 2 <= pairs) {
-                    for (int gather = 0; gather < 2; ++gather)
-                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel[gather], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                    for (int which = 0; which < 4; ++which)
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel[which >> 1][which & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                     ctx->ws = wg;
                     ctx->ws_smem = bytes;
                     ctx->ws_variant = i;
@@ -885,10 +896,10 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 // two libraries in one launch: the first shape whose two sets of event tables fit next to the stage buffers
                 // and that gives every group (library, strand) a read slot in the two-window layout
                 const size_t bytes_two = mdg::planes_ws_smem(v.teams, v.team_warps, v.cons_warps, (int)L, wg.nw_anchor, 2);
-                if (ctx->ws_variant_libraries < 0 && nl == 2 && v.kernel_two_libraries[0] && strcmp(want, "0") && !(lib_env && lib_env[0] == '0') &&
+                if (ctx->ws_variant_libraries < 0 && nl == 2 && v.kernel_two_libraries[0][0] && strcmp(want, "0") && !(lib_env && lib_env[0] == '0') &&
                     bytes_two <= ctx->smem_optin && 2 * wg.nw_anchor * 2 * 2 <= pairs) {
-                    for (int gather = 0; gather < 2; ++gather)
-                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries[gather], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_two));
+                    for (int which = 0; which < 4; ++which)
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries[which >> 1][which & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_two));
                     ctx->ws_libraries_geom = wg;
                     ctx->ws_smem_libraries = bytes_two;
                     ctx->ws_variant_libraries = i;

@@ -75,12 +75,17 @@ constexpr int WS_MAX_LIB = 2;     // libraries counted in one launch (more: one 
 constexpr int CTL_GROUP = 0;      // [4] gap-free reads of the tile per group
 constexpr int CTL_MIN = 4, CTL_MAX = 5, CTL_MODE = 6;  // columns of the gap-free reads, window layout chosen
 constexpr int CTL_CX = 8;         // [2] reads for the general kernel, per library
-constexpr int CTL_IX = 10;        // [2] one-indel reads, per library
+constexpr int CTL_IX = 10;        // [2] one-indel reads left to count_staged_kernel, per library (from the front of the list)
+constexpr int CTL_IX4 = 12;       // [2] one-indel reads staged here when the tile has two windows per read, else handed over
+                                  //     too (from the back of the list)
 constexpr int WS_CAPACITY = 4000;  // reads a counter may see between two reductions (12 bits: planes 0-3 + wide 4-11)
 
 // kGather: the stage issues all of a window's genome loads before it makes the first word (a copy of the word's code per
 // window length) -- for genomes that do not fit L2, where the gathers are DRAM accesses; otherwise one rolled loop.
-template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA, int kNL, bool kGather>
+// kIndels: reads with one short insertion / deletion (no clips) are staged here too when their tile has two windows per
+// read; otherwise all of them go to count_staged_kernel's list.  A variant of its own because the code it adds costs the
+// others 3-5 % (instruction cache): the host switches to it once a batch has shown such reads.
+template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA, int kNL, bool kGather, bool kIndels>
 __global__ void __launch_bounds__((kTeams * kTeamWarps + kConsWarps) * 32, 1)
 count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneGeom g, uint32_t *__restrict__ worklist,
                        unsigned long long *__restrict__ work_count, uint32_t *__restrict__ indel_list,
@@ -323,10 +328,139 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
         };
 
+        // ---- stage: ONE window word of a read with one insertion / deletion (two windows per read) ----
+        // Columns of the alignment are c = 0 .. cols - 1 with the gap at [a, a + k).  Exactly one of the two sequences is
+        // discontinuous there: behind an insertion the reference lags (reference offset c - k for c >= a + k, nothing under
+        // the inserted bases), behind a deletion the read does (read base c - k, nothing over the deleted bases).  So the
+        // word is made from the planes of that sequence at TWO alignments, blended by column masks, and the other one's
+        // at one.  Misincorporation positions are columns; read composition positions are read bases (statistics.py:76-83,
+        // SURVEY N1), i.e. the read's planes at the alignment of the window's anchor side.  Gap columns are events
+        // (g>- for every deleted reference base, ->b for every inserted read base; align.py:14-88), a few global atomics.
+        auto stage_indel_word = [&](const PlaneRecord &rec, uint32_t gapw, uint32_t *row_at, int word, int slab_w0, int slab_words,
+                                    int rstrand, int libx) {
+            const int side = word >= NWA, kw = side ? word - NWA : word;
+            const int cols = (int)(rec.cols & 0x7FFF), lf = (int)((rec.cols >> 16) & 0xFF), rf = (int)(rec.cols >> 24);
+            const int a = (int)(gapw & 0x7FFF), k = (int)((gapw >> 15) & 7), del = (int)((gapw >> 18) & 1);
+            const int c0 = (side ? cols + A - 32 * NWA : -A) + 32 * kw;  // column of bit 0
+            auto range = [&](int lo_col, int hi_col) { return bit_range(lo_col - c0, hi_col - c0); };
+            const uint32_t lo_mask = range(-(1 << 20), a), hi_mask = range(a + k, 1 << 20), gap_mask = range(a, a + k);
+            // the read's planes of 32 bases from base index `qn` of seq4 (five words, no carry between window words)
+            auto x_planes = [&](int64_t qn, uint32_t (&xp)[4]) {
+                const int qs = (int)(qn & 7);
+                const int64_t qw = qn >> 3, in_slab = qw - slab_w0;
+                const bool from_smem = slab_words > 0 && in_slab >= 0 && in_slab + 5 <= slab_words;
+                uint32_t w[5];
+                if (from_smem) {
+                    const uint32_t at = (uint32_t)__cvta_generic_to_shared(s_seq) + 4u * (uint32_t)in_slab;
+#pragma unroll
+                    for (int m = 0; m < 5; ++m) w[m] = lds_u32(at + 4 * m);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 5; ++m) w[m] = __ldg(seq32 + qw + m);
+                }
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    uint32_t q[5][2];
+#pragma unroll
+                    for (int m = 0; m < 5; ++m) ws_plane_bytes(w[m], pp, q[m][0], q[m][1]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t lo = __byte_perm(__byte_perm(q[0][h], q[1][h], 0x0073), __byte_perm(q[2][h], q[3][h], 0x0073), 0x5410);
+                        xp[pp + 2 * h] = __funnelshift_r(lo, q[4][h] >> 24, qs);
+                    }
+                }
+            };
+            auto y_planes = [&](int64_t rn, uint32_t (&yp)[4]) {
+                const uint4 g_lo = __ldg(planes + (rn >> 5)), g_hi = __ldg(planes + (rn >> 5) + 1);
+                const int rs = (int)(rn & 31);
+                yp[0] = __funnelshift_r(g_lo.x, g_hi.x, rs); yp[1] = __funnelshift_r(g_lo.y, g_hi.y, rs);
+                yp[2] = __funnelshift_r(g_lo.z, g_hi.z, rs); yp[3] = __funnelshift_r(g_lo.w, g_hi.w, rs);
+            };
+            const int64_t q_at = (int64_t)rec.q0 + c0, r_at = ((int64_t)rec.rg << 5) + (int)((rec.misc >> 16) & 31) + c0;
+            uint32_t x_lo[4], x_hi[4], y_m[4];
+            x_planes(q_at, x_lo);
+            y_planes(r_at, y_m);
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl) x_hi[pl] = x_lo[pl];
+            if (del) {
+                // (the right window's read composition is anchored at the read's last base: that alignment for all of it)
+                if (hi_mask || side) x_planes(q_at - k, x_hi);
+            } else if (hi_mask) {
+                uint32_t y_hi[4];
+                y_planes(r_at - k, y_hi);
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) y_m[pl] = (y_m[pl] & lo_mask) | (y_hi[pl] & hi_mask);  // nothing under the inserted bases
+            }
+            uint32_t x_m[4], x_h[4];
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl) {
+                x_m[pl] = del ? (x_lo[pl] & lo_mask) | (x_hi[pl] & hi_mask) : x_lo[pl];  // by column
+                x_h[pl] = side ? x_hi[pl] : x_lo[pl];                                     // by read base, from the window's anchor
+            }
+            const int v = min(cols, L), vh = min(cols - (del ? k : 0), L);
+            const uint32_t m_range = side ? range(cols - v, cols) : range(0, v);
+            const uint32_t h_range = side ? range(cols - vh, cols) : range(0, vh);
+            const uint32_t flank = side ? range(cols, cols + rf) : range(-lf, 0);
+            auto one_hot = [](const uint32_t (&x)[4]) { return (x[0] ^ x[1] ^ x[2] ^ x[3]) & ~((x[0] & x[1]) | (x[2] & x[3])); };
+            const uint32_t one_m = one_hot(x_m), keep_m = one_m & m_range & ~gap_mask;
+            const uint32_t keep_y = keep_m | (del ? gap_mask & m_range : 0u) | flank;  // a deleted base still counts as reference base
+            const uint32_t keep_h = one_hot(x_h) & h_range;
+            uint4 xs, ys;
+            xs.x = x_h[0] & keep_h; xs.y = x_h[1] & keep_h; xs.z = x_h[2] & keep_h; xs.w = x_h[3] & keep_h;
+            ys.x = y_m[0] & keep_y; ys.y = y_m[1] & keep_y; ys.z = y_m[2] & keep_y; ys.w = y_m[3] & keep_y;
+            uint4 *out = (uint4 *)(row_at + 8 * word);
+            out[0] = xs;
+            out[1] = ys;
+            // substitutions: aligned columns where both sides are bases and differ
+            const uint32_t g1 = y_m[1] | y_m[3], g2 = y_m[2] | y_m[3], r1 = x_m[1] | x_m[3], r2 = x_m[2] | x_m[3];
+            uint32_t ev = (y_m[0] | y_m[1] | y_m[2] | y_m[3]) & keep_m & ~((x_m[0] & y_m[0]) | (x_m[1] & y_m[1]) | (x_m[2] & y_m[2]) | (x_m[3] & y_m[3]));
+            uint32_t *const sub_at = s_sub + ((size_t)libx * 4 + rstrand) * 12 * L;
+            while (ev) {
+                const int j = __ffs(ev) - 1;
+                ev &= ev - 1;
+                const int gb = (int)((g1 >> j) & 1u) + 2 * (int)((g2 >> j) & 1u);
+                int rb = (int)((r1 >> j) & 1u) + 2 * (int)((r2 >> j) & 1u);
+                rb -= rb > gb ? 1 : 0;
+                const int col = c0 + j;
+                atomicAdd(sub_at + (3 * gb + rb) * L + (side ? 2 * 12 * L + cols - 1 - col : col), 1u);
+            }
+            // gap columns inside the table: a reference base over nothing (deletion), a read base under nothing (insertion)
+            uint32_t gaps = gap_mask & m_range & (del ? (y_m[0] | y_m[1] | y_m[2] | y_m[3]) : one_m);
+            while (gaps) {
+                const int j = __ffs(gaps) - 1;
+                gaps &= gaps - 1;
+                int base = del ? (int)((g1 >> j) & 1u) + 2 * (int)((g2 >> j) & 1u) : (int)((r1 >> j) & 1u) + 2 * (int)((r2 >> j) & 1u);
+                if (rstrand) base = 3 - base;
+                const int col = c0 + j, pos = side ? cols - 1 - col : col;
+                const int es = libx * 4 + (side ^ rstrand) * 2 + rstrand;
+                const int cls = del ? 4 + 5 * base + 4 : 4 + 5 * 4 + base;
+                atomicAdd(t.misincorp + ((size_t)es * MDG_N_CLASSES + cls) * L + pos, 1ull);
+            }
+        };
+
         // ---- parse of one read: filter, classify, per-read events (statistics.py:37-51,117-126) ----
         // kind: 0 nothing to do, 1 gap-free (record made), 2 for the general kernel, 3 one short indel
-        auto parse_read = [&](bool live, int64_t r, int q, int &kind, int &rstrand, int &libx, uint32_t &columns, PlaneRecord &rec) {
+        // FragmentLengths.update, statistics.py:117-126
+        auto count_length = [&](int lkind, int64_t length, int rstrand, int libx) {
+            if (length < MDG_LG_SMEM_BINS && length < p.lg_bins) {
+                atomicAdd(s_lg + ((libx * 2 + lkind) * 2 + rstrand) * MDG_LG_SMEM_BINS + length, 1u);
+            } else if (length < p.lg_bins) {
+                atomicAdd(t.lghist + (size_t)((libx * 2 + lkind) * 2 + rstrand) * p.lg_bins + length, 1ull);
+            } else {
+                const unsigned long long at = atomicAdd(t.lg_overflow_count, 1ull);
+                if ((int64_t)at < t.lg_overflow_cap) {
+                    int32_t *row = t.lg_overflow_rows + at * 4;
+                    row[0] = sub.list ? sub.lib : libx; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
+                }
+            }
+        };
+        // kind: 0 nothing to do, 1 gap-free (record made), 2 for the general kernel, 3 one short indel (for the staged kernel),
+        // 4 one short indel, no clips: record made and `gapw` = gap column | length << 15 | deletion << 18 |
+        // fragment-length kind << 19 (0: none, 1: single-end = reference span, 2: |tlen| of the first mate of a proper pair)
+        auto parse_read = [&](bool live, int64_t r, int q, int &kind, int &rstrand, int &libx, uint32_t &columns, PlaneRecord &rec,
+                              uint32_t &gapw) {
             kind = 0;
+            gapw = 0;
             rstrand = 0;
             libx = 0;
             columns = 0;
@@ -354,7 +488,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 return;
             }
             rstrand = (flag >> 4) & 1;
-            uint32_t lead = 0, trail = 0, cols = 0, gap_len = 0, gap_del = 0;
+            uint32_t lead = 0, trail = 0, cols = 0, gap_len = 0, gap_del = 0, gap_at = 0;
             int state = 0, n_lead = 0, n_trail = 0;
             bool simple = c1 > c0;
             if (c1 - c0 == 1 && ((0x181u >> (cig0 & 0xF)) & 1u)) {
@@ -375,6 +509,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     else if (op == OP_H) state = 3;
                     else if ((op == OP_I || op == OP_D) && !gap_len && len >= 1 && len <= 7 && cols >= 1) {
                         gap_len = len; gap_del = op == OP_D;
+                        gap_at = cols;
                         cols += len;
                         state = 4;
                     } else simple = false;
@@ -400,11 +535,11 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 kind = 2;
                 return;
             }
-            if (gap_len) {
+            if (gap_len && (!kIndels || lead || trail)) {
                 kind = 3;  // count_staged_kernel's indel variant parses this read again and does all of its bookkeeping
                 return;
             }
-            kind = 1;
+            kind = gap_len ? 4 : 1;
             columns = cols;
             const int64_t aend = pos + ref_span;
             const uint32_t lf = (uint32_t)min((int64_t)A, pos);
@@ -421,30 +556,26 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
             rec.cols = cols | (lf << 16) | (rf << 24);
             rec.misc = min(cols, (uint32_t)L) | (uint32_t)(ref0 & 31) << 16;
-            // FragmentLengths.update, statistics.py:117-126
-            int64_t length = -1;
-            int lkind = 0;
-            if (flag & 0x1) {
-                if ((flag & 0x40) && (flag & 0x2)) {
-                    const int64_t tl = b.tlen[r];
-                    length = tl < 0 ? -tl : tl;
-                }
-            } else {
-                lkind = 1;
-                length = ref_span;
+            if (kind == 4) {
+                // its fragment length is counted once it is known who counts the read (this kernel: tiles with two windows
+                // per read; count_staged_kernel otherwise, which does all of the read's bookkeeping itself)
+                const uint32_t lg = (flag & 0x1) ? (((flag & 0x40) && (flag & 0x2)) ? 2u : 0u) : 1u;
+                gapw = gap_at | gap_len << 15 | gap_del << 18 | lg << 19;
+                return;
             }
-            if (length >= 0) {
-                if (length < MDG_LG_SMEM_BINS && length < p.lg_bins) {
-                    atomicAdd(s_lg + ((libx * 2 + lkind) * 2 + rstrand) * MDG_LG_SMEM_BINS + length, 1u);
-                } else if (length < p.lg_bins) {
-                    atomicAdd(t.lghist + (size_t)((libx * 2 + lkind) * 2 + rstrand) * p.lg_bins + length, 1ull);
-                } else {
-                    const unsigned long long at = atomicAdd(t.lg_overflow_count, 1ull);
-                    if ((int64_t)at < t.lg_overflow_cap) {
-                        int32_t *row = t.lg_overflow_rows + at * 4;
-                        row[0] = sub.list ? sub.lib : libx; row[1] = lkind; row[2] = rstrand; row[3] = (int32_t)length;
+            {
+                int64_t length = -1;
+                int lkind = 0;
+                if (flag & 0x1) {
+                    if ((flag & 0x40) && (flag & 0x2)) {
+                        const int64_t tl = b.tlen[r];
+                        length = tl < 0 ? -tl : tl;
                     }
+                } else {
+                    lkind = 1;
+                    length = ref_span;
                 }
+                if (length >= 0) count_length(lkind, length, rstrand, libx);
             }
             // update_soft_clipping, statistics.py:37-51
             if (lead) {
@@ -543,14 +674,17 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             // the thread that parses a read also stages it: the record stays in its registers
             int kind, rstrand, libx;
             uint32_t rank = 0;  // of a gap-free read: its index among the tile's reads of its group (library, strand)
-            int key;            // group of a gap-free read; CTL_CX / CTL_IX + library of a read left to another kernel; -1: nothing
+            int key;            // group of a read with a row; CTL_CX / CTL_IX + library of a read left to another kernel; -1: nothing
             PlaneRecord rec{};
+            uint32_t gapw;      // kind 4: where its gap is (parse_read)
+            int64_t my_read;
             {
                 const int64_t at = tile * T + ptid;
                 const bool live = at < n_todo;
                 const int64_t r = !live ? 0 : subset ? (int64_t)subset[at] : at;
+                my_read = r;
                 uint32_t columns;
-                parse_read(live, r, ptid, kind, rstrand, libx, columns, rec);
+                parse_read(live, r, ptid, kind, rstrand, libx, columns, rec, gapw);
                 if (g.uniform) {
                     const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
                     const uint32_t hi = __reduce_max_sync(0xffffffffu, kind == 1 ? columns : 0u);
@@ -560,7 +694,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     }
                 }
                 // warp-aggregated appends: the lanes with the same key take consecutive places behind one atomic
-                key = kind == 1 ? CTL_GROUP + rstrand + 2 * libx : kind == 2 ? CTL_CX + libx : kind == 3 ? CTL_IX + libx : -1;
+                key = (kind == 1 || kind == 4) ? CTL_GROUP + rstrand + 2 * libx : kind == 2 ? CTL_CX + libx : kind == 3 ? CTL_IX + libx : -1;
                 if constexpr (kNL == 1) {
                     // four keys: one vote each (cheaper than a match)
                     const uint32_t lt = (1u << lane) - 1u;
@@ -586,13 +720,42 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 }
                 if (kind == 2) s_cx[libx * T + rank] = (uint32_t)r;
                 else if (kind == 3) s_ix[libx * T + rank] = (uint32_t)r;
+                // a one-indel read this kernel may stage has a row (its rank above) AND a place at the back of the library's
+                // list of one-indel reads, in case the tile turns out to have one window per read
+                const uint32_t m4 = kIndels ? __ballot_sync(0xffffffffu, kind == 4) : 0u;
+                if (m4) {
+#pragma unroll
+                    for (int lib = 0; lib < NL; ++lib) {
+                        const uint32_t ml = NL == 1 ? m4 : __ballot_sync(0xffffffffu, kind == 4 && libx == lib);
+                        if (!ml) continue;
+                        uint32_t base = 0;
+                        if (lane == __ffs(ml) - 1) base = atomicAdd(s_ctl + CTL_IX4 + lib, (uint32_t)__popc(ml));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(ml) - 1);
+                        if (kind == 4 && libx == lib) s_ix[lib * T + T - 1 - (base + __popc(ml & ((1u << lane) - 1u)))] = (uint32_t)r;
+                    }
+                }
             }
             named_barrier<T>(1 + team);
 
+            // ---- one window per read when every gap-free read of the tile has the same length ----
+            int want = 0;
+            {
+                const uint32_t lo = s_ctl[CTL_MIN], hi = s_ctl[CTL_MAX];
+                if (g.uniform && lo == hi && hi > 0) {
+                    const int words = ((int)hi + 2 * A + 31) / 32;
+                    if (words < WPR_MAX && PAIRS / words >= n_groups) want = (int)hi;
+                }
+            }
             // ---- reads this kernel does not count go to the two work lists ----
             if (pwarp < 2) {  // warp 0: reads for the general kernel, warp 1: one-indel reads; per library
                 for (int lib = 0; lib < NL; ++lib) {
-                    const uint32_t n = s_ctl[(pwarp ? CTL_IX : CTL_CX) + lib];
+                    const uint32_t n_front = s_ctl[(pwarp ? CTL_IX : CTL_CX) + lib];
+                    // the one-indel reads this kernel could stage itself are handed over too when the tile has one window per read
+                    const uint32_t n_back = pwarp && want ? s_ctl[CTL_IX4 + lib] : 0u;
+                    const uint32_t n = n_front + n_back;
+                    // (steers the host's choice of variants: every one-indel read met, whoever counts it)
+                    if (pwarp && lane == 0 && g.indel_seen && n_front + s_ctl[CTL_IX4 + lib])
+                        atomicAdd(g.indel_seen, (unsigned long long)(n_front + s_ctl[CTL_IX4 + lib]));
                     if (!n) continue;
                     const int at_lib = sub.list ? sub.lib : lib;  // the global lists are kept per library
                     const uint32_t *const from = (pwarp ? s_ix : s_cx) + lib * T;
@@ -600,30 +763,19 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     unsigned long long base = 0;
                     if (lane == 0) {
                         base = atomicAdd((pwarp ? indel_count : work_count) + at_lib, (unsigned long long)n);
-                        if (pwarp && g.indel_seen) atomicAdd(g.indel_seen, (unsigned long long)n);
                     }
                     base = __shfl_sync(0xffffffffu, base, 0);
-                    for (uint32_t i = lane; i < n; i += 32) to[base + i] = from[i];
+                    for (uint32_t i = lane; i < n; i += 32) to[base + i] = from[i < n_front ? i : T - 1 - (i - n_front)];
                 }
             }
             // the control block of the tile after this one (last read by the consumers two tiles ago)
             if (ptid < WS_CTL) s_ctl_next[ptid] = ptid == CTL_MIN ? 0xffffffffu : 0u;
             if (ptid == 32) issue_headers(tile_of(k + 1, team));  // everyone is done with this tile's records: the next tile's land while this one is staged
-
-            // ---- one window per read when every gap-free read of the tile has the same length ----
-            {
-                int want = 0;
-                const uint32_t lo = s_ctl[CTL_MIN], hi = s_ctl[CTL_MAX];
-                if (g.uniform && lo == hi && hi > 0) {
-                    const int words = ((int)hi + 2 * A + 31) / 32;
-                    if (words < WPR_MAX && PAIRS / words >= n_groups) want = (int)hi;
-                }
-                if (ptid == 0) s_ctl[CTL_MODE] = (uint32_t)want;
-                if (want != mode) {
-                    mode = want;
-                    fill_masks(want);
-                    named_barrier<T>(1 + team);
-                }
+            if (ptid == 0) s_ctl[CTL_MODE] = (uint32_t)want;
+            if (want != mode) {
+                mode = want;
+                fill_masks(want);
+                named_barrier<T>(1 + team);
             }
             prefetch_headers(tile_of(k + 2, team));
 
@@ -634,12 +786,12 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 mbar_wait(slab_addr, slab_phase & 1u);
                 ++slab_phase;
             }
-            if (kind == 1) {
-                int row = (int)rank;  // the groups' rows follow each other
+            int row = (int)rank;  // the groups' rows follow each other
 #pragma unroll
-                for (int lower = 0; lower < n_groups - 1; ++lower)
-                    if (lower < key) row += (int)s_ctl[CTL_GROUP + lower];
-                uint32_t *const row_at = s_stage + (size_t)row * ROW;
+            for (int lower = 0; lower < n_groups - 1; ++lower)
+                if (lower < key) row += (int)s_ctl[CTL_GROUP + lower];
+            uint32_t *const row_at = s_stage + (size_t)row * ROW;
+            if (kind == 1) {
                 const int n_words = mode ? words_of(mode) : NWA;
 #pragma unroll 1
                 for (int side = 0; side < (mode ? 1 : 2); ++side) {
@@ -648,6 +800,41 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                     if (kGather && n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, rstrand, libx);
                     else if (kGather && n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, rstrand, libx);
                     else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand, libx);
+                }
+            }
+            // ---- reads with one insertion / deletion ----
+            if (const uint32_t m4 = kIndels ? __ballot_sync(0xffffffffu, kind == 4) : 0u) {
+                if (mode) {
+                    // one window per read: count_staged_kernel has them (above); their rows hold nothing
+                    if (kind == 4)
+                        for (int w = 0; w < 2 * words_of(mode); ++w) ((uint4 *)row_at)[w] = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                    if (kind == 4) {
+                        const uint32_t lg = (gapw >> 19) & 3u, cols = rec.cols & 0x7FFFu, glen = (gapw >> 15) & 7u;
+                        if (lg == 1) count_length(1, (int64_t)(cols - (((gapw >> 18) & 1u) ? 0u : glen)), rstrand, libx);
+                        else if (lg == 2) {
+                            const int64_t tl = b.tlen[my_read];
+                            count_length(0, tl < 0 ? -tl : tl, rstrand, libx);
+                        }
+                    }
+                    // The window words of the warp's one-indel reads are dealt to ALL its lanes (the reads' records travel by
+                    // shuffles): a lane that holds such a read would otherwise make six slow words while 31 wait.
+                    const int n_items = __popc(m4) * WPR_MAX;
+                    for (int first = 0; first < n_items; first += 32) {
+                        const int item = first + lane;
+                        const bool live = item < n_items;
+                        const int src = live ? (int)__fns(m4, 0, item / WPR_MAX + 1) : 0;
+                        PlaneRecord irec;
+                        irec.q0 = __shfl_sync(0xffffffffu, rec.q0, src);
+                        irec.rg = __shfl_sync(0xffffffffu, rec.rg, src);
+                        irec.cols = __shfl_sync(0xffffffffu, rec.cols, src);
+                        irec.misc = __shfl_sync(0xffffffffu, rec.misc, src);
+                        const uint32_t igap = __shfl_sync(0xffffffffu, gapw, src);
+                        const int irow = __shfl_sync(0xffffffffu, row, src);
+                        const int iwho = __shfl_sync(0xffffffffu, rstrand | (libx << 1), src);
+                        if constexpr (kIndels)
+                            if (live) stage_indel_word(irec, igap, s_stage + (size_t)irow * ROW, item % WPR_MAX, slab_w0, slab_words, iwho & 1, iwho >> 1);
+                    }
                 }
             }
             mbar_arrive(full_addr);  // release: this thread's words of the buffer (and the control block) are visible to the consumers

@@ -300,7 +300,9 @@ def test_optional_arrays_default_on_device(name):
                                  {"MDG_PLANES_WS": "2x8+8", "MDG_PLANES_SLAB": "0"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_UNIFORM": "0"},
                                  {"MDG_PLANES_WS": "2x9+8", "MDG_SWAR_FLUSH_TILES": "5"},
                                  {"MDG_PLANES_WS": "2x8+4"}, {"MDG_PLANES_THREADS": "256"},
-                                 {"MDG_PLANES_GATHER": "1", "MDG_PLANES_PREFETCH": "3"}, {"MDG_PLANES_GATHER": "1", "MDG_PLANES_WS": "2x8+8"}])
+                                 {"MDG_PLANES_GATHER": "1", "MDG_PLANES_PREFETCH": "3"}, {"MDG_PLANES_GATHER": "1", "MDG_PLANES_WS": "2x8+8"},
+                                 {"MDG_PLANES_INDELS": "1"}, {"MDG_PLANES_INDELS": "1", "MDG_PLANES_GATHER": "1", "MDG_SWAR_FLUSH_TILES": "3"},
+                                 {"MDG_PLANES_INDELS": "1", "MDG_PLANES_WS": "2x8+8", "MDG_PLANES_SLAB": "0"}, {"MDG_PLANES_INDELS": "0"}])
 @pytest.mark.parametrize("min_qual", [0, 25])
 def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
     """1.3 M reads laid out so that every block of the bit-sliced kernel alternates between equal-length tiles
@@ -336,7 +338,8 @@ def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{}, {"MDG_PLANES_WS_LIBS": "0"}, {"MDG_PLANES_WS": "0"}, {"MDG_SWAR_FLUSH_TILES": "4"},
-                                 {"MDG_SWAR_UNIFORM": "0"}, {"MDG_PLANES_GATHER": "1", "MDG_PLANES_PREFETCH": "3"}])
+                                 {"MDG_SWAR_UNIFORM": "0"}, {"MDG_PLANES_GATHER": "1", "MDG_PLANES_PREFETCH": "3"},
+                                 {"MDG_PLANES_INDELS": "1"}, {"MDG_PLANES_INDELS": "1", "MDG_PLANES_GATHER": "1"}])
 @pytest.mark.parametrize("n_libs", [2, 3])
 def test_libraries_in_one_launch(env, n_libs, monkeypatch):
     """Two libraries are counted by ONE launch of the warp-specialised kernel (a read's library picks its counters, event
@@ -408,6 +411,25 @@ def test_identical_reads_do_not_overflow_the_block_counters(env, length, monkeyp
         dev.free()
     for name, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
         assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("name", ["pe_mixed", "short", "long"])
+@pytest.mark.parametrize("n_lib", [1, 2, 3])
+@pytest.mark.parametrize("pinned", ["1", "0"])
+def test_indel_reads_in_the_planes_kernel(name, n_lib, pinned, monkeypatch):
+    """MDG_PLANES_INDELS=1: reads with one insertion / deletion and no clips are staged by the warp-specialised bit-plane
+    kernel itself in tiles with two windows per read (the planes of the sequence that is discontinuous at the gap at two
+    alignments, gap columns as events); 0: all of them go to count_staged_kernel.  The tables do not change."""
+    monkeypatch.setenv("MDG_PLANES_INDELS", pinned)
+    reference = synth.make_reference([300_000, 150_000, 4_000], seed=5, other_rate=0.002)
+    kw = dict(SYNTH[name])
+    kw["mix"] = (2, 3, 3, 2)  # mostly indel reads
+    batch = synth.simulate_reads(reference, 60_000, seed=33, n_libs=n_lib, read_n_rate=0.02, **kw)
+    want = oracle.count(batch, reference, n_lib=n_lib, lg_bins=8192, threads=4)
+    got = run_engine(batch, reference, n_lib=n_lib, chunks=2)
+    for key, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
+        assert np.array_equal(a, b), key
+    assert want[0][:, :, :, 4 + 5 * 4:4 + 5 * 4 + 4].sum() > 1000  # insertion classes are populated
 
 
 @pytest.mark.parametrize("name", ["pe_mixed", "short", "long"])
