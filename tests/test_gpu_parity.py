@@ -424,7 +424,8 @@ def test_indel_reads_in_the_planes_kernel(name, n_lib, pinned, monkeypatch):
     reference = synth.make_reference([300_000, 150_000, 4_000], seed=5, other_rate=0.002)
     kw = dict(SYNTH[name])
     kw["mix"] = (2, 3, 3, 2)  # mostly indel reads
-    batch = synth.simulate_reads(reference, 60_000, seed=33, n_libs=n_lib, read_n_rate=0.02, **kw)
+    kw.setdefault("read_n_rate", 0.02)
+    batch = synth.simulate_reads(reference, 60_000, seed=33, n_libs=n_lib, **kw)
     want = oracle.count(batch, reference, n_lib=n_lib, lg_bins=8192, threads=4)
     got = run_engine(batch, reference, n_lib=n_lib, chunks=2)
     for key, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
