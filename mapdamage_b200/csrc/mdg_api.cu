@@ -167,6 +167,7 @@ struct mdg_ctx {
     mdg::PlaneGeom ws{};
     size_t ws_smem = 0;
     // its two-library form (a read's library picks counters and tables; smaller tiles: two sets of event tables)
+    bool ws_qual = true;  // -Q batches go through it too (MDG_PLANES_QUAL=0: through count_staged_kernel)
     int ws_variant_libraries = -1;
     mdg::PlaneGeom ws_libraries_geom{};
     size_t ws_smem_libraries = 0;
@@ -430,21 +431,26 @@ struct WsVariant {
     // genome that does not fit (all of a window's gathers in flight before its first word); second index: 1 stages reads
     // with one insertion / deletion itself
     WsKernel kernel[2][2], kernel_two_libraries[2][2];
+    WsKernel kernel_qual[2], kernel_two_libraries_qual[2];  // with the -Q mask (first index; never stage one-indel reads)
 };
 const WsVariant WS_VARIANTS[] = {
 #define MDG_WS(teams, warps, cons, nwa, libs)                                                                                         \
     {                                                                                                                                \
-        {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false, false>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false, true>}, \
-        {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true, false>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true, true>}    \
+        {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false, false, false>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false, true, false>}, \
+        {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true, false, false>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true, true, false>}    \
     }
+#define MDG_WSQ(teams, warps, cons, nwa, libs) \
+    {mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, false, false, true>, mdg::count_planes_ws_kernel<teams, warps, cons, nwa, libs, true, false, true>}
 #define MDG_WS_NONE {{nullptr, nullptr}, {nullptr, nullptr}}
-    {"2x9+8", 2, 9, 8, 3, MDG_WS(2, 9, 8, 3, 1), MDG_WS_NONE},  // the default: 0.39 ms per 4 M 100 bp reads
-    {"2x9+8", 2, 9, 8, 2, MDG_WS(2, 9, 8, 2, 1), MDG_WS_NONE},
-    {"2x8+8", 2, 8, 8, 3, MDG_WS(2, 8, 8, 3, 1), MDG_WS(2, 8, 8, 3, 2)},
-    {"2x8+8", 2, 8, 8, 2, MDG_WS(2, 8, 8, 2, 1), MDG_WS(2, 8, 8, 2, 2)},
-    {"2x8+4", 2, 8, 4, 3, MDG_WS(2, 8, 4, 3, 1), MDG_WS_NONE},
+#define MDG_WSQ_NONE {nullptr, nullptr}
+    {"2x9+8", 2, 9, 8, 3, MDG_WS(2, 9, 8, 3, 1), MDG_WS_NONE, MDG_WSQ(2, 9, 8, 3, 1), MDG_WSQ_NONE},  // the default: 0.39 ms per 4 M 100 bp reads
+    {"2x9+8", 2, 9, 8, 2, MDG_WS(2, 9, 8, 2, 1), MDG_WS_NONE, MDG_WSQ(2, 9, 8, 2, 1), MDG_WSQ_NONE},
+    {"2x8+8", 2, 8, 8, 3, MDG_WS(2, 8, 8, 3, 1), MDG_WS(2, 8, 8, 3, 2), MDG_WSQ(2, 8, 8, 3, 1), MDG_WSQ(2, 8, 8, 3, 2)},
+    {"2x8+8", 2, 8, 8, 2, MDG_WS(2, 8, 8, 2, 1), MDG_WS(2, 8, 8, 2, 2), MDG_WSQ(2, 8, 8, 2, 1), MDG_WSQ(2, 8, 8, 2, 2)},
 #undef MDG_WS
 #undef MDG_WS_NONE
+#undef MDG_WSQ
+#undef MDG_WSQ_NONE
 };
 
 // The counting kernels over one device batch.
@@ -476,7 +482,8 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
         }
         // the bit-plane kernel counts the gap-free reads (no quality mask); reads with one short indel come back in
         // a list for the staged kernel's indel variant
-        const bool use_planes = ctx->planes_enabled && !q;
+        // (under a quality mask: its warp-specialised form only, MDG_PLANES_QUAL=0: the staged kernel as in round 1)
+        const bool use_planes = ctx->planes_enabled && (!q || (ctx->ws_variant >= 0 && ctx->ws_qual));
         if (use_planes) MDG_CUDA(ctx, cudaMemsetAsync(wl->indel_count, 0, (size_t)nl * 24, stream));
         // one launch of the bit-sliced kernel over a library's reads (or all reads) into the tables `tl`
         auto launch_bitsliced = [&](const mdg::CountTables &tl, const mdg::SwarSubset &subset) {
@@ -497,7 +504,8 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
                 const WsVariant &v = WS_VARIANTS[together ? ctx->ws_variant_libraries : ctx->ws_variant];
                 const int64_t tiles = (b.n_reads + pg.tile - 1) / pg.tile;
                 const int pgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count, (tiles + v.teams - 1) / v.teams);
-                (together ? v.kernel_two_libraries : v.kernel)[gather][indels]<<<pgrid, pg.threads, together ? ctx->ws_smem_libraries : ctx->ws_smem, stream>>>(
+                (q ? (together ? v.kernel_two_libraries_qual : v.kernel_qual)[gather]
+                   : (together ? v.kernel_two_libraries : v.kernel)[gather][indels])<<<pgrid, pg.threads, together ? ctx->ws_smem_libraries : ctx->ws_smem, stream>>>(
                     b, ctx->ref, p, tl, pg, wl->reads, wl->count, wl->indel_reads, wl->indel_count, subset);
             } else if (use_planes) {
                 mdg::PlaneGeom pg = ctx->planes;
@@ -560,7 +568,7 @@ int launch_count(mdg_ctx *ctx, const mdg::DevBatch &view, bool has_qual, cudaStr
             const int64_t tiles = (b.n_reads + sg.tile - 1) / sg.tile;
             const int sgrid = (int)std::min<int64_t>((int64_t)ctx->sm_count * ctx->staged_blocks_per_sm, tiles);
             for (int lib = 0; lib < nl; ++lib)
-                staged_kernel(false, true, ctx->staged_threads)<<<sgrid, sg.threads, ctx->staged_smem_qual, stream>>>(
+                staged_kernel(q, true, ctx->staged_threads)<<<sgrid, sg.threads, ctx->staged_smem_qual, stream>>>(
                     b, ctx->ref, p, nl == 1 ? ctx->count_tables : lib_tables(ctx, lib), sg, wl->reads, wl->count,
                     mdg::SwarSubset{wl->indel_reads, bounds + lib, lib});
             MDG_CUDA(ctx, cudaGetLastError());
@@ -889,6 +897,8 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                 if (ctx->ws_variant < 0 && !strcmp(want, v.name) && bytes <= ctx->smem_optin && 2 * wg.nw_anchor * 2 <= pairs) {
                     for (int which = 0; which < 4; ++which)
                         MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel[which >> 1][which & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+                    for (int gather = 0; gather < 2; ++gather)
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_qual[gather], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
                     ctx->ws = wg;
                     ctx->ws_smem = bytes;
                     ctx->ws_variant = i;
@@ -900,12 +910,15 @@ int mdg_create(mdg_ctx **out, const mdg_config *cfg)
                     bytes_two <= ctx->smem_optin && 2 * wg.nw_anchor * 2 * 2 <= pairs) {
                     for (int which = 0; which < 4; ++which)
                         MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries[which >> 1][which & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_two));
+                    for (int gather = 0; gather < 2; ++gather)
+                        MDG_CREATE_CUDA(cudaFuncSetAttribute(v.kernel_two_libraries_qual[gather], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_two));
                     ctx->ws_libraries_geom = wg;
                     ctx->ws_smem_libraries = bytes_two;
                     ctx->ws_variant_libraries = i;
                 }
             }
             if (ctx->ws_variant < 0) ctx->ws_variant_libraries = -1;
+            if (const char *qual_env = getenv("MDG_PLANES_QUAL")) ctx->ws_qual = atoi(qual_env) != 0;
         }
         const char *env = getenv("MDG_FORCE_GENERAL");
         ctx->force_general = env && env[0] == '1';

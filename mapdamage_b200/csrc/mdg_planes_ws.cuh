@@ -85,7 +85,10 @@ constexpr int WS_CAPACITY = 4000;  // reads a counter may see between two reduct
 // kIndels: reads with one short insertion / deletion (no clips) are staged here too when their tile has two windows per
 // read; otherwise all of them go to count_staged_kernel's list.  A variant of its own because the code it adds costs the
 // others 3-5 % (instruction cache): the host switches to it once a batch has shown such reads.
-template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA, int kNL, bool kGather, bool kIndels>
+// kQual: -Q (main.py:185-197, align.py:67-71): a column whose read base has a quality below p.min_qual counts for nothing in
+// the misincorporation table (the read composition keeps it); reads without qualities are not masked.  One-indel reads
+// then go to count_staged_kernel.
+template <int kTeams, int kTeamWarps, int kConsWarps, int kNWA, int kNL, bool kGather, bool kIndels, bool kQual>
 __global__ void __launch_bounds__((kTeams * kTeamWarps + kConsWarps) * 32, 1)
 count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, PlaneGeom g, uint32_t *__restrict__ worklist,
                        unsigned long long *__restrict__ work_count, uint32_t *__restrict__ indel_list,
@@ -96,6 +99,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
     constexpr int PRODUCERS = kTeams * T;
     constexpr int NTHREADS = PRODUCERS + CT;
     static_assert(kConsWarps % 4 == 0, "consumer warps come in fours: one per reference base");
+    static_assert(!(kQual && kIndels), "one-indel reads under a quality mask are count_staged_kernel's");
     extern __shared__ __align__(16) uint32_t smem[];
     const int L = p.L, A = p.A, LA = L + A;
     // words per anchor window ceil((L + A) / 32), per read, and per staged row (rows land on different banks): compile-time,
@@ -194,7 +198,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
 
         // ---- stage: the plane words of one window of one read (see count_planes_kernel::stage_window) ----
         auto stage_window = [&](auto nw_tag, const PlaneRecord &rec, uint32_t *row_at, int first_word, int n_words, int c_start, int side,
-                                int slab_w0, int slab_words, int rstrand, int libx) {
+                                int slab_w0, int slab_words, int rstrand, int libx, uint32_t lead) {
             constexpr int kNW = decltype(nw_tag)::value;  // > 0: words of the window, known at compile time (kGather)
             const int cols = (int)(rec.cols & 0x7FFF);
             const int v = (int)(rec.misc & 0xFFFF);
@@ -219,6 +223,35 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             const uint4 *rp = planes + (rn >> 5);
             const int rs = (int)(rn & 31);
             uint32_t *const sub_at = s_sub + ((size_t)libx * 4 + rstrand) * 12 * L;
+            // bit i of the word's quality mask: the read base of column c_start + 32 k + i has a quality of at least min_qual.
+            // Quality bytes lie at the read's base indices; four at a time: a byte b < 128 is >= q  <=>  bit 7 of (b + 128 - q);
+            // the top bit is added apart so that no byte carries into its neighbour (the pad byte behind an odd-length
+            // read may hold anything, and sits right below the next read's first quality); the four bits are gathered by
+            // a multiplication.
+            const uint32_t q_bias = (uint32_t)(128 - min(p.min_qual, 127)) * 0x01010101u;
+            bool masked = false;
+            const uint32_t *qual_words = nullptr;
+            int qual_shift = 0;
+            if constexpr (kQual) {
+                // (a read without qualities carries 0xFF in its first quality byte: not masked, main.py:185)
+                masked = b.qual && __ldg(b.qual + ((int64_t)rec.q0 - (int64_t)lead)) != 0xFF;
+                const int64_t at = (int64_t)rec.q0 + c_start;  // byte of the window's bit 0
+                qual_words = (const uint32_t *)(b.qual + (at & ~3ll));
+                qual_shift = (int)(at & 3) * 8;
+            }
+            auto quality_mask = [&](int k) {
+                if (!masked) return 0xFFFFFFFFu;
+                uint32_t w[9], bits = 0;
+#pragma unroll
+                for (int m = 0; m < 9; ++m) w[m] = __ldg(qual_words + 8 * k + m);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const uint32_t four = __funnelshift_r(w[m], w[m + 1], qual_shift);
+                    const uint32_t ge = ((((four & 0x7F7F7F7Fu) + q_bias) | four) >> 7) & 0x01010101u;
+                    bits |= ((ge * 0x00204081u >> 21) & 0xFu) << (4 * m);
+                }
+                return bits;
+            };
             auto emit = [&](int k, uint32_t (&q0)[4], uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, const uint4 &g_lo, const uint4 &g_hi) {
                 uint32_t xp[4];
 #pragma unroll
@@ -258,7 +291,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 }
                 // statistics.py:27: a column counts only when the read base is A/C/G/T; flank bits carry the reference base alone
                 const uint32_t one = (xa ^ xc ^ xg ^ xt) & ~((xa & xc) | (xg & xt));
-                const uint32_t keep = one & aligned, keep_y = keep | flank;
+                const uint32_t keep = one & aligned, keep_y = (kQual ? keep & quality_mask(k) : keep) | flank;
                 uint4 xs, ys;
                 xs.x = xa & keep; xs.y = xc & keep; xs.z = xg & keep; xs.w = xt & keep;
                 ys.x = ya & keep_y; ys.y = yc & keep_y; ys.z = yg & keep_y; ys.w = yt & keep_y;
@@ -458,9 +491,10 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
         // 4 one short indel, no clips: record made and `gapw` = gap column | length << 15 | deletion << 18 |
         // fragment-length kind << 19 (0: none, 1: single-end = reference span, 2: |tlen| of the first mate of a proper pair)
         auto parse_read = [&](bool live, int64_t r, int q, int &kind, int &rstrand, int &libx, uint32_t &columns, PlaneRecord &rec,
-                              uint32_t &gapw) {
+                              uint32_t &gapw, uint32_t &lead_clip) {
             kind = 0;
             gapw = 0;
+            lead_clip = 0;
             rstrand = 0;
             libx = 0;
             columns = 0;
@@ -541,6 +575,13 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             }
             kind = gap_len ? 4 : 1;
             columns = cols;
+            lead_clip = lead;
+            if constexpr (kQual) {
+                if (b.qual) {  // the read's qualities towards L2: the stage reads them a barrier and a buffer hand-over later
+                    prefetch_l2(b.qual + boff);
+                    prefetch_l2(b.qual + boff + l_seq - 1);
+                }
+            }
             const int64_t aend = pos + ref_span;
             const uint32_t lf = (uint32_t)min((int64_t)A, pos);
             const uint32_t rf = (uint32_t)min((int64_t)A, contig_len - aend);
@@ -677,6 +718,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
             int key;            // group of a read with a row; CTL_CX / CTL_IX + library of a read left to another kernel; -1: nothing
             PlaneRecord rec{};
             uint32_t gapw;      // kind 4: where its gap is (parse_read)
+            uint32_t lead_clip; // bases soft-clipped in front of the first aligned base (kQual: where the read's qualities start)
             int64_t my_read;
             {
                 const int64_t at = tile * T + ptid;
@@ -684,7 +726,7 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 const int64_t r = !live ? 0 : subset ? (int64_t)subset[at] : at;
                 my_read = r;
                 uint32_t columns;
-                parse_read(live, r, ptid, kind, rstrand, libx, columns, rec, gapw);
+                parse_read(live, r, ptid, kind, rstrand, libx, columns, rec, gapw, lead_clip);
                 if (g.uniform) {
                     const uint32_t lo = __reduce_min_sync(0xffffffffu, kind == 1 ? columns : 0xffffffffu);
                     const uint32_t hi = __reduce_max_sync(0xffffffffu, kind == 1 ? columns : 0u);
@@ -797,9 +839,9 @@ count_planes_ws_kernel(DevBatch b, DevRef ref, CountParams p, CountTables t, Pla
                 for (int side = 0; side < (mode ? 1 : 2); ++side) {
                     const int first_word = side ? NWA : 0;
                     const int c_start = side ? (int)(rec.cols & 0x7FFF) + A - 32 * NWA : -A;
-                    if (kGather && n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, rstrand, libx);
-                    else if (kGather && n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, rstrand, libx);
-                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand, libx);
+                    if (kGather && n_words == 4) stage_window(std::integral_constant<int, 4>{}, rec, row_at, first_word, 4, c_start, side, slab_w0, slab_words, rstrand, libx, lead_clip);
+                    else if (kGather && n_words == 3) stage_window(std::integral_constant<int, 3>{}, rec, row_at, first_word, 3, c_start, side, slab_w0, slab_words, rstrand, libx, lead_clip);
+                    else stage_window(std::integral_constant<int, 0>{}, rec, row_at, first_word, n_words, c_start, side, slab_w0, slab_words, rstrand, libx, lead_clip);
                 }
             }
             // ---- reads with one insertion / deletion ----

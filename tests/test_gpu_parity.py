@@ -299,7 +299,7 @@ def test_optional_arrays_default_on_device(name):
                                  {"MDG_PLANES_WS": "0"}, {"MDG_PLANES_WS": "2x8+8"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_FLUSH_TILES": "3"},
                                  {"MDG_PLANES_WS": "2x8+8", "MDG_PLANES_SLAB": "0"}, {"MDG_PLANES_WS": "2x8+8", "MDG_SWAR_UNIFORM": "0"},
                                  {"MDG_PLANES_WS": "2x9+8", "MDG_SWAR_FLUSH_TILES": "5"},
-                                 {"MDG_PLANES_WS": "2x8+4"}, {"MDG_PLANES_THREADS": "256"},
+                                 {"MDG_PLANES_QUAL": "0"}, {"MDG_PLANES_THREADS": "256"},
                                  {"MDG_PLANES_GATHER": "1", "MDG_PLANES_PREFETCH": "3"}, {"MDG_PLANES_GATHER": "1", "MDG_PLANES_WS": "2x8+8"},
                                  {"MDG_PLANES_INDELS": "1"}, {"MDG_PLANES_INDELS": "1", "MDG_PLANES_GATHER": "1", "MDG_SWAR_FLUSH_TILES": "3"},
                                  {"MDG_PLANES_INDELS": "1", "MDG_PLANES_WS": "2x8+8", "MDG_PLANES_SLAB": "0"}, {"MDG_PLANES_INDELS": "0"}])
