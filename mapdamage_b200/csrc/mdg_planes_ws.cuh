@@ -4,21 +4,27 @@
 // reads whose CIGAR is [H][S] M/=/X+ [S][H]; bit planes, vertical carry-save counters, substitutions as events), but the
 // three block-wide phases of that kernel (parse | stage | count, a barrier after each) are taken apart:
 //
-//   * kTeams producer teams of kTeamWarps warps.  A team owns one stage buffer of T = 32 kTeamWarps reads and walks its
-//     own tiles: parse (filter, CIGAR shape, per-read events, records into lists by strand), then -- once the consumers
-//     have released the buffer -- the plane words of every read's window(s) into the buffer.  The tile's stretch of
-//     seq4 arrives by one bulk asynchronous copy (cp.async.bulk + mbarrier) issued a tile ahead.  Teams run out of step
-//     with each other: while one waits for memory in its parse, another one's transposition keeps the pipes busy.
+//   * kTeams producer teams of kTeamWarps warps.  A team owns one stage buffer of T = 32 kTeamWarps rows and walks its
+//     own tiles of T reads: parse (filter, CIGAR shape, per-read events; the read's row = its rank in its group
+//     (library, strand), one warp-aggregated atomic), then -- once the consumers have released the buffer -- the plane
+//     words of every read's window(s) into its row.  The thread that parses a read stages it: the record stays in
+//     registers.  The tile's slices of the record arrays and its stretch of seq4 arrive by bulk asynchronous copies
+//     (cp.async.bulk + mbarrier) issued a tile ahead.  Teams run out of step with each other.
 //   * kConsWarps consumer warps hold ALL the counters (planes 0-7 in registers, 4-11 in shared memory).  They wait on a
 //     buffer's `full` mbarrier, add its reads into the vertical counters (thread = read slot x window word x reference
-//     base), and arrive on its `empty` mbarrier.  They alone reduce counters into the 64-bit tables.
+//     base; a read slot belongs to one group), and arrive on its `empty` mbarrier.  They alone reduce counters into the
+//     64-bit tables.
 //
 // full / empty are mbarriers with one arrival per thread of the side that signals (release / acquire at CTA scope order
 // the staged words); producers synchronise among themselves with a named barrier per team (bar.sync id, T), consumers
 // with their own.  There is no block-wide barrier between the first tile and the last.
 //
-// Substitution events go to a block-wide table indexed by TABLE cell ([anchor][strand][class][position]), so that teams
-// working in different window layouts can share it; it is drained once, at the end.
+// Substitution events go to a block-wide table indexed by TABLE cell ([library][anchor][strand][class][position]), so that
+// teams working in different window layouts can share it; it is drained once, at the end.
+//
+// Variants (template parameters, chosen by the host): kNL = 2 counts two libraries in one launch; kGather
+// has all of a window's genome loads in flight before its first word (genomes that do not fit L2); kIndels stages reads
+// with one insertion / deletion itself (stage_indel_word); kQual applies the -Q mask.
 #pragma once
 #include "mdg_planes.cuh"
 
