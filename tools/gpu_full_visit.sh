@@ -1,6 +1,6 @@
 #!/bin/bash
 # final single-GPU visit of the round: all GPU tests, smoke, the two bench arms, ncu launch list and full capture
-OUT=gpurun_out/r2m; mkdir -p $OUT
+OUT=gpurun_out/${1:-full}; mkdir -p $OUT
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q --timeout 180 > $OUT/pytest_gpu.log 2>&1; echo "rc=$?"; tail -4 $OUT/pytest_gpu.log
 echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "rc=$?"; tail -2 $OUT/smoke.log
 echo "== bench"; timeout 1500 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?"; tail -3 $OUT/bench.err
