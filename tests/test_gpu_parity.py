@@ -337,6 +337,31 @@ def test_mode_switches_and_flushes_at_scale(env, min_qual, monkeypatch):
         assert np.array_equal(2 * a, c), name
 
 
+@pytest.mark.parametrize("n_libs", [1, 2])
+@pytest.mark.parametrize("min_qual", [0, 15])
+def test_batch_sizes_around_the_tile_size(n_libs, min_qual, monkeypatch):
+    """Batches of 1 read up to a few tiles, on and just off the tile sizes of the warp-specialised kernel (288 reads, 256
+    with two libraries): a team without a tile, a last tile with one read, bulk copies of a few bytes."""
+    monkeypatch.setenv("MDG_PLANES_INDELS", "1")
+    reference = synth.make_reference([60_000, 2_000], seed=12, other_rate=0.001)
+    sizes = (1, 2, 31, 255, 256, 257, 287, 288, 289, 511, 512, 513, 575, 576, 577, 1153)
+    whole = synth.simulate_reads(reference, sum(sizes), seed=13, length=(30, 120), mix=(6, 1, 1, 2), n_libs=n_libs, read_n_rate=0.01)
+    with DamageEngine(n_libraries=n_libs, min_qual=min_qual, max_reads=0) as engine:
+        engine.set_reference(reference)
+        at = 0
+        for n in sizes:
+            part = whole.slice(at, at + n)
+            at += n
+            want = oracle.count(part, reference, minqual=min_qual, n_lib=n_libs, lg_bins=8192, threads=1)
+            engine.reset()
+            dev = engine.upload(part)
+            engine.count_resident(dev)
+            got = engine.tables()
+            dev.free()
+            for name, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
+                assert np.array_equal(a, b), (n, name)
+
+
 @pytest.mark.parametrize("env", [{}, {"MDG_PLANES_WS_LIBS": "0"}, {"MDG_PLANES_WS": "0"}, {"MDG_SWAR_FLUSH_TILES": "4"},
                                  {"MDG_SWAR_UNIFORM": "0"}, {"MDG_PLANES_GATHER": "1", "MDG_PLANES_PREFETCH": "3"},
                                  {"MDG_PLANES_INDELS": "1"}, {"MDG_PLANES_INDELS": "1", "MDG_PLANES_GATHER": "1"}])
