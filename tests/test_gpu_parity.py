@@ -79,6 +79,21 @@ def test_counting_table_shapes(length, around):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("length,around", [(50, 10), (40, 24), (86, 10), (70, 26), (22, 10)])
+@pytest.mark.parametrize("n_lib,min_qual", [(1, 0), (2, 0), (1, 18)])
+def test_window_geometries_of_the_planes_kernels(length, around, n_lib, min_qual, monkeypatch):
+    """--length / --around at the edges of what the warp-specialised kernel is compiled for (two or three 32-position words
+    per anchor window; its largest shared-memory footprint at L + A = 96), one word per window (the one-role kernel),
+    with two libraries, with -Q, with one-indel reads staged by the planes kernel."""
+    monkeypatch.setenv("MDG_PLANES_INDELS", "1")
+    reference = synth.make_reference([80_000, 3_000], seed=21, other_rate=0.001)
+    batch = synth.simulate_reads(reference, 30_000, seed=22, length=(25, 130), mix=(5, 2, 2, 1), n_libs=n_lib, read_n_rate=0.01)
+    want = oracle.count(batch, reference, length=length, around=around, minqual=min_qual, n_lib=n_lib, lg_bins=8192, threads=4)
+    got = run_engine(batch, reference, n_lib=n_lib, length=length, around=around, min_qual=min_qual, resident=True)
+    for key, a, b in zip(("misincorp", "dnacomp", "lghist"), got, want):
+        assert np.array_equal(a, b), key
+
+
 def test_fragment_length_overflow():
     reference = synth.make_reference([50_000], seed=8)
     batch = synth.simulate_reads(reference, 5_000, seed=9, length=(30, 120), paired=True)
